@@ -1,0 +1,16 @@
+// abi.cu -- error plumbing + version for the C ABI (include/etb200.h).
+#include "common.cuh"
+#include <stdarg.h>
+#include <string.h>
+
+static thread_local char g_err[512] = "";
+
+void etb_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* etb_last_error(void) { return g_err; }
+extern "C" int etb_version(void) { return 100; }

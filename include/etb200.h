@@ -1,0 +1,177 @@
+/*
+ * etb200.h -- C ABI of libetb200.so, the B200 (sm_100a) kernels behind the EfficientTeacher SSOD step.
+ *
+ * The reference (AlibabaResearch/efficientteacher) is pure Python and has no FFI of its own
+ * (SURVEY.md section 2.1), so every entry point below replaces a *library call made from Python*;
+ * the reference call site each one stands in for is cited as file:line relative to the reference root.
+ * INTEGRATION.md shows the ctypes binding a maintainer would add on the reference side.
+ *
+ * Conventions
+ *  - plain C types only: raw device pointers, sizes, scalars, `void* stream` (a cudaStream_t).
+ *  - the caller owns every buffer (allocated as torch tensors or cudaMalloc); the library never
+ *    allocates or frees user-visible memory.  Scratch comes in through explicit workspace pointers
+ *    whose size is returned by the matching *_workspace_bytes() query.
+ *  - every launch goes to the stream passed in; nothing synchronises the device.
+ *  - return value: 0 on success, negative errno-style code otherwise; etb_last_error() gives text.
+ *    Errors are never thrown across the ABI.
+ *  - there is NO CPU fallback: every compute entry point returns ETB_ERR_CUDA if no sm_100 device
+ *    kernel image can run.
+ */
+#ifndef ETB200_H_
+#define ETB200_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ETB_OK 0
+#define ETB_ERR_INVALID (-22) /* EINVAL  */
+#define ETB_ERR_CUDA (-5)     /* EIO: a CUDA runtime call / launch failed */
+#define ETB_ERR_NOMEM (-12)   /* workspace too small */
+
+#define ETB_MAX_LEVELS 3
+#define ETB_NA 3 /* anchors per level */
+
+int etb_version(void);
+const char* etb_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * EMA  (replaces the per-tensor Python loop of ModelEMA / SemiSupModelEMA / CosineEMA .update,
+ *       utils/torch_utils.py:328-338, 364-375, 405-416; called from trainer/ssod_trainer.py:485-487)
+ *
+ * One launch updates every floating tensor of the state_dict.  The host builds a chunk table once
+ * (etb_ema_table_fill), uploads it, and passes the device copy to etb_ema_update.
+ *   v <- fl32(fl32(v*d) + fl32(fl32(1-d)*m))            (two roundings, no FMA: bit-exact with torch CPU)
+ * and, when the chunk has a second EMA `s` (the SSOD "semi" EMA of the EMA),
+ *   s <- fl32(fl32(s*d2) + fl32(fl32(1-d2)*v_new))      in the same pass (5 HBM streams instead of 6).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct EtbEmaChunk {
+  float* v;       /* EMA tensor slice (read+write)            */
+  const float* m; /* model tensor slice (read)                */
+  float* s;       /* optional second EMA slice, or NULL       */
+  int32_t n;      /* elements in this chunk (<= ETB_EMA_CHUNK) */
+  int32_t pad_;
+} EtbEmaChunk;
+#define ETB_EMA_CHUNK 4096
+
+int64_t etb_ema_table_count(const int64_t* numel, int32_t n_tensors);
+int etb_ema_table_fill(float* const* v, const float* const* m, float* const* s, const int64_t* numel,
+                       int32_t n_tensors, EtbEmaChunk* out_host, int64_t out_capacity);
+int etb_ema_update(const EtbEmaChunk* table_dev, int64_t n_chunks, float d, float one_minus_d, float d2,
+                   float one_minus_d2, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Detect eval-mode decode (models/head/yolov5_head.py:66-78): logits [B,na,ny,nx,no] of one level ->
+ * rows of pred[B,P,no] at row offset `row0`:  sigmoid; xy=(2s-0.5+grid)*stride; wh=(2s)^2*anchor*stride.
+ * ------------------------------------------------------------------------------------------- */
+int etb_detect_decode(const float* logits, float* pred, int32_t B, int32_t na, int32_t ny, int32_t nx,
+                      int32_t no, int32_t P_total, int32_t row0, const float* anchors_grid /*[na*2] host*/,
+                      float stride, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * non_max_suppression_ssod + output_to_target_ssod + FairPseudoLabel box transform
+ * (utils/general.py:887-992; utils/plots.py:485-491; utils/self_supervised_utils.py:194-245,414-454,316-321)
+ *
+ * pred [B,P,no] fp32 (decoded), multi_label=False path.  All images in one batch of launches, no host sync.
+ *   det      [B,max_det,8] fp32  rows [x1,y1,x2,y2,conf,cls,obj,cls_score] in NMS score order
+ *   det_cnt  [B] int32
+ *   When Ms != NULL (B x 13 doubles: [img, M(9 row-major), s, ud, lr], utils/datasets_ssod.py:989) the
+ *   pseudo-label rows [img,cls,cx,cy,w,h,conf,obj,cls_score] (float64, normalised, strong-aug frame) are
+ *   written image-major to pl_rows[B*max_det,9] and their number to pl_cnt[1].
+ * ------------------------------------------------------------------------------------------- */
+typedef struct EtbNmsParams {
+  int32_t B, P, no;         /* batch, predictions per image, 5+nc */
+  float conf_thres, iou_thres;
+  int32_t max_nms;          /* 30000 (general.py:911) */
+  int32_t max_det;          /* 300   (general.py:888) */
+  float max_wh;             /* 7680  (general.py:910): class offset; 0 => agnostic */
+  int32_t need_cls_conf;    /* 0: non_max_suppression_ssod candidate test (obj only, general.py:900);
+                               1: non_max_suppression (general.py:1005) candidate needs max cls > thr too */
+  int32_t img_h, img_w;     /* for the pseudo-label normalisation */
+} EtbNmsParams;
+
+size_t etb_nms_workspace_bytes(const EtbNmsParams* p);
+int etb_nms_ssod(const float* pred, const EtbNmsParams* p, float* det, int32_t* det_cnt, const double* Ms,
+                 double* pl_rows, int32_t* pl_cnt, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Pseudo-Label-Assigner routing: ComputeStudentMatchLoss.select_targets
+ * (models/loss/ssod/ssod_loss.py:130-192).  rows [N,9] float64 (N read from n_dev if non-NULL, else n_host);
+ * thr_high/thr_low [nc] float64 on device.  Outputs 4 x [cap,7] fp32 (reliable, uncertain, uncertain_obj,
+ * uncertain_cls) and out_cnt[4] int32, order preserved.
+ * ------------------------------------------------------------------------------------------- */
+int etb_select_targets(const double* rows, const int32_t* n_dev, int32_t n_host, int32_t cap,
+                       const double* thr_high, const double* thr_low, int32_t nc, int32_t with_obj,
+                       float* out /*[4][cap][7]*/, int32_t* out_cnt /*[4]*/, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * YOLOAnchorAssigner.build_targets / build_uc_targets_aug
+ * (models/assigner/yolo_anchor_assigner.py:319-372, 640-697).
+ * targets [nt,tstride] fp32 (tstride 6: img,cls,x,y,w,h ; 7: +score).  nt read from nt_dev if non-NULL.
+ * Per level l (capacity cap rows, 15*nt suffices):
+ *   idx  [cap,4] int32 = (b, a, gj, gi)      tbox [cap,4] f32 = (gx-gi', gy-gj', gw, gh)
+ *   anch [cap,2] f32                        tcls [cap] int32      tscore [cap] f32 (tstride 7 only)
+ *   cnt[l] int32.  Row order: offset-major, anchor-major, target order (bit-exact with the reference).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct EtbAssignLevels {
+  int32_t nl;
+  int32_t nx[ETB_MAX_LEVELS], ny[ETB_MAX_LEVELS];
+  float anchors[ETB_MAX_LEVELS][ETB_NA * 2]; /* grid units (anchors / stride) */
+  float anchor_t;                            /* 4.0 */
+} EtbAssignLevels;
+
+typedef struct EtbAssignOut {
+  int32_t* idx[ETB_MAX_LEVELS];
+  float* tbox[ETB_MAX_LEVELS];
+  float* anch[ETB_MAX_LEVELS];
+  int32_t* tcls[ETB_MAX_LEVELS];
+  float* tscore[ETB_MAX_LEVELS]; /* may be NULL when tstride==6 */
+  int32_t* cnt;                  /* [nl] */
+  int32_t cap;
+} EtbAssignOut;
+
+int etb_build_targets(const float* targets, const int32_t* nt_dev, int32_t nt_host, int32_t tstride,
+                      const EtbAssignLevels* lv, const EtbAssignOut* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * bbox_iou, CIoU branch, xywh 1-to-1 (utils/metrics.py:207-249).  box1,box2 [n,4] fp32 -> out [n].
+ * ------------------------------------------------------------------------------------------- */
+int etb_bbox_ciou(const float* box1, const float* box2, int32_t n, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * ComputeLoss.default_loss (models/loss/loss.py:138-208) and ComputeStudentMatchLoss.default_loss
+ * (models/loss/ssod/ssod_loss.py:194-288), forward and backward, fused:
+ *   gather ps -> decode -> CIoU -> (1-iou) mean ; cls BCE ; tobj scatter (highest row index wins, = CPU
+ *   oracle) ; uncertain soft-label override ; obj BCE over cells with tobj>=0 ; weights ; x batch.
+ * p[l] [B,na,ny,nx,no] fp32.  Target sets come from etb_build_targets (device counts, no host sync).
+ *   set 0: certain (box+cls+tobj=iou)    set 1: uncertain (tobj=score or -1)   [SSOD only]
+ *   set 2: uncertain_obj (extra box term) set 3: uncertain_cls (extra cls term) [SSOD only]
+ * out[4] fp32 = {lbox, lobj, lcls, loss*B} (already weighted like the reference's loss dict).
+ * Backward writes dense grad_p[l] (every element written; no pre-zeroing needed), scaled by *gscale_dev.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct EtbLossParams {
+  int32_t nl, B, na, no;
+  int32_t nx[ETB_MAX_LEVELS], ny[ETB_MAX_LEVELS];
+  float balance[ETB_MAX_LEVELS];
+  float box_w, obj_w, cls_w;
+  float cp, cn;            /* smoothed BCE targets */
+  int32_t nsets;           /* 1 supervised, 4 SSOD */
+  int32_t ignore_obj;      /* SSOD.ignore_obj: uncertain cells -> tobj=-1 */
+  int32_t with_bbox;       /* SSOD.pseudo_label_with_bbox */
+  int32_t with_cls;        /* SSOD.pseudo_label_with_cls  */
+} EtbLossParams;
+
+size_t etb_loss_workspace_bytes(const EtbLossParams* lp, int32_t cap);
+int etb_loss_forward(const float* const* p /*[nl]*/, const EtbLossParams* lp, const EtbAssignOut* sets /*[nsets]*/,
+                     float* out4, void* workspace, size_t workspace_bytes, void* stream);
+int etb_loss_backward(const float* const* p, float* const* grad_p, const EtbLossParams* lp,
+                      const EtbAssignOut* sets, const float* gscale_dev, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ETB200_H_ */

@@ -1,0 +1,84 @@
+"""Seeded synthetic inputs shared by the golden-vector generator, the CPU tests and the GPU parity tests.
+numpy RandomState only (bit-reproducible across machines); recipes follow SURVEY.md section 8d."""
+import numpy as np
+
+F32 = np.float32
+ANCHORS_GRID = np.array([[[1.25, 1.625], [2.0, 3.75], [4.125, 2.875]],
+                         [[1.875, 3.8125], [3.875, 2.8125], [3.6875, 7.4375]],
+                         [[3.625, 2.8125], [4.875, 6.1875], [11.65625, 10.1875]]], dtype=F32)  # YOLOv5 anchors / stride
+STRIDES = (8, 16, 32)
+
+
+def level_shapes(img=640):
+    return [(img // s, img // s) for s in STRIDES]
+
+
+def make_targets(seed, n, B, with_conf=False):
+    """[n,6] (img,cls,x,y,w,h) normalised; includes exact cell-boundary (.5) cases and same-cell duplicates."""
+    r = np.random.RandomState(seed)
+    t = np.zeros((n, 6), F32)
+    t[:, 0] = r.randint(0, B, n)
+    t[:, 1] = r.randint(0, 80, n)
+    t[:, 2:4] = r.uniform(0.1, 0.9, (n, 2))
+    t[:, 4:6] = r.uniform(0.02, 0.32, (n, 2))
+    k = n // 16
+    if k == 0:
+        return t[np.argsort(t[:, 0], kind="stable")]
+    t[:k, 2] = (r.randint(8, 72, k) + 0.5) / 80.0      # gx % 1 == 0.5 exactly on P3
+    t[k:2 * k, 3] = r.randint(8, 72, k) / 80.0          # gy % 1 == 0
+    t[2 * k:3 * k] = t[3 * k:4 * k]                     # duplicate rows -> duplicate cells
+    t = t[np.argsort(t[:, 0], kind="stable")]
+    return t
+
+
+def make_teacher_pred(seed, B, P, nc=80, cand_frac=0.02, img=640):
+    """Decoded teacher predictions [B,P,5+nc] (SURVEY.md 8d probe4 recipe): ~cand_frac of rows have obj>0.1."""
+    r = np.random.RandomState(seed)
+    x = np.empty((B, P, 5 + nc), F32)
+    x[..., 0:2] = r.uniform(0, img, (B, P, 2))
+    x[..., 2:4] = r.uniform(4, 196, (B, P, 2))
+    hot = r.uniform(0, 1, (B, P)) < cand_frac
+    x[..., 4] = np.where(hot, r.uniform(0.1, 1.0, (B, P)), r.uniform(0, 0.05, (B, P)))
+    x[..., 5:] = r.uniform(0, 1, (B, P, nc)) ** 4
+    return x.astype(F32)
+
+
+def make_Ms(seed, B, img=640):
+    """[B,13] float64 = [i, M (3x3 row-major: scale about centre + translate), s, ud, lr] (datasets_ssod.py:989)."""
+    r = np.random.RandomState(seed)
+    Ms = np.zeros((B, 13))
+    for i in range(B):
+        s = r.uniform(0.5, 1.5)
+        tx, ty = r.uniform(-0.1, 0.1, 2) * img
+        C = np.array([[1, 0, -img / 2], [0, 1, -img / 2], [0, 0, 1.0]])
+        R = np.array([[s, 0, 0], [0, s, 0], [0, 0, 1.0]])
+        T = np.array([[1, 0, img / 2 + tx], [0, 1, img / 2 + ty], [0, 0, 1.0]])
+        M = T @ R @ C
+        Ms[i, 0] = i
+        Ms[i, 1:10] = M.reshape(-1)
+        Ms[i, 10] = s
+        Ms[i, 11] = 1.0 if (i % 5 == 3) else 0.0
+        Ms[i, 12] = float(r.uniform() < 0.5)
+    return Ms
+
+
+def make_pseudo_rows(seed, n, B):
+    """[n,9] float64 pseudo-label rows with confidences straddling the 0.1 / 0.6 / 0.99 thresholds."""
+    r = np.random.RandomState(seed)
+    t = make_targets(seed + 1, n, B).astype(np.float64)
+    conf = r.uniform(0.02, 1.0, n)
+    obj = np.where(r.uniform(size=n) < 0.3, r.uniform(0.99, 1.0, n), r.uniform(0.1, 1.0, n))
+    cc = np.where(r.uniform(size=n) < 0.3, r.uniform(0.99, 1.0, n), r.uniform(0.1, 1.0, n))
+    conf[:4] = [0.6, 0.1, np.float64(np.float32(0.6)), np.float64(np.float32(0.1))]   # exact-threshold cases
+    return np.concatenate([t, conf[:, None], obj[:, None], cc[:, None]], 1)
+
+
+def make_head_logits(seed, B, img=640, no=85, scale=1.5):
+    """Raw Detect train-mode outputs: list of [B,3,ny,nx,no] fp32."""
+    r = np.random.RandomState(seed)
+    out = []
+    for (ny, nx) in level_shapes(img):
+        x = (r.standard_normal((B, 3, ny, nx, no)) * scale).astype(F32)
+        x[..., 4] -= 3.0
+        out.append(x)
+    return out
