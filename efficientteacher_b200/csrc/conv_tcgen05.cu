@@ -1,0 +1,447 @@
+// conv_tcgen05.cu -- implicit-GEMM convolution on the 5th-gen tensor cores (K1/K5).
+//
+// Replaces cuDNN conv + BN(eval) + SiLU (+ residual add / Detect bias + permute copy) behind
+//   Conv.forward        reference models/backbone/common.py:471-484
+//   Bottleneck.forward  reference models/backbone/common.py:534-544   (residual add fused in the epilogue)
+//   Detect.forward      reference models/head/yolov5_head.py:55,66     (1x1 conv + bias, scattered to [B,3,ny,nx,85])
+//
+// GEMM view per CTA:  D[128 pixels, BN couts] += A[128 pixels, 64 ch] * B[BN couts, 64 ch]^T  over taps x channel blocks.
+//   * A (activations, NHWC bf16) comes straight from global memory through a 4-D TMA tile
+//     {64 ch, TW, TH, 1 image}; the tap shift (kh,kw) is a coordinate offset and the zero padding is TMA's
+//     out-of-bounds fill, so no im2col buffer exists.  Stride-2 convs use the tensor map's element strides.
+//   * B (weights, [Cout][kh*kw*Cin] bf16, K-major) is a 2-D TMA tile {64, BN}.
+//   * both land in 128B-swizzled shared memory = the canonical K-major UMMA layout; one elected thread issues
+//     tcgen05.mma (M=128, N=BN, K=16) x4 per stage; the fp32 accumulator lives in TMEM (BN columns).
+//   * warp roles: warp0 TMA producer, warp1 TMEM alloc + MMA issue, warps2-5 epilogue (tcgen05.ld -> scale/bias
+//     (folded BN) -> SiLU -> +residual -> bf16 NHWC store, written at a channel offset of a wider buffer so
+//     torch.cat is free).
+//   * every mbarrier wait is bounded (trap after ~2 s) so a descriptor bug cannot hang the GPU.
+#include "common.cuh"
+#include <cuda.h>
+
+#define CONV_BLOCK_M 128
+#define CONV_BLOCK_K 64
+#define CONV_THREADS 192
+
+// ------------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a wrong descriptor / byte count must fail loudly, never hang the box
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) {
+      printf("etb conv: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]; issued by ONE thread
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (8 rows x 128 B = 1024 B)
+//   [46,48) version=1 (sm_100) | [61,64) layout type 2 = SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (bit 4), a/b format BF16 (bits 7, 10),
+// both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------- kernel
+struct ConvKArgs {
+  int taps_w, taps_h;     // kw, kh
+  int kblocks;            // Cin / 64
+  int stride, pad;
+  int TW, TH;             // output tile (TW*TH <= 128 rows)
+  int tiles_w, tiles_h;   // per image
+  int Ho, Wo, Cout;
+  int y_cstride, y_coffset;
+  int res_cstride, res_coffset;
+  int act;                // 0 none, 1 SiLU, 2 ReLU
+  int out_mode;           // 0: bf16 NHWC ; 1: fp32 Detect layout [N, na, Ho, Wo, no] with c = a*no + o
+  int det_no, det_hw;     // outputs per anchor, pixels per image (Detect layout)
+  const float* scale;     // [Cout] or null (=1)
+  const float* bias;      // [Cout] or null (=0)
+  const __nv_bfloat16* residual;
+  __nv_bfloat16* y;
+  float* y_f32;
+};
+
+template <int BN, int STAGES>
+struct ConvSmem {
+  static constexpr int A_BYTES = CONV_BLOCK_M * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int SB_OFF = BAR_OFF + 256;             // scale/bias staging
+  static constexpr int TOTAL = SB_OFF + 2 * BN * 4 + 1024;  // + slack for the 1024 B alignment
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const ConvKArgs a) {
+  using L = ConvSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + L::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+  float* s_scale = (float*)(smem + L::SB_OFF);
+  float* s_bias = s_scale + BN;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // tile coordinates
+  int t = blockIdx.x;
+  const int tw_i = t % a.tiles_w; t /= a.tiles_w;
+  const int th_i = t % a.tiles_h; t /= a.tiles_h;
+  const int img = t;
+  const int w0 = tw_i * a.TW, h0 = th_i * a.TH;
+  const int n0 = blockIdx.y * BN;
+  const int kiters = a.taps_w * a.taps_h * a.kblocks;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      const uint32_t a_bytes = (uint32_t)(a.TW * a.TH * 128);
+      int it = 0;
+      for (int kh = 0; kh < a.taps_h; ++kh)
+        for (int kw = 0; kw < a.taps_w; ++kw)
+          for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+            mbar_wait(&empty[s], ph ^ 1u);
+            uint8_t* sa = smem + s * L::STAGE_BYTES;
+            uint8_t* sb = sa + L::A_BYTES;
+            mbar_expect_tx(&full[s], a_bytes + (uint32_t)L::B_BYTES);
+            tma_load_4d(&mapA, &full[s], sa, kb * CONV_BLOCK_K, w0 * a.stride + kw - a.pad, h0 * a.stride + kh - a.pad, img);
+            tma_load_2d(&mapB, &full[s], sb, ((kh * a.taps_w + kw) * a.kblocks + kb) * CONV_BLOCK_K, n0);
+          }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(CONV_BLOCK_M, BN);
+      for (int it = 0; it < kiters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+        const uint64_t adesc = make_kmajor_sw128_desc(sa);
+        const uint64_t bdesc = make_kmajor_sw128_desc(sa + L::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < CONV_BLOCK_K / 16; ++k)  // +32 B per UMMA_K step inside the 128 B swizzle atom
+          umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
+        umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
+      }
+      umma_commit(tmem_full);    // accumulator complete
+    }
+  } else {
+    // ===== epilogue: 4 warps <-> 128 TMEM lanes (a warp may only touch lanes 32*(warp%4)..+31) =====
+    const int et = threadIdx.x - 64;
+    for (int c = et; c < BN; c += 128) {
+      const int gc = n0 + c;
+      s_scale[c] = (a.scale && gc < a.Cout) ? a.scale[gc] : 1.0f;
+      s_bias[c] = (a.bias && gc < a.Cout) ? a.bias[gc] : 0.0f;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int row = 32 * (warp & 3) + lane;
+    const int th = row / a.TW, tw = row - th * a.TW;
+    const int oh = h0 + th, ow = w0 + tw;
+    const bool row_ok = (row < a.TW * a.TH) && (oh < a.Ho) && (ow < a.Wo);
+    const size_t pix = ((size_t)img * a.Ho + oh) * a.Wo + ow;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= a.Cout) break;  // warp-uniform
+      uint32_t v[32];
+      tmem_ld32(lane_addr + (uint32_t)c0, v);
+      if (!row_ok) continue;
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = fmaf(__uint_as_float(v[j]), s_scale[c0 + j], s_bias[c0 + j]);
+        if (a.act == 1) x = __fdividef(x, 1.0f + __expf(-x));
+        else if (a.act == 2) x = fmaxf(x, 0.0f);
+        f[j] = x;
+      }
+      if (a.out_mode == 0) {
+        if (a.residual) {
+          const uint4* rp = reinterpret_cast<const uint4*>(a.residual + pix * a.res_cstride + a.res_coffset + n0 + c0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 rv = __ldg(rp + q);
+            const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 rf = __bfloat1622float2(r2[j]);
+              f[q * 8 + 2 * j] += rf.x;
+              f[q * 8 + 2 * j + 1] += rf.y;
+            }
+          }
+        }
+        __nv_bfloat16* yp = a.y + pix * a.y_cstride + a.y_coffset + n0 + c0;
+        if (n0 + c0 + 32 <= a.Cout) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 ov;
+            __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(f[q * 8 + 2 * j], f[q * 8 + 2 * j + 1]);
+            reinterpret_cast<uint4*>(yp)[q] = ov;
+          }
+        } else {
+          for (int j = 0; j < 32 && n0 + c0 + j < a.Cout; ++j) yp[j] = __float2bfloat16(f[j]);
+        }
+      } else {
+        // Detect train layout: y[img][anchor][oh][ow][o], channel c = anchor*no + o  (yolov5_head.py:66)
+        const size_t hw = (size_t)a.det_hw;
+        const size_t img_r = pix / hw, pin = pix - img_r * hw;   // pix is the global pixel index in both tilings
+        const int na = a.Cout / a.det_no;
+#pragma unroll 4
+        for (int j = 0; j < 32; ++j) {
+          const int gc = n0 + c0 + j;
+          if (gc < a.Cout) {
+            const int an = gc / a.det_no, o = gc - an * a.det_no;
+            a.y_f32[((img_r * na + an) * hw + pin) * a.det_no + o] = f[j];
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- host side
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled get_encode() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (PFN_tmapEncodeTiled)p;
+  }
+  return fn;
+}
+
+static void pick_tile(int Wo, int Ho, int* TW, int* TH) {
+  // maximise useful rows of the 128-row MMA tile: TW*TH <= 128, TW <= 128 (stride-2 boxes need 2*TW <= 256)
+  double best = -1.0;
+  for (int tw = 1; tw <= 128; ++tw) {
+    if (tw > Wo && tw != 1) break;
+    int th = 128 / tw;
+    if (th > Ho) th = Ho;
+    if (th < 1) continue;
+    const long tiles = (long)((Wo + tw - 1) / tw) * ((Ho + th - 1) / th);
+    const double eff = (double)Wo * Ho / ((double)tiles * 128.0);
+    if (eff > best + 1e-9) { best = eff; *TW = tw; *TH = th; }
+  }
+}
+
+template <int BN, int STAGES>
+static int launch_conv(const CUtensorMap& mA, const CUtensorMap& mB, const ConvKArgs& ka, dim3 grid, cudaStream_t st) {
+  using L = ConvSmem<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ETB_CHECK_CUDA(cudaFuncSetAttribute(conv_fwd_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_set = true;
+  }
+  conv_fwd_kernel<BN, STAGES><<<grid, CONV_THREADS, L::TOTAL, st>>>(mA, mB, ka);
+  ETB_CHECK_LAUNCH();
+  return ETB_OK;
+}
+
+extern "C" size_t etb_conv_workspace_bytes(const EtbConvParams* cp) { (void)cp; return 0; }
+
+extern "C" int etb_conv_fwd(const void* x_bf16, const void* w_bf16, const float* scale, const float* bias,
+                            const void* residual_bf16, void* y_bf16, float* y_f32, const EtbConvParams* cp, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  (void)workspace; (void)workspace_bytes;
+  ETB_CHECK_ARG(x_bf16 && w_bf16 && cp && (y_bf16 || y_f32));
+  ETB_CHECK_ARG(cp->N > 0 && cp->H > 0 && cp->W > 0 && cp->Cin > 0 && cp->Cout > 0);
+  ETB_CHECK_ARG(cp->Cin % CONV_BLOCK_K == 0);
+  ETB_CHECK_ARG(cp->kh >= 1 && cp->kw >= 1 && (cp->stride == 1 || cp->stride == 2) && cp->pad >= 0);
+  ETB_CHECK_ARG(cp->x_cstride >= cp->Cin && cp->x_cstride % 8 == 0 && (((uintptr_t)x_bf16) & 15) == 0 && (((uintptr_t)w_bf16) & 15) == 0);
+  PFN_tmapEncodeTiled enc = get_encode();
+  if (!enc) {
+    etb_set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return ETB_ERR_CUDA;
+  }
+  const int Ho = (cp->H + 2 * cp->pad - cp->kh) / cp->stride + 1;
+  const int Wo = (cp->W + 2 * cp->pad - cp->kw) / cp->stride + 1;
+  ETB_CHECK_ARG(Ho > 0 && Wo > 0);
+  const bool det = (y_f32 != nullptr);
+  if (!det) ETB_CHECK_ARG(cp->y_cstride % 8 == 0 && cp->y_coffset % 8 == 0 && cp->y_cstride >= cp->y_coffset + cp->Cout && (((uintptr_t)y_bf16) & 15) == 0);
+  if (residual_bf16) ETB_CHECK_ARG(!det && cp->res_cstride % 8 == 0 && cp->res_coffset % 8 == 0 && cp->Cout % 32 == 0);
+  if (det) ETB_CHECK_ARG(cp->det_no > 0 && cp->Cout % cp->det_no == 0);
+
+  ConvKArgs ka;
+  memset(&ka, 0, sizeof(ka));
+  // geometry: a pointwise stride-1 conv is a flat [N*H*W, Cin] GEMM (tile = 128 consecutive pixels);
+  // anything else tiles the output plane of one image.
+  const bool flat = (cp->kh == 1 && cp->kw == 1 && cp->stride == 1 && cp->pad == 0);
+  cuuint64_t gdim[4], gstr[3];
+  cuuint32_t box[4], estr[4];
+  int nimg;
+  if (flat) {
+    const long npix = (long)cp->N * cp->H * cp->W;
+    ETB_CHECK_ARG(npix < (1l << 31));
+    ka.TW = 128; ka.TH = 1;
+    ka.Ho = 1; ka.Wo = (int)npix;
+    ka.tiles_w = (int)((npix + 127) / 128); ka.tiles_h = 1;
+    nimg = 1;
+    gdim[0] = cp->Cin; gdim[1] = (cuuint64_t)npix; gdim[2] = 1; gdim[3] = 1;
+    gstr[0] = (cuuint64_t)cp->x_cstride * 2; gstr[1] = gstr[0] * (cuuint64_t)npix; gstr[2] = gstr[1];
+    box[0] = 64; box[1] = 128; box[2] = 1; box[3] = 1;
+    estr[0] = estr[1] = estr[2] = estr[3] = 1;
+  } else {
+    pick_tile(Wo, Ho, &ka.TW, &ka.TH);
+    ka.Ho = Ho; ka.Wo = Wo;
+    ka.tiles_w = (Wo + ka.TW - 1) / ka.TW; ka.tiles_h = (Ho + ka.TH - 1) / ka.TH;
+    nimg = cp->N;
+    gdim[0] = cp->Cin; gdim[1] = cp->W; gdim[2] = cp->H; gdim[3] = cp->N;
+    gstr[0] = (cuuint64_t)cp->x_cstride * 2; gstr[1] = gstr[0] * cp->W; gstr[2] = gstr[1] * cp->H;
+    // with element strides the box is measured in input elements: ceil(box/stride) elements are loaded
+    box[0] = 64; box[1] = (cuuint32_t)(ka.TW * cp->stride); box[2] = (cuuint32_t)(ka.TH * cp->stride); box[3] = 1;
+    estr[0] = 1; estr[1] = (cuuint32_t)cp->stride; estr[2] = (cuuint32_t)cp->stride; estr[3] = 1;
+    ETB_CHECK_ARG(box[1] <= 256 && box[2] <= 256);
+  }
+  CUtensorMap mA, mB;
+  CUresult r = enc(&mA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x_bf16), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    etb_set_error("cuTensorMapEncodeTiled(A) failed: %d", (int)r);
+    return ETB_ERR_CUDA;
+  }
+  const long Ktot = (long)cp->kh * cp->kw * cp->Cin;
+  const int BN = cp->Cout > 128 ? 256 : (cp->Cout > 64 ? 128 : 64);
+  cuuint64_t wdim[2] = {(cuuint64_t)Ktot, (cuuint64_t)cp->Cout};
+  cuuint64_t wstr[1] = {(cuuint64_t)Ktot * 2};
+  cuuint32_t wbox[2] = {64, (cuuint32_t)BN};
+  cuuint32_t westr[2] = {1, 1};
+  r = enc(&mB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_bf16), wdim, wstr, wbox, westr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    etb_set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r);
+    return ETB_ERR_CUDA;
+  }
+  ka.taps_w = cp->kw; ka.taps_h = cp->kh;
+  ka.kblocks = cp->Cin / CONV_BLOCK_K;
+  ka.stride = cp->stride; ka.pad = cp->pad;
+  ka.Cout = cp->Cout;
+  ka.y_cstride = cp->y_cstride; ka.y_coffset = cp->y_coffset;
+  ka.res_cstride = cp->res_cstride; ka.res_coffset = cp->res_coffset;
+  ka.act = cp->act;
+  ka.out_mode = det ? 1 : 0;
+  ka.det_no = cp->det_no;
+  ka.det_hw = Ho * Wo;
+  ka.scale = scale; ka.bias = bias;
+  ka.residual = (const __nv_bfloat16*)residual_bf16;
+  ka.y = (__nv_bfloat16*)y_bf16;
+  ka.y_f32 = y_f32;
+  dim3 grid((unsigned)(ka.tiles_w * ka.tiles_h * nimg), (unsigned)((cp->Cout + BN - 1) / BN));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (BN == 256) return launch_conv<256, 4>(mA, mB, ka, grid, st);
+  if (BN == 128) return launch_conv<128, 3>(mA, mB, ka, grid, st);   // ~97 KB smem: 2 CTAs/SM overlap epilogue and mainloop
+  return launch_conv<64, 4>(mA, mB, ka, grid, st);
+}

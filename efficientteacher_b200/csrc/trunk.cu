@@ -1,0 +1,194 @@
+// trunk.cu -- layout / pooling / folding helpers around the tcgen05 convolutions (K3, K4, K18).
+//   stem im2col + /255      reference trainer/ssod_trainer.py:694-696, models/backbone/yolov5_backbone.py:56
+//   SPPF max pools + concat reference models/backbone/common.py:702-708
+//   nearest 2x upsample     reference models/neck/yolov5_neck.py:92,97 (+ Concat common.py:796-797, free by slicing)
+//   eval BN folding         reference utils/torch_utils.py:199-219 (fuse_conv_and_bn algebra), bn eps 1e-3
+// All elementwise / gather kernels: HBM-bound, 16 B vector accesses along the channel (fastest) dimension.
+#include "common.cuh"
+
+static inline unsigned grid_for(int64_t n, int threads) {
+  int64_t b = (n + threads - 1) / threads;
+  const int64_t cap = (int64_t)etb_num_sms() * 32;
+  return (unsigned)(b > cap ? cap : (b < 1 ? 1 : b));
+}
+
+// ---- stem im2col: one thread per (pixel, 8-element K group): 16 groups x 8 = 128 K slots (108 used) ----
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H, int W, float mul) {
+  const int Ho = H / 2, Wo = W / 2;
+  const int64_t total = (int64_t)N * Ho * Wo * 16;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(e & 15);
+    const int64_t pix = e >> 4;
+    const int ow = (int)(pix % Wo), oh = (int)((pix / Wo) % Ho), n = (int)(pix / ((int64_t)Wo * Ho));
+    uint4 ov;
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(&ov);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = g * 8 + j;
+      float v = 0.f;
+      if (k < 108) {
+        const int c = k % 3, t = k / 3, kw = t % 6, kh = t / 6;
+        const int ih = oh * 2 + kh - 2, iw = ow * 2 + kw - 2;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = __fmul_rn(__ldg(x + (((int64_t)n * 3 + c) * H + ih) * W + iw), mul);
+      }
+      o[j] = __float2bfloat16(v);
+    }
+    reinterpret_cast<uint4*>(y)[e] = ov;
+  }
+}
+
+extern "C" int etb_stem_im2col(const float* x, void* y_bf16, int32_t N, int32_t H, int32_t W, float mul, void* stream) {
+  ETB_CHECK_ARG(x && y_bf16 && N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0);
+  const int64_t total = (int64_t)N * (H / 2) * (W / 2) * 16;
+  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y_bf16, N, H, W, mul);
+  ETB_CHECK_LAUNCH();
+  return ETB_OK;
+}
+
+// ---- NCHW fp32 <-> NHWC bf16 (simple gather; used at the edges of the trunk and by the tests) ----
+__global__ void __launch_bounds__(256) nchw2nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int C, int H, int W,
+                                                        int cs, int co, float mul) {
+  const int64_t total = (int64_t)N * H * W * C;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % C);
+    const int64_t pix = e / C;
+    const int w = (int)(pix % W), h = (int)((pix / W) % H), n = (int)(pix / ((int64_t)W * H));
+    y[pix * cs + co + c] = __float2bfloat16(__fmul_rn(x[(((int64_t)n * C + c) * H + h) * W + w], mul));
+  }
+}
+__global__ void __launch_bounds__(256) nhwc2nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int N, int C, int H, int W, int cs, int co) {
+  const int64_t total = (int64_t)N * H * W * C;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int w = (int)(e % W), h = (int)((e / W) % H), c = (int)((e / ((int64_t)W * H)) % C), n = (int)(e / ((int64_t)W * H * C));
+    y[e] = __bfloat162float(x[(((int64_t)n * H + h) * W + w) * cs + co + c]);
+  }
+}
+extern "C" int etb_nchw_f32_to_nhwc_bf16(const float* x, void* y, int32_t N, int32_t C, int32_t H, int32_t W, int32_t y_cstride,
+                                         int32_t y_coffset, float mul, void* stream) {
+  ETB_CHECK_ARG(x && y && N > 0 && C > 0 && H > 0 && W > 0 && y_cstride >= y_coffset + C);
+  nchw2nhwc_kernel<<<grid_for((int64_t)N * C * H * W, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, N, C, H, W, y_cstride, y_coffset, mul);
+  ETB_CHECK_LAUNCH();
+  return ETB_OK;
+}
+extern "C" int etb_nhwc_bf16_to_nchw_f32(const void* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W, int32_t x_cstride,
+                                         int32_t x_coffset, void* stream) {
+  ETB_CHECK_ARG(x && y && N > 0 && C > 0 && H > 0 && W > 0 && x_cstride >= x_coffset + C);
+  nhwc2nchw_kernel<<<grid_for((int64_t)N * C * H * W, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, y, N, C, H, W, x_cstride, x_coffset);
+  ETB_CHECK_LAUNCH();
+  return ETB_OK;
+}
+
+// ---- SPPF: three cascaded 5x5 s1 p2 max pools == 5x5, 9x9, 13x13 windows of x (max is idempotent/associative) ----
+__device__ __forceinline__ void bf8_max(uint4& acc, const uint4& v) {
+  __nv_bfloat162* a = reinterpret_cast<__nv_bfloat162*>(&acc);
+  const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) a[j] = __hmax2(a[j], b[j]);
+}
+__global__ void __launch_bounds__(256) sppf_pool_kernel(__nv_bfloat16* __restrict__ buf, int N, int H, int W, int C, int cs) {
+  const int cg = C / 8;
+  const int64_t total = (int64_t)N * H * W * cg;
+  const uint32_t ninf2 = 0xFF80FF80u;  // bf16 -inf pair (max-pool padding value)
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(e % cg);
+    const int64_t pix = e / cg;
+    const int w = (int)(pix % W), h = (int)((pix / W) % H), n = (int)(pix / ((int64_t)W * H));
+    uint4 m5 = make_uint4(ninf2, ninf2, ninf2, ninf2), m9 = m5, m13 = m5;
+    for (int dy = -6; dy <= 6; ++dy) {
+      const int ih = h + dy;
+      if (ih < 0 || ih >= H) continue;
+      for (int dx = -6; dx <= 6; ++dx) {
+        const int iw = w + dx;
+        if (iw < 0 || iw >= W) continue;
+        const uint4 v = *reinterpret_cast<const uint4*>(buf + (((int64_t)n * H + ih) * W + iw) * cs + g * 8);
+        bf8_max(m13, v);
+        if (dy >= -4 && dy <= 4 && dx >= -4 && dx <= 4) bf8_max(m9, v);
+        if (dy >= -2 && dy <= 2 && dx >= -2 && dx <= 2) bf8_max(m5, v);
+      }
+    }
+    __nv_bfloat16* o = buf + pix * cs + g * 8;
+    *reinterpret_cast<uint4*>(o + C) = m5;
+    *reinterpret_cast<uint4*>(o + 2 * C) = m9;
+    *reinterpret_cast<uint4*>(o + 3 * C) = m13;
+  }
+}
+extern "C" int etb_sppf_pool(void* buf_bf16, int32_t N, int32_t H, int32_t W, int32_t C, int32_t cstride, void* stream) {
+  ETB_CHECK_ARG(buf_bf16 && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && cstride >= 4 * C && cstride % 8 == 0);
+  sppf_pool_kernel<<<grid_for((int64_t)N * H * W * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)buf_bf16, N, H, W, C, cstride);
+  ETB_CHECK_LAUNCH();
+  return ETB_OK;
+}
+
+// ---- nearest 2x upsample into a channel slice ----
+__global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H, int W, int C,
+                                                         int xcs, int xco, int ycs, int yco) {
+  const int cg = C / 8;
+  const int Ho = 2 * H, Wo = 2 * W;
+  const int64_t total = (int64_t)N * Ho * Wo * cg;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(e % cg);
+    const int64_t pix = e / cg;
+    const int w = (int)(pix % Wo), h = (int)((pix / Wo) % Ho), n = (int)(pix / ((int64_t)Wo * Ho));
+    const uint4 v = *reinterpret_cast<const uint4*>(x + (((int64_t)n * H + (h >> 1)) * W + (w >> 1)) * xcs + xco + g * 8);
+    *reinterpret_cast<uint4*>(y + pix * ycs + yco + g * 8) = v;
+  }
+}
+extern "C" int etb_upsample2x_nhwc(const void* x_bf16, void* y_bf16, int32_t N, int32_t H, int32_t W, int32_t C, int32_t x_cstride,
+                                   int32_t x_coffset, int32_t y_cstride, int32_t y_coffset, void* stream) {
+  ETB_CHECK_ARG(x_bf16 && y_bf16 && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0);
+  ETB_CHECK_ARG(x_cstride % 8 == 0 && x_coffset % 8 == 0 && y_cstride % 8 == 0 && y_coffset % 8 == 0);
+  upsample2x_kernel<<<grid_for((int64_t)N * 4 * H * W * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x_bf16, (__nv_bfloat16*)y_bf16, N, H, W, C, x_cstride, x_coffset, y_cstride, y_coffset);
+  ETB_CHECK_LAUNCH();
+  return ETB_OK;
+}
+
+// ---- BN folding + weight packing ----
+__global__ void fold_bn_kernel(const float* g, const float* b, const float* m, const float* v, float eps, float* scale, float* bias, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float s = g[c] / sqrtf(v[c] + eps);
+  scale[c] = s;
+  bias[c] = b[c] - m[c] * s;
+}
+extern "C" int etb_fold_bn(const float* gamma, const float* beta, const float* mean, const float* var, float eps, float* scale,
+                           float* bias, int32_t C, void* stream) {
+  ETB_CHECK_ARG(gamma && beta && mean && var && scale && bias && C > 0);
+  fold_bn_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gamma, beta, mean, var, eps, scale, bias, C);
+  ETB_CHECK_LAUNCH();
+  return ETB_OK;
+}
+
+__global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o, int Cout, int Cin, int kh, int kw, int Cp) {
+  const int64_t total = (int64_t)Cout * kh * kw * Cp;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % Cp);
+    const int64_t t = e / Cp;
+    const int x = (int)(t % kw), y = (int)((t / kw) % kh), oc = (int)(t / ((int64_t)kw * kh));
+    o[e] = __float2bfloat16(c < Cin ? w[(((int64_t)oc * Cin + c) * kh + y) * kw + x] : 0.f);
+  }
+}
+extern "C" int etb_pack_weight(const float* w_oihw, void* w_bf16, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw, int32_t Cin_pad, void* stream) {
+  ETB_CHECK_ARG(w_oihw && w_bf16 && Cout > 0 && Cin > 0 && kh > 0 && kw > 0 && Cin_pad >= Cin);
+  pack_weight_kernel<<<grid_for((int64_t)Cout * kh * kw * Cin_pad, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, (__nv_bfloat16*)w_bf16, Cout, Cin, kh, kw, Cin_pad);
+  ETB_CHECK_LAUNCH();
+  return ETB_OK;
+}
+
+__global__ void pack_stem_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o, int Cout) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= Cout * 128) return;
+  const int k = e & 127, oc = e >> 7;
+  float v = 0.f;
+  if (k < 108) {
+    const int c = k % 3, t = k / 3, kw = t % 6, kh = t / 6;
+    v = w[((oc * 3 + c) * 6 + kh) * 6 + kw];
+  }
+  o[e] = __float2bfloat16(v);
+}
+extern "C" int etb_pack_stem_weight(const float* w_oihw, void* w_bf16, int32_t Cout, void* stream) {
+  ETB_CHECK_ARG(w_oihw && w_bf16 && Cout > 0);
+  pack_stem_weight_kernel<<<(Cout * 128 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w_oihw, (__nv_bfloat16*)w_bf16, Cout);
+  ETB_CHECK_LAUNCH();
+  return ETB_OK;
+}

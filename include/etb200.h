@@ -171,6 +171,56 @@ int etb_loss_backward(const float* const* p, float* const* grad_p, const EtbLoss
                       const EtbAssignOut* sets, const float* gscale_dev, void* workspace, size_t workspace_bytes,
                       void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Conv trunk (models/backbone/common.py:471-484 Conv = conv2d(bias=False)+BN+SiLU; Bottleneck :534-544;
+ * models/head/yolov5_head.py:55 Detect 1x1).  tcgen05 implicit GEMM, NHWC bf16 operands, fp32 accumulate
+ * in TMEM, TMA-fed.  x [N,H,W,Cin] bf16 (channel stride x_cstride >= Cin so a concat slice can be read in
+ * place), w [Cout, kh*kw*Cin] bf16 (K-major), y [N,Ho,Wo,*] bf16 written at channel offset into a buffer
+ * with y_cstride channels (so concat is free).
+ *   epilogue: v = acc*scale[c] + bias[c]  (folded eval-mode BN, or conv bias with scale=NULL)
+ *             act 0: none, 1: SiLU, 2: ReLU ;  optional residual add (Bottleneck shortcut) after act.
+ *   y_f32 != NULL: write fp32 in the Detect train layout [N,na,Ho,Wo,det_no] instead (channel c = a*det_no+o).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct EtbConvParams {
+  int32_t N, H, W, Cin, Cout;
+  int32_t kh, kw, stride, pad;
+  int32_t x_cstride, y_cstride, y_coffset; /* channel strides of the NHWC buffers, output channel offset */
+  int32_t res_cstride, res_coffset;        /* residual buffer geometry (if residual != NULL) */
+  int32_t act;                             /* 0 none, 1 SiLU, 2 ReLU */
+  int32_t det_no;                          /* y_f32 path: outputs per anchor (85); Cout = na*det_no */
+} EtbConvParams;
+
+size_t etb_conv_workspace_bytes(const EtbConvParams* cp);
+int etb_conv_fwd(const void* x_bf16, const void* w_bf16, const float* scale, const float* bias,
+                 const void* residual_bf16, void* y_bf16, float* y_f32, const EtbConvParams* cp,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* small layout / elementwise helpers of the trunk (all HBM-bound, coalesced 16 B vectors) */
+
+/* input prep + stem im2col (trainer/ssod_trainer.py:694-696 `.float()/255` fused with the 6x6 s2 p2 stem patch
+ * gather of models/backbone/yolov5_backbone.py:56): x [N,3,H,W] fp32 NCHW -> y [N,H/2,W/2,128] bf16 with
+ * K index (kh*6+kw)*3+c for K<108 and zeros above; `mul` scales the pixels (1/255 for uint8-range input, else 1). */
+int etb_stem_im2col(const float* x, void* y_bf16, int32_t N, int32_t H, int32_t W, float mul, void* stream);
+/* NCHW fp32 <-> NHWC bf16 (channel stride / offset on the NHWC side) */
+int etb_nchw_f32_to_nhwc_bf16(const float* x, void* y, int32_t N, int32_t C, int32_t H, int32_t W,
+                              int32_t y_cstride, int32_t y_coffset, float mul, void* stream);
+int etb_nhwc_bf16_to_nchw_f32(const void* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W,
+                              int32_t x_cstride, int32_t x_coffset, void* stream);
+/* SPPF (models/backbone/common.py:702-708): buf [N,H,W,cstride>=4C] holds x in channels [0,C); writes
+ * maxpool5(x), maxpool5^2(x)=maxpool9(x), maxpool5^3(x)=maxpool13(x) into [C,2C),[2C,3C),[3C,4C) (the concat). */
+int etb_sppf_pool(void* buf_bf16, int32_t N, int32_t H, int32_t W, int32_t C, int32_t cstride, void* stream);
+/* nn.Upsample(scale_factor=2, nearest) written into a channel slice of the concat buffer (yolov5_neck.py:92,97) */
+int etb_upsample2x_nhwc(const void* x_bf16, void* y_bf16, int32_t N, int32_t H, int32_t W, int32_t C,
+                        int32_t x_cstride, int32_t x_coffset, int32_t y_cstride, int32_t y_coffset, void* stream);
+/* eval-mode BatchNorm folded to per-channel scale/bias: scale = g/sqrt(var+eps), bias = b - mean*scale */
+int etb_fold_bn(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                float* scale, float* bias, int32_t C, void* stream);
+/* conv weight [Cout,Cin,kh,kw] fp32 -> [Cout][kh][kw][Cin_pad] bf16 (K-major GEMM operand), zero padded */
+int etb_pack_weight(const float* w_oihw, void* w_bf16, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw,
+                    int32_t Cin_pad, void* stream);
+/* stem weight [Cout,3,6,6] fp32 -> [Cout][128] bf16 in the etb_stem_im2col K order */
+int etb_pack_stem_weight(const float* w_oihw, void* w_bf16, int32_t Cout, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
