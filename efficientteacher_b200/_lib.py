@@ -53,7 +53,7 @@ class EtbConvParams(C.Structure):
     _fields_ = [("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32),
                 ("kh", C.c_int32), ("kw", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
                 ("x_cstride", C.c_int32), ("y_cstride", C.c_int32), ("y_coffset", C.c_int32),
-                ("res_cstride", C.c_int32), ("res_coffset", C.c_int32), ("act", C.c_int32)]
+                ("res_cstride", C.c_int32), ("res_coffset", C.c_int32), ("act", C.c_int32), ("det_no", C.c_int32)]
 
 
 _SIGS = {
@@ -76,6 +76,18 @@ _SIGS = {
                                    C.c_size_t, vp]),
     "etb_loss_backward": (C.c_int, [C.POINTER(vp), C.POINTER(vp), C.POINTER(EtbLossParams),
                                     C.POINTER(EtbAssignOut), vp, vp, C.c_size_t, vp]),
+    "etb_conv_workspace_bytes": (C.c_size_t, [C.POINTER(EtbConvParams)]),
+    "etb_conv_fwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.POINTER(EtbConvParams), vp, C.c_size_t, vp]),
+    "etb_stem_im2col": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, vp]),
+    "etb_nchw_f32_to_nhwc_bf16": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                            C.c_float, vp]),
+    "etb_nhwc_bf16_to_nchw_f32": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
+    "etb_sppf_pool": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
+    "etb_upsample2x_nhwc": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_int32, C.c_int32, vp]),
+    "etb_fold_bn": (C.c_int, [vp, vp, vp, vp, C.c_float, vp, vp, C.c_int32, vp]),
+    "etb_pack_weight": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
+    "etb_pack_stem_weight": (C.c_int, [vp, vp, C.c_int32, vp]),
 }
 
 _lib = None

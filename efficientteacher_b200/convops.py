@@ -1,0 +1,111 @@
+"""Thin Python wrappers over the tcgen05 convolution and the trunk layout kernels (NHWC bf16 tensors)."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import EtbConvParams
+
+ACT = {None: 0, "none": 0, "silu": 1, "relu": 2}
+
+
+def nhwc_empty(N, H, W, C, device):
+    return torch.empty((N, H, W, C), dtype=torch.bfloat16, device=device)
+
+
+def to_nhwc_bf16(x_nchw, out=None, coffset=0, mul=1.0):
+    _lib.require_cuda(x_nchw)
+    x = x_nchw.float().contiguous()
+    N, Cc, H, W = x.shape
+    if out is None:
+        out = nhwc_empty(N, H, W, Cc, x.device)
+    _lib.check(_lib.lib().etb_nchw_f32_to_nhwc_bf16(_lib.ptr(x), _lib.ptr(out), N, Cc, H, W, out.shape[3], coffset,
+                                                    float(mul), _lib.stream_ptr()), "etb_nchw_f32_to_nhwc_bf16")
+    return out
+
+
+def to_nchw_f32(x_nhwc, C_=None, coffset=0):
+    N, H, W, cs = x_nhwc.shape
+    Cc = cs - coffset if C_ is None else C_
+    y = torch.empty((N, Cc, H, W), dtype=torch.float32, device=x_nhwc.device)
+    _lib.check(_lib.lib().etb_nhwc_bf16_to_nchw_f32(_lib.ptr(x_nhwc), _lib.ptr(y), N, Cc, H, W, cs, coffset,
+                                                    _lib.stream_ptr()), "etb_nhwc_bf16_to_nchw_f32")
+    return y
+
+
+def pack_weight(w_oihw, cin_pad=None):
+    w = w_oihw.detach().float().contiguous()
+    Cout, Cin, kh, kw = w.shape
+    cp = Cin if cin_pad is None else cin_pad
+    out = torch.empty((Cout, kh * kw * cp), dtype=torch.bfloat16, device=w.device)
+    _lib.check(_lib.lib().etb_pack_weight(_lib.ptr(w), _lib.ptr(out), Cout, Cin, kh, kw, cp, _lib.stream_ptr()), "etb_pack_weight")
+    return out
+
+
+def pack_stem_weight(w_oihw):
+    w = w_oihw.detach().float().contiguous()
+    assert tuple(w.shape[1:]) == (3, 6, 6)
+    out = torch.empty((w.shape[0], 128), dtype=torch.bfloat16, device=w.device)
+    _lib.check(_lib.lib().etb_pack_stem_weight(_lib.ptr(w), _lib.ptr(out), w.shape[0], _lib.stream_ptr()), "etb_pack_stem_weight")
+    return out
+
+
+def fold_bn(bn):
+    Cc = bn.weight.shape[0]
+    scale = torch.empty(Cc, dtype=torch.float32, device=bn.weight.device)
+    bias = torch.empty_like(scale)
+    _lib.check(_lib.lib().etb_fold_bn(_lib.ptr(bn.weight.detach()), _lib.ptr(bn.bias.detach()), _lib.ptr(bn.running_mean),
+                                      _lib.ptr(bn.running_var), float(bn.eps), _lib.ptr(scale), _lib.ptr(bias), Cc,
+                                      _lib.stream_ptr()), "etb_fold_bn")
+    return scale, bias
+
+
+def stem_im2col(x_nchw_f32, mul=1.0):
+    x = x_nchw_f32.float().contiguous()
+    N, Cc, H, W = x.shape
+    assert Cc == 3
+    out = nhwc_empty(N, H // 2, W // 2, 128, x.device)
+    _lib.check(_lib.lib().etb_stem_im2col(_lib.ptr(x), _lib.ptr(out), N, H, W, float(mul), _lib.stream_ptr()), "etb_stem_im2col")
+    return out
+
+
+def conv_fwd(x, w_packed, Cin, Cout, k, stride, pad, scale=None, bias=None, act="silu", out=None, out_coffset=0,
+             x_coffset=0, residual=None, res_coffset=0, det_out=None, det_no=0):
+    """x: [N,H,W,Cs] bf16 NHWC (logical channels [x_coffset, x_coffset+Cin)).  Returns `out` (bf16 NHWC, written at
+    channel offset out_coffset) or det_out (fp32 [N,na,Ho,Wo,det_no])."""
+    _lib.require_cuda(x, w_packed)
+    N, H, W, cs = x.shape
+    Ho = (H + 2 * pad - k) // stride + 1
+    Wo = (W + 2 * pad - k) // stride + 1
+    cp = EtbConvParams()
+    cp.N, cp.H, cp.W, cp.Cin, cp.Cout = N, H, W, Cin, Cout
+    cp.kh = cp.kw = k
+    cp.stride, cp.pad = stride, pad
+    cp.x_cstride = cs
+    cp.act = ACT[act]
+    cp.det_no = det_no
+    xp = x.data_ptr() + 2 * x_coffset
+    if det_out is None:
+        if out is None:
+            out = nhwc_empty(N, Ho, Wo, Cout, x.device)
+        assert tuple(out.shape[:3]) == (N, Ho, Wo)
+        cp.y_cstride, cp.y_coffset = out.shape[3], out_coffset
+    if residual is not None:
+        cp.res_cstride, cp.res_coffset = residual.shape[3], res_coffset
+    _lib.check(_lib.lib().etb_conv_fwd(C.c_void_p(xp), _lib.ptr(w_packed), _lib.ptr(scale), _lib.ptr(bias), _lib.ptr(residual),
+                                       _lib.ptr(out) if det_out is None else C.c_void_p(0), _lib.ptr(det_out), C.byref(cp),
+                                       C.c_void_p(0), 0, _lib.stream_ptr()), "etb_conv_fwd")
+    return out if det_out is None else det_out
+
+
+def sppf_pool(buf, Cq):
+    N, H, W, cs = buf.shape
+    _lib.check(_lib.lib().etb_sppf_pool(_lib.ptr(buf), N, H, W, Cq, cs, _lib.stream_ptr()), "etb_sppf_pool")
+    return buf
+
+
+def upsample2x(x, Cc, out, out_coffset, x_coffset=0):
+    N, H, W, cs = x.shape
+    _lib.check(_lib.lib().etb_upsample2x_nhwc(_lib.ptr(x), _lib.ptr(out), N, H, W, Cc, cs, x_coffset, out.shape[3], out_coffset,
+                                              _lib.stream_ptr()), "etb_upsample2x_nhwc")
+    return out

@@ -1,0 +1,311 @@
+"""YOLOv5 detector with the reference's module tree, attribute names and state_dict keys
+(models/detector/yolo_ssod.py:44-118, models/detector/yolo.py:45-110, models/backbone/yolov5_backbone.py:26-88,
+models/neck/yolov5_neck.py:6-109, models/head/yolov5_head.py:7-87, models/backbone/common.py Conv/Bottleneck/C3/SPPF),
+so reference checkpoints / EMA deep copies / optimizer param grouping keep working.
+
+Execution:
+  * eval / no-grad forward (the teacher-EMA pass of trainer/ssod_trainer.py:595-599) runs on the native engine
+    (engine.TrunkEngine: tcgen05 implicit-GEMM convs, NHWC bf16, BN folded, concat-by-offset, fused Detect).
+  * training forward/backward of the trunk currently goes through torch autograd with bf16 autocast and
+    channels_last (library kernels) -- stated in DESIGN.md as the remaining scaffold; every other step of the
+    training path (losses, assigners, pseudo labels, EMA) is native.
+There is no CPU path: forward raises without a CUDA device + libetb200.so.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .head import decode_levels
+
+
+def make_divisible(x, divisor):
+    return math.ceil(x / divisor) * divisor
+
+
+def autopad(k, p=None):
+    return k // 2 if p is None else p
+
+
+class Conv(nn.Module):
+    """conv2d(bias=False) + BatchNorm2d(eps 1e-3, momentum 0.03) + SiLU   (common.py:471-484, torch_utils.py:168-169)"""
+
+    def __init__(self, c1, c2, k=1, s=1, p=None, g=1, act=True):
+        super().__init__()
+        assert g == 1
+        self.conv = nn.Conv2d(c1, c2, k, s, autopad(k, p), groups=g, bias=False)
+        self.bn = nn.BatchNorm2d(c2, eps=1e-3, momentum=0.03)
+        self.act = nn.SiLU() if act is True or act == "silu" else (nn.ReLU(inplace=True) if act == "relu" else nn.Identity())
+        self.act_name = "relu" if act == "relu" else None
+
+    def forward(self, x):
+        return self.act(self.bn(self.conv(x)))
+
+
+class Bottleneck(nn.Module):
+    def __init__(self, c1, c2, shortcut=True, g=1, k=(1, 3), e=0.5, act=True):
+        super().__init__()
+        c_ = int(c2 * e)
+        self.cv1 = Conv(c1, c_, k[0], 1, act=act)
+        self.cv2 = Conv(c_, c2, k[1], 1, g=g, act=act)
+        self.add = shortcut and c1 == c2
+
+    def forward(self, x):
+        return x + self.cv2(self.cv1(x)) if self.add else self.cv2(self.cv1(x))
+
+
+class C3(nn.Module):
+    def __init__(self, c1, c2, n=1, shortcut=True, g=1, e=0.5, act=True):
+        super().__init__()
+        c_ = int(c2 * e)
+        self.cv1 = Conv(c1, c_, 1, 1, act=act)
+        self.cv2 = Conv(c1, c_, 1, 1, act=act)
+        self.cv3 = Conv(2 * c_, c2, 1, act=act)
+        self.m = nn.Sequential(*[Bottleneck(c_, c_, shortcut, g, e=1.0, act=act) for _ in range(n)])
+
+    def forward(self, x):
+        return self.cv3(torch.cat((self.m(self.cv1(x)), self.cv2(x)), dim=1))
+
+
+class SPPF(nn.Module):
+    def __init__(self, c1, c2, k=5, act=True):
+        super().__init__()
+        c_ = c1 // 2
+        self.cv1 = Conv(c1, c_, 1, 1, act=act)
+        self.cv2 = Conv(c_ * 4, c2, 1, 1, act=act)
+        self.m = nn.MaxPool2d(kernel_size=k, stride=1, padding=k // 2)
+
+    def forward(self, x):
+        x = self.cv1(x)
+        y1 = self.m(x)
+        y2 = self.m(y1)
+        return self.cv2(torch.cat([x, y1, y2, self.m(y2)], 1))
+
+
+class Concat(nn.Module):
+    def __init__(self, dimension=1):
+        super().__init__()
+        self.d = dimension
+
+    def forward(self, x):
+        return torch.cat(x, self.d)
+
+
+class YoloV5BackBone(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.gd, self.gw = cfg.Model.depth_multiple, cfg.Model.width_multiple
+        w = lambda n: make_divisible(n * self.gw, 8)  # noqa: E731
+        d = lambda n: max(round(n * self.gd), 1) if n > 1 else n  # noqa: E731
+        act = 'silu' if cfg.Model.Backbone.activation == 'SiLU' else None
+        if act is None:
+            raise NotImplementedError("only SiLU YOLOv5 trunks are on the B200 hot path")
+        c1, c2, c3, c4, c5 = w(64), w(128), w(256), w(512), w(1024)
+        self.stage1 = Conv(3, c1, 6, 2, 2, 1, act)
+        self.stage2_1 = Conv(c1, c2, 3, 2, None, 1, act)
+        self.stage2_2 = C3(c2, c2, d(3), True, 1, 0.5, act)
+        self.stage3_1 = Conv(c2, c3, 3, 2, None, 1, act)
+        self.stage3_2 = C3(c3, c3, d(6), True, 1, 0.5, act)
+        self.stage4_1 = Conv(c3, c4, 3, 2, None, 1, act)
+        self.stage4_2 = C3(c4, c4, d(9), True, 1, 0.5, act)
+        self.stage5_1 = Conv(c4, c5, 3, 2, None, 1, act)
+        self.stage5_2 = C3(c5, c5, d(3), True, 1, 0.5, act)
+        self.sppf = SPPF(c5, c5, 5, act)
+        self.out_shape = {'C3_size': c3, 'C4_size': c4, 'C5_size': c5}
+
+    def forward(self, x):
+        x = self.stage2_2(self.stage2_1(self.stage1(x)))
+        c3 = self.stage3_2(self.stage3_1(x))
+        c4 = self.stage4_2(self.stage4_1(c3))
+        return c3, c4, self.sppf(self.stage5_2(self.stage5_1(c4)))
+
+
+class YoloV5Neck(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.gd, self.gw = cfg.Model.depth_multiple, cfg.Model.width_multiple
+        w = lambda n: make_divisible(n * self.gw, 8)  # noqa: E731
+        d = lambda n: max(round(n * self.gd), 1) if n > 1 else n  # noqa: E731
+        ip3, ip4, ip5 = [w(c) for c in cfg.Model.Neck.in_channels]
+        op3, op4, op5 = [w(c) for c in cfg.Model.Neck.out_channels]
+        self.input_p3, self.input_p4, self.input_p5 = ip3, ip4, ip5
+        self.output_p3, self.output_p4, self.output_p5 = op3, op4, op5
+        act = 'silu' if cfg.Model.Neck.activation == 'SiLU' else None
+        if act is None:
+            raise NotImplementedError("only SiLU YOLOv5 trunks are on the B200 hot path")
+        self.conv1 = Conv(ip5, int(ip5 / 2), 1, 1, None, 1, act)
+        self.upsample1 = nn.Upsample(scale_factor=2, mode="nearest")
+        self.C1 = C3(int(ip5 / 2) + ip4, ip4, d(3), False, 1, 0.5, act)
+        self.conv2 = Conv(ip4, ip3, 1, 1, None, 1, act)
+        self.upsample2 = nn.Upsample(scale_factor=2, mode="nearest")
+        self.C2 = C3(ip3 + ip3, op3, d(3), False, 1, 0.5, act)
+        self.conv3 = Conv(op3, op3, 3, 2, None, 1, act)
+        self.C3 = C3(op3 + ip3, op4, d(3), False, 1, 0.5, act)
+        self.conv4 = Conv(op4, op4, 3, 2, None, 1, act)
+        self.C4 = C3(op4 + int(ip5 / 2), op5, d(3), False, 1, 0.5, act)
+        self.concat = Concat()
+
+    def forward(self, inputs):
+        P3, P4, P5 = inputs
+        xp_1 = self.conv1(P5)
+        x1 = self.C1(self.concat([self.upsample1(xp_1), P4]))
+        xp_2 = self.conv2(x1)
+        x2 = self.C2(self.concat([self.upsample2(xp_2), P3]))
+        x3 = self.C3(self.concat([self.conv3(x2), xp_2]))
+        x4 = self.C4(self.concat([self.conv4(x3), xp_1]))
+        return x2, x3, x4
+
+
+class Detect(nn.Module):
+    """models/head/yolov5_head.py:7-87.  Train: list of [B,na,ny,nx,no]; eval: (pred [B,P,no], list)."""
+    stride = None
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.nc = cfg.Dataset.nc
+        self.num_keypoints = cfg.Dataset.np
+        if self.num_keypoints:
+            raise NotImplementedError("keypoint heads are out of scope")
+        anchors = cfg.Model.anchors
+        ch = [int(c * cfg.Model.width_multiple) for c in cfg.Model.Neck.out_channels]
+        self.no = self.nc + 5
+        self.nl = len(anchors)
+        self.na = len(anchors[0]) // 2
+        self.register_buffer('anchors', torch.tensor(anchors).float().view(self.nl, -1, 2))
+        self.m = nn.ModuleList(nn.Conv2d(x, self.no * self.na, 1) for x in ch)
+        self.stride = cfg.Model.Head.strides
+        self.export = False
+
+    def initialize_biases(self, cf=None):
+        for mi, s in zip(self.m, self.stride):
+            b = mi.bias.view(self.na, -1)
+            b.data[:, 4] += math.log(8 / (640 / s) ** 2)
+            b.data[:, 5:] += math.log(0.6 / (self.nc - 0.99)) if cf is None else torch.log(cf / cf.sum())
+            mi.bias = torch.nn.Parameter(b.view(-1), requires_grad=True)
+
+    def forward(self, x):
+        x = list(x)
+        for i in range(self.nl):
+            x[i] = self.m[i](x[i])
+            bs, _, ny, nx = x[i].shape
+            x[i] = x[i].view(bs, self.na, self.no, ny, nx).permute(0, 1, 3, 4, 2).contiguous()
+        if self.training:
+            return x
+        raw = [xi.float() for xi in x]
+        return decode_levels(raw, self.anchors, [float(s) for s in self.stride]), x
+
+
+class GradReverse(torch.autograd.Function):  # yolo_ssod.py:158-172
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return -g
+
+
+class netD(nn.Module):  # yolo_ssod.py:224-238
+    def __init__(self, channel, ratio, context=False):
+        super().__init__()
+        self.ratio = ratio
+        c = int(channel * ratio)
+        self.conv1 = nn.Conv2d(c, c, 1, 1, 0, bias=False)
+        self.conv2 = nn.Conv2d(c, 2, 1, 1, 0, bias=False)
+        self.relu = nn.ReLU(inplace=True)
+
+    def forward(self, x):
+        return self.conv2(self.relu(self.conv1(x)))
+
+
+def _check_head(model, cfg):
+    m = model.head
+    s = 256
+    m.inplace = model.inplace
+    # the reference discovers the strides with a 256x256 dummy forward (yolo_ssod.py:76-78); the YOLOv5 trunk
+    # halves the resolution 3/4/5 times before the three heads, so they are 8/16/32 by construction.
+    m.stride = torch.tensor([float(x) for x in cfg.Model.Head.strides])
+    assert [s / (s // int(t)) for t in m.stride] == [8.0, 16.0, 32.0]
+    m.anchors /= m.stride.view(-1, 1, 1)
+    a = m.anchors.prod(-1).view(-1)
+    if (a[-1] - a[0]).sign() != (m.stride[-1] - m.stride[0]).sign():
+        m.anchors[:] = m.anchors.flip(0)
+    model.stride = m.stride
+    m.initialize_biases()
+
+
+class _ModelBase(nn.Module):
+    def _init_common(self, cfg):
+        self.cfg = cfg
+        self.backbone = YoloV5BackBone(cfg)
+        self.neck = YoloV5Neck(cfg)
+        self.head = Detect(cfg)
+        self.names = cfg.Dataset.names
+        self.nc = cfg.Dataset.nc
+        self.inplace = cfg.Model.inplace
+        self.model_type = 'yolov5'
+        self.export = False
+        self._engine = None
+
+    def _require(self, x):
+        _lib.require_cuda(x)
+        _lib.lib()
+
+    def engine(self):
+        from .engine import TrunkEngine
+        if self._engine is None:
+            self._engine = TrunkEngine(self)
+        return self._engine
+
+    def __deepcopy__(self, memo):  # the engine holds raw device pointers: EMA / checkpoint copies rebuild their own
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        from copy import deepcopy
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = None if k == "_engine" else deepcopy(v, memo)
+        return new
+
+    def __getstate__(self):
+        s = dict(self.__dict__)
+        s["_engine"] = None
+        return s
+
+
+class Model(_ModelBase):
+    """SSOD detector (models/detector/yolo_ssod.py:44-118): forward -> (head_out, [d8, d16, d32])."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self._init_common(cfg)
+        oc = cfg.Model.Neck.out_channels
+        self.det_8 = netD(oc[0], cfg.Model.width_multiple)
+        self.det_16 = netD(oc[1], cfg.Model.width_multiple)
+        self.det_32 = netD(oc[2], cfg.Model.width_multiple)
+        _check_head(self, cfg)
+
+    def forward(self, x, augment=False, profile=False, visualize=False):
+        self._require(x)
+        if not self.training and not torch.is_grad_enabled():
+            return self.engine().forward(x, with_features=True)
+        f = self.neck(self.backbone(x))
+        out = self.head(f)
+        f8, f16, f32 = f
+        feature = [self.det_8(GradReverse.apply(f8)), self.det_16(GradReverse.apply(f16)), self.det_32(GradReverse.apply(f32))]
+        return out, feature
+
+
+class SupModel(_ModelBase):
+    """Supervised detector (models/detector/yolo.py:45-110): forward -> head_out."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self._init_common(cfg)
+        _check_head(self, cfg)
+
+    def forward(self, x, augment=False, profile=False, visualize=False):
+        self._require(x)
+        if not self.training and not torch.is_grad_enabled():
+            return self.engine().forward(x, with_features=False)[0]
+        return self.head(self.neck(self.backbone(x)))

@@ -1,0 +1,174 @@
+"""The SSOD training step with the reference's flow (trainer/ssod_trainer.py:587-680 train_instance,
+:458-488 update_optimizer, trainer/trainer.py:193-251 build_optimizer) for `model_type == 'yolov5'`:
+
+  teacher-EMA forward (native tcgen05 engine) -> NMS + pseudo labels (native, device resident) ->
+  student forward on cat(labeled, strong-aug unlabeled) -> ComputeLoss + ComputeStudentMatchLoss (native fused
+  fwd/bwd) -> backward -> [NCCL all-reduce of the student gradients] -> SGD-Nesterov -> ema / semi-ema update
+  (native fused 5-stream kernel).
+
+Data parallelism: one process per GPU, per-rank batch and per-rank BN statistics exactly like the
+reference's DDP without SyncBN; the only collective is one SUM all-reduce of the flattened gradient arena per step
+(loss*WORLD_SIZE followed by DDP's mean == sum of per-rank gradients); teachers stay bit-identical on all ranks
+because the reduced gradients are.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .ema import ModelEMA, CosineEMA, SemiSupModelEMA, update_ema_pair
+from .loss import ComputeLoss
+from .model import Model
+from .pseudo_label import FairPseudoLabel
+from .ssod_loss import ComputeStudentMatchLoss
+
+
+def one_cycle(y1=0.0, y2=1.0, steps=100):  # reference utils/general.py:480-482
+    return lambda x: ((1 - math.cos(x * math.pi / steps)) / 2) * (y2 - y1) + y1
+
+
+def domain_focal_loss(feature, label, gamma=2.0):
+    """DomainLoss (label 0) / TargetLoss (label 1): 0.5 * mean(-(1-p)^gamma * log p), p = softmax(netD logits)[label]
+    over all positions of the three levels (reference models/loss/loss.py:312-421)."""
+    logits = torch.cat([f.permute(0, 2, 3, 1).reshape(-1, 2) for f in feature], 0).float()
+    logp = torch.log_softmax(logits, dim=1)[:, label]
+    p = logp.exp()
+    return 0.5 * (-(1 - p) ** gamma * logp).mean()
+
+
+class SSODTrainerStep:
+    def __init__(self, cfg, device, rank=-1, world_size=1, epochs=None, batch_size=None, amp_dtype=torch.bfloat16):
+        self.cfg, self.device = cfg, device
+        self.RANK, self.WORLD_SIZE = rank, world_size
+        self.epochs = epochs if epochs is not None else cfg.epochs
+        self.epoch = 0
+        self.batch_size = batch_size if batch_size is not None else cfg.Dataset.batch_size
+        self.amp_dtype = amp_dtype
+        self.model = Model(cfg).to(device)
+        self.model_type = self.model.model_type
+        self.ema = ModelEMA(self.model)
+        if cfg.hyp.burn_epochs > 0:
+            self.semi_ema = None
+        elif cfg.SSOD.cosine_ema:
+            self.semi_ema = CosineEMA(self.ema.ema, decay_start=cfg.SSOD.ema_rate, total_epoch=self.epochs)
+        else:
+            self.semi_ema = SemiSupModelEMA(self.ema.ema, cfg.SSOD.ema_rate)
+        self.fixed_accumulate = cfg.SSOD.fixed_accumulate
+        self.build_optimizer(cfg)
+        self.compute_loss = ComputeLoss(self.model, cfg)
+        self.compute_un_sup_loss = ComputeStudentMatchLoss(self.model, cfg)
+        self.pseudo_label_creator = FairPseudoLabel(cfg)
+        self.da_loss_weights = cfg.SSOD.da_loss_weights
+        self.last_opt_step = -1
+        self.nw = 0          # warm-up iterations (the bench runs past warm-up)
+        self._arena = None
+        self.last = {}
+
+    # trainer/trainer.py:193-217
+    def build_optimizer(self, cfg):
+        nbs = 64
+        self.accumulate = max(round(nbs / self.batch_size), 1)
+        weight_decay = cfg.hyp.weight_decay * self.batch_size * self.accumulate / nbs
+        g_bnw, g_w, g_b = [], [], []
+        for v in self.model.modules():
+            if hasattr(v, 'bias') and isinstance(v.bias, nn.Parameter):
+                g_b.append(v.bias)
+            if isinstance(v, nn.BatchNorm2d):
+                g_bnw.append(v.weight)
+            elif hasattr(v, 'weight') and isinstance(v.weight, nn.Parameter):
+                g_w.append(v.weight)
+        self.optimizer = torch.optim.SGD(g_b, lr=cfg.hyp.lr0, momentum=cfg.hyp.momentum, nesterov=True)
+        self.optimizer.add_param_group({'params': g_w, 'weight_decay': weight_decay})
+        self.optimizer.add_param_group({'params': g_bnw})
+        if cfg.linear_lr:
+            self.lf = lambda x: (1 - x / (self.epochs - 1)) * (1.0 - cfg.hyp.lrf) + cfg.hyp.lrf
+        else:
+            self.lf = one_cycle(1, cfg.hyp.lrf, self.epochs)
+        self.scheduler = torch.optim.lr_scheduler.LambdaLR(self.optimizer, lr_lambda=self.lf)
+        self.warmup_bias_lr, self.warmup_momentum, self.momentum = cfg.hyp.warmup_bias_lr, cfg.hyp.warmup_momentum, cfg.hyp.momentum
+
+    # ---- gradient arena: all student gradients live in one flat fp32 buffer -> ONE all-reduce per step ----
+    def _ensure_arena(self):
+        if self._arena is None:
+            params = [p for p in self.model.parameters() if p.requires_grad]
+            n = sum(p.numel() for p in params)
+            self._arena = torch.zeros(n, dtype=torch.float32, device=self.device)
+            o = 0
+            for p in params:
+                p.grad = self._arena[o:o + p.numel()].view_as(p)
+                o += p.numel()
+        return self._arena
+
+    def _allreduce_grads(self):
+        if self.WORLD_SIZE > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self._arena, op=dist.ReduceOp.SUM)
+
+    # trainer/ssod_trainer.py:458-488 (bf16 autocast needs no GradScaler; loss scale == 1)
+    def update_optimizer(self, loss, ni):
+        self._ensure_arena()
+        loss.backward()
+        self._allreduce_grads()
+        self.accumulate = 1 if self.fixed_accumulate else max(round(64 / self.batch_size), 1)
+        if ni <= self.nw:
+            xi = [0, self.nw]
+            self.accumulate = max(1, np.interp(ni, xi, [1, 1 if self.fixed_accumulate else 64 / self.batch_size]).round())
+            for j, x in enumerate(self.optimizer.param_groups):
+                x['lr'] = np.interp(ni, xi, [self.warmup_bias_lr if j == 2 else 0.0, x['initial_lr'] * self.lf(self.epoch)])
+                if 'momentum' in x:
+                    x['momentum'] = np.interp(ni, xi, [self.warmup_momentum, self.momentum])
+        if ni - self.last_opt_step >= self.accumulate:
+            self.optimizer.step()
+            self._arena.zero_()          # optimizer.zero_grad() keeping the arena views
+            if self.semi_ema:
+                update_ema_pair(self.ema, self.semi_ema, self.model)   # == ema.update(model); semi_ema.update(ema.ema)
+            else:
+                self.ema.update(self.model)
+            self.last_opt_step = ni
+
+    def split_predict_and_feature(self, total_pred, total_feature, n_img):
+        sup_feature = [f[:n_img] for f in total_feature]
+        un_sup_feature = [f[n_img:] for f in total_feature]
+        sup_pred = [p[:n_img] for p in total_pred]
+        un_sup_pred = [p[n_img:] for p in total_pred]
+        return sup_pred, sup_feature, un_sup_pred, un_sup_feature
+
+    # trainer/ssod_trainer.py:587-680 (logging / meters excluded: rank-0 host bookkeeping)
+    def train_instance(self, imgs, targets, unlabeled_imgs, unlabeled_imgs_ori, unlabeled_gt, unlabeled_M, ni,
+                       host_pseudo_labels=False):
+        n_img = imgs.shape[0]
+        with torch.no_grad():
+            (teacher_pred, train_out), teacher_feature = self.ema.ema(unlabeled_imgs_ori, augment=False)
+        if host_pseudo_labels:   # the reference's return contract: CPU float64 rows + flag (one D2H sync)
+            unlabeled_targets, invalid_target_shape = self.pseudo_label_creator.create_pseudo_label_online_with_gt(
+                teacher_pred, unlabeled_imgs, unlabeled_M, unlabeled_imgs_ori, unlabeled_gt, self.RANK)
+            n_dev = None
+            if not invalid_target_shape:
+                unlabeled_targets = unlabeled_targets.to(self.device)
+        else:                    # device-resident twin: no host sync between teacher and student
+            h, w = unlabeled_imgs.shape[2:]
+            unlabeled_targets, n_dev = self.pseudo_label_creator.create_pseudo_label_device(teacher_pred, unlabeled_M, h, w)
+            invalid_target_shape = False
+        total_imgs = torch.cat([imgs, unlabeled_imgs], 0)
+        with torch.autocast("cuda", dtype=self.amp_dtype):
+            total_pred, total_feature = self.model(total_imgs.contiguous(memory_format=torch.channels_last))
+        sup_pred, sup_feature, un_sup_pred, un_sup_feature = self.split_predict_and_feature(total_pred, total_feature, n_img)
+        sup_loss, sup_loss_items = self.compute_loss(sup_pred, targets)
+        d_loss = domain_focal_loss(sup_feature, 0)
+        t_loss = domain_focal_loss(un_sup_feature, 1)
+        if self.cfg.SSOD.with_da_loss:
+            sup_loss = sup_loss + d_loss * self.da_loss_weights + t_loss * self.da_loss_weights
+        else:
+            sup_loss = sup_loss + d_loss * 0 + t_loss * 0
+        if invalid_target_shape:
+            un_sup_loss = torch.zeros(1, device=self.device)
+            un_sup_loss_items = dict(ss_box=0, ss_obj=0, ss_cls=0)
+        else:
+            un_sup_loss, un_sup_loss_items = self.compute_un_sup_loss(un_sup_pred, unlabeled_targets, n_dev)
+        # DDP: loss*WORLD_SIZE then gradient mean == plain SUM all-reduce of per-rank gradients (no scaling here)
+        loss = sup_loss + un_sup_loss * self.cfg.SSOD.teacher_loss_weight
+        self.update_optimizer(loss, ni)
+        self.last = dict(loss=loss.detach(), sup=sup_loss_items, unsup=un_sup_loss_items)
+        return loss.detach()

@@ -1,0 +1,110 @@
+"""GPU (B200): the tcgen05 implicit-GEMM convolution and the trunk helpers against a plain PyTorch fp32 reference
+of the same op on bf16-rounded operands (floating-point kernel => torch reference, tolerance = bf16 output rounding)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    import __graft_entry__ as g
+    g.build()
+    torch.cuda.set_device(0)
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(DEV)
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+def _check(got, want, tol=2e-2):
+    err = (got - want).abs().max().item()
+    ref = want.abs().max().item()
+    assert err <= tol * max(ref, 1.0), (err, ref)
+
+
+CASES = [
+    # N, Cin, H, W, Cout, k, s, p
+    (2, 64, 16, 16, 64, 1, 1, 0),      # flat pointwise, BN=64
+    (2, 128, 20, 20, 128, 1, 1, 0),    # flat, ragged M (800 px), BN=128
+    (1, 256, 8, 8, 512, 1, 1, 0),      # flat, BN=256 x2 N-tiles, M < 128
+    (2, 64, 16, 16, 64, 3, 1, 1),      # 3x3 s1 exact tiles
+    (2, 64, 20, 20, 128, 3, 1, 1),     # 3x3 s1 ragged tiles (20x20)
+    (1, 128, 40, 40, 256, 3, 1, 1),    # 3x3 s1 40x40, BN=256
+    (2, 64, 32, 32, 128, 3, 2, 1),     # 3x3 s2 (TMA element strides)
+    (1, 128, 40, 40, 128, 3, 2, 1),    # 3x3 s2 -> 20x20
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_conv_bn_silu(case):
+    from efficientteacher_b200 import convops as co
+    N, Cin, H, W, Cout, k, s, p = case
+    x = _rand((N, Cin, H, W), 1)
+    w = _rand((Cout, Cin, k, k), 2, scale=(Cin * k * k) ** -0.5)
+    scale = torch.rand(Cout, device=DEV) + 0.5
+    bias = torch.randn(Cout, device=DEV) * 0.1
+    y = co.conv_fwd(co.to_nhwc_bf16(x), co.pack_weight(w), Cin, Cout, k, s, p, scale, bias, act="silu")
+    got = co.to_nchw_f32(y)
+    ref = F.conv2d(_bf(x), _bf(w), None, s, p) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
+    _check(got, F.silu(ref))
+
+
+def test_conv_residual_and_concat_slices():
+    from efficientteacher_b200 import convops as co
+    N, C_, H, W = 2, 64, 16, 16
+    x = _rand((N, C_, H, W), 3)
+    r = _rand((N, C_, H, W), 4)
+    w = _rand((C_, C_, 3, 3), 5, scale=(C_ * 9) ** -0.5)
+    # input lives in channels [64,128) of a 192-wide buffer, output goes to [128,192), residual read from [0,64)
+    buf = torch.zeros((N, H, W, 192), dtype=torch.bfloat16, device=DEV)
+    co.to_nhwc_bf16(r, out=buf, coffset=0)
+    co.to_nhwc_bf16(x, out=buf, coffset=64)
+    co.conv_fwd(buf, co.pack_weight(w), C_, C_, 3, 1, 1, None, None, act="silu", out=buf, out_coffset=128, x_coffset=64,
+                residual=buf, res_coffset=0)
+    got = co.to_nchw_f32(buf, C_, 128)
+    _check(got, F.silu(F.conv2d(_bf(x), _bf(w), None, 1, 1)) + _bf(r))
+    assert torch.equal(co.to_nchw_f32(buf, C_, 64), _bf(x))       # neighbours untouched
+
+
+def test_detect_head_layout():
+    from efficientteacher_b200 import convops as co
+    N, Cin, H, W, no = 2, 128, 20, 20, 85
+    x = _rand((N, Cin, H, W), 6)
+    w = _rand((3 * no, Cin, 1, 1), 7, scale=Cin ** -0.5)
+    b = _rand((3 * no,), 8)
+    out = torch.empty((N, 3, H, W, no), dtype=torch.float32, device=DEV)
+    co.conv_fwd(co.to_nhwc_bf16(x), co.pack_weight(w), Cin, 3 * no, 1, 1, 0, None, b, act=None, det_out=out, det_no=no)
+    ref = F.conv2d(_bf(x), _bf(w), b).view(N, 3, no, H, W).permute(0, 1, 3, 4, 2).contiguous()   # yolov5_head.py:66
+    _check(out, ref, tol=1e-3)
+
+
+def test_stem_im2col_conv():
+    from efficientteacher_b200 import convops as co
+    x = torch.rand((2, 3, 64, 64), generator=torch.Generator().manual_seed(9)).to(DEV) * 255.0
+    w = _rand((64, 3, 6, 6), 10, scale=108 ** -0.5)
+    col = co.stem_im2col(x, mul=1.0 / 255.0)
+    y = co.conv_fwd(col, co.pack_stem_weight(w), 128, 64, 1, 1, 0, None, None, act="silu")
+    ref = F.silu(F.conv2d(_bf(x * np.float32(1.0 / 255.0)), _bf(w), None, 2, 2))
+    _check(co.to_nchw_f32(y), ref)
+
+
+def test_sppf_and_upsample():
+    from efficientteacher_b200 import convops as co
+    x = _rand((2, 64, 20, 20), 11)
+    buf = torch.zeros((2, 20, 20, 256), dtype=torch.bfloat16, device=DEV)
+    co.to_nhwc_bf16(x, out=buf, coffset=0)
+    co.sppf_pool(buf, 64)
+    y1 = F.max_pool2d(_bf(x), 5, 1, 2); y2 = F.max_pool2d(y1, 5, 1, 2); y3 = F.max_pool2d(y2, 5, 1, 2)
+    assert torch.equal(co.to_nchw_f32(buf, 256, 0), torch.cat([_bf(x), y1, y2, y3], 1))     # common.py:702-708
+    up = torch.zeros((2, 40, 40, 128), dtype=torch.bfloat16, device=DEV)
+    co.upsample2x(buf, 64, up, 64, x_coffset=0)
+    assert torch.equal(co.to_nchw_f32(up, 64, 64), F.interpolate(_bf(x), scale_factor=2, mode="nearest"))
