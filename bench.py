@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of the YOLOv5l semi-supervised (SSOD) training step @640, 16 labeled + 16 unlabeled per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+  (N>1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...)
+
+One "step" = SSODTrainerStep.train_instance: teacher-EMA forward on the unlabeled batch (native tcgen05 engine) ->
+NMS + pseudo labels (native) -> student forward/backward on cat(labeled, strong-aug) -> ComputeLoss +
+ComputeStudentMatchLoss (native fused) -> gradient all-reduce (N>1) -> SGD-Nesterov -> both EMA updates (native fused).
+Nothing is skipped inside the timed region.  Prints ONE JSON line (rank 0).
+
+  value : images/s (B_l+B_u summed over ranks / max-over-ranks device time), inputs resident in HBM as fp32 [0,1]
+  e2e   : same metric through the public step API from PINNED HOST uint8 batches: H2D copies + .float()/255 inside
+          the timed region and a D2H read of the loss every step
+  roofline : dominant native kernel class = conv_fwd_kernel (tcgen05 implicit GEMM, teacher trunk): algorithmic conv
+          FLOPs of the teacher forward / CUDA-event time of the teacher_forward phase, vs the measured bf16 peak
+  cpu_baseline : the oracle's CPU restatement of the same step (oracle/step_ref.py), bounded sample, rank 0, N=1 only
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+B_L, B_U, IMG = 16, 16, 640
+METRIC = "images/sec YOLOv5l SSOD step @640 bs32 (16 labeled + 16 unlabeled per GPU)"
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._halt = index, [], threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def summary(self):
+        self._halt.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def synth_batch(rank, device=None, pinned=False):
+    """Per-rank seeded synthetic batch: uint8 images like the loaders produce, 8 targets/img."""
+    import synth
+    r = np.random.RandomState(1 + rank)
+    mk = lambda n: torch.from_numpy(r.randint(0, 256, (n, 3, IMG, IMG), dtype=np.uint8))  # noqa: E731
+    imgs, u_weak = mk(B_L), mk(B_U)
+    u_strong = u_weak.flip(3).contiguous()
+    targets = torch.from_numpy(synth.make_targets(100 + rank, 8 * B_L, B_L))
+    Ms = torch.from_numpy(synth.make_Ms(200 + rank, B_U, IMG))
+    out = dict(imgs=imgs, u_weak=u_weak, u_strong=u_strong, targets=targets, Ms=Ms)
+    if pinned:
+        out = {k: v.pin_memory() for k, v in out.items()}
+    return out
+
+
+def conv_flops_teacher(engine_model, n_img, img):
+    """Algorithmic conv FLOPs (2*MACs, real Cin -- the stem counts K=108) of one eval forward of trunk + Detect."""
+    flops = 0   # the spatial size of every conv's OUTPUT follows from its module path
+    for name, mod in engine_model.named_modules():
+        conv = getattr(mod, "conv", None) if hasattr(mod, "bn") else (mod if isinstance(mod, torch.nn.Conv2d) and name.startswith("head.m") else None)
+        if conv is None:
+            continue
+        if name.startswith("backbone.stage1"): hw = img // 2
+        elif name.startswith("backbone.stage2"): hw = img // 4
+        elif name.startswith("backbone.stage3"): hw = img // 8
+        elif name.startswith("backbone.stage4"): hw = img // 16
+        elif name.startswith("backbone.stage5") or name.startswith("backbone.sppf"): hw = img // 32
+        elif name.startswith("neck.conv1") or name.startswith("neck.conv4") or name.startswith("neck.C4"): hw = img // 32
+        elif name.startswith("neck.C1") or name.startswith("neck.conv2") or name.startswith("neck.conv3") or name.startswith("neck.C3"): hw = img // 16
+        elif name.startswith("neck.C2"): hw = img // 8
+        elif name.startswith("head.m.0"): hw = img // 8
+        elif name.startswith("head.m.1"): hw = img // 16
+        elif name.startswith("head.m.2"): hw = img // 32
+        else: continue
+        co, ci, kh, kw = conv.weight.shape
+        flops += 2 * n_img * hw * hw * co * ci * kh * kw
+    return flops
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path of the step (oracle restatement; /root/reference cannot travel to the
+    GPU box).  Rank 0 only.  Each step = one full SSOD step on a bounded sample (2 labeled + 2 unlabeled images)."""
+    if rank != 0:
+        return
+    from oracle.step_ref import CpuSSODStep
+    from efficientteacher_b200.config import yolov5_ssod_cfg
+    from efficientteacher_b200.model import Model
+    import synth
+    torch.set_num_threads(os.cpu_count())
+    torch.manual_seed(0)
+    model = Model(yolov5_ssod_cfg('l'))
+    bl = bu = 2
+    step = CpuSSODStep(model.state_dict(), (3, 6, 9, 3), 3, batch_size=B_L + B_U, ema_updates=100000)
+    r = np.random.RandomState(1)
+    imgs = torch.from_numpy(r.rand(bl, 3, IMG, IMG).astype(np.float32))
+    uw = torch.from_numpy(r.rand(bu, 3, IMG, IMG).astype(np.float32))
+    tg = synth.make_targets(100, 8 * bl, bl)
+    Ms = synth.make_Ms(200, bu, IMG)
+    ts = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        step.step(imgs, tg, uw.flip(3), uw, Ms)
+        if i >= args.warmup:
+            ts.append(time.perf_counter() - t0)
+    sec = float(np.mean(ts))
+    val = (bl + bu) / sec
+    sample = "full SSOD step (teacher fwd, NMS+pseudo-label, student fwd/bwd, both losses, SGD, 2x EMA) on 2 labeled + 2 unlabeled 640x640 images, fp32 torch CPU, %d threads" % torch.get_num_threads()
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": "YOLOv5l SSOD 640, CPU bounded sample 2+2 images/step"},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+
+
+def cpu_baseline_quick():
+    from oracle.step_ref import CpuSSODStep
+    from efficientteacher_b200.config import yolov5_ssod_cfg
+    from efficientteacher_b200.model import Model
+    import synth
+    nthr = os.cpu_count()
+    torch.set_num_threads(nthr)
+    torch.manual_seed(0)
+    model = Model(yolov5_ssod_cfg('l'))
+    step = CpuSSODStep(model.state_dict(), (3, 6, 9, 3), 3, batch_size=B_L + B_U, ema_updates=100000)
+    r = np.random.RandomState(1)
+    bl = bu = 2
+    imgs = torch.from_numpy(r.rand(bl, 3, IMG, IMG).astype(np.float32))
+    uw = torch.from_numpy(r.rand(bu, 3, IMG, IMG).astype(np.float32))
+    tg = synth.make_targets(100, 8 * bl, bl)
+    Ms = synth.make_Ms(200, bu, IMG)
+    step.step(imgs, tg, uw.flip(3), uw, Ms)      # warm-up
+    ts = []
+    t_all = time.perf_counter()
+    while len(ts) < 3 and time.perf_counter() - t_all < 25:
+        t0 = time.perf_counter()
+        step.step(imgs, tg, uw.flip(3), uw, Ms)
+        ts.append(time.perf_counter() - t0)
+    sec = float(np.min(ts))
+    return {"value": (bl + bu) / sec, "unit": "images/s", "cores": nthr, "kind": "port",
+            "sample": "%d full SSOD steps on 2 labeled + 2 unlabeled 640x640 images (oracle/step_ref.py, torch fp32 CPU), min step time %.2f s" % (len(ts), sec)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    assert world == args.gpus, "launch with torch.distributed.run --nproc-per-node %d" % args.gpus
+    assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+    import __graft_entry__ as g
+    if rank == 0:
+        g.build()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+    from efficientteacher_b200 import _lib
+    from efficientteacher_b200.config import yolov5_ssod_cfg
+    from efficientteacher_b200.trainer import SSODTrainerStep
+    lib = _lib.lib()
+
+    torch.manual_seed(0)                       # identical initial student on every rank (DDP broadcasts rank 0's)
+    cfg = yolov5_ssod_cfg('l', batch_size=(B_L + B_U) * world, img_size=IMG)
+    st = SSODTrainerStep(cfg, dev, rank=rank if world > 1 else -1, world_size=world, epochs=300)
+    st.ema.updates = 100000                    # steady-state decay (0.9999): the teacher does not collapse onto the student
+    host = synth_batch(rank, pinned=True)
+    f01 = lambda t: t.to(dev).float() / 255.0  # noqa: E731  trainer/ssod_trainer.py:694-696
+    d_imgs, d_uw, d_us = f01(host["imgs"]), f01(host["u_weak"]), f01(host["u_strong"])
+    d_tg, d_Ms = host["targets"].to(dev), host["Ms"].to(dev)
+
+    # calibrate the teacher's objectness bias so ~2% of the 25,200 predictions/img are NMS candidates (SURVEY.md 8d:
+    # random-init weights give none, which would leave the pseudo-label path idle); weights stay random-init.
+    with torch.no_grad():
+        (pred, raw), _ = st.ema.ema(d_uw)
+        for l, m in enumerate(st.ema.ema.head.m):
+            obj = raw[l][..., 4].flatten().float()
+            shift = float(np.log(0.1 / 0.9)) + 0.05 - torch.quantile(obj[:2_000_000], 0.98).item()
+            b = m.bias.view(3, -1)
+            b[:, 4] += shift
+            b[:, 5:] += 5.0      # class scores ~0.5 so that conf = obj * max(cls) can clear the 0.1 NMS threshold
+            st.model.head.m[l].bias.data.copy_(m.bias.data)
+            if st.semi_ema:
+                st.semi_ema.ema.head.m[l].bias.data.copy_(m.bias.data)
+
+    def step_resident(i):
+        return st.train_instance(d_imgs, d_tg, d_us, d_uw, None, d_Ms, i)
+
+    def step_e2e(i):
+        imgs = host["imgs"].to(dev, non_blocking=True).float() / 255.0
+        us = host["u_strong"].to(dev, non_blocking=True).float() / 255.0
+        uw = host["u_weak"].to(dev, non_blocking=True).float() / 255.0
+        tg = host["targets"].to(dev, non_blocking=True)
+        Ms = host["Ms"].to(dev, non_blocking=True)
+        loss = st.train_instance(imgs, tg, us, uw, None, Ms, i)
+        return float(loss.item())            # D2H read of the step's result
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, first):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(steps):
+            fn(first + i)
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    ni = 0
+    for _ in range(args.warmup):
+        step_resident(ni); ni += 1
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    st.profile, st.phase_events = True, []
+    l0 = lib.etb_launch_count()
+    ms = timed(step_resident, args.steps, ni); ni += args.steps
+    launches = (lib.etb_launch_count() - l0) / args.steps
+    phases = {k: v / args.steps for k, v in st.phase_times_ms().items()}
+    st.profile = False
+    for _ in range(3):
+        step_e2e(ni); ni += 1
+    ms_e2e = timed(step_e2e, args.steps, ni); ni += args.steps
+    clocks = sampler.summary() if sampler else None
+    n_pl = int(st.pseudo_label_creator.last_count_dev.item())
+
+    if rank == 0:
+        pk, pk_kind = peaks()
+        imgs_per_step = (B_L + B_U) * world
+        value = imgs_per_step * args.steps / (ms / 1e3)
+        e2e_val = imgs_per_step * args.steps / (ms_e2e / 1e3)
+        t_flops = conv_flops_teacher(st.ema.ema, B_U, IMG)
+        t_ms = phases.get("teacher_forward", float("nan"))
+        achieved = t_flops / (t_ms / 1e3) / 1e12
+        peak = pk["bf16_tflops_sustained"]
+        h2d = sum(host[k].numel() * host[k].element_size() for k in host)
+        out = {
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic (seeded uint8 images, 8 gt boxes/img, random-init YOLOv5l; teacher objectness bias calibrated to ~2% NMS candidates)",
+            "config": {"workload": "YOLOv5l SSOD 640: 16 labeled + 16 unlabeled per GPU (BASELINE configs[2] per-GPU batch), optimizer+2xEMA every step",
+                       "global_batch": imgs_per_step, "img_size": IMG, "parallelism": "dp%d" % world,
+                       "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
+                       "student_trunk": "torch autograd bf16 channels_last (cuDNN) -- scaffold; teacher trunk, head, NMS/pseudo-label, assigners, losses fwd/bwd, EMA native",
+                       "pseudo_labels_last_step": n_pl},
+            "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "phases_ms": phases,
+            "roofline": {"bound": "tensor", "kernel": "conv_fwd_kernel (tcgen05 implicit GEMM), teacher trunk+head, %d images" % B_U,
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "peak_kind": pk_kind + " bf16_tflops_sustained", "flops_per_forward": t_flops, "ms": t_ms},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline_quick()
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -59,6 +59,7 @@ class EtbConvParams(C.Structure):
 _SIGS = {
     "etb_version": (C.c_int, []),
     "etb_last_error": (C.c_char_p, []),
+    "etb_launch_count": (C.c_longlong, []),
     "etb_ema_table_count": (C.c_int64, [C.POINTER(C.c_int64), C.c_int32]),
     "etb_ema_table_fill": (C.c_int, [C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int64), C.c_int32,
                                      C.POINTER(EtbEmaChunk), C.c_int64]),
@@ -78,6 +79,11 @@ _SIGS = {
                                     C.POINTER(EtbAssignOut), vp, vp, C.c_size_t, vp]),
     "etb_conv_workspace_bytes": (C.c_size_t, [C.POINTER(EtbConvParams)]),
     "etb_conv_fwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.POINTER(EtbConvParams), vp, C.c_size_t, vp]),
+    "etb_dgrad_weight_elems": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "etb_pack_weight_dgrad": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
+    "etb_conv_dgrad": (C.c_int, [vp, vp, vp, C.POINTER(EtbConvParams), C.c_int32, vp]),
+    "etb_conv_wgrad": (C.c_int, [vp, vp, vp, C.POINTER(EtbConvParams), vp]),
+    "etb_unpack_wgrad": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
     "etb_stem_im2col": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, vp]),
     "etb_nchw_f32_to_nhwc_bf16": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                             C.c_float, vp]),

@@ -1,0 +1,130 @@
+"""torch.autograd bridge for the tcgen05 convolutions: forward = implicit-GEMM conv, backward = dgrad (same kernel,
+transposed taps) + wgrad (pixel-reduction GEMM).  Tensors stay NHWC bf16 in HBM and are exposed to torch as
+channels_last NCHW views (zero copy), so torch's BatchNorm/SiLU/cat/upsample/maxpool can sit between the convs while
+the dense contractions (97% of the step's FLOPs) run on the hand-written kernels.
+
+Replaces cuDNN fprop/dgrad/wgrad behind Conv.forward (reference models/backbone/common.py:480-481), the Detect 1x1
+convs (models/head/yolov5_head.py:55) and netD.conv1 (models/detector/yolo_ssod.py:228).
+"""
+import torch
+
+from . import _lib
+from . import convops as co
+
+
+def _as_nhwc(t, C_):
+    """(view [N,H,W,C] bf16 whose channel stride may exceed C, channel_stride) for an NCHW-shaped tensor; copies only if
+    the layout is not NHWC.  A channel-slice of a channels_last tensor (what torch.cat's backward hands out) is used in
+    place: the kernels take the pixel stride separately and never touch channels outside the slice."""
+    N, C2, H, W = t.shape
+    assert C2 == C_
+    if t.dtype != torch.bfloat16:
+        t = t.to(torch.bfloat16)
+    sN, sC, sH, sW = t.stride()
+    cs = sW
+    ok = sC == 1 and cs >= C_ and cs % 8 == 0 and sH == W * cs and sN == H * W * cs and t.data_ptr() % 16 == 0
+    if not ok:
+        t = t.contiguous(memory_format=torch.channels_last)
+        cs = C_
+        if t.stride() != (H * W * C_, 1, W * C_, C_):     # degenerate shapes (H=W=1 ...): force the NHWC strides
+            t = t.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    return t.permute(0, 2, 3, 1), cs
+
+
+class ConvFn(torch.autograd.Function):
+    """y = conv2d(x, w) (no bias, no activation), bf16 channels_last in / out."""
+
+    @staticmethod
+    def forward(ctx, x, weight, stride, pad):
+        Cout, Cin, k, _ = weight.shape
+        xb, xcs = _as_nhwc(x, Cin)
+        wp = co.pack_weight(weight)
+        y = co.conv_fwd(xb, wp, Cin, Cout, k, stride, pad, None, None, None, x_cstride=xcs)
+        ctx.save_for_backward(x, weight)
+        ctx.geom = (stride, pad)
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        stride, pad = ctx.geom
+        Cout, Cin, k, _ = weight.shape
+        N, _, H, W = x.shape
+        dyb, dycs = _as_nhwc(dy, Cout)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            wd = co.pack_weight_dgrad(weight, stride, pad)
+            dx = co.conv_dgrad(dyb, wd, N, H, W, Cin, Cout, k, stride, pad, dy_cstride=dycs).permute(0, 3, 1, 2)
+        if ctx.needs_input_grad[1]:
+            xb, xcs = _as_nhwc(x, Cin)
+            dw = co.conv_wgrad(xb, dyb, Cin, Cout, k, stride, pad, x_cstride=xcs, dy_cstride=dycs)
+        return dx, dw, None, None
+
+
+class StemFn(torch.autograd.Function):
+    """The 6x6 s2 p2 stem on the raw fp32 NCHW image: im2col (K=108 padded to 128) + pointwise GEMM.  No input grad."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        col = co.stem_im2col(x, 1.0)
+        y = co.conv_fwd(col, co.pack_stem_weight(weight), 128, weight.shape[0], 1, 1, 0, None, None, None)
+        ctx.save_for_backward(col)
+        ctx.cout = weight.shape[0]
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (col,) = ctx.saved_tensors
+        dyb, dycs = _as_nhwc(dy, ctx.cout)
+        dw = co.conv_wgrad(col, dyb, 128, ctx.cout, 1, 1, 0, dy_cstride=dycs, stem=True)
+        return None, dw
+
+
+class DetectConvFn(torch.autograd.Function):
+    """Detect's 1x1 conv + bias, emitting fp32 logits directly in the train layout [N,na,ny,nx,no]
+    (the view/permute/contiguous of models/head/yolov5_head.py:66 is fused into the epilogue)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, na, no):
+        Cout, Cin = weight.shape[0], weight.shape[1]
+        xb, xcs = _as_nhwc(x, Cin)
+        N, H, W, _ = xb.shape
+        out = torch.empty((N, na, H, W, no), dtype=torch.float32, device=x.device)
+        co.conv_fwd(xb, co.pack_weight(weight), Cin, Cout, 1, 1, 0, None, bias.detach().float().contiguous(), None, x_cstride=xcs,
+                    det_out=out, det_no=no)
+        ctx.save_for_backward(x, weight)
+        ctx.meta = (na, no)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        na, no = ctx.meta
+        Cout, Cin = weight.shape[0], weight.shape[1]
+        N, _, H, W, _ = g.shape
+        # [N,na,H,W,no] fp32 -> NHWC bf16 [N,H,W,256] (channel c = a*no+o; padded to a multiple of 8 channels)
+        cpad = (Cout + 7) // 8 * 8
+        dyb = torch.zeros((N, H, W, cpad), dtype=torch.bfloat16, device=g.device)
+        dyb[..., :Cout] = g.permute(0, 2, 3, 1, 4).reshape(N, H, W, Cout)
+        db = g.sum((0, 2, 3)).reshape(-1) if ctx.needs_input_grad[2] else None
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            # dgrad needs K = Cout to be a multiple of 64: use the zero-padded 256-channel view of dy and of W^T
+            kpad = (Cout + 63) // 64 * 64
+            if kpad != cpad:
+                d2 = torch.zeros((N, H, W, kpad), dtype=torch.bfloat16, device=g.device)
+                d2[..., :Cout] = dyb[..., :Cout]
+            else:
+                d2 = dyb
+            wpad = torch.zeros((kpad, Cin, 1, 1), dtype=torch.float32, device=g.device)
+            wpad[:Cout] = weight.detach().float()
+            dx = co.conv_dgrad(d2, co.pack_weight_dgrad(wpad, 1, 0), N, H, W, Cin, kpad, 1, 1, 0).permute(0, 3, 1, 2)
+        if ctx.needs_input_grad[1]:
+            xb, xcs = _as_nhwc(x, Cin)
+            dw = co.conv_wgrad(xb, dyb, Cin, Cout, 1, 1, 0, x_cstride=xcs)
+        return dx, dw, db, None, None
+
+
+def conv2d_native(x, weight, stride, pad):
+    _lib.require_cuda(x, weight)
+    return ConvFn.apply(x, weight, stride, pad)

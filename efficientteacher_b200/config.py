@@ -37,7 +37,7 @@ def _ssod():
 
 
 def yolov5_ssod_cfg(size='l', batch_size=32, img_size=640):
-    depth, width = {'l': (1.0, 1.0), 's': (0.33, 0.50), 'm': (0.67, 0.75)}[size]
+    depth, width = {'l': (1.0, 1.0), 's': (0.33, 0.50), 'm': (0.67, 0.75), 'l_shallow': (0.33, 1.0)}[size]
     return NS(epochs=300, adam=False, linear_lr=True, single_cls=False, sync_bn=False,
               hyp=_hyp(), Model=_model(depth, width), Loss=_loss(), SSOD=_ssod(),
               Dataset=NS(nc=80, np=0, names=list(COCO_NAMES), img_size=img_size, batch_size=batch_size))

@@ -70,11 +70,13 @@ def stem_im2col(x_nchw_f32, mul=1.0):
 
 
 def conv_fwd(x, w_packed, Cin, Cout, k, stride, pad, scale=None, bias=None, act="silu", out=None, out_coffset=0,
-             x_coffset=0, residual=None, res_coffset=0, det_out=None, det_no=0):
+             x_coffset=0, residual=None, res_coffset=0, det_out=None, det_no=0, x_cstride=None):
     """x: [N,H,W,Cs] bf16 NHWC (logical channels [x_coffset, x_coffset+Cin)).  Returns `out` (bf16 NHWC, written at
     channel offset out_coffset) or det_out (fp32 [N,na,Ho,Wo,det_no])."""
     _lib.require_cuda(x, w_packed)
     N, H, W, cs = x.shape
+    if x_cstride is not None:     # x is a strided channel-slice view: pixel stride given explicitly
+        cs = x_cstride
     Ho = (H + 2 * pad - k) // stride + 1
     Wo = (W + 2 * pad - k) // stride + 1
     cp = EtbConvParams()
@@ -108,4 +110,56 @@ def upsample2x(x, Cc, out, out_coffset, x_coffset=0):
     N, H, W, cs = x.shape
     _lib.check(_lib.lib().etb_upsample2x_nhwc(_lib.ptr(x), _lib.ptr(out), N, H, W, Cc, cs, x_coffset, out.shape[3], out_coffset,
                                               _lib.stream_ptr()), "etb_upsample2x_nhwc")
+    return out
+
+
+def pack_weight_dgrad(w_oihw, stride, pad):
+    w = w_oihw.detach().float().contiguous()
+    Cout, Cin, k, _ = w.shape
+    n = int(_lib.lib().etb_dgrad_weight_elems(Cout, Cin, k, stride))
+    out = torch.empty(n, dtype=torch.bfloat16, device=w.device)
+    _lib.check(_lib.lib().etb_pack_weight_dgrad(_lib.ptr(w), _lib.ptr(out), Cout, Cin, k, stride, pad, _lib.stream_ptr()),
+               "etb_pack_weight_dgrad")
+    return out
+
+
+def conv_dgrad(dy, wd_packed, N, H, W, Cin, Cout, k, stride, pad, out=None, out_coffset=0, dy_coffset=0, accumulate=False,
+               dy_cstride=None):
+    """dy: [N,Ho,Wo,Cs] bf16 NHWC (channels [dy_coffset, +Cout)) -> dx [N,H,W,*] bf16 at channel offset out_coffset."""
+    _lib.require_cuda(dy, wd_packed)
+    cp = EtbConvParams()
+    cp.N, cp.H, cp.W, cp.Cin, cp.Cout = N, H, W, Cin, Cout
+    cp.kh = cp.kw = k
+    cp.stride, cp.pad = stride, pad
+    cp.x_cstride = dy.shape[3] if dy_cstride is None else dy_cstride
+    if out is None:
+        out = nhwc_empty(N, H, W, Cin, dy.device)
+    cp.y_cstride, cp.y_coffset = out.shape[3], out_coffset
+    _lib.check(_lib.lib().etb_conv_dgrad(C.c_void_p(dy.data_ptr() + 2 * dy_coffset), _lib.ptr(wd_packed), _lib.ptr(out), C.byref(cp),
+                                         int(accumulate), _lib.stream_ptr()), "etb_conv_dgrad")
+    return out
+
+
+def conv_wgrad(x, dy, Cin, Cout, k, stride, pad, x_coffset=0, dy_coffset=0, stem=False, x_cstride=None, dy_cstride=None):
+    """x [N,H,W,*] bf16, dy [N,Ho,Wo,*] bf16 -> dW [Cout,Cin,k,k] fp32 (parameter layout)."""
+    _lib.require_cuda(x, dy)
+    N, H, W, xcs = x.shape
+    cp = EtbConvParams()
+    cp.N, cp.H, cp.W, cp.Cin, cp.Cout = N, H, W, Cin, Cout
+    cp.kh = cp.kw = k
+    cp.stride, cp.pad = stride, pad
+    cp.x_cstride = xcs if x_cstride is None else x_cstride
+    cp.y_cstride = dy.shape[3] if dy_cstride is None else dy_cstride
+    packed = torch.empty((Cout, k * k, Cin), dtype=torch.float32, device=x.device)
+    lib = _lib.lib()
+    _lib.check(lib.etb_conv_wgrad(C.c_void_p(x.data_ptr() + 2 * x_coffset), C.c_void_p(dy.data_ptr() + 2 * dy_coffset), _lib.ptr(packed),
+                                  C.byref(cp), _lib.stream_ptr()), "etb_conv_wgrad")
+    if stem:
+        out = torch.empty((Cout, 3, 6, 6), dtype=torch.float32, device=x.device)
+        _lib.check(lib.etb_unpack_wgrad(_lib.ptr(packed), _lib.ptr(out), Cout, 3, 6, 6, 1, _lib.stream_ptr()), "etb_unpack_wgrad")
+        return out
+    if k == 1:
+        return packed.view(Cout, Cin, 1, 1)
+    out = torch.empty((Cout, Cin, k, k), dtype=torch.float32, device=x.device)
+    _lib.check(lib.etb_unpack_wgrad(_lib.ptr(packed), _lib.ptr(out), Cout, Cin, k, k, 0, _lib.stream_ptr()), "etb_unpack_wgrad")
     return out

@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include <stdarg.h>
 #include <string.h>
+#include <atomic>
 
 static thread_local char g_err[512] = "";
 
@@ -14,3 +15,8 @@ void etb_set_error(const char* fmt, ...) {
 
 extern "C" const char* etb_last_error(void) { return g_err; }
 extern "C" int etb_version(void) { return 100; }
+
+static std::atomic<long long> g_launches{0};
+void etb_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+// number of kernels this library has launched in this process (bench.py reports the per-step delta as gpu_launches)
+extern "C" long long etb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

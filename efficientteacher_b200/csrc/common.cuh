@@ -9,6 +9,7 @@
 #include "../../include/etb200.h"
 
 void etb_set_error(const char* fmt, ...);
+void etb_count_launch();   // every ETB_CHECK_LAUNCH() follows exactly one kernel launch of this library
 
 #define ETB_CHECK_ARG(cond)                                                   \
   do {                                                                        \
@@ -25,6 +26,7 @@ void etb_set_error(const char* fmt, ...);
       etb_set_error("%s:%d: CUDA launch failed: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
       return ETB_ERR_CUDA;                                                               \
     }                                                                                    \
+    etb_count_launch();                                                                  \
   } while (0)
 
 #define ETB_CHECK_CUDA(call)                                                             \

@@ -123,9 +123,13 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 
 // ------------------------------------------------------------------------------------------------- kernel
 struct ConvKArgs {
-  int taps_w, taps_h;     // kw, kh
-  int kblocks;            // Cin / 64
-  int stride, pad;
+  int ntaps;              // filter taps visited (kh*kw forward; 1/2/4 per parity class of a stride-2 dgrad)
+  signed char tap_dh[12], tap_dw[12];   // input coordinate = tile origin * stride + tap offset (zero padding = TMA OOB fill)
+  int kblocks;            // K channels / 64 per tap
+  int stride;
+  int out_os, out_ph, out_pw;           // output pixel (oh,ow) is stored at (oh*out_os+out_ph, ow*out_os+out_pw) ...
+  int out_H, out_W;                     // ... of an out_H x out_W plane (dgrad of stride-2 convs fills one parity lattice)
+  int accumulate;         // out_mode 0: y += result (gradient accumulation for tensors with several consumers)
   int TW, TH;             // output tile (TW*TH <= 128 rows)
   int tiles_w, tiles_h;   // per image
   int Ho, Wo, Cout;
@@ -172,7 +176,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   const int img = t;
   const int w0 = tw_i * a.TW, h0 = th_i * a.TH;
   const int n0 = blockIdx.y * BN;
-  const int kiters = a.taps_w * a.taps_h * a.kblocks;
+  const int kiters = a.ntaps * a.kblocks;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&mapA);
@@ -192,8 +196,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     if (lane == 0) {
       const uint32_t a_bytes = (uint32_t)(a.TW * a.TH * 128);
       int it = 0;
-      for (int kh = 0; kh < a.taps_h; ++kh)
-        for (int kw = 0; kw < a.taps_w; ++kw)
+      for (int tp = 0; tp < a.ntaps; ++tp)
           for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (uint32_t)((it / STAGES) & 1);
@@ -201,8 +204,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             uint8_t* sa = smem + s * L::STAGE_BYTES;
             uint8_t* sb = sa + L::A_BYTES;
             mbar_expect_tx(&full[s], a_bytes + (uint32_t)L::B_BYTES);
-            tma_load_4d(&mapA, &full[s], sa, kb * CONV_BLOCK_K, w0 * a.stride + kw - a.pad, h0 * a.stride + kh - a.pad, img);
-            tma_load_2d(&mapB, &full[s], sb, ((kh * a.taps_w + kw) * a.kblocks + kb) * CONV_BLOCK_K, n0);
+            tma_load_4d(&mapA, &full[s], sa, kb * CONV_BLOCK_K, w0 * a.stride + a.tap_dw[tp], h0 * a.stride + a.tap_dh[tp], img);
+            tma_load_2d(&mapB, &full[s], sb, (tp * a.kblocks + kb) * CONV_BLOCK_K, n0);
           }
     }
   } else if (warp == 1) {
@@ -237,7 +240,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const int th = row / a.TW, tw = row - th * a.TW;
     const int oh = h0 + th, ow = w0 + tw;
     const bool row_ok = (row < a.TW * a.TH) && (oh < a.Ho) && (ow < a.Wo);
-    const size_t pix = ((size_t)img * a.Ho + oh) * a.Wo + ow;
+    const size_t pix = ((size_t)img * a.out_H + (size_t)(oh * a.out_os + a.out_ph)) * a.out_W + (size_t)(ow * a.out_os + a.out_pw);
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
@@ -271,6 +274,19 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           }
         }
         __nv_bfloat16* yp = a.y + pix * a.y_cstride + a.y_coffset + n0 + c0;
+        if (a.accumulate && n0 + c0 + 32 <= a.Cout) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 pv = reinterpret_cast<const uint4*>(yp)[q];
+            const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&pv);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 pf = __bfloat1622float2(p2[j]);
+              f[q * 8 + 2 * j] += pf.x;
+              f[q * 8 + 2 * j + 1] += pf.y;
+            }
+          }
+        }
         if (n0 + c0 + 32 <= a.Cout) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -350,6 +366,80 @@ static int launch_conv(const CUtensorMap& mA, const CUtensorMap& mB, const ConvK
   return ETB_OK;
 }
 
+// One implicit-GEMM launch: D[pixels, rows_B] = sum_taps A(shifted) * B^T.  `ka` carries the epilogue.
+struct GemmGeom {
+  const void* a_ptr;          // NHWC bf16 tensor the A tiles come from
+  int aN, aH, aW, aC, a_cstride;
+  const void* b_ptr;          // [b_rows][ntaps*aC] bf16, K-major
+  int b_rows;
+  int tile_H, tile_W;         // per-image extent of the output-tile index space
+  bool flat;                  // pointwise stride-1: all N*H*W pixels as one row-major [pixels, C] matrix
+};
+
+static int launch_gemm(const GemmGeom& g, ConvKArgs ka, cudaStream_t st) {
+  PFN_tmapEncodeTiled enc = get_encode();
+  if (!enc) {
+    etb_set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return ETB_ERR_CUDA;
+  }
+  ETB_CHECK_ARG(g.aC % CONV_BLOCK_K == 0 && g.a_cstride >= g.aC && g.a_cstride % 8 == 0);
+  ETB_CHECK_ARG((((uintptr_t)g.a_ptr) & 15) == 0 && (((uintptr_t)g.b_ptr) & 15) == 0);
+  ETB_CHECK_ARG(ka.ntaps >= 1 && ka.ntaps <= 12);
+  cuuint64_t gdim[4], gstr[3];
+  cuuint32_t box[4], estr[4];
+  int nimg;
+  if (g.flat) {
+    const long npix = (long)g.aN * g.aH * g.aW;
+    ETB_CHECK_ARG(npix < (1l << 31));
+    ka.TW = 128; ka.TH = 1;
+    ka.Ho = 1; ka.Wo = (int)npix;
+    ka.tiles_w = (int)((npix + 127) / 128); ka.tiles_h = 1;
+    ka.out_os = 1; ka.out_ph = ka.out_pw = 0; ka.out_H = 1; ka.out_W = (int)npix;
+    nimg = 1;
+    gdim[0] = g.aC; gdim[1] = (cuuint64_t)npix; gdim[2] = 1; gdim[3] = 1;
+    gstr[0] = (cuuint64_t)g.a_cstride * 2; gstr[1] = gstr[0] * (cuuint64_t)npix; gstr[2] = gstr[1];
+    box[0] = 64; box[1] = 128; box[2] = 1; box[3] = 1;
+    estr[0] = estr[1] = estr[2] = estr[3] = 1;
+  } else {
+    pick_tile(g.tile_W, g.tile_H, &ka.TW, &ka.TH);
+    ka.Ho = g.tile_H; ka.Wo = g.tile_W;
+    ka.tiles_w = (g.tile_W + ka.TW - 1) / ka.TW; ka.tiles_h = (g.tile_H + ka.TH - 1) / ka.TH;
+    nimg = g.aN;
+    gdim[0] = g.aC; gdim[1] = g.aW; gdim[2] = g.aH; gdim[3] = g.aN;
+    gstr[0] = (cuuint64_t)g.a_cstride * 2; gstr[1] = gstr[0] * g.aW; gstr[2] = gstr[1] * g.aH;
+    // with element strides the box is measured in input elements: ceil(box/stride) elements are loaded
+    box[0] = 64; box[1] = (cuuint32_t)(ka.TW * ka.stride); box[2] = (cuuint32_t)(ka.TH * ka.stride); box[3] = 1;
+    estr[0] = 1; estr[1] = (cuuint32_t)ka.stride; estr[2] = (cuuint32_t)ka.stride; estr[3] = 1;
+    ETB_CHECK_ARG(box[1] <= 256 && box[2] <= 256);
+  }
+  CUtensorMap mA, mB;
+  CUresult r = enc(&mA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(g.a_ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    etb_set_error("cuTensorMapEncodeTiled(A) failed: %d", (int)r);
+    return ETB_ERR_CUDA;
+  }
+  const long Ktot = (long)ka.ntaps * g.aC;
+  const int BN = g.b_rows > 128 ? 256 : (g.b_rows > 64 ? 128 : 64);
+  cuuint64_t wdim[2] = {(cuuint64_t)Ktot, (cuuint64_t)g.b_rows};
+  cuuint64_t wstr[1] = {(cuuint64_t)Ktot * 2};
+  cuuint32_t wbox[2] = {64, (cuuint32_t)BN};
+  cuuint32_t westr[2] = {1, 1};
+  r = enc(&mB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(g.b_ptr), wdim, wstr, wbox, westr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    etb_set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r);
+    return ETB_ERR_CUDA;
+  }
+  ka.kblocks = g.aC / CONV_BLOCK_K;
+  ka.Cout = g.b_rows;
+  dim3 grid((unsigned)(ka.tiles_w * ka.tiles_h * nimg), (unsigned)((g.b_rows + BN - 1) / BN));
+  if (BN == 256) return launch_conv<256, 4>(mA, mB, ka, grid, st);
+  if (BN == 128) return launch_conv<128, 3>(mA, mB, ka, grid, st);   // ~97 KB smem: 2 CTAs/SM overlap epilogue and mainloop
+  return launch_conv<64, 4>(mA, mB, ka, grid, st);
+}
+
 extern "C" size_t etb_conv_workspace_bytes(const EtbConvParams* cp) { (void)cp; return 0; }
 
 extern "C" int etb_conv_fwd(const void* x_bf16, const void* w_bf16, const float* scale, const float* bias,
@@ -358,14 +448,7 @@ extern "C" int etb_conv_fwd(const void* x_bf16, const void* w_bf16, const float*
   (void)workspace; (void)workspace_bytes;
   ETB_CHECK_ARG(x_bf16 && w_bf16 && cp && (y_bf16 || y_f32));
   ETB_CHECK_ARG(cp->N > 0 && cp->H > 0 && cp->W > 0 && cp->Cin > 0 && cp->Cout > 0);
-  ETB_CHECK_ARG(cp->Cin % CONV_BLOCK_K == 0);
-  ETB_CHECK_ARG(cp->kh >= 1 && cp->kw >= 1 && (cp->stride == 1 || cp->stride == 2) && cp->pad >= 0);
-  ETB_CHECK_ARG(cp->x_cstride >= cp->Cin && cp->x_cstride % 8 == 0 && (((uintptr_t)x_bf16) & 15) == 0 && (((uintptr_t)w_bf16) & 15) == 0);
-  PFN_tmapEncodeTiled enc = get_encode();
-  if (!enc) {
-    etb_set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
-    return ETB_ERR_CUDA;
-  }
+  ETB_CHECK_ARG(cp->kh >= 1 && cp->kw >= 1 && cp->kh * cp->kw <= 12 && (cp->stride == 1 || cp->stride == 2) && cp->pad >= 0);
   const int Ho = (cp->H + 2 * cp->pad - cp->kh) / cp->stride + 1;
   const int Wo = (cp->W + 2 * cp->pad - cp->kw) / cp->stride + 1;
   ETB_CHECK_ARG(Ho > 0 && Wo > 0);
@@ -373,62 +456,21 @@ extern "C" int etb_conv_fwd(const void* x_bf16, const void* w_bf16, const float*
   if (!det) ETB_CHECK_ARG(cp->y_cstride % 8 == 0 && cp->y_coffset % 8 == 0 && cp->y_cstride >= cp->y_coffset + cp->Cout && (((uintptr_t)y_bf16) & 15) == 0);
   if (residual_bf16) ETB_CHECK_ARG(!det && cp->res_cstride % 8 == 0 && cp->res_coffset % 8 == 0 && cp->Cout % 32 == 0);
   if (det) ETB_CHECK_ARG(cp->det_no > 0 && cp->Cout % cp->det_no == 0);
-
   ConvKArgs ka;
   memset(&ka, 0, sizeof(ka));
-  // geometry: a pointwise stride-1 conv is a flat [N*H*W, Cin] GEMM (tile = 128 consecutive pixels);
-  // anything else tiles the output plane of one image.
-  const bool flat = (cp->kh == 1 && cp->kw == 1 && cp->stride == 1 && cp->pad == 0);
-  cuuint64_t gdim[4], gstr[3];
-  cuuint32_t box[4], estr[4];
-  int nimg;
-  if (flat) {
-    const long npix = (long)cp->N * cp->H * cp->W;
-    ETB_CHECK_ARG(npix < (1l << 31));
-    ka.TW = 128; ka.TH = 1;
-    ka.Ho = 1; ka.Wo = (int)npix;
-    ka.tiles_w = (int)((npix + 127) / 128); ka.tiles_h = 1;
-    nimg = 1;
-    gdim[0] = cp->Cin; gdim[1] = (cuuint64_t)npix; gdim[2] = 1; gdim[3] = 1;
-    gstr[0] = (cuuint64_t)cp->x_cstride * 2; gstr[1] = gstr[0] * (cuuint64_t)npix; gstr[2] = gstr[1];
-    box[0] = 64; box[1] = 128; box[2] = 1; box[3] = 1;
-    estr[0] = estr[1] = estr[2] = estr[3] = 1;
-  } else {
-    pick_tile(Wo, Ho, &ka.TW, &ka.TH);
-    ka.Ho = Ho; ka.Wo = Wo;
-    ka.tiles_w = (Wo + ka.TW - 1) / ka.TW; ka.tiles_h = (Ho + ka.TH - 1) / ka.TH;
-    nimg = cp->N;
-    gdim[0] = cp->Cin; gdim[1] = cp->W; gdim[2] = cp->H; gdim[3] = cp->N;
-    gstr[0] = (cuuint64_t)cp->x_cstride * 2; gstr[1] = gstr[0] * cp->W; gstr[2] = gstr[1] * cp->H;
-    // with element strides the box is measured in input elements: ceil(box/stride) elements are loaded
-    box[0] = 64; box[1] = (cuuint32_t)(ka.TW * cp->stride); box[2] = (cuuint32_t)(ka.TH * cp->stride); box[3] = 1;
-    estr[0] = 1; estr[1] = (cuuint32_t)cp->stride; estr[2] = (cuuint32_t)cp->stride; estr[3] = 1;
-    ETB_CHECK_ARG(box[1] <= 256 && box[2] <= 256);
-  }
-  CUtensorMap mA, mB;
-  CUresult r = enc(&mA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x_bf16), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    etb_set_error("cuTensorMapEncodeTiled(A) failed: %d", (int)r);
-    return ETB_ERR_CUDA;
-  }
-  const long Ktot = (long)cp->kh * cp->kw * cp->Cin;
-  const int BN = cp->Cout > 128 ? 256 : (cp->Cout > 64 ? 128 : 64);
-  cuuint64_t wdim[2] = {(cuuint64_t)Ktot, (cuuint64_t)cp->Cout};
-  cuuint64_t wstr[1] = {(cuuint64_t)Ktot * 2};
-  cuuint32_t wbox[2] = {64, (cuuint32_t)BN};
-  cuuint32_t westr[2] = {1, 1};
-  r = enc(&mB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_bf16), wdim, wstr, wbox, westr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    etb_set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r);
-    return ETB_ERR_CUDA;
-  }
-  ka.taps_w = cp->kw; ka.taps_h = cp->kh;
-  ka.kblocks = cp->Cin / CONV_BLOCK_K;
-  ka.stride = cp->stride; ka.pad = cp->pad;
-  ka.Cout = cp->Cout;
+  GemmGeom g;
+  g.a_ptr = x_bf16; g.aN = cp->N; g.aH = cp->H; g.aW = cp->W; g.aC = cp->Cin; g.a_cstride = cp->x_cstride;
+  g.b_ptr = w_bf16; g.b_rows = cp->Cout;
+  g.tile_H = Ho; g.tile_W = Wo;
+  g.flat = (cp->kh == 1 && cp->kw == 1 && cp->stride == 1 && cp->pad == 0);
+  ka.ntaps = cp->kh * cp->kw;
+  for (int kh = 0; kh < cp->kh; ++kh)
+    for (int kw = 0; kw < cp->kw; ++kw) {
+      ka.tap_dh[kh * cp->kw + kw] = (signed char)(kh - cp->pad);
+      ka.tap_dw[kh * cp->kw + kw] = (signed char)(kw - cp->pad);
+    }
+  ka.stride = cp->stride;
+  ka.out_os = 1; ka.out_ph = ka.out_pw = 0; ka.out_H = Ho; ka.out_W = Wo;
   ka.y_cstride = cp->y_cstride; ka.y_coffset = cp->y_coffset;
   ka.res_cstride = cp->res_cstride; ka.res_coffset = cp->res_coffset;
   ka.act = cp->act;
@@ -439,9 +481,376 @@ extern "C" int etb_conv_fwd(const void* x_bf16, const void* w_bf16, const float*
   ka.residual = (const __nv_bfloat16*)residual_bf16;
   ka.y = (__nv_bfloat16*)y_bf16;
   ka.y_f32 = y_f32;
-  dim3 grid((unsigned)(ka.tiles_w * ka.tiles_h * nimg), (unsigned)((cp->Cout + BN - 1) / BN));
+  return launch_gemm(g, ka, (cudaStream_t)stream);
+}
+
+// ---- data gradient (K2): dx = conv_transpose(dy, W) as implicit GEMMs on the same kernel ------------------------------
+// For each output-parity class (ph,pw) of dx (one class when stride==1):  dx[n, s*i+ph, s*j+pw, :] =
+//   sum over the taps (kh,kw) with (ph+pad-kh) % s == 0, (pw+pad-kw) % s == 0 of  dy[n, i+dh, j+dw, :] * W[:, :, kh, kw]
+//   with dh = (ph+pad-kh)/s, dw = (pw+pad-kw)/s.   B operand: etb_pack_weight_dgrad (same tap order).
+static int dgrad_taps(int k, int s, int pad, int ph, int pw, signed char* kh_l, signed char* kw_l, signed char* dh, signed char* dw) {
+  int n = 0;
+  for (int kh = 0; kh < k; ++kh) {
+    if ((ph + pad - kh) % s != 0) continue;
+    for (int kw = 0; kw < k; ++kw) {
+      if ((pw + pad - kw) % s != 0) continue;
+      kh_l[n] = (signed char)kh; kw_l[n] = (signed char)kw;
+      // floor division is exact here (remainder checked); C division of negatives truncates toward zero, also exact
+      dh[n] = (signed char)((ph + pad - kh) / s); dw[n] = (signed char)((pw + pad - kw) / s);
+      ++n;
+    }
+  }
+  return n;
+}
+
+extern "C" int64_t etb_dgrad_weight_elems(int32_t Cout, int32_t Cin, int32_t k, int32_t stride) {
+  (void)stride;
+  return (int64_t)Cin * k * k * Cout;   // all parity classes together visit every tap exactly once
+}
+
+struct TapTable { signed char v[24]; };
+__global__ void __launch_bounds__(256) pack_weight_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o, int Cout, int Cin, int k, int ntaps, TapTable tt) {
+  const int64_t total = (int64_t)Cin * ntaps * Cout;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int co = (int)(e % Cout);
+    const int t = (int)((e / Cout) % ntaps);
+    const int ci = (int)(e / ((int64_t)Cout * ntaps));
+    o[e] = __float2bfloat16(w[(((int64_t)co * Cin + ci) * k + tt.v[t]) * k + tt.v[12 + t]]);
+  }
+}
+
+// w [Cout,Cin,k,k] fp32 -> for each parity class c (row-major ph,pw) a [Cin][ntaps_c*Cout] bf16 block, blocks concatenated
+extern "C" int etb_pack_weight_dgrad(const float* w_oihw, void* out_bf16, int32_t Cout, int32_t Cin, int32_t k, int32_t stride,
+                                     int32_t pad, void* stream) {
+  ETB_CHECK_ARG(w_oihw && out_bf16 && Cout > 0 && Cin > 0 && k >= 1 && k * k <= 12 && (stride == 1 || stride == 2));
+  __nv_bfloat16* o = (__nv_bfloat16*)out_bf16;
+  for (int ph = 0; ph < stride; ++ph)
+    for (int pw = 0; pw < stride; ++pw) {
+      TapTable tt;
+      signed char dh[12], dw[12];
+      const int nt = dgrad_taps(k, stride, pad, ph, pw, tt.v, tt.v + 12, dh, dw);
+      if (nt == 0) continue;
+      const int64_t total = (int64_t)Cin * nt * Cout;
+      int64_t blocks = (total + 255) / 256;
+      if (blocks > 148 * 16) blocks = 148 * 16;
+      pack_weight_dgrad_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, o, Cout, Cin, k, nt, tt);
+      ETB_CHECK_LAUNCH();
+      o += total;
+    }
+  return ETB_OK;
+}
+
+// dy [N,Ho,Wo,*] bf16 (channels [dy_coffset.. +Cout) of stride dy_cstride) -> dx [N,H,W,*] bf16 at channel offset.
+// cp describes the FORWARD conv (N,H,W,Cin,Cout,k,stride,pad); x_cstride/ y_* name the dy / dx buffers:
+//   cp->x_cstride = channel stride of dy, cp->y_cstride/y_coffset = geometry of dx.  cp->act==3 -> dx += (accumulate).
+extern "C" int etb_conv_dgrad(const void* dy_bf16, const void* wd_bf16, void* dx_bf16, const EtbConvParams* cp, int32_t accumulate,
+                              void* stream) {
+  ETB_CHECK_ARG(dy_bf16 && wd_bf16 && dx_bf16 && cp);
+  ETB_CHECK_ARG(cp->kh == cp->kw && cp->kh * cp->kw <= 12 && (cp->stride == 1 || cp->stride == 2));
+  ETB_CHECK_ARG(cp->Cout % CONV_BLOCK_K == 0 && cp->y_cstride % 8 == 0 && cp->y_coffset % 8 == 0 && cp->y_cstride >= cp->y_coffset + cp->Cin);
+  const int k = cp->kh, s = cp->stride, pad = cp->pad;
+  const int Ho = (cp->H + 2 * pad - k) / s + 1, Wo = (cp->W + 2 * pad - k) / s + 1;
+  const __nv_bfloat16* wd = (const __nv_bfloat16*)wd_bf16;
+  for (int ph = 0; ph < s; ++ph)
+    for (int pw = 0; pw < s; ++pw) {
+      ConvKArgs ka;
+      memset(&ka, 0, sizeof(ka));
+      signed char kh_l[12], kw_l[12];
+      const int nt = dgrad_taps(k, s, pad, ph, pw, kh_l, kw_l, ka.tap_dh, ka.tap_dw);
+      const int subH = (cp->H - ph + s - 1) / s, subW = (cp->W - pw + s - 1) / s;
+      if (subH <= 0 || subW <= 0) continue;
+      ETB_CHECK_ARG(nt > 0);   // k >= stride for every conv of the trunk, so every parity class is reached
+      GemmGeom g;
+      g.a_ptr = dy_bf16; g.aN = cp->N; g.aH = Ho; g.aW = Wo; g.aC = cp->Cout; g.a_cstride = cp->x_cstride;
+      g.b_ptr = wd; g.b_rows = cp->Cin;
+      g.tile_H = subH; g.tile_W = subW;
+      g.flat = (k == 1 && s == 1 && pad == 0);
+      ka.ntaps = nt;
+      ka.stride = 1;
+      ka.out_os = s; ka.out_ph = ph; ka.out_pw = pw; ka.out_H = cp->H; ka.out_W = cp->W;
+      ka.y_cstride = cp->y_cstride; ka.y_coffset = cp->y_coffset;
+      ka.act = 0; ka.out_mode = 0; ka.accumulate = accumulate;
+      ka.y = (__nv_bfloat16*)dx_bf16;
+      int rc = launch_gemm(g, ka, (cudaStream_t)stream);
+      if (rc != ETB_OK) return rc;
+      wd += (size_t)cp->Cin * nt * cp->Cout;
+    }
+  return ETB_OK;
+}
+
+// =====================================================================================================================
+// weight gradient (K2):  dW[co][tap][ci] = sum over pixels  dy[n,oh,ow,co] * x[n, oh*s+kh-p, ow*s+kw-p, ci]
+//
+// GEMM with the PIXELS as the reduction (K) dimension: D[128 co, BN ci] += A[128 co, kpix]*B[BN ci, kpix]^T where both
+// operands are "MN-major" (the channel index is the contiguous one in NHWC).  Each K block is one spatial tile of one
+// image, fetched for both operands by 4-D TMA boxes {64 ch, TW, TH, 1} (x with the tap shift / element strides, zero
+// padding = OOB fill) into 128B-swizzled smem = the canonical MN-major UMMA layout:
+//   64-channel group = kpix rows x 128 B;  8-row K atoms 1024 B apart (SBO);  channel groups one region apart (LBO).
+// One CTA owns one (co tile, ci tile, tap) and a contiguous slice of the K blocks (split-K across gridDim.y); partial
+// tiles are reduced with fp32 atomics (red.global.add.f32) into dW, which the entry point zeroes first.
+// =====================================================================================================================
+struct WgradArgs {
+  int ntaps;
+  signed char tap_dh[12], tap_dw[12];
+  int stride;
+  int TW, TH, tiles_w, tiles_h, nimg;
+  int kpix;                 // TW*TH, multiple of 16, <= 128
+  int co_tiles, ci_tiles;
+  int Cout, Cin;
+  int flat;
+  float* dw;
+};
+
+template <int BN, int STAGES>
+struct WgradSmem {
+  static constexpr int GROUP_BYTES = 128 * 128;          // one 64-channel group, up to 128 K rows
+  static constexpr int A_BYTES = 2 * GROUP_BYTES;        // 128 co
+  static constexpr int B_BYTES = (BN / 64) * GROUP_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+};
+
+// MN-major SWIZZLE_128B descriptor: LBO = byte distance between 64-element channel groups, SBO = 1024 (8 K rows)
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t saddr, uint32_t lbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int M, int N) {   // both operands MN-major (bits 15, 16)
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ CUtensorMap mapX, const WgradArgs a) {
+  using L = WgradSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + L::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int t = blockIdx.x;
+  const int tap = t % a.ntaps; t /= a.ntaps;
+  const int ci_t = t % a.ci_tiles; t /= a.ci_tiles;
+  const int co_t = t;
+  const int co0 = co_t * 128, ci0 = ci_t * BN;
+  const int total_kb = a.nimg * a.tiles_h * a.tiles_w;
+  const int chunk = (total_kb + gridDim.y - 1) / gridDim.y;
+  const int kb0 = blockIdx.y * chunk;
+  const int kb1 = min(total_kb, kb0 + chunk);
+  if (kb0 >= kb1) return;   // uniform for the CTA, before any barrier / allocation
+  const int kiters = kb1 - kb0;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&mapDy);
+    tma_prefetch_desc(&mapX);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t group_bytes = (uint32_t)a.kpix * 128u;   // bytes one TMA box writes (all rows, OOB rows zero-filled)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < kiters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+        int kb = kb0 + it;
+        const int tw_i = kb % a.tiles_w; kb /= a.tiles_w;
+        const int th_i = kb % a.tiles_h; kb /= a.tiles_h;
+        const int img = kb;
+        const int w0 = tw_i * a.TW, h0 = th_i * a.TH;
+        mbar_wait(&empty[s], ph ^ 1u);
+        uint8_t* sa = smem + s * L::STAGE_BYTES;
+        uint8_t* sb = sa + L::A_BYTES;
+        mbar_expect_tx(&full[s], group_bytes * (2u + BN / 64));
+#pragma unroll
+        for (int g = 0; g < 2; ++g) tma_load_4d(&mapDy, &full[s], sa + g * L::GROUP_BYTES, co0 + 64 * g, w0, h0, img);
+#pragma unroll
+        for (int g = 0; g < BN / 64; ++g)
+          tma_load_4d(&mapX, &full[s], sb + g * L::GROUP_BYTES, ci0 + 64 * g, w0 * a.stride + a.tap_dw[tap], h0 * a.stride + a.tap_dh[tap], img);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16_mn(128, BN);
+      const int ksteps = a.kpix / 16;
+      for (int it = 0; it < kiters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+        const uint64_t adesc = make_mnmajor_sw128_desc(sa, L::GROUP_BYTES);
+        const uint64_t bdesc = make_mnmajor_sw128_desc(sa + L::A_BYTES, L::GROUP_BYTES);
+        for (int k = 0; k < ksteps; ++k)   // 16 K rows = two 1024 B atoms per UMMA_K step
+          umma_bf16(tmem_base, adesc + (uint64_t)(k * (2048 >> 4)), bdesc + (uint64_t)(k * (2048 >> 4)), idesc, (it | k) != 0 ? 1u : 0u);
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    const int row = 32 * (warp & 3) + lane;
+    const int co = co0 + row;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
+    float* dst = a.dw + ((size_t)co * a.ntaps + tap) * a.Cin + ci0;
+    const bool atomic = gridDim.y > 1;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (ci0 + c0 >= a.Cin) break;
+      uint32_t v[32];
+      tmem_ld32(lane_addr + (uint32_t)c0, v);
+      if (co < a.Cout) {
+        if (atomic) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            reinterpret_cast<float4*>(dst + c0)[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                                                 __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+static void pick_tile16(int Wo, int Ho, int* TW, int* TH) {
+  // K tiles must be a whole number of UMMA_K steps: TW*TH % 16 == 0, <= 128; out-of-image rows are zero-filled by TMA
+  double best = -1.0;
+  for (int tw = 1; tw <= 128; ++tw)
+    for (int th = 1; th * tw <= 128; ++th) {
+      if ((tw * th) % 16) continue;
+      if (tw > 2 * Wo || th > 2 * Ho) continue;
+      const long tiles = (long)((Wo + tw - 1) / tw) * ((Ho + th - 1) / th);
+      const double eff = (double)Wo * Ho / ((double)tiles * tw * th) * (tw * th >= 64 ? 1.0 : 0.8);
+      if (eff > best + 1e-9) { best = eff; *TW = tw; *TH = th; }
+    }
+}
+
+template <int BN, int STAGES>
+static int launch_wgrad(const CUtensorMap& mDy, const CUtensorMap& mX, const WgradArgs& wa, dim3 grid, cudaStream_t st) {
+  using L = WgradSmem<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ETB_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_set = true;
+  }
+  wgrad_kernel<BN, STAGES><<<grid, CONV_THREADS, L::TOTAL, st>>>(mDy, mX, wa);
+  ETB_CHECK_LAUNCH();
+  return ETB_OK;
+}
+
+// x [N,H,W,*] bf16 (cp->x_cstride), dy [N,Ho,Wo,*] bf16 (channel stride cp->y_cstride) -> dw [Cout][kh*kw][Cin] fp32.
+extern "C" int etb_conv_wgrad(const void* x_bf16, const void* dy_bf16, float* dw_f32, const EtbConvParams* cp, void* stream) {
+  ETB_CHECK_ARG(x_bf16 && dy_bf16 && dw_f32 && cp);
+  ETB_CHECK_ARG(cp->N > 0 && cp->H > 0 && cp->W > 0 && cp->Cin > 0 && cp->Cout > 0 && cp->Cin % 64 == 0);
+  ETB_CHECK_ARG(cp->kh * cp->kw <= 12 && (cp->stride == 1 || cp->stride == 2));
+  ETB_CHECK_ARG(cp->x_cstride % 8 == 0 && cp->y_cstride % 8 == 0 && (((uintptr_t)x_bf16) & 15) == 0 && (((uintptr_t)dy_bf16) & 15) == 0);
+  PFN_tmapEncodeTiled enc = get_encode();
+  if (!enc) {
+    etb_set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return ETB_ERR_CUDA;
+  }
+  const int Ho = (cp->H + 2 * cp->pad - cp->kh) / cp->stride + 1;
+  const int Wo = (cp->W + 2 * cp->pad - cp->kw) / cp->stride + 1;
+  WgradArgs wa;
+  memset(&wa, 0, sizeof(wa));
+  wa.ntaps = cp->kh * cp->kw;
+  for (int kh = 0; kh < cp->kh; ++kh)
+    for (int kw = 0; kw < cp->kw; ++kw) {
+      wa.tap_dh[kh * cp->kw + kw] = (signed char)(kh - cp->pad);
+      wa.tap_dw[kh * cp->kw + kw] = (signed char)(kw - cp->pad);
+    }
+  wa.stride = cp->stride;
+  wa.Cout = cp->Cout; wa.Cin = cp->Cin;
+  wa.dw = dw_f32;
+  const bool flat = (cp->kh == 1 && cp->kw == 1 && cp->stride == 1 && cp->pad == 0);
+  cuuint64_t ddim[4], dstr[3], xdim[4], xstr[3];
+  cuuint32_t dbox[4], xbox[4], one[4] = {1, 1, 1, 1}, xes[4];
+  if (flat) {
+    const long npix = (long)cp->N * cp->H * cp->W;
+    ETB_CHECK_ARG(npix < (1l << 31));
+    wa.TW = 128; wa.TH = 1; wa.kpix = 128;
+    wa.tiles_w = (int)((npix + 127) / 128); wa.tiles_h = 1; wa.nimg = 1;
+    ddim[0] = cp->Cout; ddim[1] = (cuuint64_t)npix; ddim[2] = 1; ddim[3] = 1;
+    dstr[0] = (cuuint64_t)cp->y_cstride * 2; dstr[1] = dstr[0] * (cuuint64_t)npix; dstr[2] = dstr[1];
+    xdim[0] = cp->Cin; xdim[1] = (cuuint64_t)npix; xdim[2] = 1; xdim[3] = 1;
+    xstr[0] = (cuuint64_t)cp->x_cstride * 2; xstr[1] = xstr[0] * (cuuint64_t)npix; xstr[2] = xstr[1];
+    dbox[0] = 64; dbox[1] = 128; dbox[2] = 1; dbox[3] = 1;
+    xbox[0] = 64; xbox[1] = 128; xbox[2] = 1; xbox[3] = 1;
+    xes[0] = xes[1] = xes[2] = xes[3] = 1;
+  } else {
+    pick_tile16(Wo, Ho, &wa.TW, &wa.TH);
+    wa.kpix = wa.TW * wa.TH;
+    wa.tiles_w = (Wo + wa.TW - 1) / wa.TW; wa.tiles_h = (Ho + wa.TH - 1) / wa.TH; wa.nimg = cp->N;
+    ddim[0] = cp->Cout; ddim[1] = Wo; ddim[2] = Ho; ddim[3] = cp->N;
+    dstr[0] = (cuuint64_t)cp->y_cstride * 2; dstr[1] = dstr[0] * Wo; dstr[2] = dstr[1] * Ho;
+    xdim[0] = cp->Cin; xdim[1] = cp->W; xdim[2] = cp->H; xdim[3] = cp->N;
+    xstr[0] = (cuuint64_t)cp->x_cstride * 2; xstr[1] = xstr[0] * cp->W; xstr[2] = xstr[1] * cp->H;
+    dbox[0] = 64; dbox[1] = wa.TW; dbox[2] = wa.TH; dbox[3] = 1;
+    xbox[0] = 64; xbox[1] = wa.TW * cp->stride; xbox[2] = wa.TH * cp->stride; xbox[3] = 1;
+    xes[0] = 1; xes[1] = cp->stride; xes[2] = cp->stride; xes[3] = 1;
+    ETB_CHECK_ARG(xbox[1] <= 256 && xbox[2] <= 256);
+  }
+  CUtensorMap mDy, mX;
+  CUresult r = enc(&mDy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dy_bf16), ddim, dstr, dbox, one, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { etb_set_error("cuTensorMapEncodeTiled(dy) failed: %d", (int)r); return ETB_ERR_CUDA; }
+  r = enc(&mX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x_bf16), xdim, xstr, xbox, xes, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { etb_set_error("cuTensorMapEncodeTiled(x) failed: %d", (int)r); return ETB_ERR_CUDA; }
+  const int BN = (cp->Cin >= 128) ? 128 : 64;
+  wa.flat = flat ? 1 : 0;
+  wa.co_tiles = (cp->Cout + 127) / 128;
+  wa.ci_tiles = (cp->Cin + BN - 1) / BN;
+  const int out_tiles = wa.co_tiles * wa.ci_tiles * wa.ntaps;
+  const int total_kb = wa.nimg * wa.tiles_h * wa.tiles_w;
+  int splitk = (2 * etb_num_sms() + out_tiles - 1) / out_tiles;
+  if (splitk > total_kb) splitk = total_kb;
+  if (splitk < 1) splitk = 1;
+  // no empty slices: ceil-div chunking must leave the last slice non-empty
+  while (splitk > 1 && (long)(splitk - 1) * ((total_kb + splitk - 1) / splitk) >= total_kb) --splitk;
   cudaStream_t st = (cudaStream_t)stream;
-  if (BN == 256) return launch_conv<256, 4>(mA, mB, ka, grid, st);
-  if (BN == 128) return launch_conv<128, 3>(mA, mB, ka, grid, st);   // ~97 KB smem: 2 CTAs/SM overlap epilogue and mainloop
-  return launch_conv<64, 4>(mA, mB, ka, grid, st);
+  if (splitk > 1) ETB_CHECK_CUDA(cudaMemsetAsync(dw_f32, 0, sizeof(float) * (size_t)cp->Cout * wa.ntaps * cp->Cin, st));
+  dim3 grid((unsigned)out_tiles, (unsigned)splitk);
+  if (BN == 128) return launch_wgrad<128, 3>(mDy, mX, wa, grid, st);
+  return launch_wgrad<64, 4>(mDy, mX, wa, grid, st);
+}
+
+// dW [Cout][kh*kw][Cin] fp32 -> [Cout,Cin,kh,kw] fp32 (the nn.Parameter layout); stem: [Cout][128] -> [Cout,3,6,6]
+__global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restrict__ dw, float* __restrict__ o, int Cout, int Cin, int kk, int stem) {
+  const int64_t total = (int64_t)Cout * Cin * kk;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int t = (int)(e % kk);
+    const int ci = (int)((e / kk) % Cin);
+    const int co = (int)(e / ((int64_t)kk * Cin));
+    o[e] = stem ? dw[(int64_t)co * 128 + t * 3 + ci] : dw[((int64_t)co * kk + t) * Cin + ci];
+  }
+}
+extern "C" int etb_unpack_wgrad(const float* dw_packed, float* w_oihw, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw, int32_t stem,
+                                void* stream) {
+  ETB_CHECK_ARG(dw_packed && w_oihw && Cout > 0 && Cin > 0 && kh > 0 && kw > 0);
+  const int64_t total = (int64_t)Cout * Cin * kh * kw;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  unpack_wgrad_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dw_packed, w_oihw, Cout, Cin, kh * kw, stem);
+  ETB_CHECK_LAUNCH();
+  return ETB_OK;
 }

@@ -71,7 +71,8 @@ class TrunkEngine:
     def _conv(self, name, x, x_coffset=0, out=None, out_coffset=0, residual=None, res_coffset=0, cin=None):
         q = self.params[name]
         self.launches += 1
-        return co.conv_fwd(x, q.w, q.Cin if cin is None else cin, q.Cout, q.k, q.s, q.p, q.scale, q.bias, q.act, out=out,
+        k, st, pd = (1, 1, 0) if q.stem else (q.k, q.s, q.p)   # the stem runs as a pointwise GEMM over its im2col buffer
+        return co.conv_fwd(x, q.w, q.Cin if cin is None else cin, q.Cout, k, st, pd, q.scale, q.bias, q.act, out=out,
                            out_coffset=out_coffset, x_coffset=x_coffset, residual=residual, res_coffset=res_coffset)
 
     def _c3(self, prefix, x, x_coffset, c_in, out=None, out_coffset=0):

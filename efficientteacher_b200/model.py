@@ -39,7 +39,18 @@ class Conv(nn.Module):
         self.act = nn.SiLU() if act is True or act == "silu" else (nn.ReLU(inplace=True) if act == "relu" else nn.Identity())
         self.act_name = "relu" if act == "relu" else None
 
+    NATIVE = True        # training convs on the tcgen05 fwd/dgrad/wgrad kernels (False: torch/cuDNN scaffold)
+    is_stem = False
+
     def forward(self, x):
+        if Conv.NATIVE and x.is_cuda:
+            from .autograd_conv import ConvFn, StemFn
+            w = self.conv.weight
+            if self.is_stem:
+                y = StemFn.apply(x.float(), w)
+            else:
+                y = ConvFn.apply(x, w, self.conv.stride[0], self.conv.padding[0])
+            return self.act(self.bn(y))
         return self.act(self.bn(self.conv(x)))
 
 
@@ -103,6 +114,7 @@ class YoloV5BackBone(nn.Module):
             raise NotImplementedError("only SiLU YOLOv5 trunks are on the B200 hot path")
         c1, c2, c3, c4, c5 = w(64), w(128), w(256), w(512), w(1024)
         self.stage1 = Conv(3, c1, 6, 2, 2, 1, act)
+        self.stage1.is_stem = True
         self.stage2_1 = Conv(c1, c2, 3, 2, None, 1, act)
         self.stage2_2 = C3(c2, c2, d(3), True, 1, 0.5, act)
         self.stage3_1 = Conv(c2, c3, 3, 2, None, 1, act)
@@ -187,6 +199,10 @@ class Detect(nn.Module):
     def forward(self, x):
         x = list(x)
         for i in range(self.nl):
+            if Conv.NATIVE and x[i].is_cuda:
+                from .autograd_conv import DetectConvFn
+                x[i] = DetectConvFn.apply(x[i], self.m[i].weight, self.m[i].bias, self.na, self.no)
+                continue
             x[i] = self.m[i](x[i])
             bs, _, ny, nx = x[i].shape
             x[i] = x[i].view(bs, self.na, self.no, ny, nx).permute(0, 1, 3, 4, 2).contiguous()
@@ -216,6 +232,9 @@ class netD(nn.Module):  # yolo_ssod.py:224-238
         self.relu = nn.ReLU(inplace=True)
 
     def forward(self, x):
+        if Conv.NATIVE and x.is_cuda:
+            from .autograd_conv import ConvFn
+            return self.conv2(self.relu(ConvFn.apply(x, self.conv1.weight, 1, 0)))   # conv2 (C->2) stays a library op
         return self.conv2(self.relu(self.conv1(x)))
 
 

@@ -65,6 +65,8 @@ class SSODTrainerStep:
         self.nw = 0          # warm-up iterations (the bench runs past warm-up)
         self._arena = None
         self.last = {}
+        self.profile = False     # record CUDA events at the phase boundaries of train_instance
+        self.phase_events = []
 
     # trainer/trainer.py:193-217
     def build_optimizer(self, cfg):
@@ -110,7 +112,9 @@ class SSODTrainerStep:
     def update_optimizer(self, loss, ni):
         self._ensure_arena()
         loss.backward()
+        self._mark("backward")
         self._allreduce_grads()
+        self._mark("allreduce")
         self.accumulate = 1 if self.fixed_accumulate else max(round(64 / self.batch_size), 1)
         if ni <= self.nw:
             xi = [0, self.nw]
@@ -128,6 +132,20 @@ class SSODTrainerStep:
                 self.ema.update(self.model)
             self.last_opt_step = ni
 
+    def _mark(self, name):
+        if self.profile:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.phase_events.append((name, ev))
+
+    def phase_times_ms(self):
+        """After a synchronize: {phase: total ms} accumulated over the recorded steps."""
+        out = {}
+        for (n0, e0), (n1, e1) in zip(self.phase_events[:-1], self.phase_events[1:]):
+            if n1 != "start":
+                out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
+        return out
+
     def split_predict_and_feature(self, total_pred, total_feature, n_img):
         sup_feature = [f[:n_img] for f in total_feature]
         un_sup_feature = [f[n_img:] for f in total_feature]
@@ -139,8 +157,10 @@ class SSODTrainerStep:
     def train_instance(self, imgs, targets, unlabeled_imgs, unlabeled_imgs_ori, unlabeled_gt, unlabeled_M, ni,
                        host_pseudo_labels=False):
         n_img = imgs.shape[0]
+        self._mark("start")
         with torch.no_grad():
             (teacher_pred, train_out), teacher_feature = self.ema.ema(unlabeled_imgs_ori, augment=False)
+        self._mark("teacher_forward")
         if host_pseudo_labels:   # the reference's return contract: CPU float64 rows + flag (one D2H sync)
             unlabeled_targets, invalid_target_shape = self.pseudo_label_creator.create_pseudo_label_online_with_gt(
                 teacher_pred, unlabeled_imgs, unlabeled_M, unlabeled_imgs_ori, unlabeled_gt, self.RANK)
@@ -151,9 +171,11 @@ class SSODTrainerStep:
             h, w = unlabeled_imgs.shape[2:]
             unlabeled_targets, n_dev = self.pseudo_label_creator.create_pseudo_label_device(teacher_pred, unlabeled_M, h, w)
             invalid_target_shape = False
+        self._mark("nms_pseudo_label")
         total_imgs = torch.cat([imgs, unlabeled_imgs], 0)
         with torch.autocast("cuda", dtype=self.amp_dtype):
             total_pred, total_feature = self.model(total_imgs.contiguous(memory_format=torch.channels_last))
+        self._mark("student_forward")
         sup_pred, sup_feature, un_sup_pred, un_sup_feature = self.split_predict_and_feature(total_pred, total_feature, n_img)
         sup_loss, sup_loss_items = self.compute_loss(sup_pred, targets)
         d_loss = domain_focal_loss(sup_feature, 0)
@@ -169,6 +191,8 @@ class SSODTrainerStep:
             un_sup_loss, un_sup_loss_items = self.compute_un_sup_loss(un_sup_pred, unlabeled_targets, n_dev)
         # DDP: loss*WORLD_SIZE then gradient mean == plain SUM all-reduce of per-rank gradients (no scaling here)
         loss = sup_loss + un_sup_loss * self.cfg.SSOD.teacher_loss_weight
+        self._mark("losses")
         self.update_optimizer(loss, ni)
+        self._mark("optimizer_ema")
         self.last = dict(loss=loss.detach(), sup=sup_loss_items, unsup=un_sup_loss_items)
         return loss.detach()

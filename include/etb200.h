@@ -37,6 +37,8 @@ extern "C" {
 
 int etb_version(void);
 const char* etb_last_error(void);
+/* kernels launched by this library in this process so far (bench.py: gpu_launches = delta per timed region) */
+long long etb_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * EMA  (replaces the per-tensor Python loop of ModelEMA / SemiSupModelEMA / CosineEMA .update,
@@ -194,6 +196,25 @@ size_t etb_conv_workspace_bytes(const EtbConvParams* cp);
 int etb_conv_fwd(const void* x_bf16, const void* w_bf16, const float* scale, const float* bias,
                  const void* residual_bf16, void* y_bf16, float* y_f32, const EtbConvParams* cp,
                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* data gradient of the same convolution (autograd of Conv.forward): dx = conv_transpose(dy, W), run as
+ * implicit GEMMs on the same tcgen05 kernel -- one launch per output-parity class (1 for stride 1, 4 for stride 2).
+ * `cp` describes the FORWARD conv; cp->x_cstride is the channel stride of dy, cp->y_cstride / y_coffset place dx.
+ * wd = etb_pack_weight_dgrad(w) (etb_dgrad_weight_elems bf16 elements).  accumulate != 0: dx += result. */
+int64_t etb_dgrad_weight_elems(int32_t Cout, int32_t Cin, int32_t k, int32_t stride);
+int etb_pack_weight_dgrad(const float* w_oihw, void* out_bf16, int32_t Cout, int32_t Cin, int32_t k, int32_t stride,
+                          int32_t pad, void* stream);
+int etb_conv_dgrad(const void* dy_bf16, const void* wd_bf16, void* dx_bf16, const EtbConvParams* cp, int32_t accumulate,
+                   void* stream);
+
+/* weight gradient: dW[co][tap][ci] = sum_pixels dy * x(shifted): tcgen05 GEMM with the pixels as the
+ * reduction dimension (MN-major operands straight from the NHWC tensors via TMA), split-K with fp32 atomics.
+ * `cp` describes the FORWARD conv; cp->x_cstride is x's channel stride, cp->y_cstride dy's.  dw_f32 holds
+ * Cout*kh*kw*Cin floats in [Cout][kh*kw][Cin] order; etb_unpack_wgrad converts to the parameter layout [Cout,Cin,kh,kw]
+ * (stem != 0: dw is [Cout][128] in the etb_stem_im2col K order -> [Cout,3,6,6]). */
+int etb_conv_wgrad(const void* x_bf16, const void* dy_bf16, float* dw_f32, const EtbConvParams* cp, void* stream);
+int etb_unpack_wgrad(const float* dw_packed, float* w_oihw, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw, int32_t stem,
+                     void* stream);
 
 /* small layout / elementwise helpers of the trunk (all HBM-bound, coalesced 16 B vectors) */
 

@@ -108,3 +108,67 @@ def test_sppf_and_upsample():
     up = torch.zeros((2, 40, 40, 128), dtype=torch.bfloat16, device=DEV)
     co.upsample2x(buf, 64, up, 64, x_coffset=0)
     assert torch.equal(co.to_nchw_f32(up, 64, 64), F.interpolate(_bf(x), scale_factor=2, mode="nearest"))
+
+
+DGRAD_CASES = [
+    # N, Cin, H, W, Cout, k, s, p
+    (2, 64, 16, 16, 128, 1, 1, 0),
+    (2, 128, 20, 20, 64, 3, 1, 1),
+    (1, 64, 40, 40, 128, 3, 1, 1),
+    (2, 64, 32, 32, 128, 3, 2, 1),     # stride 2: four parity-class launches
+    (1, 128, 40, 40, 256, 3, 2, 1),
+]
+
+
+@pytest.mark.parametrize("case", DGRAD_CASES)
+def test_conv_dgrad(case):
+    from efficientteacher_b200 import convops as co
+    N, Cin, H, W, Cout, k, s, p = case
+    Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    dy = _rand((N, Cout, Ho, Wo), 21)
+    w = _rand((Cout, Cin, k, k), 22, scale=(Cout * k * k) ** -0.5)
+    dx = co.conv_dgrad(co.to_nhwc_bf16(dy), co.pack_weight_dgrad(w, s, p), N, H, W, Cin, Cout, k, s, p)
+    ref = torch.nn.grad.conv2d_input((N, Cin, H, W), _bf(w), _bf(dy), stride=s, padding=p)
+    _check(co.to_nchw_f32(dx), ref)
+    # accumulate into an existing gradient (tensors with two consumers)
+    base = _rand((N, Cin, H, W), 23)
+    buf = co.to_nhwc_bf16(base)
+    co.conv_dgrad(co.to_nhwc_bf16(dy), co.pack_weight_dgrad(w, s, p), N, H, W, Cin, Cout, k, s, p, out=buf, accumulate=True)
+    _check(co.to_nchw_f32(buf), ref + _bf(base))
+
+
+WGRAD_CASES = [
+    # N, Cin, H, W, Cout, k, s, p
+    (2, 64, 16, 16, 128, 1, 1, 0),     # flat, single K block per split
+    (4, 128, 20, 20, 255, 1, 1, 0),    # Detect head shape (Cout not a multiple of 64/128), ragged pixel count
+    (2, 64, 16, 16, 64, 3, 1, 1),      # 9 taps, Cout < 128 (zero-filled M half)
+    (2, 128, 20, 20, 128, 3, 1, 1),    # 20x20: K tiles with out-of-image rows
+    (2, 64, 32, 32, 128, 3, 2, 1),     # stride 2
+    (8, 256, 40, 40, 256, 3, 1, 1),    # split-K with atomics
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES)
+def test_conv_wgrad(case):
+    from efficientteacher_b200 import convops as co
+    N, Cin, H, W, Cout, k, s, p = case
+    Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    x = _rand((N, Cin, H, W), 31)
+    dy = _rand((N, Cout, Ho, Wo), 32, scale=0.1)
+    dyp = torch.zeros((N, Ho, Wo, (Cout + 7) // 8 * 8), dtype=torch.bfloat16, device=DEV)
+    co.to_nhwc_bf16(dy, out=dyp, coffset=0)
+    dw = co.conv_wgrad(co.to_nhwc_bf16(x), dyp, Cin, Cout, k, s, p)
+    ref = torch.nn.grad.conv2d_weight(_bf(x), (Cout, Cin, k, k), _bf(dy), stride=s, padding=p)
+    err = (dw - ref).abs().max().item()
+    assert err <= 2e-3 * max(ref.abs().max().item(), 1.0), (err, ref.abs().max().item())
+
+
+def test_stem_wgrad():
+    from efficientteacher_b200 import convops as co
+    x = torch.rand((2, 3, 64, 64), generator=torch.Generator().manual_seed(41)).to(DEV)
+    dy = _rand((2, 64, 32, 32), 42, scale=0.1)
+    col = co.stem_im2col(x, 1.0)
+    dw = co.conv_wgrad(col, co.to_nhwc_bf16(dy), 128, 64, 1, 1, 0, stem=True)
+    ref = torch.nn.grad.conv2d_weight(_bf(x), (64, 3, 6, 6), _bf(dy), stride=2, padding=2)
+    err = (dw - ref).abs().max().item()
+    assert err <= 2e-3 * max(ref.abs().max().item(), 1.0), (err, ref.abs().max().item())

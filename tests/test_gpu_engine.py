@@ -1,0 +1,131 @@
+"""GPU (B200): the native teacher engine (tcgen05 trunk + Detect, NHWC bf16, folded BN, concat-by-offset) against the
+plain PyTorch fp32 forward of the same weights (oracle/trunk_ref.py, itself bit-identical to the reference modules),
+and one whole SSOD step against the oracle's CPU step."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    import __graft_entry__ as g
+    g.build()
+    torch.cuda.set_device(0)
+
+
+def _model(size="l_shallow", seed=0):
+    from efficientteacher_b200.config import yolov5_ssod_cfg
+    from efficientteacher_b200.model import Model
+    torch.manual_seed(seed)
+    m = Model(yolov5_ssod_cfg(size))
+    g = torch.Generator().manual_seed(seed + 1)
+    for mod in m.modules():          # non-trivial BN statistics so the folding is exercised
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.copy_(torch.randn(mod.running_mean.shape, generator=g) * 0.1)
+            mod.running_var.copy_(torch.rand(mod.running_var.shape, generator=g) + 0.5)
+            mod.weight.data.copy_(torch.rand(mod.weight.shape, generator=g) + 0.5)
+            mod.bias.data.copy_(torch.randn(mod.bias.shape, generator=g) * 0.1)
+    return m.to(DEV)
+
+
+def _rel(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-6)).item()
+
+
+@pytest.mark.parametrize("size,img,B", [("l_shallow", 256, 2), ("l", 320, 1)])
+def test_teacher_forward_vs_torch_fp32(size, img, B):
+    from oracle.trunk_ref import TrunkRef
+    from oracle import port
+    import synth
+    m = _model(size).eval()
+    x = torch.rand(B, 3, img, img, generator=torch.Generator().manual_seed(5)).to(DEV)
+    with torch.no_grad():
+        (pred, raw), feat = m(x)
+        rraw, rfeat = TrunkRef.from_module(m).forward(x, train=False)
+    for a, b in zip(raw, rraw):
+        assert a.shape == b.shape and a.dtype == torch.float32
+        assert _rel(a, b) < 0.05, _rel(a, b)                    # ~100 bf16 layers deep
+        cos = torch.nn.functional.cosine_similarity(a.flatten(), b.flatten(), dim=0).item()
+        assert cos > 0.999, cos
+    for a, b in zip(feat, rfeat):
+        assert a.shape == b.shape and _rel(a, b) < 0.06
+    # decode of the engine's own logits == oracle decode (tight)
+    want = port.detect_decode([r.cpu() for r in raw], synth.ANCHORS_GRID, synth.STRIDES)
+    assert pred.shape == want.shape
+    torch.testing.assert_close(pred.cpu(), want, rtol=1e-5, atol=1e-4)
+
+
+def test_full_ssod_step_runs_and_matches_cpu_step():
+    from efficientteacher_b200.config import yolov5_ssod_cfg
+    from efficientteacher_b200.trainer import SSODTrainerStep
+    from oracle.step_ref import CpuSSODStep
+    import synth
+    img, bl, bu = 256, 2, 2
+    torch.manual_seed(0)
+    cfg = yolov5_ssod_cfg('l_shallow', batch_size=bl + bu, img_size=img)   # full width (Cin % 64 == 0), depth 0.33
+    st = SSODTrainerStep(cfg, torch.device(DEV), epochs=300, amp_dtype=torch.bfloat16)
+    # make the teacher produce candidates: raise every objectness bias
+    with torch.no_grad():
+        for mm in (st.model, st.ema.ema, st.semi_ema.ema):
+            for h in mm.head.m:
+                h.bias.view(3, -1)[:, 4] += 6.5      # objectness ~0.5
+                h.bias.view(3, -1)[:, 5:] += 5.0     # class scores ~0.5 -> conf = obj*cls clears the 0.1 threshold for some rows
+    cpu = CpuSSODStep({k: v.cpu() for k, v in st.model.state_dict().items()}, (1, 2, 3, 1), 1, batch_size=bl + bu)
+    r = np.random.RandomState(3)
+    imgs = torch.from_numpy(r.rand(bl, 3, img, img).astype(np.float32))
+    uw = torch.from_numpy(r.rand(bu, 3, img, img).astype(np.float32))
+    us = uw.flip(3).contiguous()
+    tg = synth.make_targets(7, 8 * bl, bl)
+    Ms = synth.make_Ms(9, bu, img)
+    before = {k: v.clone() for k, v in st.ema.ema.state_dict().items()}
+    loss = st.train_instance(imgs.to(DEV), torch.from_numpy(tg).to(DEV), us.to(DEV), uw.to(DEV), None, torch.from_numpy(Ms).to(DEV), 0)
+    n_pl = int(st.pseudo_label_creator.last_count_dev.item())
+    ref_loss, ref_n = cpu.step(imgs, tg, us, uw, Ms)
+    assert torch.isfinite(loss).all()
+    assert n_pl > 0 and abs(n_pl - ref_n) <= max(3, 0.1 * ref_n), (n_pl, ref_n)   # bf16 teacher: near-threshold rows may differ
+    assert abs(loss.item() - ref_loss) <= 0.05 * abs(ref_loss), (loss.item(), ref_loss)
+    changed = sum(int(not torch.equal(v, before[k])) for k, v in st.ema.ema.state_dict().items() if v.dtype.is_floating_point)
+    assert changed > 100 and st.ema.updates == 1
+    # host-contract variant of the pseudo-label call (CPU float64 rows) also runs
+    loss2 = st.train_instance(imgs.to(DEV), torch.from_numpy(tg).to(DEV), us.to(DEV), uw.to(DEV), None, torch.from_numpy(Ms), 1,
+                              host_pseudo_labels=True)
+    assert torch.isfinite(loss2).all()
+
+
+def test_native_training_convs_match_cudnn_scaffold():
+    """Student forward/backward with every trunk/head conv on the tcgen05 fwd/dgrad/wgrad kernels vs the same step on
+    torch/cuDNN (both bf16 autocast): loss and parameter gradients agree to bf16 accuracy."""
+    from efficientteacher_b200 import model as M
+    from efficientteacher_b200.config import yolov5_ssod_cfg
+    from efficientteacher_b200.loss import ComputeLoss
+    import synth
+    torch.manual_seed(0)
+    cfg = yolov5_ssod_cfg('l_shallow', batch_size=4, img_size=256)
+    m = M.Model(cfg).to(DEV).train()
+    crit = ComputeLoss(m, cfg)
+    x = torch.rand(4, 3, 256, 256, generator=torch.Generator().manual_seed(1)).to(DEV)
+    tg = torch.from_numpy(synth.make_targets(2, 32, 4)).to(DEV)
+    res = {}
+    for native in (True, False):
+        M.Conv.NATIVE = native
+        m.zero_grad(set_to_none=True)
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.reset_running_stats()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            pred, feat = m(x.contiguous(memory_format=torch.channels_last))
+        loss, _ = crit([p.float() for p in pred], tg)
+        (loss + sum(f.float().mean() for f in feat) * 0.1).backward()
+        res[native] = (loss.item(), {k: p.grad.clone() for k, p in m.named_parameters()})
+    M.Conv.NATIVE = True
+    assert abs(res[True][0] - res[False][0]) <= 0.02 * abs(res[False][0]), (res[True][0], res[False][0])
+    bad = []
+    for k, g in res[False][1].items():
+        a = res[True][1][k]
+        cos = torch.nn.functional.cosine_similarity(a.flatten().float(), g.flatten().float(), dim=0).item()
+        if g.abs().max() > 0 and cos < 0.98:
+            bad.append((k, cos))
+    assert not bad, bad[:10]
