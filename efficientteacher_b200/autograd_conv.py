@@ -31,6 +31,20 @@ def _as_nhwc(t, C_):
     return t.permute(0, 2, 3, 1), cs
 
 
+def _empty_cl(N, C_, H, W, device):
+    """NCHW-shaped bf16 tensor with channels_last strides (physically NHWC); returned from the Functions as a real
+    tensor (not a view) so downstream in-place ops (ReLU(inplace)) are legal."""
+    return torch.empty((N, C_, H, W), dtype=torch.bfloat16, device=device, memory_format=torch.channels_last)
+
+
+def _nhwc_of(t):
+    N, C_, H, W = t.shape
+    v = t.permute(0, 2, 3, 1)
+    if v.stride() != (H * W * C_, W * C_, C_, 1):       # degenerate sizes: channels_last strides are ambiguous
+        raise RuntimeError("unexpected channels_last strides %s for %s" % (t.stride(), tuple(t.shape)))
+    return v
+
+
 class ConvFn(torch.autograd.Function):
     """y = conv2d(x, w) (no bias, no activation), bf16 channels_last in / out."""
 
@@ -39,10 +53,13 @@ class ConvFn(torch.autograd.Function):
         Cout, Cin, k, _ = weight.shape
         xb, xcs = _as_nhwc(x, Cin)
         wp = co.pack_weight(weight)
-        y = co.conv_fwd(xb, wp, Cin, Cout, k, stride, pad, None, None, None, x_cstride=xcs)
+        N, _, H, W = x.shape
+        Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+        y = _empty_cl(N, Cout, Ho, Wo, x.device)
+        co.conv_fwd(xb, wp, Cin, Cout, k, stride, pad, None, None, None, x_cstride=xcs, out=_nhwc_of(y))
         ctx.save_for_backward(x, weight)
         ctx.geom = (stride, pad)
-        return y.permute(0, 3, 1, 2)
+        return y
 
     @staticmethod
     def backward(ctx, dy):
@@ -54,7 +71,8 @@ class ConvFn(torch.autograd.Function):
         dx = dw = None
         if ctx.needs_input_grad[0]:
             wd = co.pack_weight_dgrad(weight, stride, pad)
-            dx = co.conv_dgrad(dyb, wd, N, H, W, Cin, Cout, k, stride, pad, dy_cstride=dycs).permute(0, 3, 1, 2)
+            dx = _empty_cl(N, Cin, H, W, dy.device)
+            co.conv_dgrad(dyb, wd, N, H, W, Cin, Cout, k, stride, pad, dy_cstride=dycs, out=_nhwc_of(dx))
         if ctx.needs_input_grad[1]:
             xb, xcs = _as_nhwc(x, Cin)
             dw = co.conv_wgrad(xb, dyb, Cin, Cout, k, stride, pad, x_cstride=xcs, dy_cstride=dycs)
@@ -67,10 +85,12 @@ class StemFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight):
         col = co.stem_im2col(x, 1.0)
-        y = co.conv_fwd(col, co.pack_stem_weight(weight), 128, weight.shape[0], 1, 1, 0, None, None, None)
+        N, H2, W2, _ = col.shape
+        y = _empty_cl(N, weight.shape[0], H2, W2, x.device)
+        co.conv_fwd(col, co.pack_stem_weight(weight), 128, weight.shape[0], 1, 1, 0, None, None, None, out=_nhwc_of(y))
         ctx.save_for_backward(col)
         ctx.cout = weight.shape[0]
-        return y.permute(0, 3, 1, 2)
+        return y
 
     @staticmethod
     def backward(ctx, dy):
@@ -118,7 +138,8 @@ class DetectConvFn(torch.autograd.Function):
                 d2 = dyb
             wpad = torch.zeros((kpad, Cin, 1, 1), dtype=torch.float32, device=g.device)
             wpad[:Cout] = weight.detach().float()
-            dx = co.conv_dgrad(d2, co.pack_weight_dgrad(wpad, 1, 0), N, H, W, Cin, kpad, 1, 1, 0).permute(0, 3, 1, 2)
+            dx = _empty_cl(N, Cin, H, W, g.device)
+            co.conv_dgrad(d2, co.pack_weight_dgrad(wpad, 1, 0), N, H, W, Cin, kpad, 1, 1, 0, out=_nhwc_of(dx))
         if ctx.needs_input_grad[1]:
             xb, xcs = _as_nhwc(x, Cin)
             dw = co.conv_wgrad(xb, dyb, Cin, Cout, 1, 1, 0, x_cstride=xcs)

@@ -132,6 +132,7 @@ struct ConvKArgs {
   int accumulate;         // out_mode 0: y += result (gradient accumulation for tensors with several consumers)
   int TW, TH;             // output tile (TW*TH <= 128 rows)
   int tiles_w, tiles_h;   // per image
+  int nimg;               // images (1 in the flat pointwise tiling)
   int Ho, Wo, Cout;
   int y_cstride, y_coffset;
   int res_cstride, res_coffset;
@@ -151,10 +152,17 @@ struct ConvSmem {
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int SB_OFF = BAR_OFF + 256;             // scale/bias staging
-  static constexpr int TOTAL = SB_OFF + 2 * BN * 4 + 1024;  // + slack for the 1024 B alignment
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;        // barriers + slack for the 1024 B alignment
+  static constexpr int TMEM_COLS = 2 * BN;                  // double-buffered accumulator
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent: gridDim.x CTAs walk the tile list (tile = blockIdx.x + i*gridDim.x; N tile fastest so the CTAs running
+// concurrently share A tiles in L2).  The smem ring and the two TMEM accumulators run across tile boundaries, so the
+// epilogue of tile i (tcgen05.ld -> BN/SiLU -> stores) overlaps the TMA/MMA main loop of tile i+1.
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const ConvKArgs a) {
@@ -163,29 +171,24 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = (uint64_t*)(smem + L::BAR_OFF);
   uint64_t* empty = full + STAGES;
-  uint64_t* tmem_full = empty + STAGES;
-  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
-  float* s_scale = (float*)(smem + L::SB_OFF);
-  float* s_bias = s_scale + BN;
+  uint64_t* tmem_full = empty + STAGES;     // [2]
+  uint64_t* tmem_empty = tmem_full + 2;     // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // tile coordinates
-  int t = blockIdx.x;
-  const int tw_i = t % a.tiles_w; t /= a.tiles_w;
-  const int th_i = t % a.tiles_h; t /= a.tiles_h;
-  const int img = t;
-  const int w0 = tw_i * a.TW, h0 = th_i * a.TH;
-  const int n0 = blockIdx.y * BN;
+  const int n_tiles = (a.Cout + BN - 1) / BN;
+  const int m_tiles = a.tiles_w * a.tiles_h * a.nimg;
+  const int total_tiles = n_tiles * m_tiles;
   const int kiters = a.ntaps * a.kblocks;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(tmem_full, 1);
+    for (int q = 0; q < 2; ++q) { mbar_init(&tmem_full[q], 1); mbar_init(&tmem_empty[q], 4); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  if (warp == 1) tmem_alloc(tmem_slot, L::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -196,7 +199,14 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     if (lane == 0) {
       const uint32_t a_bytes = (uint32_t)(a.TW * a.TH * 128);
       int it = 0;
-      for (int tp = 0; tp < a.ntaps; ++tp)
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n0 = (tile % n_tiles) * BN;
+        int t = tile / n_tiles;
+        const int tw_i = t % a.tiles_w; t /= a.tiles_w;
+        const int th_i = t % a.tiles_h; t /= a.tiles_h;
+        const int img = t;
+        const int w0 = tw_i * a.TW, h0 = th_i * a.TH;
+        for (int tp = 0; tp < a.ntaps; ++tp)
           for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (uint32_t)((it / STAGES) & 1);
@@ -207,119 +217,136 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             tma_load_4d(&mapA, &full[s], sa, kb * CONV_BLOCK_K, w0 * a.stride + a.tap_dw[tp], h0 * a.stride + a.tap_dh[tp], img);
             tma_load_2d(&mapB, &full[s], sb, (tp * a.kblocks + kb) * CONV_BLOCK_K, n0);
           }
+      }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(CONV_BLOCK_M, BN);
-      for (int it = 0; it < kiters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)((it / STAGES) & 1);
-        mbar_wait(&full[s], ph);
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        const int acc = lt & 1;
+        mbar_wait(&tmem_empty[acc], (uint32_t)(((lt >> 1) & 1) ^ 1));   // epilogue drained this accumulator
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
-        const uint64_t adesc = make_kmajor_sw128_desc(sa);
-        const uint64_t bdesc = make_kmajor_sw128_desc(sa + L::A_BYTES);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int ki = 0; ki < kiters; ++ki, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint64_t adesc = make_kmajor_sw128_desc(sa);
+          const uint64_t bdesc = make_kmajor_sw128_desc(sa + L::A_BYTES);
 #pragma unroll
-        for (int k = 0; k < CONV_BLOCK_K / 16; ++k)  // +32 B per UMMA_K step inside the 128 B swizzle atom
-          umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
-        umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
+          for (int k = 0; k < CONV_BLOCK_K / 16; ++k)  // +32 B per UMMA_K step inside the 128 B swizzle atom
+            umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ki | k) != 0 ? 1u : 0u);
+          umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete
       }
-      umma_commit(tmem_full);    // accumulator complete
     }
   } else {
     // ===== epilogue: 4 warps <-> 128 TMEM lanes (a warp may only touch lanes 32*(warp%4)..+31) =====
-    const int et = threadIdx.x - 64;
-    for (int c = et; c < BN; c += 128) {
-      const int gc = n0 + c;
-      s_scale[c] = (a.scale && gc < a.Cout) ? a.scale[gc] : 1.0f;
-      s_bias[c] = (a.bias && gc < a.Cout) ? a.bias[gc] : 0.0f;
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
     const int row = 32 * (warp & 3) + lane;
     const int th = row / a.TW, tw = row - th * a.TW;
-    const int oh = h0 + th, ow = w0 + tw;
-    const bool row_ok = (row < a.TW * a.TH) && (oh < a.Ho) && (ow < a.Wo);
-    const size_t pix = ((size_t)img * a.out_H + (size_t)(oh * a.out_os + a.out_ph)) * a.out_W + (size_t)(ow * a.out_os + a.out_pw);
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      const int acc = lt & 1;
+      const int n0 = (tile % n_tiles) * BN;
+      int t = tile / n_tiles;
+      const int tw_i = t % a.tiles_w; t /= a.tiles_w;
+      const int th_i = t % a.tiles_h; t /= a.tiles_h;
+      const int img = t;
+      const int oh = th_i * a.TH + th, ow = tw_i * a.TW + tw;
+      const bool row_ok = (row < a.TW * a.TH) && (oh < a.Ho) && (ow < a.Wo);
+      const size_t pix = ((size_t)img * a.out_H + (size_t)(oh * a.out_os + a.out_ph)) * a.out_W + (size_t)(ow * a.out_os + a.out_pw);
+      mbar_wait(&tmem_full[acc], (uint32_t)((lt >> 1) & 1));
+      tc_fence_after();
+      const uint32_t lane_addr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(32 * (warp & 3)) << 16);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      if (n0 + c0 >= a.Cout) break;  // warp-uniform
-      uint32_t v[32];
-      tmem_ld32(lane_addr + (uint32_t)c0, v);
-      if (!row_ok) continue;
-      float f[32];
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= a.Cout) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(lane_addr + (uint32_t)c0, v);
+        if (!row_ok) continue;
+        float f[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = fmaf(__uint_as_float(v[j]), s_scale[c0 + j], s_bias[c0 + j]);
-        if (a.act == 1) x = __fdividef(x, 1.0f + __expf(-x));
-        else if (a.act == 2) x = fmaxf(x, 0.0f);
-        f[j] = x;
-      }
-      if (a.out_mode == 0) {
-        if (a.residual) {
-          const uint4* rp = reinterpret_cast<const uint4*>(a.residual + pix * a.res_cstride + a.res_coffset + n0 + c0);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 rv = __ldg(rp + q);
-            const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 rf = __bfloat1622float2(r2[j]);
-              f[q * 8 + 2 * j] += rf.x;
-              f[q * 8 + 2 * j + 1] += rf.y;
-            }
-          }
-        }
-        __nv_bfloat16* yp = a.y + pix * a.y_cstride + a.y_coffset + n0 + c0;
-        if (a.accumulate && n0 + c0 + 32 <= a.Cout) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 pv = reinterpret_cast<const uint4*>(yp)[q];
-            const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&pv);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 pf = __bfloat1622float2(p2[j]);
-              f[q * 8 + 2 * j] += pf.x;
-              f[q * 8 + 2 * j + 1] += pf.y;
-            }
-          }
-        }
-        if (n0 + c0 + 32 <= a.Cout) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 ov;
-            __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(f[q * 8 + 2 * j], f[q * 8 + 2 * j + 1]);
-            reinterpret_cast<uint4*>(yp)[q] = ov;
-          }
-        } else {
-          for (int j = 0; j < 32 && n0 + c0 + j < a.Cout; ++j) yp[j] = __float2bfloat16(f[j]);
-        }
-      } else {
-        // Detect train layout: y[img][anchor][oh][ow][o], channel c = anchor*no + o  (yolov5_head.py:66)
-        const size_t hw = (size_t)a.det_hw;
-        const size_t img_r = pix / hw, pin = pix - img_r * hw;   // pix is the global pixel index in both tilings
-        const int na = a.Cout / a.det_no;
-#pragma unroll 4
         for (int j = 0; j < 32; ++j) {
           const int gc = n0 + c0 + j;
-          if (gc < a.Cout) {
-            const int an = gc / a.det_no, o = gc - an * a.det_no;
-            a.y_f32[((img_r * na + an) * hw + pin) * a.det_no + o] = f[j];
+          const float sc = (a.scale && gc < a.Cout) ? __ldg(a.scale + gc) : 1.0f;
+          const float bi = (a.bias && gc < a.Cout) ? __ldg(a.bias + gc) : 0.0f;
+          float x = fmaf(__uint_as_float(v[j]), sc, bi);
+          if (a.act == 1) x = __fdividef(x, 1.0f + __expf(-x));
+          else if (a.act == 2) x = fmaxf(x, 0.0f);
+          f[j] = x;
+        }
+        if (a.out_mode == 0) {
+          if (a.residual) {
+            const uint4* rp = reinterpret_cast<const uint4*>(a.residual + pix * a.res_cstride + a.res_coffset + n0 + c0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 rv = __ldg(rp + q);
+              const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 rf = __bfloat1622float2(r2[j]);
+                f[q * 8 + 2 * j] += rf.x;
+                f[q * 8 + 2 * j + 1] += rf.y;
+              }
+            }
+          }
+          __nv_bfloat16* yp = a.y + pix * a.y_cstride + a.y_coffset + n0 + c0;
+          if (a.accumulate && n0 + c0 + 32 <= a.Cout) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 pv = reinterpret_cast<const uint4*>(yp)[q];
+              const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&pv);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 pf = __bfloat1622float2(p2[j]);
+                f[q * 8 + 2 * j] += pf.x;
+                f[q * 8 + 2 * j + 1] += pf.y;
+              }
+            }
+          }
+          if (n0 + c0 + 32 <= a.Cout) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 ov;
+              __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(f[q * 8 + 2 * j], f[q * 8 + 2 * j + 1]);
+              reinterpret_cast<uint4*>(yp)[q] = ov;
+            }
+          } else {
+            for (int j = 0; j < 32 && n0 + c0 + j < a.Cout; ++j) yp[j] = __float2bfloat16(f[j]);
+          }
+        } else {
+          // Detect train layout: y[img][anchor][oh][ow][o], channel c = anchor*no + o  (yolov5_head.py:66)
+          const size_t hw = (size_t)a.det_hw;
+          const size_t img_r = pix / hw, pin = pix - img_r * hw;   // pix is the global pixel index in both tilings
+          const int na = a.Cout / a.det_no;
+#pragma unroll 4
+          for (int j = 0; j < 32; ++j) {
+            const int gc = n0 + c0 + j;
+            if (gc < a.Cout) {
+              const int an = gc / a.det_no, o = gc - an * a.det_no;
+              a.y_f32[((img_r * na + an) * hw + pin) * a.det_no + o] = f[j];
+            }
           }
         }
       }
+      // all tcgen05.ld of this warp have completed (wait::ld inside tmem_ld32): hand the accumulator back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, L::TMEM_COLS);
   }
 }
 
@@ -434,9 +461,13 @@ static int launch_gemm(const GemmGeom& g, ConvKArgs ka, cudaStream_t st) {
   }
   ka.kblocks = g.aC / CONV_BLOCK_K;
   ka.Cout = g.b_rows;
-  dim3 grid((unsigned)(ka.tiles_w * ka.tiles_h * nimg), (unsigned)((g.b_rows + BN - 1) / BN));
+  ka.nimg = nimg;
+  const long total_tiles = (long)ka.tiles_w * ka.tiles_h * nimg * ((g.b_rows + BN - 1) / BN);
+  // persistent grid: one CTA per SM for BN=256 (512 TMEM columns, 192 KB smem), two for the narrower tiles
+  const long resident = (long)etb_num_sms() * (BN == 256 ? 1 : 2);
+  dim3 grid((unsigned)(total_tiles < resident ? total_tiles : resident), 1);
   if (BN == 256) return launch_conv<256, 4>(mA, mB, ka, grid, st);
-  if (BN == 128) return launch_conv<128, 3>(mA, mB, ka, grid, st);   // ~97 KB smem: 2 CTAs/SM overlap epilogue and mainloop
+  if (BN == 128) return launch_conv<128, 3>(mA, mB, ka, grid, st);
   return launch_conv<64, 4>(mA, mB, ka, grid, st);
 }
 

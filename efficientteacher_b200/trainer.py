@@ -21,6 +21,7 @@ from . import _lib
 from .ema import ModelEMA, CosineEMA, SemiSupModelEMA, update_ema_pair
 from .loss import ComputeLoss
 from .model import Model
+from .parallel import GradArena
 from .pseudo_label import FairPseudoLabel
 from .ssod_loss import ComputeStudentMatchLoss
 
@@ -94,19 +95,11 @@ class SSODTrainerStep:
     # ---- gradient arena: all student gradients live in one flat fp32 buffer -> ONE all-reduce per step ----
     def _ensure_arena(self):
         if self._arena is None:
-            params = [p for p in self.model.parameters() if p.requires_grad]
-            n = sum(p.numel() for p in params)
-            self._arena = torch.zeros(n, dtype=torch.float32, device=self.device)
-            o = 0
-            for p in params:
-                p.grad = self._arena[o:o + p.numel()].view_as(p)
-                o += p.numel()
+            self._arena = GradArena(self.model.parameters(), self.device)
         return self._arena
 
     def _allreduce_grads(self):
-        if self.WORLD_SIZE > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self._arena, op=dist.ReduceOp.SUM)
+        self._arena.all_reduce_sum(self.WORLD_SIZE)
 
     # trainer/ssod_trainer.py:458-488 (bf16 autocast needs no GradScaler; loss scale == 1)
     def update_optimizer(self, loss, ni):
@@ -125,7 +118,7 @@ class SSODTrainerStep:
                     x['momentum'] = np.interp(ni, xi, [self.warmup_momentum, self.momentum])
         if ni - self.last_opt_step >= self.accumulate:
             self.optimizer.step()
-            self._arena.zero_()          # optimizer.zero_grad() keeping the arena views
+            self._arena.zero()           # optimizer.zero_grad() keeping the arena views
             if self.semi_ema:
                 update_ema_pair(self.ema, self.semi_ema, self.model)   # == ema.update(model); semi_ema.update(ema.ema)
             else:

@@ -95,37 +95,51 @@ def test_full_ssod_step_runs_and_matches_cpu_step():
     assert torch.isfinite(loss2).all()
 
 
-def test_native_training_convs_match_cudnn_scaffold():
-    """Student forward/backward with every trunk/head conv on the tcgen05 fwd/dgrad/wgrad kernels vs the same step on
-    torch/cuDNN (both bf16 autocast): loss and parameter gradients agree to bf16 accuracy."""
+def test_native_training_convs_vs_fp32_reference():
+    """Student forward/backward with every trunk/head conv on the tcgen05 fwd/dgrad/wgrad kernels (bf16 autocast).
+    At random init with a tiny batch the parameter gradients of ANY bf16 implementation only correlate ~0.8 with fp32
+    (tools/debug_grad_noise.py: native 0.81, torch/cuDNN bf16 0.77), so the criterion is: against an fp32 (TF32 off) torch
+    reference of the same step the native path is at least as accurate as the library bf16 path, per parameter; the
+    per-kernel tolerance tests live in test_gpu_conv.py and tools/debug_train_convs.py checks every layer in situ."""
     from efficientteacher_b200 import model as M
     from efficientteacher_b200.config import yolov5_ssod_cfg
     from efficientteacher_b200.loss import ComputeLoss
     import synth
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     torch.manual_seed(0)
     cfg = yolov5_ssod_cfg('l_shallow', batch_size=4, img_size=256)
     m = M.Model(cfg).to(DEV).train()
     crit = ComputeLoss(m, cfg)
     x = torch.rand(4, 3, 256, 256, generator=torch.Generator().manual_seed(1)).to(DEV)
     tg = torch.from_numpy(synth.make_targets(2, 32, 4)).to(DEV)
-    res = {}
-    for native in (True, False):
+
+    def run(native, amp):
         M.Conv.NATIVE = native
         m.zero_grad(set_to_none=True)
-        for mod in m.modules():
-            if isinstance(mod, torch.nn.BatchNorm2d):
-                mod.reset_running_stats()
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            pred, feat = m(x.contiguous(memory_format=torch.channels_last))
-        loss, _ = crit([p.float() for p in pred], tg)
-        (loss + sum(f.float().mean() for f in feat) * 0.1).backward()
-        res[native] = (loss.item(), {k: p.grad.clone() for k, p in m.named_parameters()})
-    M.Conv.NATIVE = True
-    assert abs(res[True][0] - res[False][0]) <= 0.02 * abs(res[False][0]), (res[True][0], res[False][0])
-    bad = []
-    for k, g in res[False][1].items():
-        a = res[True][1][k]
-        cos = torch.nn.functional.cosine_similarity(a.flatten().float(), g.flatten().float(), dim=0).item()
-        if g.abs().max() > 0 and cos < 0.98:
-            bad.append((k, cos))
-    assert not bad, bad[:10]
+        try:
+            if amp:
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    pred, feat = m(x.contiguous(memory_format=torch.channels_last))
+            else:
+                pred, feat = m(x)
+            loss, _ = crit([p.float() for p in pred], tg)
+            (loss + sum(f.float().mean() for f in feat) * 0.1).backward()
+        finally:
+            M.Conv.NATIVE = True
+        return loss.item(), {k: p.grad.detach().float().clone() for k, p in m.named_parameters()}
+
+    l32, g32 = run(False, False)
+    ln, gn = run(True, True)
+    lc, gc = run(False, True)
+    assert abs(ln - l32) <= 0.01 * abs(l32), (ln, l32)
+    cos = torch.nn.functional.cosine_similarity
+    worse, cn, cc = [], [], []
+    for k in g32:
+        a = cos(gn[k].flatten(), g32[k].flatten(), dim=0).item()
+        b = cos(gc[k].flatten(), g32[k].flatten(), dim=0).item()
+        cn.append(a); cc.append(b)
+        if a < b - 0.08:
+            worse.append((k, a, b))
+    assert not worse, worse[:10]
+    assert np.mean(cn) >= np.mean(cc) - 0.02, (np.mean(cn), np.mean(cc))
