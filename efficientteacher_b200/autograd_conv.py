@@ -79,6 +79,55 @@ class ConvFn(torch.autograd.Function):
         return dx, dw, None, None
 
 
+class ConvBnActFn(torch.autograd.Function):
+    """a = act(BatchNorm_train(conv2d(x, w))) -- the whole Conv module (common.py:480-481) in training mode:
+    tcgen05 conv -> per-channel batch statistics -> fused normalise+SiLU; backward = fused SiLU'/BN backward (2 passes)
+    -> dgrad + wgrad.  Saves x, the raw conv output and [4,C] statistics (not the normalised tensor)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, gamma, beta, running_mean, running_var, stride, pad, eps, momentum, act, is_stem):
+        Cout = weight.shape[0]
+        if is_stem:
+            xb = co.stem_im2col(x.float(), 1.0)               # [N,H/2,W/2,128]; saved instead of the image
+            xcs, Cin, k, st, pd = 128, 128, 1, 1, 0
+            wp = co.pack_stem_weight(weight)
+            N, Ho, Wo = xb.shape[0], xb.shape[1], xb.shape[2]
+        else:
+            Cin, k = weight.shape[1], weight.shape[2]
+            xb, xcs = _as_nhwc(x, Cin)
+            st, pd = stride, pad
+            wp = co.pack_weight(weight)
+            N, _, H, W = x.shape
+            Ho, Wo = (H + 2 * pd - k) // st + 1, (W + 2 * pd - k) // st + 1
+        y = torch.empty((N, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.device)
+        co.conv_fwd(xb, wp, Cin, Cout, k, st, pd, None, None, None, x_cstride=xcs, out=y)
+        a = _empty_cl(N, Cout, Ho, Wo, x.device)
+        _, stats = co.bn_forward(y, Cout, gamma.detach(), beta.detach(), running_mean, running_var, eps, momentum, act, out=_nhwc_of(a))
+        ctx.save_for_backward(xb if is_stem else x, weight, y, stats)
+        ctx.meta = (stride, pad, act, is_stem)
+        return a
+
+    @staticmethod
+    def backward(ctx, da):
+        xs, weight, y, stats = ctx.saved_tensors
+        stride, pad, act, is_stem = ctx.meta
+        Cout = weight.shape[0]
+        dab, dacs = _as_nhwc(da, Cout)
+        dy, dgamma, dbeta = co.bn_backward(dab, y, Cout, stats, act, da_cstride=dacs)
+        dx = dw = None
+        if is_stem:
+            dw = co.conv_wgrad(xs, dy, 128, Cout, 1, 1, 0, stem=True)
+        else:
+            Cin, k = weight.shape[1], weight.shape[2]
+            N, _, H, W = xs.shape
+            if ctx.needs_input_grad[0]:
+                dx = _empty_cl(N, Cin, H, W, da.device)
+                co.conv_dgrad(dy, co.pack_weight_dgrad(weight, stride, pad), N, H, W, Cin, Cout, k, stride, pad, out=_nhwc_of(dx))
+            xb, xcs = _as_nhwc(xs, Cin)
+            dw = co.conv_wgrad(xb, dy, Cin, Cout, k, stride, pad, x_cstride=xcs)
+        return dx, dw, dgamma, dbeta, None, None, None, None, None, None, None, None
+
+
 class StemFn(torch.autograd.Function):
     """The 6x6 s2 p2 stem on the raw fp32 NCHW image: im2col (K=108 padded to 128) + pointwise GEMM.  No input grad."""
 

@@ -163,3 +163,45 @@ def conv_wgrad(x, dy, Cin, Cout, k, stride, pad, x_coffset=0, dy_coffset=0, stem
     out = torch.empty((Cout, Cin, k, k), dtype=torch.float32, device=x.device)
     _lib.check(lib.etb_unpack_wgrad(_lib.ptr(packed), _lib.ptr(out), Cout, Cin, k, k, 0, _lib.stream_ptr()), "etb_unpack_wgrad")
     return out
+
+
+# ---- training-mode BatchNorm + activation around the convs (csrc/bn.cu) ----
+def bn_forward(y, C_, gamma, beta, running_mean, running_var, eps, momentum, act, y_cstride=None, out=None):
+    """y [N,H,W,*] bf16 raw conv output -> (a bf16 same geometry, stats [4,C] fp32 = scale, shift, mean, invstd)."""
+    N, H, W, cs = y.shape
+    if y_cstride is not None:
+        cs = y_cstride
+    M = N * H * W
+    lib = _lib.lib()
+    sums = torch.empty(2 * C_, dtype=torch.float32, device=y.device)
+    _lib.check(lib.etb_bn_stats(_lib.ptr(y), M, C_, cs, _lib.ptr(sums), _lib.stream_ptr()), "etb_bn_stats")
+    stats = torch.empty((4, C_), dtype=torch.float32, device=y.device)
+    _lib.check(lib.etb_bn_finalize(_lib.ptr(sums), M, C_, _lib.ptr(gamma), _lib.ptr(beta), float(eps), float(momentum),
+                                   _lib.ptr(running_mean), _lib.ptr(running_var), _lib.ptr(stats[0]), _lib.ptr(stats[1]),
+                                   _lib.ptr(stats[2]), _lib.ptr(stats[3]), _lib.stream_ptr()), "etb_bn_finalize")
+    if out is None:
+        out = nhwc_empty(N, H, W, C_, y.device)
+    _lib.check(lib.etb_bn_act_apply(_lib.ptr(y), _lib.ptr(stats[0]), _lib.ptr(stats[1]), _lib.ptr(out), M, C_, cs, out.shape[3],
+                                    ACT[act], _lib.stream_ptr()), "etb_bn_act_apply")
+    return out, stats
+
+
+def bn_backward(da, y, C_, stats, act, da_cstride=None, y_cstride=None, out=None):
+    """da, y [N,H,W,*] bf16 -> (dy_raw bf16 [N,H,W,C], dgamma [C], dbeta [C])."""
+    N, H, W, ycs = y.shape
+    if y_cstride is not None:
+        ycs = y_cstride
+    dacs = da.shape[3] if da_cstride is None else da_cstride
+    M = N * H * W
+    lib = _lib.lib()
+    sums = torch.empty(2 * C_, dtype=torch.float32, device=y.device)
+    _lib.check(lib.etb_bn_act_bwd_reduce(_lib.ptr(da), _lib.ptr(y), _lib.ptr(stats[0]), _lib.ptr(stats[1]), _lib.ptr(stats[2]),
+                                         _lib.ptr(stats[3]), M, C_, dacs, ycs, ACT[act], _lib.ptr(sums), _lib.stream_ptr()),
+               "etb_bn_act_bwd_reduce")
+    if out is None:
+        out = nhwc_empty(N, H, W, C_, y.device)
+    dgb = torch.empty((2, C_), dtype=torch.float32, device=y.device)
+    _lib.check(lib.etb_bn_act_bwd_apply(_lib.ptr(da), _lib.ptr(y), _lib.ptr(stats[0]), _lib.ptr(stats[1]), _lib.ptr(stats[2]),
+                                        _lib.ptr(stats[3]), _lib.ptr(sums), M, C_, dacs, ycs, out.shape[3], ACT[act], _lib.ptr(out),
+                                        _lib.ptr(dgb[0]), _lib.ptr(dgb[1]), _lib.stream_ptr()), "etb_bn_act_bwd_apply")
+    return out, dgb[0], dgb[1]

@@ -1,0 +1,248 @@
+// bn.cu -- training-mode BatchNorm2d + SiLU around the tcgen05 convolutions, forward and backward (K1/K2 tails).
+//   Conv.forward = act(bn(conv(x)))           reference models/backbone/common.py:480-481
+//   BN settings eps=1e-3, momentum=0.03       reference utils/torch_utils.py:162-171 (initialize_weights)
+// Replaces, per Conv, ATen's batch_norm_collect_statistics + batch_norm_transform_input + SiLU (5 passes over the
+// activation) by stats (1 read) + apply (1 read, 1 write), and in backward SiLU' + batch_norm_backward_reduce +
+// batch_norm_backward_elemt (8 passes) by reduce (2 reads) + apply (2 reads, 1 write).
+// Layout: y[M][cstride] bf16 (NHWC, M = N*H*W pixels), C % 8 == 0; one thread = one 16 B vector of 8 channels.
+// All HBM-bound: algorithmic bytes = 2 B/element per pass listed above.
+#include "common.cuh"
+
+#define BN_THREADS 256
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float* f) {
+  const uint4 v = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = __bfloat1622float2(h[j]);
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void ldf8(const float* p, float* f) {   // 8 consecutive per-channel parameters
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float* f) {
+  uint4 v;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+  *reinterpret_cast<uint4*>(p) = v;
+}
+
+// Per-channel reduction of up to two quantities.  Thread t owns channel group g = t % G (G = C/8 divides 256) and
+// pixel lane t / G; rows advance by (256/G)*gridDim.x so g never changes.  Block partials are combined through shared
+// memory, then one atomicAdd per channel per block.
+template <int NQ, typename F>
+__device__ __forceinline__ void channel_reduce(int M, int C, F&& per_row, float* __restrict__ out /*[NQ][C]*/) {
+  __shared__ float sh[NQ][BN_THREADS][8 + 1];
+  const int G = C >> 3;
+  const int g = threadIdx.x % G, pl = threadIdx.x / G, PL = BN_THREADS / G;
+  float acc[NQ][8];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[q][j] = 0.f;
+  for (long r = (long)blockIdx.x * PL + pl; r < M; r += (long)gridDim.x * PL) per_row(r, g, acc);
+#pragma unroll
+  for (int q = 0; q < NQ; ++q)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sh[q][threadIdx.x][j] = acc[q][j];
+  __syncthreads();
+  // thread t < C*NQ... : channel c = t % C handled by threads [0, C) for each quantity
+  for (int idx = threadIdx.x; idx < NQ * C; idx += BN_THREADS) {
+    const int q = idx / C, c = idx - q * C;
+    const int cg = c >> 3, cj = c & 7;
+    float s = 0.f;
+    for (int p = 0; p < PL; ++p) s += sh[q][p * G + cg][cj];
+    atomicAdd(out + (size_t)q * C + c, s);
+  }
+}
+
+// ---- forward statistics: sums[0][c] = sum y, sums[1][c] = sum y^2 ----
+__global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const __nv_bfloat16* __restrict__ y, int M, int C, int cs, float* __restrict__ sums) {
+  channel_reduce<2>(M, C, [&](long r, int g, float (*acc)[8]) {
+    float f[8];
+    load8(y + r * cs + g * 8, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc[0][j] += f[j]; acc[1][j] = fmaf(f[j], f[j], acc[1][j]); }
+  }, sums);
+}
+
+// ---- finalize: batch mean / biased var -> scale, shift; running stats with the unbiased variance (torch semantics) ----
+__global__ void bn_finalize_kernel(const float* __restrict__ sums, int M, int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float eps, float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out, float* __restrict__ invstd_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float inv = 1.0f / (float)M;
+  const float mean = sums[c] * inv;
+  float var = fmaf(-mean, mean, sums[C + c] * inv);
+  var = fmaxf(var, 0.0f);
+  const float invstd = rsqrtf(var + eps);
+  const float sc = gamma[c] * invstd;
+  scale[c] = sc;
+  shift[c] = fmaf(-mean, sc, beta[c]);
+  mean_out[c] = mean;
+  invstd_out[c] = invstd;
+  if (running_mean) {
+    const float unbiased = M > 1 ? var * ((float)M / (float)(M - 1)) : var;
+    running_mean[c] = fmaf(momentum, mean - running_mean[c], running_mean[c]);
+    running_var[c] = fmaf(momentum, unbiased - running_var[c], running_var[c]);
+  }
+}
+
+__device__ __forceinline__ float silu_f(float z) { return __fdividef(z, 1.0f + __expf(-z)); }
+// d silu(z)/dz = s*(1 + z*(1-s)),  s = sigmoid(z)
+__device__ __forceinline__ float dsilu_f(float z) {
+  const float s = __fdividef(1.0f, 1.0f + __expf(-z));
+  return s * fmaf(z, 1.0f - s, 1.0f);
+}
+
+// ---- forward apply: a = act(y*scale + shift) ----
+__global__ void __launch_bounds__(BN_THREADS) bn_act_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+                                                                  const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, long M, int C,
+                                                                  int ycs, int ocs, int act) {
+  const int G = C >> 3;
+  const long total = M * G;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const long r = e / G;
+    const int g = (int)(e - r * G);
+    float f[8], sc[8], sh[8];
+    load8(y + r * ycs + g * 8, f);
+    ldf8(scale + g * 8, sc); ldf8(shift + g * 8, sh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float z = fmaf(f[j], sc[j], sh[j]);
+      f[j] = act == 1 ? silu_f(z) : (act == 2 ? fmaxf(z, 0.f) : z);
+    }
+    store8(out + r * ocs + g * 8, f);
+  }
+}
+
+// ---- backward reduce: sums[0][c] = sum dz, sums[1][c] = sum dz*xhat,  dz = da * act'(z) ----
+__global__ void __launch_bounds__(BN_THREADS) bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ y,
+                                                                       const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                       const float* __restrict__ mean, const float* __restrict__ invstd, int M,
+                                                                       int C, int dacs, int ycs, int act, float* __restrict__ sums) {
+  channel_reduce<2>(M, C, [&](long r, int g, float (*acc)[8]) {
+    float fy[8], fd[8], sc[8], sh[8], mu[8], is[8];
+    load8(y + r * ycs + g * 8, fy);
+    load8(da + r * dacs + g * 8, fd);
+    ldf8(scale + g * 8, sc); ldf8(shift + g * 8, sh); ldf8(mean + g * 8, mu); ldf8(invstd + g * 8, is);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float z = fmaf(fy[j], sc[j], sh[j]);
+      const float dz = fd[j] * (act == 1 ? dsilu_f(z) : (act == 2 ? (z > 0.f ? 1.f : 0.f) : 1.f));
+      const float xh = (fy[j] - mu[j]) * is[j];
+      acc[0][j] += dz;
+      acc[1][j] = fmaf(dz, xh, acc[1][j]);
+    }
+  }, sums);
+}
+
+// ---- backward apply: dy = gamma*invstd * (dz - sum_dz/M - xhat*sum_dz_xhat/M); also writes dgamma, dbeta (block 0) ----
+__global__ void __launch_bounds__(BN_THREADS) bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ y,
+                                                                      const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                      const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                      const float* __restrict__ sums, long M, int C, int dacs, int ycs, int ocs,
+                                                                      int act, __nv_bfloat16* __restrict__ dy, float* __restrict__ dgamma,
+                                                                      float* __restrict__ dbeta) {
+  const int G = C >> 3;
+  const long total = M * G;
+  const float invM = 1.0f / (float)M;
+  if (blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      dbeta[c] = sums[c];
+      dgamma[c] = sums[C + c];
+    }
+  }
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const long r = e / G;
+    const int g = (int)(e - r * G);
+    float fy[8], fd[8], sc[8], sh[8], mu[8], is[8], s0[8], s1[8];
+    load8(y + r * ycs + g * 8, fy);
+    load8(da + r * dacs + g * 8, fd);
+    ldf8(scale + g * 8, sc); ldf8(shift + g * 8, sh); ldf8(mean + g * 8, mu); ldf8(invstd + g * 8, is);
+    ldf8(sums + g * 8, s0); ldf8(sums + C + g * 8, s1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float z = fmaf(fy[j], sc[j], sh[j]);
+      const float dz = fd[j] * (act == 1 ? dsilu_f(z) : (act == 2 ? (z > 0.f ? 1.f : 0.f) : 1.f));
+      const float xh = (fy[j] - mu[j]) * is[j];
+      fd[j] = sc[j] * (dz - s0[j] * invM - xh * s1[j] * invM);   // sc = gamma*invstd
+    }
+    store8(dy + r * ocs + g * 8, fd);
+  }
+}
+
+static inline unsigned bn_grid(long work_threads) {
+  long b = (work_threads + BN_THREADS - 1) / BN_THREADS;
+  const long cap = (long)etb_num_sms() * 8;
+  return (unsigned)(b > cap ? cap : (b < 1 ? 1 : b));
+}
+static inline bool bn_c_ok(int C) { return C >= 8 && C % 8 == 0 && (C / 8) <= BN_THREADS && BN_THREADS % (C / 8) == 0; }
+
+// sums must hold 2*C floats (zeroed here).  y [M][y_cstride] bf16.
+extern "C" int etb_bn_stats(const void* y_bf16, int64_t M, int32_t C, int32_t y_cstride, float* sums, void* stream) {
+  ETB_CHECK_ARG(y_bf16 && sums && M > 0 && M < (1ll << 31) && bn_c_ok(C) && y_cstride % 8 == 0 && y_cstride >= C);
+  cudaStream_t st = (cudaStream_t)stream;
+  ETB_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, st));
+  const int PL = BN_THREADS / (C / 8);
+  long blocks = (M + PL - 1) / PL;
+  const long cap = (long)etb_num_sms() * 4;
+  if (blocks > cap) blocks = cap;
+  bn_stats_kernel<<<(unsigned)blocks, BN_THREADS, 0, st>>>((const __nv_bfloat16*)y_bf16, (int)M, C, y_cstride, sums);
+  ETB_CHECK_LAUNCH();
+  return ETB_OK;
+}
+
+extern "C" int etb_bn_finalize(const float* sums, int64_t M, int32_t C, const float* gamma, const float* beta, float eps, float momentum,
+                               float* running_mean, float* running_var, float* scale, float* shift, float* mean, float* invstd, void* stream) {
+  ETB_CHECK_ARG(sums && gamma && beta && scale && shift && mean && invstd && M > 0 && C > 0);
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, (int)M, C, gamma, beta, eps, momentum, running_mean, running_var, scale,
+                                                                       shift, mean, invstd);
+  ETB_CHECK_LAUNCH();
+  return ETB_OK;
+}
+
+extern "C" int etb_bn_act_apply(const void* y_bf16, const float* scale, const float* shift, void* out_bf16, int64_t M, int32_t C,
+                                int32_t y_cstride, int32_t out_cstride, int32_t act, void* stream) {
+  ETB_CHECK_ARG(y_bf16 && scale && shift && out_bf16 && M > 0 && C >= 8 && C % 8 == 0 && y_cstride % 8 == 0 && out_cstride % 8 == 0);
+  bn_act_apply_kernel<<<bn_grid(M * (C / 8)), BN_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)y_bf16, scale, shift,
+                                                                                     (__nv_bfloat16*)out_bf16, (long)M, C, y_cstride, out_cstride, act);
+  ETB_CHECK_LAUNCH();
+  return ETB_OK;
+}
+
+// sums: 2*C floats (zeroed here): [sum dz][sum dz*xhat]
+extern "C" int etb_bn_act_bwd_reduce(const void* da_bf16, const void* y_bf16, const float* scale, const float* shift, const float* mean,
+                                     const float* invstd, int64_t M, int32_t C, int32_t da_cstride, int32_t y_cstride, int32_t act,
+                                     float* sums, void* stream) {
+  ETB_CHECK_ARG(da_bf16 && y_bf16 && scale && shift && mean && invstd && sums && M > 0 && M < (1ll << 31) && bn_c_ok(C));
+  ETB_CHECK_ARG(da_cstride % 8 == 0 && y_cstride % 8 == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  ETB_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, st));
+  const int PL = BN_THREADS / (C / 8);
+  long blocks = (M + PL - 1) / PL;
+  const long cap = (long)etb_num_sms() * 4;
+  if (blocks > cap) blocks = cap;
+  bn_act_bwd_reduce_kernel<<<(unsigned)blocks, BN_THREADS, 0, st>>>((const __nv_bfloat16*)da_bf16, (const __nv_bfloat16*)y_bf16, scale, shift, mean,
+                                                                   invstd, (int)M, C, da_cstride, y_cstride, act, sums);
+  ETB_CHECK_LAUNCH();
+  return ETB_OK;
+}
+
+extern "C" int etb_bn_act_bwd_apply(const void* da_bf16, const void* y_bf16, const float* scale, const float* shift, const float* mean,
+                                    const float* invstd, const float* sums, int64_t M, int32_t C, int32_t da_cstride, int32_t y_cstride,
+                                    int32_t dy_cstride, int32_t act, void* dy_bf16, float* dgamma, float* dbeta, void* stream) {
+  ETB_CHECK_ARG(da_bf16 && y_bf16 && scale && shift && mean && invstd && sums && dy_bf16 && dgamma && dbeta && M > 0 && C >= 8 && C % 8 == 0);
+  ETB_CHECK_ARG(da_cstride % 8 == 0 && y_cstride % 8 == 0 && dy_cstride % 8 == 0);
+  bn_act_bwd_apply_kernel<<<bn_grid(M * (C / 8)), BN_THREADS, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)da_bf16, (const __nv_bfloat16*)y_bf16, scale, shift, mean, invstd, sums, (long)M, C, da_cstride, y_cstride, dy_cstride,
+      act, (__nv_bfloat16*)dy_bf16, dgamma, dbeta);
+  ETB_CHECK_LAUNCH();
+  return ETB_OK;
+}

@@ -21,7 +21,8 @@
 
 #define CONV_BLOCK_M 128
 #define CONV_BLOCK_K 64
-#define CONV_THREADS 192
+#define CONV_THREADS 320     // warp0 TMA, warp1 MMA, warps2-9 epilogue
+#define WGRAD_THREADS 192
 
 // ------------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -163,7 +164,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // Persistent: gridDim.x CTAs walk the tile list (tile = blockIdx.x + i*gridDim.x; N tile fastest so the CTAs running
 // concurrently share A tiles in L2).  The smem ring and the two TMEM accumulators run across tile boundaries, so the
 // epilogue of tile i (tcgen05.ld -> BN/SiLU -> stores) overlaps the TMA/MMA main loop of tile i+1.
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const ConvKArgs a) {
   using L = ConvSmem<BN, STAGES>;
@@ -185,7 +186,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int q = 0; q < 2; ++q) { mbar_init(&tmem_full[q], 1); mbar_init(&tmem_empty[q], 4); }
+    for (int q = 0; q < 2; ++q) { mbar_init(&tmem_full[q], 1); mbar_init(&tmem_empty[q], 8); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, L::TMEM_COLS);
@@ -246,9 +247,18 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       }
     }
   } else {
-    // ===== epilogue: 4 warps <-> 128 TMEM lanes (a warp may only touch lanes 32*(warp%4)..+31) =====
-    const int row = 32 * (warp & 3) + lane;
+    // ===== epilogue: 8 warps.  A warp may only touch TMEM lanes 32*(warp%4)..+31, so warps w and w+4 share a lane
+    // quadrant (= 32 output pixels) and split the BN columns in halves.  EPI selects the fused tail at compile time so
+    // every register array is statically indexed (no local memory):
+    //   EPI 0: raw bf16 store (+= existing when a.accumulate)       -- dgrad, training forward
+    //   EPI 1: v*scale+bias (folded BN) -> SiLU/ReLU -> (+residual) -- teacher forward
+    //   EPI 2: +bias, fp32 scatter into the Detect layout           -- head
+    const int ew = warp - 2;
+    const int quad = warp & 3;
+    const int chalf = ew >> 2;
+    const int row = 32 * quad + lane;
     const int th = row / a.TW, tw = row - th * a.TW;
+    constexpr int HALF = BN / 2;
     int lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
       const int acc = lt & 1;
@@ -262,77 +272,92 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       const size_t pix = ((size_t)img * a.out_H + (size_t)(oh * a.out_os + a.out_ph)) * a.out_W + (size_t)(ow * a.out_os + a.out_pw);
       mbar_wait(&tmem_full[acc], (uint32_t)((lt >> 1) & 1));
       tc_fence_after();
-      const uint32_t lane_addr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(32 * (warp & 3)) << 16);
+      const uint32_t lane_addr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(32 * quad) << 16);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int cc = 0; cc < HALF; cc += 32) {
+        const int c0 = chalf * HALF + cc;
         if (n0 + c0 >= a.Cout) break;  // warp-uniform
         uint32_t v[32];
         tmem_ld32(lane_addr + (uint32_t)c0, v);
         if (!row_ok) continue;
-        float f[32];
+        const int gc0 = n0 + c0;
+        const bool full = gc0 + 32 <= a.Cout;
+        if (EPI == 2) {
+          // Detect train layout: y[img][anchor][oh][ow][o], channel c = anchor*no + o  (yolov5_head.py:66)
+          const size_t hw = (size_t)a.det_hw;
+          const size_t img_r = pix / hw, pin = pix - img_r * hw;   // pix is the global pixel index in both tilings
+          const int na = a.Cout / a.det_no;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int gc = n0 + c0 + j;
-          const float sc = (a.scale && gc < a.Cout) ? __ldg(a.scale + gc) : 1.0f;
-          const float bi = (a.bias && gc < a.Cout) ? __ldg(a.bias + gc) : 0.0f;
-          float x = fmaf(__uint_as_float(v[j]), sc, bi);
-          if (a.act == 1) x = __fdividef(x, 1.0f + __expf(-x));
-          else if (a.act == 2) x = fmaxf(x, 0.0f);
-          f[j] = x;
+          for (int j = 0; j < 32; ++j) {
+            const int gc = gc0 + j;
+            if (gc < a.Cout) {
+              const int an = gc / a.det_no, o = gc - an * a.det_no;
+              a.y_f32[((img_r * na + an) * hw + pin) * a.det_no + o] = __uint_as_float(v[j]) + (a.bias ? __ldg(a.bias + gc) : 0.0f);
+            }
+          }
+          continue;
         }
-        if (a.out_mode == 0) {
-          if (a.residual) {
-            const uint4* rp = reinterpret_cast<const uint4*>(a.residual + pix * a.res_cstride + a.res_coffset + n0 + c0);
+        __nv_bfloat16* yp = a.y + pix * a.y_cstride + a.y_coffset + gc0;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 rv = __ldg(rp + q);
+        for (int q = 0; q < 4; ++q) {         // 8 channels = one 16 B store
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[q * 8 + j]);
+          if (EPI == 1) {
+            float sc[8], bi[8];
+            if (full) {
+              const float4 s0 = a.scale ? __ldg(reinterpret_cast<const float4*>(a.scale + gc0) + 2 * q) : make_float4(1.f, 1.f, 1.f, 1.f);
+              const float4 s1 = a.scale ? __ldg(reinterpret_cast<const float4*>(a.scale + gc0) + 2 * q + 1) : make_float4(1.f, 1.f, 1.f, 1.f);
+              const float4 b0 = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + gc0) + 2 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+              const float4 b1 = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + gc0) + 2 * q + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+              sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+              bi[0] = b0.x; bi[1] = b0.y; bi[2] = b0.z; bi[3] = b0.w; bi[4] = b1.x; bi[5] = b1.y; bi[6] = b1.z; bi[7] = b1.w;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int gc = gc0 + q * 8 + j;
+                sc[j] = (a.scale && gc < a.Cout) ? __ldg(a.scale + gc) : 1.0f;
+                bi[j] = (a.bias && gc < a.Cout) ? __ldg(a.bias + gc) : 0.0f;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float x = fmaf(f[j], sc[j], bi[j]);
+              if (a.act == 1) x = __fdividef(x, 1.0f + __expf(-x));
+              else if (a.act == 2) x = fmaxf(x, 0.0f);
+              f[j] = x;
+            }
+            if (a.residual && full) {
+              const uint4 rv = __ldg(reinterpret_cast<const uint4*>(a.residual + pix * a.res_cstride + a.res_coffset + gc0) + q);
               const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float2 rf = __bfloat1622float2(r2[j]);
-                f[q * 8 + 2 * j] += rf.x;
-                f[q * 8 + 2 * j + 1] += rf.y;
+                f[2 * j] += rf.x;
+                f[2 * j + 1] += rf.y;
               }
             }
           }
-          __nv_bfloat16* yp = a.y + pix * a.y_cstride + a.y_coffset + n0 + c0;
-          if (a.accumulate && n0 + c0 + 32 <= a.Cout) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
+          if (full) {
+            if (EPI == 0 && a.accumulate) {
               const uint4 pv = reinterpret_cast<const uint4*>(yp)[q];
               const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&pv);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float2 pf = __bfloat1622float2(p2[j]);
-                f[q * 8 + 2 * j] += pf.x;
-                f[q * 8 + 2 * j + 1] += pf.y;
+                f[2 * j] += pf.x;
+                f[2 * j + 1] += pf.y;
               }
             }
-          }
-          if (n0 + c0 + 32 <= a.Cout) {
+            uint4 ov;
+            __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 ov;
-              __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(f[q * 8 + 2 * j], f[q * 8 + 2 * j + 1]);
-              reinterpret_cast<uint4*>(yp)[q] = ov;
-            }
+            for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            reinterpret_cast<uint4*>(yp)[q] = ov;
           } else {
-            for (int j = 0; j < 32 && n0 + c0 + j < a.Cout; ++j) yp[j] = __float2bfloat16(f[j]);
-          }
-        } else {
-          // Detect train layout: y[img][anchor][oh][ow][o], channel c = anchor*no + o  (yolov5_head.py:66)
-          const size_t hw = (size_t)a.det_hw;
-          const size_t img_r = pix / hw, pin = pix - img_r * hw;   // pix is the global pixel index in both tilings
-          const int na = a.Cout / a.det_no;
-#pragma unroll 4
-          for (int j = 0; j < 32; ++j) {
-            const int gc = n0 + c0 + j;
-            if (gc < a.Cout) {
-              const int an = gc / a.det_no, o = gc - an * a.det_no;
-              a.y_f32[((img_r * na + an) * hw + pin) * a.det_no + o] = f[j];
-            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (gc0 + q * 8 + j < a.Cout) yp[q * 8 + j] = __float2bfloat16(f[j]);
           }
         }
       }
@@ -380,17 +405,23 @@ static void pick_tile(int Wo, int Ho, int* TW, int* TH) {
   }
 }
 
-template <int BN, int STAGES>
-static int launch_conv(const CUtensorMap& mA, const CUtensorMap& mB, const ConvKArgs& ka, dim3 grid, cudaStream_t st) {
+template <int BN, int STAGES, int EPI>
+static int launch_conv_e(const CUtensorMap& mA, const CUtensorMap& mB, const ConvKArgs& ka, dim3 grid, cudaStream_t st) {
   using L = ConvSmem<BN, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
-    ETB_CHECK_CUDA(cudaFuncSetAttribute(conv_fwd_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    ETB_CHECK_CUDA(cudaFuncSetAttribute(conv_fwd_kernel<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_set = true;
   }
-  conv_fwd_kernel<BN, STAGES><<<grid, CONV_THREADS, L::TOTAL, st>>>(mA, mB, ka);
+  conv_fwd_kernel<BN, STAGES, EPI><<<grid, CONV_THREADS, L::TOTAL, st>>>(mA, mB, ka);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
+}
+template <int BN, int STAGES>
+static int launch_conv(const CUtensorMap& mA, const CUtensorMap& mB, const ConvKArgs& ka, dim3 grid, cudaStream_t st) {
+  if (ka.out_mode == 1) return launch_conv_e<BN, STAGES, 2>(mA, mB, ka, grid, st);
+  if (ka.scale || ka.bias || ka.act || ka.residual) return launch_conv_e<BN, STAGES, 1>(mA, mB, ka, grid, st);
+  return launch_conv_e<BN, STAGES, 0>(mA, mB, ka, grid, st);
 }
 
 // One implicit-GEMM launch: D[pixels, rows_B] = sum_taps A(shifted) * B^T.  `ka` carries the epilogue.
@@ -463,12 +494,11 @@ static int launch_gemm(const GemmGeom& g, ConvKArgs ka, cudaStream_t st) {
   ka.Cout = g.b_rows;
   ka.nimg = nimg;
   const long total_tiles = (long)ka.tiles_w * ka.tiles_h * nimg * ((g.b_rows + BN - 1) / BN);
-  // persistent grid: one CTA per SM for BN=256 (512 TMEM columns, 192 KB smem), two for the narrower tiles
-  const long resident = (long)etb_num_sms() * (BN == 256 ? 1 : 2);
+  const long resident = (long)etb_num_sms();   // persistent: one CTA per SM; overlap comes from the 2 TMEM accumulators
   dim3 grid((unsigned)(total_tiles < resident ? total_tiles : resident), 1);
   if (BN == 256) return launch_conv<256, 4>(mA, mB, ka, grid, st);
-  if (BN == 128) return launch_conv<128, 3>(mA, mB, ka, grid, st);
-  return launch_conv<64, 4>(mA, mB, ka, grid, st);
+  if (BN == 128) return launch_conv<128, 6>(mA, mB, ka, grid, st);
+  return launch_conv<64, 8>(mA, mB, ka, grid, st);
 }
 
 extern "C" size_t etb_conv_workspace_bytes(const EtbConvParams* cp) { (void)cp; return 0; }
@@ -652,7 +682,7 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int M, int N) {   // b
 }
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(CONV_THREADS, 1)
+__global__ void __launch_bounds__(WGRAD_THREADS, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ CUtensorMap mapX, const WgradArgs a) {
   using L = WgradSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
@@ -783,7 +813,7 @@ static int launch_wgrad(const CUtensorMap& mDy, const CUtensorMap& mX, const Wgr
     ETB_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_set = true;
   }
-  wgrad_kernel<BN, STAGES><<<grid, CONV_THREADS, L::TOTAL, st>>>(mDy, mX, wa);
+  wgrad_kernel<BN, STAGES><<<grid, WGRAD_THREADS, L::TOTAL, st>>>(mDy, mX, wa);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }

@@ -40,12 +40,18 @@ class Conv(nn.Module):
         self.act_name = "relu" if act == "relu" else None
 
     NATIVE = True        # training convs on the tcgen05 fwd/dgrad/wgrad kernels (False: torch/cuDNN scaffold)
+    FUSED_BN = True      # BatchNorm(train)+SiLU forward/backward on the fused kernels of csrc/bn.cu (False: torch ops)
     is_stem = False
 
     def forward(self, x):
         if Conv.NATIVE and x.is_cuda:
-            from .autograd_conv import ConvFn, StemFn
+            from .autograd_conv import ConvBnActFn, ConvFn, StemFn
             w = self.conv.weight
+            if Conv.FUSED_BN and self.training and isinstance(self.act, (nn.SiLU, nn.ReLU)):
+                bn = self.bn
+                act = "silu" if isinstance(self.act, nn.SiLU) else "relu"
+                return ConvBnActFn.apply(x, w, bn.weight, bn.bias, bn.running_mean, bn.running_var, self.conv.stride[0],
+                                         self.conv.padding[0], bn.eps, bn.momentum, act, self.is_stem)
             if self.is_stem:
                 y = StemFn.apply(x.float(), w)
             else:
@@ -271,6 +277,14 @@ class _ModelBase(nn.Module):
         _lib.require_cuda(x)
         _lib.lib()
 
+    def _count_bn_batches(self):
+        """BatchNorm2d.num_batches_tracked += 1 for every BN (what nn.BatchNorm2d does per training forward), as ONE
+        multi-tensor op; the fused BN kernels update running_mean / running_var themselves."""
+        if Conv.NATIVE and Conv.FUSED_BN and self.training:
+            if getattr(self, "_nbt", None) is None:
+                self._nbt = [m.num_batches_tracked for m in self.modules() if isinstance(m, nn.BatchNorm2d)]
+            torch._foreach_add_(self._nbt, 1)
+
     def engine(self):
         from .engine import TrunkEngine
         if self._engine is None:
@@ -283,12 +297,13 @@ class _ModelBase(nn.Module):
         memo[id(self)] = new
         from copy import deepcopy
         for k, v in self.__dict__.items():
-            new.__dict__[k] = None if k == "_engine" else deepcopy(v, memo)
+            new.__dict__[k] = None if k in ("_engine", "_nbt") else deepcopy(v, memo)
         return new
 
     def __getstate__(self):
         s = dict(self.__dict__)
         s["_engine"] = None
+        s["_nbt"] = None
         return s
 
 
@@ -308,6 +323,7 @@ class Model(_ModelBase):
         self._require(x)
         if not self.training and not torch.is_grad_enabled():
             return self.engine().forward(x, with_features=True)
+        self._count_bn_batches()
         f = self.neck(self.backbone(x))
         out = self.head(f)
         f8, f16, f32 = f
@@ -327,4 +343,5 @@ class SupModel(_ModelBase):
         self._require(x)
         if not self.training and not torch.is_grad_enabled():
             return self.engine().forward(x, with_features=False)[0]
+        self._count_bn_batches()
         return self.head(self.neck(self.backbone(x)))

@@ -216,6 +216,25 @@ int etb_conv_wgrad(const void* x_bf16, const void* dy_bf16, float* dw_f32, const
 int etb_unpack_wgrad(const float* dw_packed, float* w_oihw, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw, int32_t stem,
                      void* stream);
 
+/* training-mode BatchNorm2d (eps, momentum, batch statistics, running-stat update with the unbiased variance) + SiLU/ReLU
+ * around the convolutions (models/backbone/common.py:480-481; utils/torch_utils.py:162-171), forward and backward.
+ * y / da / dy / out are NHWC bf16 [M][cstride] with M = N*H*W; per-channel vectors are fp32.  act: 0 none, 1 SiLU, 2 ReLU.
+ *   forward : etb_bn_stats (sums[2C] = sum y, sum y^2) -> etb_bn_finalize (scale, shift, mean, invstd, running stats)
+ *             -> etb_bn_act_apply (a = act(y*scale+shift))
+ *   backward: etb_bn_act_bwd_reduce (sums[2C] = sum dz, sum dz*xhat; dz = da*act'(z)) -> etb_bn_act_bwd_apply
+ *             (dy = gamma*invstd*(dz - sum_dz/M - xhat*sum_dz_xhat/M), dgamma, dbeta) */
+int etb_bn_stats(const void* y_bf16, int64_t M, int32_t C, int32_t y_cstride, float* sums, void* stream);
+int etb_bn_finalize(const float* sums, int64_t M, int32_t C, const float* gamma, const float* beta, float eps, float momentum,
+                    float* running_mean, float* running_var, float* scale, float* shift, float* mean, float* invstd, void* stream);
+int etb_bn_act_apply(const void* y_bf16, const float* scale, const float* shift, void* out_bf16, int64_t M, int32_t C,
+                     int32_t y_cstride, int32_t out_cstride, int32_t act, void* stream);
+int etb_bn_act_bwd_reduce(const void* da_bf16, const void* y_bf16, const float* scale, const float* shift, const float* mean,
+                          const float* invstd, int64_t M, int32_t C, int32_t da_cstride, int32_t y_cstride, int32_t act,
+                          float* sums, void* stream);
+int etb_bn_act_bwd_apply(const void* da_bf16, const void* y_bf16, const float* scale, const float* shift, const float* mean,
+                         const float* invstd, const float* sums, int64_t M, int32_t C, int32_t da_cstride, int32_t y_cstride,
+                         int32_t dy_cstride, int32_t act, void* dy_bf16, float* dgamma, float* dbeta, void* stream);
+
 /* small layout / elementwise helpers of the trunk (all HBM-bound, coalesced 16 B vectors) */
 
 /* input prep + stem im2col (trainer/ssod_trainer.py:694-696 `.float()/255` fused with the 6x6 s2 p2 stem patch

@@ -172,3 +172,30 @@ def test_stem_wgrad():
     ref = torch.nn.grad.conv2d_weight(_bf(x), (64, 3, 6, 6), _bf(dy), stride=2, padding=2)
     err = (dw - ref).abs().max().item()
     assert err <= 2e-3 * max(ref.abs().max().item(), 1.0), (err, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("C_,H,act", [(64, 16, "silu"), (256, 20, "silu"), (1024, 8, "silu"), (128, 12, "relu")])
+def test_fused_bn_act_forward_backward(C_, H, act):
+    """Training-mode BatchNorm+activation kernels vs torch (fp32 math on the same bf16 inputs), incl. running stats."""
+    from efficientteacher_b200 import convops as co
+    N = 4
+    y = _rand((N, C_, H, H), 51) * 2.0 + 0.3
+    da = _rand((N, C_, H, H), 52)
+    gamma = torch.rand(C_, device=DEV) + 0.5
+    beta = torch.randn(C_, device=DEV) * 0.1
+    rm, rv = torch.zeros(C_, device=DEV), torch.ones(C_, device=DEV)
+    yb, dab = co.to_nhwc_bf16(y), co.to_nhwc_bf16(da)
+    a, stats = co.bn_forward(yb, C_, gamma, beta, rm, rv, 1e-3, 0.03, act)
+    dy, dg, db = co.bn_backward(dab, yb, C_, stats, act)
+    yr = _bf(y).requires_grad_(True)
+    g2, b2 = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm2, rv2 = torch.zeros(C_, device=DEV), torch.ones(C_, device=DEV)
+    z = F.batch_norm(yr, rm2, rv2, g2, b2, True, 0.03, 1e-3)
+    ar = F.silu(z) if act == "silu" else F.relu(z)
+    ar.backward(_bf(da))
+    _check(co.to_nchw_f32(a), ar.detach(), tol=1e-2)
+    _check(co.to_nchw_f32(dy), yr.grad, tol=2e-2)
+    torch.testing.assert_close(dg, g2.grad, rtol=2e-2, atol=2e-2 * g2.grad.abs().max().item())
+    torch.testing.assert_close(db, b2.grad, rtol=2e-2, atol=2e-2 * b2.grad.abs().max().item())
+    torch.testing.assert_close(rm, rm2, rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(rv, rv2, rtol=1e-3, atol=1e-4)
