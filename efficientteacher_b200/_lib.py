@@ -64,6 +64,7 @@ _SIGS = {
     "etb_ema_table_fill": (C.c_int, [C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int64), C.c_int32,
                                      C.POINTER(EtbEmaChunk), C.c_int64]),
     "etb_ema_update": (C.c_int, [vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, vp]),
+    "etb_ema_update_dev": (C.c_int, [vp, C.c_int64, vp, vp]),
     "etb_detect_decode": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                     C.c_int32, c_f32p, C.c_float, vp]),
     "etb_nms_workspace_bytes": (C.c_size_t, [C.POINTER(EtbNmsParams)]),

@@ -71,12 +71,19 @@ def _float_pairs(ema_module, model):
     return v_list, m_list
 
 
-def _launch(table, d, d2=0.0):
-    # python scalars are rounded to fp32 when they meet an fp32 tensor
-    d32, omd32 = np.float32(d), np.float32(1.0 - d)
-    d2_32, omd2_32 = np.float32(d2), np.float32(1.0 - d2)
-    _lib.check(_lib.lib().etb_ema_update(_lib.ptr(table.dev), table.n_chunks, float(d32), float(omd32), float(d2_32),
-                                         float(omd2_32), _lib.stream_ptr()), "etb_ema_update")
+def ema_scalars(d, d2=0.0):
+    """{d, 1-d, d2, 1-d2} rounded to fp32 the way python scalars are when they meet an fp32 tensor."""
+    return [float(np.float32(d)), float(np.float32(1.0 - d)), float(np.float32(d2)), float(np.float32(1.0 - d2))]
+
+
+def _launch(table, d, d2=0.0, scalars_dev=None):
+    if scalars_dev is not None:      # graph-capture mode: the decays live in device memory, refreshed before each replay
+        _lib.check(_lib.lib().etb_ema_update_dev(_lib.ptr(table.dev), table.n_chunks, _lib.ptr(scalars_dev), _lib.stream_ptr()),
+                   "etb_ema_update_dev")
+        return
+    sc = ema_scalars(d, d2)
+    _lib.check(_lib.lib().etb_ema_update(_lib.ptr(table.dev), table.n_chunks, sc[0], sc[1], sc[2], sc[3], _lib.stream_ptr()),
+               "etb_ema_update")
 
 
 class _EMABase:
@@ -155,24 +162,24 @@ class CosineEMA(_EMABase):
 _pair_tables = {}
 
 
-def update_ema_pair(ema, semi_ema, model):
+def next_pair_decays(ema, semi_ema, advance=True):
+    """(d1, d2) of the next `ema.update(model); semi_ema.update(ema.ema)`; advances the update counters like .update()."""
+    def one(e):
+        if isinstance(e, ModelEMA):
+            if advance:
+                e.updates += 1
+            return e.decay(e.updates if advance else e.updates + 1)
+        if isinstance(e, SemiSupModelEMA) and advance:
+            e.updates += 1
+        return e.decay
+    return one(ema), one(semi_ema)
+
+
+def update_ema_pair(ema, semi_ema, model, scalars_dev=None):
     """`ema.update(model); semi_ema.update(ema.ema)` (trainer/ssod_trainer.py:485-487) in ONE pass over HBM:
     5 streams (read v,m,s ; write v,s) instead of 6, one launch instead of two.  Bit-identical results."""
     with torch.no_grad():
-        if isinstance(ema, ModelEMA):
-            ema.updates += 1
-            d1 = ema.decay(ema.updates)
-        else:
-            if isinstance(ema, SemiSupModelEMA):
-                ema.updates += 1
-            d1 = ema.decay
-        if isinstance(semi_ema, ModelEMA):
-            semi_ema.updates += 1
-            d2 = semi_ema.decay(semi_ema.updates)
-        else:
-            if isinstance(semi_ema, SemiSupModelEMA):
-                semi_ema.updates += 1
-            d2 = semi_ema.decay
+        d1, d2 = (0.0, 0.0) if scalars_dev is not None else next_pair_decays(ema, semi_ema)
         v_list, m_list = _float_pairs(ema.ema, model)
         s_list, v2_list = _float_pairs(semi_ema.ema, ema.ema)
         assert len(s_list) == len(v_list) and all(a.data_ptr() == b.data_ptr() for a, b in zip(v2_list, v_list))
@@ -181,5 +188,5 @@ def update_ema_pair(ema, semi_ema, model):
         want = tuple(t.data_ptr() for t in v_list) + tuple(t.data_ptr() for t in m_list) + tuple(t.data_ptr() for t in s_list)
         if tab is None or tab.key != want:
             tab = _pair_tables[key] = _ChunkTable(v_list, m_list, s_list)
-        _launch(tab, d1, d2)
+        _launch(tab, d1, d2, scalars_dev)
         return tab

@@ -6,6 +6,9 @@ import torch
 from . import _lib
 
 
+_ANCHOR_CACHE = {}
+
+
 def decode_levels(levels, anchors_grid, strides):
     """Eval-mode decode of Detect (yolov5_head.py:66-78): list of logits [B,na,ny,nx,no] -> pred [B,P,no].
     One elementwise launch per level, written straight into the concatenated output (no torch.cat copy)."""
@@ -13,7 +16,10 @@ def decode_levels(levels, anchors_grid, strides):
     B, na, _, _, no = levels[0].shape
     P = sum(int(x.shape[1] * x.shape[2] * x.shape[3]) for x in levels)
     pred = torch.empty((B, P, no), dtype=torch.float32, device=levels[0].device)
-    anc = anchors_grid.detach().float().cpu().contiguous()
+    key = (anchors_grid.data_ptr(), anchors_grid._version)
+    anc = _ANCHOR_CACHE.get(key)
+    if anc is None:                       # one D2H per anchor tensor version, not per call (keeps the step sync-free)
+        anc = _ANCHOR_CACHE[key] = anchors_grid.detach().float().cpu().contiguous()
     row0 = 0
     lib = _lib.lib()
     for l, x in enumerate(levels):

@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .ema import ModelEMA, CosineEMA, SemiSupModelEMA, update_ema_pair
+from .ema import ModelEMA, CosineEMA, SemiSupModelEMA, update_ema_pair, next_pair_decays, ema_scalars
 from .loss import ComputeLoss
 from .model import Model
 from .parallel import GradArena
@@ -68,6 +68,8 @@ class SSODTrainerStep:
         self.last = {}
         self.profile = False     # record CUDA events at the phase boundaries of train_instance
         self.phase_events = []
+        self._graph = None       # captured CUDA graph of the whole step (train_instance_graphed)
+        self._ema_scalars_dev = None
 
     # trainer/trainer.py:193-217
     def build_optimizer(self, cfg):
@@ -120,7 +122,8 @@ class SSODTrainerStep:
             self.optimizer.step()
             self._arena.zero()           # optimizer.zero_grad() keeping the arena views
             if self.semi_ema:
-                update_ema_pair(self.ema, self.semi_ema, self.model)   # == ema.update(model); semi_ema.update(ema.ema)
+                # == ema.update(model); semi_ema.update(ema.ema); inside a captured graph the decays come from device memory
+                update_ema_pair(self.ema, self.semi_ema, self.model, scalars_dev=self._ema_scalars_dev)
             else:
                 self.ema.update(self.model)
             self.last_opt_step = ni
@@ -189,3 +192,75 @@ class SSODTrainerStep:
         self._mark("optimizer_ema")
         self.last = dict(loss=loss.detach(), sup=sup_loss_items, unsup=un_sup_loss_items)
         return loss.detach()
+
+    # ---- the whole step as ONE CUDA graph ---------------------------------------------------------------------------
+    def train_instance_graphed(self, imgs, targets, unlabeled_imgs, unlabeled_imgs_ori, unlabeled_gt, unlabeled_M, ni):
+        """train_instance captured once (static shapes, device-resident pseudo labels, no host sync anywhere in the step)
+        and replayed: ~1.5k kernel launches + the autograd traversal collapse into one cudaGraphLaunch.  Inputs are copied
+        into static buffers; the EMA decays of this step are written to device memory before the replay; the learning
+        rate is baked at capture time, so call `reset_graph()` whenever the scheduler / warm-up changes it."""
+        if self.semi_ema is None:
+            raise NotImplementedError("graphed step needs the fused ema/semi_ema pair (burn_epochs == 0)")
+        shapes = (tuple(imgs.shape), tuple(targets.shape), tuple(unlabeled_imgs.shape), tuple(unlabeled_M.shape))
+        if self._graph is not None and self._graph["shapes"] != shapes:
+            self.reset_graph()
+        if self._graph is None:
+            self._capture(imgs, targets, unlabeled_imgs, unlabeled_imgs_ori, unlabeled_M, ni, shapes)
+        g = self._graph
+        g["imgs"].copy_(imgs, non_blocking=True)
+        g["targets"].copy_(targets, non_blocking=True)
+        g["us"].copy_(unlabeled_imgs, non_blocking=True)
+        g["uw"].copy_(unlabeled_imgs_ori, non_blocking=True)
+        g["Ms"].copy_(unlabeled_M, non_blocking=True)
+        d1, d2 = next_pair_decays(self.ema, self.semi_ema)
+        g["sc_host"].copy_(torch.tensor(ema_scalars(d1, d2), dtype=torch.float32))
+        self._ema_scalars_dev.copy_(g["sc_host"], non_blocking=True)
+        g["graph"].replay()
+        self.last_opt_step = ni
+        return g["loss"]
+
+    def reset_graph(self):
+        self._graph = None
+        self._ema_scalars_dev = None
+
+    def _capture(self, imgs, targets, us, uw, Ms, ni, shapes):
+        dev = self.device
+        st = dict(shapes=shapes, imgs=imgs.clone(), targets=targets.clone(), us=us.clone(), uw=uw.clone(),
+                  Ms=Ms.to(dev, torch.float64).clone(), sc_host=torch.zeros(4, dtype=torch.float32).pin_memory())
+        self._ema_scalars_dev = torch.zeros(4, dtype=torch.float32, device=dev)
+        was_profile, self.profile = self.profile, False
+        d1, d2 = next_pair_decays(self.ema, self.semi_ema, advance=False)
+        self._ema_scalars_dev.copy_(torch.tensor(ema_scalars(d1, d2), dtype=torch.float32))
+        # the warm-up steps below really train: snapshot every piece of state they touch and restore it afterwards
+        had_momentum = any(len(self.optimizer.state[p]) for g_ in self.optimizer.param_groups for p in g_["params"])
+        tensors = [t for m in (self.model, self.ema.ema, self.semi_ema.ema) for t in m.state_dict().values()]
+        if had_momentum:
+            tensors += [self.optimizer.state[p]["momentum_buffer"] for g_ in self.optimizer.param_groups for p in g_["params"]
+                        if self.optimizer.state[p].get("momentum_buffer") is not None]
+        snap = [t.clone() for t in tensors]
+        saved_step = self.last_opt_step
+        # warm-up on a side stream (allocator + lazily-created state: momentum buffers, chunk tables, workspaces, TMA/func attrs)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self.train_instance(st["imgs"], st["targets"], st["us"], st["uw"], None, st["Ms"], ni)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            st["loss"] = self.train_instance(st["imgs"], st["targets"], st["us"], st["uw"], None, st["Ms"], ni)
+        st["graph"] = graph
+        with torch.no_grad():
+            for t, c in zip(tensors, snap):
+                t.copy_(c)
+            if not had_momentum:      # buffers created by the warm-up: zero == "not yet created" for SGD (buf = grad on first use)
+                for g_ in self.optimizer.param_groups:
+                    for p in g_["params"]:
+                        b = self.optimizer.state[p].get("momentum_buffer")
+                        if b is not None:
+                            b.zero_()
+            self._arena.zero()
+        self.last_opt_step = saved_step
+        self.profile = was_profile
+        self._graph = st

@@ -64,6 +64,8 @@ int etb_ema_table_fill(float* const* v, const float* const* m, float* const* s, 
                        int32_t n_tensors, EtbEmaChunk* out_host, int64_t out_capacity);
 int etb_ema_update(const EtbEmaChunk* table_dev, int64_t n_chunks, float d, float one_minus_d, float d2,
                    float one_minus_d2, void* stream);
+/* same, with {d, 1-d, d2, 1-d2} read from device memory: a captured CUDA graph of the step replays with fresh decays */
+int etb_ema_update_dev(const EtbEmaChunk* table_dev, int64_t n_chunks, const float* scalars4_dev, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Detect eval-mode decode (models/head/yolov5_head.py:66-78): logits [B,na,ny,nx,no] of one level ->
