@@ -12,6 +12,9 @@ from . import _lib
 from . import convops as co
 
 
+ACCUMULATE_INTO_GRAD = True
+
+
 def _as_nhwc(t, C_):
     """(view [N,H,W,C] bf16 whose channel stride may exceed C, channel_stride) for an NCHW-shaped tensor; copies only if
     the layout is not NHWC.  A channel-slice of a channels_last tensor (what torch.cat's backward hands out) is used in
@@ -115,8 +118,11 @@ class ConvBnActFn(torch.autograd.Function):
         dab, dacs = _as_nhwc(da, Cout)
         dy, dgamma, dbeta = co.bn_backward(dab, y, Cout, stats, act, da_cstride=dacs)
         dx = dw = None
+        # gradient arena: when p.grad already exists (trainer.GradArena) the wgrad is added into it in place and autograd
+        # gets None for the weight (no separate AccumulateGrad add pass, no temporary)
+        tgt = weight.grad if (ACCUMULATE_INTO_GRAD and weight.grad is not None and weight.grad.is_contiguous()) else None
         if is_stem:
-            dw = co.conv_wgrad(xs, dy, 128, Cout, 1, 1, 0, stem=True)
+            dw = co.conv_wgrad(xs, dy, 128, Cout, 1, 1, 0, stem=True, accumulate_into=tgt)
         else:
             Cin, k = weight.shape[1], weight.shape[2]
             N, _, H, W = xs.shape
@@ -124,7 +130,9 @@ class ConvBnActFn(torch.autograd.Function):
                 dx = _empty_cl(N, Cin, H, W, da.device)
                 co.conv_dgrad(dy, co.pack_weight_dgrad(weight, stride, pad), N, H, W, Cin, Cout, k, stride, pad, out=_nhwc_of(dx))
             xb, xcs = _as_nhwc(xs, Cin)
-            dw = co.conv_wgrad(xb, dy, Cin, Cout, k, stride, pad, x_cstride=xcs)
+            dw = co.conv_wgrad(xb, dy, Cin, Cout, k, stride, pad, x_cstride=xcs, accumulate_into=tgt)
+        if tgt is not None:
+            dw = None
         return dx, dw, dgamma, dbeta, None, None, None, None, None, None, None, None
 
 

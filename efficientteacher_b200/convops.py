@@ -140,8 +140,11 @@ def conv_dgrad(dy, wd_packed, N, H, W, Cin, Cout, k, stride, pad, out=None, out_
     return out
 
 
-def conv_wgrad(x, dy, Cin, Cout, k, stride, pad, x_coffset=0, dy_coffset=0, stem=False, x_cstride=None, dy_cstride=None):
-    """x [N,H,W,*] bf16, dy [N,Ho,Wo,*] bf16 -> dW [Cout,Cin,k,k] fp32 (parameter layout)."""
+def conv_wgrad(x, dy, Cin, Cout, k, stride, pad, x_coffset=0, dy_coffset=0, stem=False, x_cstride=None, dy_cstride=None,
+               accumulate_into=None):
+    """x [N,H,W,*] bf16, dy [N,Ho,Wo,*] bf16 -> dW [Cout,Cin,k,k] fp32 (parameter layout).
+    accumulate_into: an existing contiguous fp32 gradient of that shape (the arena view p.grad): dW is ADDED into it and
+    returned (saves the separate AccumulateGrad pass)."""
     _lib.require_cuda(x, dy)
     N, H, W, xcs = x.shape
     cp = EtbConvParams()
@@ -150,18 +153,25 @@ def conv_wgrad(x, dy, Cin, Cout, k, stride, pad, x_coffset=0, dy_coffset=0, stem
     cp.stride, cp.pad = stride, pad
     cp.x_cstride = xcs if x_cstride is None else x_cstride
     cp.y_cstride = dy.shape[3] if dy_cstride is None else dy_cstride
-    packed = torch.empty((Cout, k * k, Cin), dtype=torch.float32, device=x.device)
     lib = _lib.lib()
-    _lib.check(lib.etb_conv_wgrad(C.c_void_p(x.data_ptr() + 2 * x_coffset), C.c_void_p(dy.data_ptr() + 2 * dy_coffset), _lib.ptr(packed),
-                                  C.byref(cp), _lib.stream_ptr()), "etb_conv_wgrad")
+    xp, dyp = C.c_void_p(x.data_ptr() + 2 * x_coffset), C.c_void_p(dy.data_ptr() + 2 * dy_coffset)
+    acc = accumulate_into
+    if acc is not None and not (acc.is_contiguous() and acc.dtype == torch.float32):
+        acc = None
+    if k == 1 and not stem and acc is not None and N * H * W >= 256:
+        _lib.check(lib.etb_conv_wgrad_acc(xp, dyp, _lib.ptr(acc), C.byref(cp), _lib.stream_ptr()), "etb_conv_wgrad_acc")
+        return acc
+    packed = torch.empty((Cout, k * k, Cin), dtype=torch.float32, device=x.device)
+    _lib.check(lib.etb_conv_wgrad(xp, dyp, _lib.ptr(packed), C.byref(cp), _lib.stream_ptr()), "etb_conv_wgrad")
+    flag = 2 if acc is not None else 0
     if stem:
-        out = torch.empty((Cout, 3, 6, 6), dtype=torch.float32, device=x.device)
-        _lib.check(lib.etb_unpack_wgrad(_lib.ptr(packed), _lib.ptr(out), Cout, 3, 6, 6, 1, _lib.stream_ptr()), "etb_unpack_wgrad")
+        out = acc if acc is not None else torch.empty((Cout, 3, 6, 6), dtype=torch.float32, device=x.device)
+        _lib.check(lib.etb_unpack_wgrad(_lib.ptr(packed), _lib.ptr(out), Cout, 3, 6, 6, 1 | flag, _lib.stream_ptr()), "etb_unpack_wgrad")
         return out
-    if k == 1:
+    if k == 1 and acc is None:
         return packed.view(Cout, Cin, 1, 1)
-    out = torch.empty((Cout, Cin, k, k), dtype=torch.float32, device=x.device)
-    _lib.check(lib.etb_unpack_wgrad(_lib.ptr(packed), _lib.ptr(out), Cout, Cin, k, k, 0, _lib.stream_ptr()), "etb_unpack_wgrad")
+    out = acc if acc is not None else torch.empty((Cout, Cin, k, k), dtype=torch.float32, device=x.device)
+    _lib.check(lib.etb_unpack_wgrad(_lib.ptr(packed), _lib.ptr(out), Cout, Cin, k, k, flag, _lib.stream_ptr()), "etb_unpack_wgrad")
     return out
 
 

@@ -45,7 +45,15 @@ __device__ __forceinline__ void channel_reduce(int M, int C, F&& per_row, float*
   for (int q = 0; q < NQ; ++q)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[q][j] = 0.f;
-  for (long r = (long)blockIdx.x * PL + pl; r < M; r += (long)gridDim.x * PL) per_row(r, g, acc);
+  const int step = (int)gridDim.x * PL;
+  int r = (int)blockIdx.x * PL + pl;
+  for (; r + 3 * step < M; r += 4 * step) {      // 4 independent rows in flight per thread
+    per_row(r, g, acc);
+    per_row(r + step, g, acc);
+    per_row(r + 2 * step, g, acc);
+    per_row(r + 3 * step, g, acc);
+  }
+  for (; r < M; r += step) per_row(r, g, acc);
 #pragma unroll
   for (int q = 0; q < NQ; ++q)
 #pragma unroll
@@ -63,9 +71,9 @@ __device__ __forceinline__ void channel_reduce(int M, int C, F&& per_row, float*
 
 // ---- forward statistics: sums[0][c] = sum y, sums[1][c] = sum y^2 ----
 __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const __nv_bfloat16* __restrict__ y, int M, int C, int cs, float* __restrict__ sums) {
-  channel_reduce<2>(M, C, [&](long r, int g, float (*acc)[8]) {
+  channel_reduce<2>(M, C, [&](int r, int g, float (*acc)[8]) {
     float f[8];
-    load8(y + r * cs + g * 8, f);
+    load8(y + (size_t)r * cs + g * 8, f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) { acc[0][j] += f[j]; acc[1][j] = fmaf(f[j], f[j], acc[1][j]); }
   }, sums);
@@ -106,10 +114,11 @@ __global__ void __launch_bounds__(BN_THREADS) bn_act_apply_kernel(const __nv_bfl
                                                                   const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, long M, int C,
                                                                   int ycs, int ocs, int act) {
   const int G = C >> 3;
+  const int lg = 31 - __clz(G);            // G is a power of two (checked on the host): no 64-bit divisions
   const long total = M * G;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-    const long r = e / G;
-    const int g = (int)(e - r * G);
+    const long r = e >> lg;
+    const int g = (int)(e & (G - 1));
     float f[8], sc[8], sh[8];
     load8(y + r * ycs + g * 8, f);
     ldf8(scale + g * 8, sc); ldf8(shift + g * 8, sh);
@@ -127,11 +136,16 @@ __global__ void __launch_bounds__(BN_THREADS) bn_act_bwd_reduce_kernel(const __n
                                                                        const float* __restrict__ scale, const float* __restrict__ shift,
                                                                        const float* __restrict__ mean, const float* __restrict__ invstd, int M,
                                                                        int C, int dacs, int ycs, int act, float* __restrict__ sums) {
-  channel_reduce<2>(M, C, [&](long r, int g, float (*acc)[8]) {
-    float fy[8], fd[8], sc[8], sh[8], mu[8], is[8];
-    load8(y + r * ycs + g * 8, fy);
-    load8(da + r * dacs + g * 8, fd);
-    ldf8(scale + g * 8, sc); ldf8(shift + g * 8, sh); ldf8(mean + g * 8, mu); ldf8(invstd + g * 8, is);
+  // per-thread channel group is fixed: hoist its parameters out of the row loop
+  float sc[8], sh[8], mu[8], is[8];
+  {
+    const int g0 = threadIdx.x % (C >> 3);
+    ldf8(scale + g0 * 8, sc); ldf8(shift + g0 * 8, sh); ldf8(mean + g0 * 8, mu); ldf8(invstd + g0 * 8, is);
+  }
+  channel_reduce<2>(M, C, [&](int r, int g, float (*acc)[8]) {
+    float fy[8], fd[8];
+    load8(y + (size_t)r * ycs + g * 8, fy);
+    load8(da + (size_t)r * dacs + g * 8, fd);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float z = fmaf(fy[j], sc[j], sh[j]);
@@ -151,6 +165,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_act_bwd_apply_kernel(const __nv
                                                                       int act, __nv_bfloat16* __restrict__ dy, float* __restrict__ dgamma,
                                                                       float* __restrict__ dbeta) {
   const int G = C >> 3;
+  const int lg = 31 - __clz(G);
   const long total = M * G;
   const float invM = 1.0f / (float)M;
   if (blockIdx.x == 0) {
@@ -160,8 +175,8 @@ __global__ void __launch_bounds__(BN_THREADS) bn_act_bwd_apply_kernel(const __nv
     }
   }
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-    const long r = e / G;
-    const int g = (int)(e - r * G);
+    const long r = e >> lg;
+    const int g = (int)(e & (G - 1));
     float fy[8], fd[8], sc[8], sh[8], mu[8], is[8], s0[8], s1[8];
     load8(y + r * ycs + g * 8, fy);
     load8(da + r * dacs + g * 8, fd);
@@ -183,7 +198,7 @@ static inline unsigned bn_grid(long work_threads) {
   const long cap = (long)etb_num_sms() * 8;
   return (unsigned)(b > cap ? cap : (b < 1 ? 1 : b));
 }
-static inline bool bn_c_ok(int C) { return C >= 8 && C % 8 == 0 && (C / 8) <= BN_THREADS && BN_THREADS % (C / 8) == 0; }
+static inline bool bn_c_ok(int C) { return C >= 8 && C % 8 == 0 && (C / 8) <= BN_THREADS && ((C / 8) & (C / 8 - 1)) == 0; }
 
 // sums must hold 2*C floats (zeroed here).  y [M][y_cstride] bf16.
 extern "C" int etb_bn_stats(const void* y_bf16, int64_t M, int32_t C, int32_t y_cstride, float* sums, void* stream) {
@@ -192,7 +207,7 @@ extern "C" int etb_bn_stats(const void* y_bf16, int64_t M, int32_t C, int32_t y_
   ETB_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, st));
   const int PL = BN_THREADS / (C / 8);
   long blocks = (M + PL - 1) / PL;
-  const long cap = (long)etb_num_sms() * 4;
+  const long cap = (long)etb_num_sms() * 8;
   if (blocks > cap) blocks = cap;
   bn_stats_kernel<<<(unsigned)blocks, BN_THREADS, 0, st>>>((const __nv_bfloat16*)y_bf16, (int)M, C, y_cstride, sums);
   ETB_CHECK_LAUNCH();
@@ -210,7 +225,7 @@ extern "C" int etb_bn_finalize(const float* sums, int64_t M, int32_t C, const fl
 
 extern "C" int etb_bn_act_apply(const void* y_bf16, const float* scale, const float* shift, void* out_bf16, int64_t M, int32_t C,
                                 int32_t y_cstride, int32_t out_cstride, int32_t act, void* stream) {
-  ETB_CHECK_ARG(y_bf16 && scale && shift && out_bf16 && M > 0 && C >= 8 && C % 8 == 0 && y_cstride % 8 == 0 && out_cstride % 8 == 0);
+  ETB_CHECK_ARG(y_bf16 && scale && shift && out_bf16 && M > 0 && bn_c_ok(C) && y_cstride % 8 == 0 && out_cstride % 8 == 0);
   bn_act_apply_kernel<<<bn_grid(M * (C / 8)), BN_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)y_bf16, scale, shift,
                                                                                      (__nv_bfloat16*)out_bf16, (long)M, C, y_cstride, out_cstride, act);
   ETB_CHECK_LAUNCH();
@@ -227,7 +242,7 @@ extern "C" int etb_bn_act_bwd_reduce(const void* da_bf16, const void* y_bf16, co
   ETB_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, st));
   const int PL = BN_THREADS / (C / 8);
   long blocks = (M + PL - 1) / PL;
-  const long cap = (long)etb_num_sms() * 4;
+  const long cap = (long)etb_num_sms() * 8;
   if (blocks > cap) blocks = cap;
   bn_act_bwd_reduce_kernel<<<(unsigned)blocks, BN_THREADS, 0, st>>>((const __nv_bfloat16*)da_bf16, (const __nv_bfloat16*)y_bf16, scale, shift, mean,
                                                                    invstd, (int)M, C, da_cstride, y_cstride, act, sums);
@@ -238,7 +253,7 @@ extern "C" int etb_bn_act_bwd_reduce(const void* da_bf16, const void* y_bf16, co
 extern "C" int etb_bn_act_bwd_apply(const void* da_bf16, const void* y_bf16, const float* scale, const float* shift, const float* mean,
                                     const float* invstd, const float* sums, int64_t M, int32_t C, int32_t da_cstride, int32_t y_cstride,
                                     int32_t dy_cstride, int32_t act, void* dy_bf16, float* dgamma, float* dbeta, void* stream) {
-  ETB_CHECK_ARG(da_bf16 && y_bf16 && scale && shift && mean && invstd && sums && dy_bf16 && dgamma && dbeta && M > 0 && C >= 8 && C % 8 == 0);
+  ETB_CHECK_ARG(da_bf16 && y_bf16 && scale && shift && mean && invstd && sums && dy_bf16 && dgamma && dbeta && M > 0 && bn_c_ok(C));
   ETB_CHECK_ARG(da_cstride % 8 == 0 && y_cstride % 8 == 0 && dy_cstride % 8 == 0);
   bn_act_bwd_apply_kernel<<<bn_grid(M * (C / 8)), BN_THREADS, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)da_bf16, (const __nv_bfloat16*)y_bf16, scale, shift, mean, invstd, sums, (long)M, C, da_cstride, y_cstride, dy_cstride,

@@ -662,14 +662,17 @@ struct WgradArgs {
   float* dw;
 };
 
-template <int BN, int STAGES>
+// Tile = (128*MT co) x (BN ci) per CTA, K block = up to KP pixels.  Bigger tiles raise the FLOP per L2 byte
+// (128x128: 65, 256x256: 131 flop/B) -- the kernel is L2-bandwidth bound, not MMA bound.
+template <int MT, int BN, int KP, int STAGES>
 struct WgradSmem {
-  static constexpr int GROUP_BYTES = 128 * 128;          // one 64-channel group, up to 128 K rows
-  static constexpr int A_BYTES = 2 * GROUP_BYTES;        // 128 co
+  static constexpr int GROUP_BYTES = KP * 128;            // one 64-channel group, up to KP K rows
+  static constexpr int A_BYTES = 2 * MT * GROUP_BYTES;    // 128*MT co
   static constexpr int B_BYTES = (BN / 64) * GROUP_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+  static constexpr int TMEM_COLS = MT * BN;
 };
 
 // MN-major SWIZZLE_128B descriptor: LBO = byte distance between 64-element channel groups, SBO = 1024 (8 K rows)
@@ -681,10 +684,10 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int M, int N) {   // b
   return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <int BN, int STAGES>
+template <int MT, int BN, int KP, int STAGES>
 __global__ void __launch_bounds__(WGRAD_THREADS, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ CUtensorMap mapX, const WgradArgs a) {
-  using L = WgradSmem<BN, STAGES>;
+  using L = WgradSmem<MT, BN, KP, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = (uint64_t*)(smem + L::BAR_OFF);
@@ -697,7 +700,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ 
   const int tap = t % a.ntaps; t /= a.ntaps;
   const int ci_t = t % a.ci_tiles; t /= a.ci_tiles;
   const int co_t = t;
-  const int co0 = co_t * 128, ci0 = ci_t * BN;
+  const int co0 = co_t * 128 * MT, ci0 = ci_t * BN;
   const int total_kb = a.nimg * a.tiles_h * a.tiles_w;
   const int chunk = (total_kb + gridDim.y - 1) / gridDim.y;
   const int kb0 = blockIdx.y * chunk;
@@ -712,12 +715,12 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ 
     mbar_init(tmem_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  if (warp == 1) tmem_alloc(tmem_slot, L::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t group_bytes = (uint32_t)a.kpix * 128u;   // bytes one TMA box writes (all rows, OOB rows zero-filled)
+  const uint32_t box_bytes = (uint32_t)a.kpix * 128u;   // bytes one TMA box writes (all rows, OOB rows zero-filled)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -732,9 +735,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ 
         mbar_wait(&empty[s], ph ^ 1u);
         uint8_t* sa = smem + s * L::STAGE_BYTES;
         uint8_t* sb = sa + L::A_BYTES;
-        mbar_expect_tx(&full[s], group_bytes * (2u + BN / 64));
+        mbar_expect_tx(&full[s], box_bytes * (2u * MT + BN / 64));
 #pragma unroll
-        for (int g = 0; g < 2; ++g) tma_load_4d(&mapDy, &full[s], sa + g * L::GROUP_BYTES, co0 + 64 * g, w0, h0, img);
+        for (int g = 0; g < 2 * MT; ++g) tma_load_4d(&mapDy, &full[s], sa + g * L::GROUP_BYTES, co0 + 64 * g, w0, h0, img);
 #pragma unroll
         for (int g = 0; g < BN / 64; ++g)
           tma_load_4d(&mapX, &full[s], sb + g * L::GROUP_BYTES, ci0 + 64 * g, w0 * a.stride + a.tap_dw[tap], h0 * a.stride + a.tap_dh[tap], img);
@@ -750,36 +753,43 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ 
         mbar_wait(&full[s], ph);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
-        const uint64_t adesc = make_mnmajor_sw128_desc(sa, L::GROUP_BYTES);
         const uint64_t bdesc = make_mnmajor_sw128_desc(sa + L::A_BYTES, L::GROUP_BYTES);
-        for (int k = 0; k < ksteps; ++k)   // 16 K rows = two 1024 B atoms per UMMA_K step
-          umma_bf16(tmem_base, adesc + (uint64_t)(k * (2048 >> 4)), bdesc + (uint64_t)(k * (2048 >> 4)), idesc, (it | k) != 0 ? 1u : 0u);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const uint64_t adesc = make_mnmajor_sw128_desc(sa + mt * 2 * L::GROUP_BYTES, L::GROUP_BYTES);
+          for (int k = 0; k < ksteps; ++k)   // 16 K rows = two 1024 B atoms per UMMA_K step
+            umma_bf16(tmem_base + (uint32_t)(mt * BN), adesc + (uint64_t)(k * (2048 >> 4)), bdesc + (uint64_t)(k * (2048 >> 4)), idesc,
+                      (it | k) != 0 ? 1u : 0u);
+        }
         umma_commit(&empty[s]);
       }
       umma_commit(tmem_full);
     }
   } else {
     const int row = 32 * (warp & 3) + lane;
-    const int co = co0 + row;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
-    float* dst = a.dw + ((size_t)co * a.ntaps + tap) * a.Cin + ci0;
     const bool atomic = gridDim.y > 1;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      if (ci0 + c0 >= a.Cin) break;
-      uint32_t v[32];
-      tmem_ld32(lane_addr + (uint32_t)c0, v);
-      if (co < a.Cout) {
-        if (atomic) {
+    for (int mt = 0; mt < MT; ++mt) {
+      const int co = co0 + mt * 128 + row;
+      const uint32_t lane_addr = tmem_base + (uint32_t)(mt * BN) + ((uint32_t)(32 * (warp & 3)) << 16);
+      float* dst = a.dw + ((size_t)co * a.ntaps + tap) * a.Cin + ci0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (ci0 + c0 >= a.Cin) break;
+        uint32_t v[32];
+        tmem_ld32(lane_addr + (uint32_t)c0, v);
+        if (co < a.Cout) {
+          if (atomic) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
-        } else {
+            for (int j = 0; j < 32; ++j) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
+          } else {
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            reinterpret_cast<float4*>(dst + c0)[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                                                                 __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+            for (int q = 0; q < 8; ++q)
+              reinterpret_cast<float4*>(dst + c0)[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                                                   __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+          }
         }
       }
     }
@@ -788,38 +798,39 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ 
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, L::TMEM_COLS);
   }
 }
 
-static void pick_tile16(int Wo, int Ho, int* TW, int* TH) {
-  // K tiles must be a whole number of UMMA_K steps: TW*TH % 16 == 0, <= 128; out-of-image rows are zero-filled by TMA
+static void pick_tile16(int Wo, int Ho, int maxrows, int* TW, int* TH) {
+  // K tiles must be a whole number of UMMA_K steps: TW*TH % 16 == 0, <= maxrows; out-of-image rows are zero-filled by TMA
   double best = -1.0;
-  for (int tw = 1; tw <= 128; ++tw)
-    for (int th = 1; th * tw <= 128; ++th) {
+  for (int tw = 1; tw <= maxrows; ++tw)
+    for (int th = 1; th * tw <= maxrows; ++th) {
       if ((tw * th) % 16) continue;
       if (tw > 2 * Wo || th > 2 * Ho) continue;
       const long tiles = (long)((Wo + tw - 1) / tw) * ((Ho + th - 1) / th);
-      const double eff = (double)Wo * Ho / ((double)tiles * tw * th) * (tw * th >= 64 ? 1.0 : 0.8);
+      const double eff = (double)Wo * Ho / ((double)tiles * tw * th) * (tw * th >= maxrows / 2 ? 1.0 : 0.8);
       if (eff > best + 1e-9) { best = eff; *TW = tw; *TH = th; }
     }
 }
 
-template <int BN, int STAGES>
+template <int MT, int BN, int KP, int STAGES>
 static int launch_wgrad(const CUtensorMap& mDy, const CUtensorMap& mX, const WgradArgs& wa, dim3 grid, cudaStream_t st) {
-  using L = WgradSmem<BN, STAGES>;
+  using L = WgradSmem<MT, BN, KP, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
-    ETB_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    ETB_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel<MT, BN, KP, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_set = true;
   }
-  wgrad_kernel<BN, STAGES><<<grid, WGRAD_THREADS, L::TOTAL, st>>>(mDy, mX, wa);
+  wgrad_kernel<MT, BN, KP, STAGES><<<grid, WGRAD_THREADS, L::TOTAL, st>>>(mDy, mX, wa);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }
 
 // x [N,H,W,*] bf16 (cp->x_cstride), dy [N,Ho,Wo,*] bf16 (channel stride cp->y_cstride) -> dw [Cout][kh*kw][Cin] fp32.
-extern "C" int etb_conv_wgrad(const void* x_bf16, const void* dy_bf16, float* dw_f32, const EtbConvParams* cp, void* stream) {
+// accumulate != 0: dw += result (dw already holds a gradient, e.g. the flat arena) -- always uses atomics, never zeroes.
+static int wgrad_impl(const void* x_bf16, const void* dy_bf16, float* dw_f32, const EtbConvParams* cp, int accumulate, void* stream) {
   ETB_CHECK_ARG(x_bf16 && dy_bf16 && dw_f32 && cp);
   ETB_CHECK_ARG(cp->N > 0 && cp->H > 0 && cp->W > 0 && cp->Cin > 0 && cp->Cout > 0 && cp->Cin % 64 == 0);
   ETB_CHECK_ARG(cp->kh * cp->kw <= 12 && (cp->stride == 1 || cp->stride == 2));
@@ -831,6 +842,10 @@ extern "C" int etb_conv_wgrad(const void* x_bf16, const void* dy_bf16, float* dw
   }
   const int Ho = (cp->H + 2 * cp->pad - cp->kh) / cp->stride + 1;
   const int Wo = (cp->W + 2 * cp->pad - cp->kw) / cp->stride + 1;
+  // tile configuration
+  const int MT = cp->Cout >= 256 ? 2 : 1;
+  const int BN = cp->Cin >= 256 ? 256 : (cp->Cin >= 128 ? 128 : 64);
+  const int KP = (MT == 2 || BN == 256) ? 64 : 128;
   WgradArgs wa;
   memset(&wa, 0, sizeof(wa));
   wa.ntaps = cp->kh * cp->kw;
@@ -848,17 +863,17 @@ extern "C" int etb_conv_wgrad(const void* x_bf16, const void* dy_bf16, float* dw
   if (flat) {
     const long npix = (long)cp->N * cp->H * cp->W;
     ETB_CHECK_ARG(npix < (1l << 31));
-    wa.TW = 128; wa.TH = 1; wa.kpix = 128;
-    wa.tiles_w = (int)((npix + 127) / 128); wa.tiles_h = 1; wa.nimg = 1;
+    wa.TW = KP; wa.TH = 1; wa.kpix = KP;
+    wa.tiles_w = (int)((npix + KP - 1) / KP); wa.tiles_h = 1; wa.nimg = 1;
     ddim[0] = cp->Cout; ddim[1] = (cuuint64_t)npix; ddim[2] = 1; ddim[3] = 1;
     dstr[0] = (cuuint64_t)cp->y_cstride * 2; dstr[1] = dstr[0] * (cuuint64_t)npix; dstr[2] = dstr[1];
     xdim[0] = cp->Cin; xdim[1] = (cuuint64_t)npix; xdim[2] = 1; xdim[3] = 1;
     xstr[0] = (cuuint64_t)cp->x_cstride * 2; xstr[1] = xstr[0] * (cuuint64_t)npix; xstr[2] = xstr[1];
-    dbox[0] = 64; dbox[1] = 128; dbox[2] = 1; dbox[3] = 1;
-    xbox[0] = 64; xbox[1] = 128; xbox[2] = 1; xbox[3] = 1;
+    dbox[0] = 64; dbox[1] = KP; dbox[2] = 1; dbox[3] = 1;
+    xbox[0] = 64; xbox[1] = KP; xbox[2] = 1; xbox[3] = 1;
     xes[0] = xes[1] = xes[2] = xes[3] = 1;
   } else {
-    pick_tile16(Wo, Ho, &wa.TW, &wa.TH);
+    pick_tile16(Wo, Ho, KP, &wa.TW, &wa.TH);
     wa.kpix = wa.TW * wa.TH;
     wa.tiles_w = (Wo + wa.TW - 1) / wa.TW; wa.tiles_h = (Ho + wa.TH - 1) / wa.TH; wa.nimg = cp->N;
     ddim[0] = cp->Cout; ddim[1] = Wo; ddim[2] = Ho; ddim[3] = cp->N;
@@ -877,32 +892,47 @@ extern "C" int etb_conv_wgrad(const void* x_bf16, const void* dy_bf16, float* dw
   r = enc(&mX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x_bf16), xdim, xstr, xbox, xes, CU_TENSOR_MAP_INTERLEAVE_NONE,
           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { etb_set_error("cuTensorMapEncodeTiled(x) failed: %d", (int)r); return ETB_ERR_CUDA; }
-  const int BN = (cp->Cin >= 128) ? 128 : 64;
   wa.flat = flat ? 1 : 0;
-  wa.co_tiles = (cp->Cout + 127) / 128;
+  wa.co_tiles = (cp->Cout + 128 * MT - 1) / (128 * MT);
   wa.ci_tiles = (cp->Cin + BN - 1) / BN;
   const int out_tiles = wa.co_tiles * wa.ci_tiles * wa.ntaps;
   const int total_kb = wa.nimg * wa.tiles_h * wa.tiles_w;
   int splitk = (2 * etb_num_sms() + out_tiles - 1) / out_tiles;
   if (splitk > total_kb) splitk = total_kb;
   if (splitk < 1) splitk = 1;
+  if (accumulate && splitk < 2 && total_kb >= 2) splitk = 2;   // the atomic path is the accumulating one
   // no empty slices: ceil-div chunking must leave the last slice non-empty
   while (splitk > 1 && (long)(splitk - 1) * ((total_kb + splitk - 1) / splitk) >= total_kb) --splitk;
+  ETB_CHECK_ARG(!accumulate || splitk > 1);
   cudaStream_t st = (cudaStream_t)stream;
-  if (splitk > 1) ETB_CHECK_CUDA(cudaMemsetAsync(dw_f32, 0, sizeof(float) * (size_t)cp->Cout * wa.ntaps * cp->Cin, st));
+  if (splitk > 1 && !accumulate) ETB_CHECK_CUDA(cudaMemsetAsync(dw_f32, 0, sizeof(float) * (size_t)cp->Cout * wa.ntaps * cp->Cin, st));
   dim3 grid((unsigned)out_tiles, (unsigned)splitk);
-  if (BN == 128) return launch_wgrad<128, 3>(mDy, mX, wa, grid, st);
-  return launch_wgrad<64, 4>(mDy, mX, wa, grid, st);
+  if (MT == 2 && BN == 256) return launch_wgrad<2, 256, 64, 3>(mDy, mX, wa, grid, st);
+  if (MT == 2 && BN == 128) return launch_wgrad<2, 128, 64, 4>(mDy, mX, wa, grid, st);
+  if (MT == 2) return launch_wgrad<2, 64, 64, 4>(mDy, mX, wa, grid, st);
+  if (BN == 256) return launch_wgrad<1, 256, 64, 4>(mDy, mX, wa, grid, st);
+  if (BN == 128) return launch_wgrad<1, 128, 128, 3>(mDy, mX, wa, grid, st);
+  return launch_wgrad<1, 64, 128, 4>(mDy, mX, wa, grid, st);
+}
+
+extern "C" int etb_conv_wgrad(const void* x_bf16, const void* dy_bf16, float* dw_f32, const EtbConvParams* cp, void* stream) {
+  return wgrad_impl(x_bf16, dy_bf16, dw_f32, cp, 0, stream);
+}
+// dw_f32 += dW (pointwise convs: dw has the parameter layout [Cout][Cin], so it can be the gradient arena slice itself)
+extern "C" int etb_conv_wgrad_acc(const void* x_bf16, const void* dy_bf16, float* dw_f32, const EtbConvParams* cp, void* stream) {
+  return wgrad_impl(x_bf16, dy_bf16, dw_f32, cp, 1, stream);
 }
 
 // dW [Cout][kh*kw][Cin] fp32 -> [Cout,Cin,kh,kw] fp32 (the nn.Parameter layout); stem: [Cout][128] -> [Cout,3,6,6]
 __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restrict__ dw, float* __restrict__ o, int Cout, int Cin, int kk, int stem) {
+  // stem & 2: accumulate into o (the gradient arena) instead of overwriting
   const int64_t total = (int64_t)Cout * Cin * kk;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int t = (int)(e % kk);
     const int ci = (int)((e / kk) % Cin);
     const int co = (int)(e / ((int64_t)kk * Cin));
-    o[e] = stem ? dw[(int64_t)co * 128 + t * 3 + ci] : dw[((int64_t)co * kk + t) * Cin + ci];
+    const float v = (stem & 1) ? dw[(int64_t)co * 128 + t * 3 + ci] : dw[((int64_t)co * kk + t) * Cin + ci];
+    o[e] = (stem & 2) ? o[e] + v : v;
   }
 }
 extern "C" int etb_unpack_wgrad(const float* dw_packed, float* w_oihw, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw, int32_t stem,

@@ -244,10 +244,12 @@ class SSODTrainerStep:
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(2):
+                self.last_opt_step = ni - 10**6      # the optimizer + EMA branch must be taken (and captured) every time
                 self.train_instance(st["imgs"], st["targets"], st["us"], st["uw"], None, st["Ms"], ni)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
+        self.last_opt_step = ni - 10**6
         with torch.cuda.graph(graph):
             st["loss"] = self.train_instance(st["imgs"], st["targets"], st["us"], st["uw"], None, st["Ms"], ni)
         st["graph"] = graph

@@ -215,6 +215,9 @@ int etb_conv_dgrad(const void* dy_bf16, const void* wd_bf16, void* dx_bf16, cons
  * Cout*kh*kw*Cin floats in [Cout][kh*kw][Cin] order; etb_unpack_wgrad converts to the parameter layout [Cout,Cin,kh,kw]
  * (stem != 0: dw is [Cout][128] in the etb_stem_im2col K order -> [Cout,3,6,6]). */
 int etb_conv_wgrad(const void* x_bf16, const void* dy_bf16, float* dw_f32, const EtbConvParams* cp, void* stream);
+/* same, but dw_f32 += dW (always through the split-K atomics): for pointwise convs dw has the parameter layout, so it can
+ * be the gradient-arena slice itself.  etb_unpack_wgrad: stem bit0 = stem layout, bit1 = accumulate into w_oihw. */
+int etb_conv_wgrad_acc(const void* x_bf16, const void* dy_bf16, float* dw_f32, const EtbConvParams* cp, void* stream);
 int etb_unpack_wgrad(const float* dw_packed, float* w_oihw, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw, int32_t stem,
                      void* stream);
 

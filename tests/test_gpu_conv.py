@@ -199,3 +199,18 @@ def test_fused_bn_act_forward_backward(C_, H, act):
     torch.testing.assert_close(db, b2.grad, rtol=2e-2, atol=2e-2 * b2.grad.abs().max().item())
     torch.testing.assert_close(rm, rm2, rtol=1e-3, atol=1e-4)
     torch.testing.assert_close(rv, rv2, rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("case", [(4, 128, 20, 20, 256, 1, 1, 0), (2, 256, 16, 16, 256, 3, 1, 1), (2, 512, 8, 8, 512, 1, 1, 0)])
+def test_conv_wgrad_accumulates_into_existing_grad(case):
+    from efficientteacher_b200 import convops as co
+    N, Cin, H, W, Cout, k, s, p = case
+    x = _rand((N, Cin, H, W), 61)
+    dy = _rand((N, Cout, H, W), 62, scale=0.1)
+    base = _rand((Cout, Cin, k, k), 63)
+    g = base.clone()
+    out = co.conv_wgrad(co.to_nhwc_bf16(x), co.to_nhwc_bf16(dy), Cin, Cout, k, s, p, accumulate_into=g)
+    assert out.data_ptr() == g.data_ptr()
+    ref = base + torch.nn.grad.conv2d_weight(_bf(x), (Cout, Cin, k, k), _bf(dy), stride=s, padding=p)
+    err = (g - ref).abs().max().item()
+    assert err <= 2e-3 * max(ref.abs().max().item(), 1.0), err
