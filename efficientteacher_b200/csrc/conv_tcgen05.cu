@@ -843,9 +843,12 @@ static int wgrad_impl(const void* x_bf16, const void* dy_bf16, float* dw_f32, co
   const int Ho = (cp->H + 2 * cp->pad - cp->kh) / cp->stride + 1;
   const int Wo = (cp->W + 2 * cp->pad - cp->kw) / cp->stride + 1;
   // tile configuration
-  const int MT = cp->Cout >= 256 ? 2 : 1;
-  const int BN = cp->Cin >= 256 ? 256 : (cp->Cin >= 128 ? 128 : 64);
-  const int KP = (MT == 2 || BN == 256) ? 64 : 128;
+  // Measured on B200 (tools/conv_bench.py): with the split-K partials reduced by fp32 atomics the atomic volume is
+  // ~(#CTAs x tile area), so 256x256 tiles (4x the atomics, 4x the contention per address) lose more in the epilogue than
+  // they gain in L2 operand traffic: 128x128 tiles are the fastest configuration of this reduction scheme.
+  const int MT = 1;
+  const int BN = cp->Cin >= 128 ? 128 : 64;
+  const int KP = 128;
   WgradArgs wa;
   memset(&wa, 0, sizeof(wa));
   wa.ntaps = cp->kh * cp->kw;
