@@ -49,6 +49,19 @@ class EtbLossParams(C.Structure):
                 ("ignore_obj", C.c_int32), ("with_bbox", C.c_int32), ("with_cls", C.c_int32)]
 
 
+class EtbPackDesc(C.Structure):
+    _fields_ = [("w", vp), ("out", vp), ("elems", C.c_int64), ("Cout", C.c_int32), ("Cin", C.c_int32), ("k", C.c_int32),
+                ("mode", C.c_int32), ("ntaps", C.c_int32), ("out_ld", C.c_int32), ("kh", C.c_int8 * 12), ("kw", C.c_int8 * 12)]
+
+
+class EtbFoldDesc(C.Structure):
+    _fields_ = [("gamma", vp), ("beta", vp), ("mean", vp), ("var", vp), ("scale", vp), ("bias", vp), ("C", C.c_int32),
+                ("eps", C.c_float)]
+
+
+ETB_PACK_CHUNK = 4096
+
+
 class EtbConvParams(C.Structure):
     _fields_ = [("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32),
                 ("kh", C.c_int32), ("kw", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
@@ -101,6 +114,8 @@ _SIGS = {
                                       C.c_int32, C.c_int32, vp]),
     "etb_fold_bn": (C.c_int, [vp, vp, vp, vp, C.c_float, vp, vp, C.c_int32, vp]),
     "etb_pack_weight": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
+    "etb_pack_multi": (C.c_int, [vp, vp, C.c_int32, vp]),
+    "etb_fold_bn_multi": (C.c_int, [vp, C.c_int32, vp]),
     "etb_pack_stem_weight": (C.c_int, [vp, vp, C.c_int32, vp]),
 }
 

@@ -88,18 +88,22 @@ class ConvBnActFn(torch.autograd.Function):
     -> dgrad + wgrad.  Saves x, the raw conv output and [4,C] statistics (not the normalised tensor)."""
 
     @staticmethod
-    def forward(ctx, x, weight, gamma, beta, running_mean, running_var, stride, pad, eps, momentum, act, is_stem):
+    def forward(ctx, x, weight, gamma, beta, running_mean, running_var, stride, pad, eps, momentum, act, is_stem,
+                wp=None, wd=None):
         Cout = weight.shape[0]
+        ctx.wd = wd
         if is_stem:
             xb = co.stem_im2col(x.float(), 1.0)               # [N,H/2,W/2,128]; saved instead of the image
             xcs, Cin, k, st, pd = 128, 128, 1, 1, 0
-            wp = co.pack_stem_weight(weight)
+            if wp is None:
+                wp = co.pack_stem_weight(weight)
             N, Ho, Wo = xb.shape[0], xb.shape[1], xb.shape[2]
         else:
             Cin, k = weight.shape[1], weight.shape[2]
             xb, xcs = _as_nhwc(x, Cin)
             st, pd = stride, pad
-            wp = co.pack_weight(weight)
+            if wp is None:
+                wp = co.pack_weight(weight)
             N, _, H, W = x.shape
             Ho, Wo = (H + 2 * pd - k) // st + 1, (W + 2 * pd - k) // st + 1
         y = torch.empty((N, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.device)
@@ -128,12 +132,13 @@ class ConvBnActFn(torch.autograd.Function):
             N, _, H, W = xs.shape
             if ctx.needs_input_grad[0]:
                 dx = _empty_cl(N, Cin, H, W, da.device)
-                co.conv_dgrad(dy, co.pack_weight_dgrad(weight, stride, pad), N, H, W, Cin, Cout, k, stride, pad, out=_nhwc_of(dx))
+                wd = ctx.wd if ctx.wd is not None else co.pack_weight_dgrad(weight, stride, pad)
+                co.conv_dgrad(dy, wd, N, H, W, Cin, Cout, k, stride, pad, out=_nhwc_of(dx))
             xb, xcs = _as_nhwc(xs, Cin)
             dw = co.conv_wgrad(xb, dy, Cin, Cout, k, stride, pad, x_cstride=xcs, accumulate_into=tgt)
         if tgt is not None:
             dw = None
-        return dx, dw, dgamma, dbeta, None, None, None, None, None, None, None, None
+        return dx, dw, dgamma, dbeta, None, None, None, None, None, None, None, None, None, None
 
 
 class StemFn(torch.autograd.Function):

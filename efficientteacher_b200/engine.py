@@ -29,15 +29,17 @@ class _ConvParams:
         self.act = "silu" if isinstance(act, nn.SiLU) else ("relu" if isinstance(act, nn.ReLU) else None)
         self.w = self.scale = self.bias = None
 
-    def refresh(self):
-        if self.stem:
-            self.w = co.pack_stem_weight(self.conv.weight)
-        else:
-            self.w = co.pack_weight(self.conv.weight)
+    def register(self, packer):
+        pc = packer.add(self.conv.weight, self.s, self.p, want_dgrad=False, stem=self.stem)
+        self.w = pc.fwd
         if self.bn is not None:
-            self.scale, self.bias = co.fold_bn(self.bn)
-        elif self.conv.bias is not None:
-            self.scale, self.bias = None, self.conv.bias.detach().float().contiguous()
+            packer.add_fold(self.bn, pc)
+            self.scale, self.bias = pc.scale, pc.bias
+        self._pc = pc
+
+    def refresh_bias(self):
+        if self.bn is None and self.conv.bias is not None:
+            self.scale, self.bias = None, self.conv.bias.detach()
 
 
 class TrunkEngine:
@@ -60,13 +62,20 @@ class TrunkEngine:
             if q.Cin % 64 != 0 and not q.stem:
                 raise NotImplementedError("tcgen05 conv path needs Cin %% 64 == 0 (got %d)" % q.Cin)
         self.launches = 0
+        self.packer = None
 
     # -- helpers ------------------------------------------------------------------------------------------
     def refresh(self):
         """Re-pack weights / re-fold BN from the current fp32 parameters (the EMA teacher changes every step)."""
+        if self.packer is None or self.packer.device != next(self.model.parameters()).device:
+            from .packing import WeightPacker
+            self.packer = WeightPacker(next(self.model.parameters()).device)
+            for q in self.params.values():
+                q.register(self.packer)
+        self.packer.run()                      # ONE pack launch + ONE BN-fold launch for the whole model
         for q in self.params.values():
-            q.refresh()
-        self.launches += 2 * len(self.params)
+            q.refresh_bias()
+        self.launches += 2
 
     def _conv(self, name, x, x_coffset=0, out=None, out_coffset=0, residual=None, res_coffset=0, cin=None):
         q = self.params[name]

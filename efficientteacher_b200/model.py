@@ -39,6 +39,20 @@ class Conv(nn.Module):
         self.act = nn.SiLU() if act is True or act == "silu" else (nn.ReLU(inplace=True) if act == "relu" else nn.Identity())
         self.act_name = "relu" if act == "relu" else None
 
+    def __deepcopy__(self, memo):   # `_packed` aliases the owning model's packer buffers: copies start without it
+        from copy import deepcopy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k != "_packed":
+                new.__dict__[k] = deepcopy(v, memo)
+        return new
+
+    def __getstate__(self):
+        s = dict(self.__dict__)
+        s.pop("_packed", None)
+        return s
+
     NATIVE = True        # training convs on the tcgen05 fwd/dgrad/wgrad kernels (False: torch/cuDNN scaffold)
     FUSED_BN = True      # BatchNorm(train)+SiLU forward/backward on the fused kernels of csrc/bn.cu (False: torch ops)
     is_stem = False
@@ -50,8 +64,10 @@ class Conv(nn.Module):
             if Conv.FUSED_BN and self.training and isinstance(self.act, (nn.SiLU, nn.ReLU)):
                 bn = self.bn
                 act = "silu" if isinstance(self.act, nn.SiLU) else "relu"
+                pc = getattr(self, "_packed", None)     # operands prepared by Model.pack_weights() (one launch per step)
                 return ConvBnActFn.apply(x, w, bn.weight, bn.bias, bn.running_mean, bn.running_var, self.conv.stride[0],
-                                         self.conv.padding[0], bn.eps, bn.momentum, act, self.is_stem)
+                                         self.conv.padding[0], bn.eps, bn.momentum, act, self.is_stem,
+                                         None if pc is None else pc.fwd, None if pc is None else pc.dgrad)
             if self.is_stem:
                 y = StemFn.apply(x.float(), w)
             else:
@@ -277,6 +293,22 @@ class _ModelBase(nn.Module):
         _lib.require_cuda(x)
         _lib.lib()
 
+    def pack_weights(self):
+        """bf16 GEMM operands (forward + dgrad) of every Conv for this training step, in ONE launch (packing.WeightPacker);
+        the Conv modules pick them up through `_packed`."""
+        if not (Conv.NATIVE and Conv.FUSED_BN and self.training):
+            return
+        dev = next(self.parameters()).device
+        pk = getattr(self, "_packer", None)
+        if pk is None or pk.device != dev:
+            from .packing import WeightPacker
+            pk = WeightPacker(dev)
+            for m in self.modules():
+                if isinstance(m, Conv):
+                    m._packed = pk.add(m.conv.weight, m.conv.stride[0], m.conv.padding[0], want_dgrad=not m.is_stem, stem=m.is_stem)
+            self._packer = pk
+        pk.run()
+
     def _count_bn_batches(self):
         """BatchNorm2d.num_batches_tracked += 1 for every BN (what nn.BatchNorm2d does per training forward), as ONE
         multi-tensor op; the fused BN kernels update running_mean / running_var themselves."""
@@ -297,13 +329,14 @@ class _ModelBase(nn.Module):
         memo[id(self)] = new
         from copy import deepcopy
         for k, v in self.__dict__.items():
-            new.__dict__[k] = None if k in ("_engine", "_nbt") else deepcopy(v, memo)
+            new.__dict__[k] = None if k in ("_engine", "_nbt", "_packer") else deepcopy(v, memo)
         return new
 
     def __getstate__(self):
         s = dict(self.__dict__)
         s["_engine"] = None
         s["_nbt"] = None
+        s["_packer"] = None
         return s
 
 
@@ -324,6 +357,7 @@ class Model(_ModelBase):
         if not self.training and not torch.is_grad_enabled():
             return self.engine().forward(x, with_features=True)
         self._count_bn_batches()
+        self.pack_weights()
         f = self.neck(self.backbone(x))
         out = self.head(f)
         f8, f16, f32 = f
@@ -344,4 +378,5 @@ class SupModel(_ModelBase):
         if not self.training and not torch.is_grad_enabled():
             return self.engine().forward(x, with_features=False)[0]
         self._count_bn_batches()
+        self.pack_weights()
         return self.head(self.neck(self.backbone(x)))

@@ -263,6 +263,25 @@ int etb_fold_bn(const float* gamma, const float* beta, const float* mean, const 
 /* conv weight [Cout,Cin,kh,kw] fp32 -> [Cout][kh][kw][Cin_pad] bf16 (K-major GEMM operand), zero padded */
 int etb_pack_weight(const float* w_oihw, void* w_bf16, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw,
                     int32_t Cin_pad, void* stream);
+/* multi-tensor variants: one launch packs every conv weight of the model (descs and the chunk list live in device memory;
+ * chunk = {desc index, chunk index} covering ETB_PACK_CHUNK destination elements).  mode 0: forward operand
+ * [Cout][kh][kw][Cin]; mode 1: one dgrad parity class [Cin][ntaps][out_ld] (tap t = (kh[t],kw[t])); mode 2: stem [Cout][128]. */
+#define ETB_PACK_CHUNK 4096
+typedef struct EtbPackDesc {
+  const float* w;   /* [Cout,Cin,k,k] fp32 */
+  void* out;        /* bf16 destination */
+  int64_t elems;    /* destination elements to produce */
+  int32_t Cout, Cin, k, mode, ntaps, out_ld;
+  int8_t kh[12], kw[12];
+} EtbPackDesc;
+int etb_pack_multi(const EtbPackDesc* descs_dev, const void* chunks_dev /* int32 pairs */, int32_t n_chunks, void* stream);
+typedef struct EtbFoldDesc {
+  const float *gamma, *beta, *mean, *var;
+  float *scale, *bias;
+  int32_t C;
+  float eps;
+} EtbFoldDesc;
+int etb_fold_bn_multi(const EtbFoldDesc* descs_dev, int32_t n, void* stream);
 /* stem weight [Cout,3,6,6] fp32 -> [Cout][128] bf16 in the etb_stem_im2col K order */
 int etb_pack_stem_weight(const float* w_oihw, void* w_bf16, int32_t Cout, void* stream);
 
