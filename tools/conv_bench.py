@@ -72,6 +72,7 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "conv_bench.json"))
     ap.add_argument("--modes", default="fwd,dgrad,wgrad")
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--only", default="", help="substring filter on the shape name")
     args = ap.parse_args()
     global ITERS
     ITERS = args.iters
@@ -83,6 +84,8 @@ def main():
     res = []
     tot = {m: [0.0, 0.0] for m in args.modes.split(",")}
     for name, Cin, Cout, k, s, H, cnt in SHAPES:
+        if args.only and args.only not in name:
+            continue
         p = k // 2
         Ho = (H + 2 * p - k) // s + 1
         x = torch.randn(N, H, H, Cin, device=dev).to(torch.bfloat16)
