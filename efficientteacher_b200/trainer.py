@@ -103,13 +103,14 @@ class SSODTrainerStep:
     def _allreduce_grads(self):
         self._arena.all_reduce_sum(self.WORLD_SIZE)
 
-    # trainer/ssod_trainer.py:458-488 (bf16 autocast needs no GradScaler; loss scale == 1)
-    def update_optimizer(self, loss, ni):
+    # trainer/ssod_trainer.py:458-488 (bf16 autocast needs no GradScaler; loss scale == 1), in three parts so that the
+    # gradient all-reduce can sit between two captured CUDA graphs when WORLD_SIZE > 1
+    def _backward(self, loss):
         self._ensure_arena()
         loss.backward()
         self._mark("backward")
-        self._allreduce_grads()
-        self._mark("allreduce")
+
+    def _optimizer_ema(self, ni):
         self.accumulate = 1 if self.fixed_accumulate else max(round(64 / self.batch_size), 1)
         if ni <= self.nw:
             xi = [0, self.nw]
@@ -127,6 +128,12 @@ class SSODTrainerStep:
             else:
                 self.ema.update(self.model)
             self.last_opt_step = ni
+
+    def update_optimizer(self, loss, ni):
+        self._backward(loss)
+        self._allreduce_grads()
+        self._mark("allreduce")
+        self._optimizer_ema(ni)
 
     def _mark(self, name):
         if self.profile:
@@ -151,7 +158,7 @@ class SSODTrainerStep:
 
     # trainer/ssod_trainer.py:587-680 (logging / meters excluded: rank-0 host bookkeeping)
     def train_instance(self, imgs, targets, unlabeled_imgs, unlabeled_imgs_ori, unlabeled_gt, unlabeled_M, ni,
-                       host_pseudo_labels=False):
+                       host_pseudo_labels=False, _stop_after_backward=False):
         n_img = imgs.shape[0]
         self._mark("start")
         with torch.no_grad():
@@ -188,6 +195,9 @@ class SSODTrainerStep:
         # DDP: loss*WORLD_SIZE then gradient mean == plain SUM all-reduce of per-rank gradients (no scaling here)
         loss = sup_loss + un_sup_loss * self.cfg.SSOD.teacher_loss_weight
         self._mark("losses")
+        if _stop_after_backward:         # graph capture with WORLD_SIZE > 1: the NCCL all-reduce runs between two graphs
+            self._backward(loss)
+            return loss.detach()
         self.update_optimizer(loss, ni)
         self._mark("optimizer_ema")
         self.last = dict(loss=loss.detach(), sup=sup_loss_items, unsup=un_sup_loss_items)
@@ -216,6 +226,9 @@ class SSODTrainerStep:
         # pageable source: the runtime stages the 16 bytes before returning, so the next step cannot overwrite them early
         self._ema_scalars_dev.copy_(torch.tensor(ema_scalars(d1, d2), dtype=torch.float32))
         g["graph"].replay()
+        if g["graph_b"] is not None:     # WORLD_SIZE > 1: [graph A: ... backward] -> NCCL all-reduce (eager) -> [graph B: SGD + EMA]
+            self._allreduce_grads()
+            g["graph_b"].replay()
         self.last_opt_step = ni
         return g["loss"]
 
@@ -246,13 +259,21 @@ class SSODTrainerStep:
             for _ in range(2):
                 self.last_opt_step = ni - 10**6      # the optimizer + EMA branch must be taken (and captured) every time
                 self.train_instance(st["imgs"], st["targets"], st["us"], st["uw"], None, st["Ms"], ni)
+        split = self.WORLD_SIZE > 1
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
         self.last_opt_step = ni - 10**6
         with torch.cuda.graph(graph):
-            st["loss"] = self.train_instance(st["imgs"], st["targets"], st["us"], st["uw"], None, st["Ms"], ni)
+            st["loss"] = self.train_instance(st["imgs"], st["targets"], st["us"], st["uw"], None, st["Ms"], ni, _stop_after_backward=split)
         st["graph"] = graph
+        st["graph_b"] = None
+        if split:
+            gb = torch.cuda.CUDAGraph()
+            self.last_opt_step = ni - 10**6
+            with torch.cuda.graph(gb, pool=graph.pool()):
+                self._optimizer_ema(ni)
+            st["graph_b"] = gb
         with torch.no_grad():
             for t, c in zip(tensors, snap):
                 t.copy_(c)

@@ -186,6 +186,7 @@ def test_graphed_step_matches_eager_step():
     c = torch.cat([out["eager2"][1][k].flatten() for k in ke])
     rel_eager = ((a - c).norm() / a.norm()).item()
     assert rel <= 3.0 * rel_eager + 2e-3, (rel, rel_eager)
-    for k in out["eager"][1]:
-        if "running_var" in k:
-            torch.testing.assert_close(out["eager"][1][k], out["graph"][1][k], rtol=0.2, atol=1e-2)
+    kr = [k for k in out["eager"][1] if "running_var" in k]
+    ra = torch.cat([out["eager"][1][k].flatten() for k in kr]); rb = torch.cat([out["graph"][1][k].flatten() for k in kr])
+    rc = torch.cat([out["eager2"][1][k].flatten() for k in kr])
+    assert ((ra - rb).norm() / ra.norm()).item() <= 3.0 * ((ra - rc).norm() / ra.norm()).item() + 5e-3
