@@ -115,6 +115,37 @@ def conv_flops_teacher(engine_model, n_img, img):
     return flops
 
 
+def dominant_kernel_roofline(dev, peak_tflops, peak_kind):
+    """conv_fwd_kernel (tcgen05 implicit GEMM) on the shape family that carries 57% of the trunk FLOPs (3x3 s1 C->C
+    Bottleneck conv; here 256->256 on 40x40 maps, batch 32 = the student's batch), 30 back-to-back launches timed with CUDA
+    events on the launching stream.  Algorithmic FLOPs = 2*N*H*W*Cout*Cin*9; DRAM traffic from the committed ncu capture
+    (profiles/r1_kernel_metrics.md)."""
+    from efficientteacher_b200 import convops as co
+    N, H, C_ = 32, 40, 256
+    x = torch.randn(N, H, H, C_, device=dev).to(torch.bfloat16)
+    w = co.pack_weight(torch.randn(C_, C_, 3, 3, device=dev) * (C_ * 9) ** -0.5)
+    sc, bi = torch.ones(C_, device=dev), torch.zeros(C_, device=dev)
+    y = torch.empty(N, H, H, C_, dtype=torch.bfloat16, device=dev)
+    f = lambda: co.conv_fwd(x, w, C_, C_, 3, 1, 1, sc, bi, "silu", out=y)  # noqa: E731
+    for _ in range(5):
+        f()
+    torch.cuda.synchronize()
+    n = 30
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(n):
+        f()
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / n
+    flops = 2.0 * N * H * H * C_ * C_ * 9
+    ach = flops / ms / 1e9
+    return {"bound": "tensor", "kernel": "conv_fwd_kernel<256,4,1> (tcgen05 implicit GEMM, TMA-fed, folded BN+SiLU epilogue), 3x3 s1 256->256 @40x40, batch 32",
+            "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops,
+            "traffic": 27.44e6 + 8.45e6, "traffic_note": "dram__bytes_read+write per launch from ncu --set full (profiles/prof_conv_fwd_3x3_256.ncu-rep); algorithmic bytes 26.2 MB in + 1.2 MB weights + 26.2 MB out (output still L2-resident at kernel end)",
+            "peak_kind": peak_kind, "flops_per_launch": flops, "us_per_launch": ms * 1e3, "launches_timed": n}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU path of the step (oracle restatement; /root/reference cannot travel to the
     GPU box).  Rank 0 only.  Each step = one full SSOD step on a bounded sample (2 labeled + 2 unlabeled images)."""
@@ -322,8 +353,14 @@ def main():
         e2e_val = imgs_per_step * args.steps / (ms_e2e / 1e3)
         t_flops = conv_flops_teacher(st.ema.ema, B_U, IMG)
         t_ms = phases.get("teacher_forward", float("nan"))
-        achieved = t_flops / (t_ms / 1e3) / 1e12
         peak = pk["bf16_tflops_sustained"]
+        # conv FLOPs of the whole step: teacher fwd (B_U) + student fwd/dgrad/wgrad (B_L+B_U; the stem has no dgrad)
+        f_img = t_flops / B_U
+        step_flops = f_img * (B_U + 3 * (B_L + B_U))
+        roof = dominant_kernel_roofline(dev, peak, pk_kind + " bf16_tflops_sustained")
+        roof["step_level"] = {"conv_flops_per_step": step_flops, "achieved_tflops": step_flops / (ms / args.steps / 1e3) / 1e12,
+                              "frac_of_peak": step_flops / (ms / args.steps / 1e3) / 1e12 / peak,
+                              "teacher_forward_phase_tflops": t_flops / (t_ms / 1e3) / 1e12}
         h2d = sum(host[k].numel() * host[k].element_size() for k in host)
         out = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -332,15 +369,13 @@ def main():
             "config": {"workload": "YOLOv5l SSOD 640: 16 labeled + 16 unlabeled per GPU (BASELINE configs[2] per-GPU batch), optimizer+2xEMA every step",
                        "global_batch": imgs_per_step, "img_size": IMG, "parallelism": "dp%d" % world, "cuda_graph": use_graph,
                        "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
-                       "native": "teacher trunk+head, student conv fwd/dgrad/wgrad (tcgen05), NMS/pseudo-label, assigners, losses fwd/bwd, EMA",
-                       "library_ops_left": "student BatchNorm(train)/SiLU/cat/upsample/maxpool + their autograd, SGD (torch)",
+                       "native": "teacher trunk+head, student conv fwd/dgrad/wgrad (tcgen05) + BatchNorm(train)+SiLU fwd/bwd, weight packing, NMS/pseudo-label, assigners, losses fwd/bwd, EMA",
+                       "library_ops_left": "student cat / residual add / upsample / maxpool and their autograd, netD C->2 conv, domain focal loss (x0), SGD-Nesterov (torch foreach)",
                        "pseudo_labels_last_step": n_pl, "nms_candidates_per_img_at_start": cand_per_img, "nms_detections_per_img_last_step": det_per_img},
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
             "phases_ms": phases,
-            "roofline": {"bound": "tensor", "kernel": "conv_fwd_kernel (tcgen05 implicit GEMM), teacher trunk+head, %d images" % B_U,
-                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                         "peak_kind": pk_kind + " bf16_tflops_sustained", "flops_per_forward": t_flops, "ms": t_ms},
+            "roofline": roof,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -72,6 +72,27 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// multicast variant: the box lands at the same CTA-relative smem offset of every CTA in `mask` and signals each one's
+// mbarrier at the same offset
+__device__ __forceinline__ void tma_load_4d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
@@ -684,9 +705,14 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int M, int N) {   // b
   return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <int MT, int BN, int KP, int STAGES>
+// CL = 1: 2x2 thread-block cluster (2 co tiles x 2 ci tiles of the same tap and K slice).  Each CTA fetches only ONE
+// 64-channel group of dy and ONE of x per K block and TMA-multicasts it to the CTA that shares that operand, halving the
+// L2 -> SM operand traffic (65 -> 131 FLOP per L2 byte).  A stage is recycled only when this CTA's MMAs and those of the
+// two CTAs it multicasts into have consumed it (empty barrier count 3, multicast tcgen05.commit).
+template <int MT, int BN, int KP, int STAGES, int CL>
 __global__ void __launch_bounds__(WGRAD_THREADS, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ CUtensorMap mapX, const WgradArgs a) {
+  static_assert(CL == 0 || (MT == 1 && BN == 128), "cluster variant: 128x128 tiles");
   using L = WgradSmem<MT, BN, KP, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -697,10 +723,23 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   int t = blockIdx.x;
-  const int tap = t % a.ntaps; t /= a.ntaps;
-  const int ci_t = t % a.ci_tiles; t /= a.ci_tiles;
-  const int co_t = t;
+  int tap, ci_t, co_t;
+  uint32_t crank = 0;
+  if (CL) {
+    crank = cluster_ctarank();           // == blockIdx.x & 3 for a (4,1,1) cluster
+    t >>= 2;
+    tap = t % a.ntaps; t /= a.ntaps;
+    const int cip = a.ci_tiles >> 1;
+    ci_t = (t % cip) * 2 + (int)(crank & 1); t /= cip;
+    co_t = t * 2 + (int)(crank >> 1);
+  } else {
+    tap = t % a.ntaps; t /= a.ntaps;
+    ci_t = t % a.ci_tiles; t /= a.ci_tiles;
+    co_t = t;
+  }
   const int co0 = co_t * 128 * MT, ci0 = ci_t * BN;
+  const uint16_t mask_a = (uint16_t)((1u << crank) | (1u << (crank ^ 1u)));   // CTAs with the same co tile (share dy)
+  const uint16_t mask_b = (uint16_t)((1u << crank) | (1u << (crank ^ 2u)));   // CTAs with the same ci tile (share x)
   const int total_kb = a.nimg * a.tiles_h * a.tiles_w;
   const int chunk = (total_kb + gridDim.y - 1) / gridDim.y;
   const int kb0 = blockIdx.y * chunk;
@@ -711,7 +750,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&mapDy);
     tma_prefetch_desc(&mapX);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL ? 3 : 1); }
     mbar_init(tmem_full, 1);
     fence_barrier_init();
   }
@@ -719,6 +758,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (CL) cluster_sync_all();            // every CTA's barriers are initialised before any remote complete_tx / arrive
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t box_bytes = (uint32_t)a.kpix * 128u;   // bytes one TMA box writes (all rows, OOB rows zero-filled)
 
@@ -736,11 +776,17 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ 
         uint8_t* sa = smem + s * L::STAGE_BYTES;
         uint8_t* sb = sa + L::A_BYTES;
         mbar_expect_tx(&full[s], box_bytes * (2u * MT + BN / 64));
+        if (CL) {
+          const int ga = (int)(crank & 1), gb = (int)(crank >> 1);   // my share: one dy group, one x group
+          tma_load_4d_mc(&mapDy, &full[s], sa + ga * L::GROUP_BYTES, co0 + 64 * ga, w0, h0, img, mask_a);
+          tma_load_4d_mc(&mapX, &full[s], sb + gb * L::GROUP_BYTES, ci0 + 64 * gb, w0 * a.stride + a.tap_dw[tap], h0 * a.stride + a.tap_dh[tap], img, mask_b);
+        } else {
 #pragma unroll
-        for (int g = 0; g < 2 * MT; ++g) tma_load_4d(&mapDy, &full[s], sa + g * L::GROUP_BYTES, co0 + 64 * g, w0, h0, img);
+          for (int g = 0; g < 2 * MT; ++g) tma_load_4d(&mapDy, &full[s], sa + g * L::GROUP_BYTES, co0 + 64 * g, w0, h0, img);
 #pragma unroll
-        for (int g = 0; g < BN / 64; ++g)
-          tma_load_4d(&mapX, &full[s], sb + g * L::GROUP_BYTES, ci0 + 64 * g, w0 * a.stride + a.tap_dw[tap], h0 * a.stride + a.tap_dh[tap], img);
+          for (int g = 0; g < BN / 64; ++g)
+            tma_load_4d(&mapX, &full[s], sb + g * L::GROUP_BYTES, ci0 + 64 * g, w0 * a.stride + a.tap_dw[tap], h0 * a.stride + a.tap_dh[tap], img);
+        }
       }
     }
   } else if (warp == 1) {
@@ -761,7 +807,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ 
             umma_bf16(tmem_base + (uint32_t)(mt * BN), adesc + (uint64_t)(k * (2048 >> 4)), bdesc + (uint64_t)(k * (2048 >> 4)), idesc,
                       (it | k) != 0 ? 1u : 0u);
         }
-        umma_commit(&empty[s]);
+        if (CL) umma_commit_mc(&empty[s], (uint16_t)(mask_a | mask_b));   // me + the two CTAs that write into my stage
+        else umma_commit(&empty[s]);
       }
       umma_commit(tmem_full);
     }
@@ -796,6 +843,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if (CL) cluster_sync_all();            // no CTA leaves while a peer may still multicast into it / arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, L::TMEM_COLS);
@@ -815,15 +863,26 @@ static void pick_tile16(int Wo, int Ho, int maxrows, int* TW, int* TH) {
     }
 }
 
-template <int MT, int BN, int KP, int STAGES>
+template <int MT, int BN, int KP, int STAGES, int CL>
 static int launch_wgrad(const CUtensorMap& mDy, const CUtensorMap& mX, const WgradArgs& wa, dim3 grid, cudaStream_t st) {
   using L = WgradSmem<MT, BN, KP, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
-    ETB_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel<MT, BN, KP, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    ETB_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel<MT, BN, KP, STAGES, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_set = true;
   }
-  wgrad_kernel<MT, BN, KP, STAGES><<<grid, WGRAD_THREADS, L::TOTAL, st>>>(mDy, mX, wa);
+  if (CL) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(WGRAD_THREADS); cfg.dynamicSmemBytes = L::TOTAL; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    ETB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, wgrad_kernel<MT, BN, KP, STAGES, CL>, mDy, mX, wa));
+    etb_count_launch();
+    return ETB_OK;
+  }
+  wgrad_kernel<MT, BN, KP, STAGES, CL><<<grid, WGRAD_THREADS, L::TOTAL, st>>>(mDy, mX, wa);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }
@@ -910,12 +969,11 @@ static int wgrad_impl(const void* x_bf16, const void* dy_bf16, float* dw_f32, co
   cudaStream_t st = (cudaStream_t)stream;
   if (splitk > 1 && !accumulate) ETB_CHECK_CUDA(cudaMemsetAsync(dw_f32, 0, sizeof(float) * (size_t)cp->Cout * wa.ntaps * cp->Cin, st));
   dim3 grid((unsigned)out_tiles, (unsigned)splitk);
-  if (MT == 2 && BN == 256) return launch_wgrad<2, 256, 64, 3>(mDy, mX, wa, grid, st);
-  if (MT == 2 && BN == 128) return launch_wgrad<2, 128, 64, 4>(mDy, mX, wa, grid, st);
-  if (MT == 2) return launch_wgrad<2, 64, 64, 4>(mDy, mX, wa, grid, st);
-  if (BN == 256) return launch_wgrad<1, 256, 64, 4>(mDy, mX, wa, grid, st);
-  if (BN == 128) return launch_wgrad<1, 128, 128, 3>(mDy, mX, wa, grid, st);
-  return launch_wgrad<1, 64, 128, 4>(mDy, mX, wa, grid, st);
+  // 2x2 cluster with TMA multicast whenever both tile counts are even (Cout, Cin multiples of 256: the bulk of the trunk)
+  const bool cluster = (BN == 128) && (wa.co_tiles % 2 == 0) && (wa.ci_tiles % 2 == 0) && !getenv("ETB_WGRAD_NO_CLUSTER");
+  if (cluster) return launch_wgrad<1, 128, 128, 3, 1>(mDy, mX, wa, grid, st);
+  if (BN == 128) return launch_wgrad<1, 128, 128, 3, 0>(mDy, mX, wa, grid, st);
+  return launch_wgrad<1, 64, 128, 4, 0>(mDy, mX, wa, grid, st);
 }
 
 extern "C" int etb_conv_wgrad(const void* x_bf16, const void* dy_bf16, float* dw_f32, const EtbConvParams* cp, void* stream) {
