@@ -96,9 +96,8 @@ _SIGS = {
     "etb_dgrad_weight_elems": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "etb_pack_weight_dgrad": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
     "etb_conv_dgrad": (C.c_int, [vp, vp, vp, C.POINTER(EtbConvParams), C.c_int32, vp]),
-    "etb_conv_wgrad": (C.c_int, [vp, vp, vp, C.POINTER(EtbConvParams), vp]),
-    "etb_conv_wgrad_acc": (C.c_int, [vp, vp, vp, C.POINTER(EtbConvParams), vp]),
-    "etb_unpack_wgrad": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
+    "etb_conv_wgrad_workspace_bytes": (C.c_size_t, [C.POINTER(EtbConvParams)]),
+    "etb_conv_wgrad": (C.c_int, [vp, vp, vp, C.POINTER(EtbConvParams), C.c_int32, vp, C.c_size_t, vp]),
     "etb_bn_stats": (C.c_int, [vp, C.c_int64, C.c_int32, C.c_int32, vp, vp]),
     "etb_bn_finalize": (C.c_int, [vp, C.c_int64, C.c_int32, vp, vp, C.c_float, C.c_float, vp, vp, vp, vp, vp, vp, vp]),
     "etb_bn_act_apply": (C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),

@@ -158,20 +158,11 @@ def conv_wgrad(x, dy, Cin, Cout, k, stride, pad, x_coffset=0, dy_coffset=0, stem
     acc = accumulate_into
     if acc is not None and not (acc.is_contiguous() and acc.dtype == torch.float32):
         acc = None
-    if k == 1 and not stem and acc is not None and N * H * W >= 256:
-        _lib.check(lib.etb_conv_wgrad_acc(xp, dyp, _lib.ptr(acc), C.byref(cp), _lib.stream_ptr()), "etb_conv_wgrad_acc")
-        return acc
-    packed = torch.empty((Cout, k * k, Cin), dtype=torch.float32, device=x.device)
-    _lib.check(lib.etb_conv_wgrad(xp, dyp, _lib.ptr(packed), C.byref(cp), _lib.stream_ptr()), "etb_conv_wgrad")
-    flag = 2 if acc is not None else 0
-    if stem:
-        out = acc if acc is not None else torch.empty((Cout, 3, 6, 6), dtype=torch.float32, device=x.device)
-        _lib.check(lib.etb_unpack_wgrad(_lib.ptr(packed), _lib.ptr(out), Cout, 3, 6, 6, 1 | flag, _lib.stream_ptr()), "etb_unpack_wgrad")
-        return out
-    if k == 1 and acc is None:
-        return packed.view(Cout, Cin, 1, 1)
-    out = acc if acc is not None else torch.empty((Cout, Cin, k, k), dtype=torch.float32, device=x.device)
-    _lib.check(lib.etb_unpack_wgrad(_lib.ptr(packed), _lib.ptr(out), Cout, Cin, k, k, flag, _lib.stream_ptr()), "etb_unpack_wgrad")
+    shape = (Cout, 3, 6, 6) if stem else (Cout, Cin, k, k)
+    out = acc if acc is not None else torch.empty(shape, dtype=torch.float32, device=x.device)
+    ws = torch.empty(int(lib.etb_conv_wgrad_workspace_bytes(C.byref(cp))), dtype=torch.uint8, device=x.device)
+    flags = (1 if stem else 0) | (2 if acc is not None else 0)
+    _lib.check(lib.etb_conv_wgrad(xp, dyp, _lib.ptr(out), C.byref(cp), flags, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "etb_conv_wgrad")
     return out
 
 

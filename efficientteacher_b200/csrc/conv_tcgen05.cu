@@ -680,7 +680,8 @@ struct WgradArgs {
   int co_tiles, ci_tiles;
   int Cout, Cin;
   int flat;
-  float* dw;
+  float* dw;                // split-K partials: slice `blockIdx.y` of [splitk][Cout][ntaps][Cin] fp32
+  long dw_split_stride;     // elements per slice
 };
 
 // Tile = (128*MT co) x (BN ci) per CTA, K block = up to KP pixels.  Bigger tiles raise the FLOP per L2 byte
@@ -816,27 +817,23 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ 
     const int row = 32 * (warp & 3) + lane;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
-    const bool atomic = gridDim.y > 1;
 #pragma unroll 1
     for (int mt = 0; mt < MT; ++mt) {
       const int co = co0 + mt * 128 + row;
       const uint32_t lane_addr = tmem_base + (uint32_t)(mt * BN) + ((uint32_t)(32 * (warp & 3)) << 16);
-      float* dst = a.dw + ((size_t)co * a.ntaps + tap) * a.Cin + ci0;
+      // two-stage split-K: every CTA writes its partial tile with plain coalesced stores into its own slice; the
+      // slices are summed (and laid out as [Cout,Cin,kh,kw]) by wgrad_reduce_kernel.  No atomics, no memset.
+      float* dst = a.dw + (size_t)blockIdx.y * a.dw_split_stride + ((size_t)co * a.ntaps + tap) * a.Cin + ci0;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         if (ci0 + c0 >= a.Cin) break;
         uint32_t v[32];
         tmem_ld32(lane_addr + (uint32_t)c0, v);
         if (co < a.Cout) {
-          if (atomic) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
-          } else {
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              reinterpret_cast<float4*>(dst + c0)[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                                                                   __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
-          }
+          for (int q = 0; q < 8; ++q)
+            reinterpret_cast<float4*>(dst + c0)[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                                                 __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
         }
       }
     }
@@ -887,13 +884,79 @@ static int launch_wgrad(const CUtensorMap& mDy, const CUtensorMap& mX, const Wgr
   return ETB_OK;
 }
 
-// x [N,H,W,*] bf16 (cp->x_cstride), dy [N,Ho,Wo,*] bf16 (channel stride cp->y_cstride) -> dw [Cout][kh*kw][Cin] fp32.
-// accumulate != 0: dw += result (dw already holds a gradient, e.g. the flat arena) -- always uses atomics, never zeroes.
-static int wgrad_impl(const void* x_bf16, const void* dy_bf16, float* dw_f32, const EtbConvParams* cp, int accumulate, void* stream) {
-  ETB_CHECK_ARG(x_bf16 && dy_bf16 && dw_f32 && cp);
+// ---- second stage of the split-K: sum the slices, emit the parameter layout, optionally accumulate ----
+// thread = 4 consecutive ci of one (co, tap): coalesced float4 reads of every slice.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, long slice, int splitk, float* __restrict__ out, int Cout,
+                                                           int Cin, int kk, int flags) {
+  const long n4 = (long)Cout * kk * Cin / 4;
+  for (long e4 = (long)blockIdx.x * blockDim.x + threadIdx.x; e4 < n4; e4 += (long)gridDim.x * blockDim.x) {
+    const float4* p = reinterpret_cast<const float4*>(ws) + e4;
+    float4 acc = __ldg(p);
+    for (int s = 1; s < splitk; ++s) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(ws + (size_t)s * slice) + e4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    const long e = e4 * 4;
+    const int ci = (int)(e % Cin);
+    const long t2 = e / Cin;
+    const int t = (int)(t2 % kk), co = (int)(t2 / kk);
+    const float vals[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      long dst;
+      if (flags & 1) {                       // stem: [Cout][128 = (kh*6+kw)*3+c] -> [Cout,3,6,6]
+        const int k = ci + j;
+        if (k >= 108) continue;
+        const int c = k % 3, tt = k / 3;
+        dst = ((long)co * 3 + c) * 36 + tt;
+      } else {
+        dst = ((long)co * Cin + ci + j) * kk + t;
+      }
+      out[dst] = (flags & 2) ? out[dst] + vals[j] : vals[j];
+    }
+  }
+}
+
+static void wgrad_plan(const EtbConvParams* cp, int* BN_, int* KP_, int* TW, int* TH, int* tiles_w, int* tiles_h, int* nimg, int* out_tiles,
+                       int* splitk) {
+  const int Ho = (cp->H + 2 * cp->pad - cp->kh) / cp->stride + 1;
+  const int Wo = (cp->W + 2 * cp->pad - cp->kw) / cp->stride + 1;
+  const int BN = cp->Cin >= 128 ? 128 : 64, KP = 128;
+  const bool flat = (cp->kh == 1 && cp->kw == 1 && cp->stride == 1 && cp->pad == 0);
+  if (flat) {
+    const long npix = (long)cp->N * cp->H * cp->W;
+    *TW = KP; *TH = 1; *tiles_w = (int)((npix + KP - 1) / KP); *tiles_h = 1; *nimg = 1;
+  } else {
+    pick_tile16(Wo, Ho, KP, TW, TH);
+    *tiles_w = (Wo + *TW - 1) / *TW; *tiles_h = (Ho + *TH - 1) / *TH; *nimg = cp->N;
+  }
+  const int ntaps = cp->kh * cp->kw;
+  *out_tiles = ((cp->Cout + 127) / 128) * ((cp->Cin + BN - 1) / BN) * ntaps;
+  const int total_kb = *nimg * *tiles_h * *tiles_w;
+  int sk = (2 * etb_num_sms() + *out_tiles - 1) / *out_tiles;   // ~2 waves of CTAs
+  if (sk > total_kb) sk = total_kb;
+  if (sk < 1) sk = 1;
+  while (sk > 1 && (long)(sk - 1) * ((total_kb + sk - 1) / sk) >= total_kb) --sk;   // no empty slices
+  *splitk = sk; *BN_ = BN; *KP_ = KP;
+}
+
+extern "C" size_t etb_conv_wgrad_workspace_bytes(const EtbConvParams* cp) {
+  if (!cp || cp->Cin <= 0 || cp->Cout <= 0) return 0;
+  int BN, KP, TW, TH, tw, th, ni, ot, sk;
+  wgrad_plan(cp, &BN, &KP, &TW, &TH, &tw, &th, &ni, &ot, &sk);
+  return (size_t)sk * cp->Cout * cp->kh * cp->kw * cp->Cin * sizeof(float);
+}
+
+// x [N,H,W,*] bf16 (cp->x_cstride), dy [N,Ho,Wo,*] bf16 (channel stride cp->y_cstride) -> dw [Cout,Cin,kh,kw] fp32 (the
+// nn.Parameter layout).  flags bit0: stem (cp describes the K=128 pointwise GEMM over the im2col buffer, dw is [Cout,3,6,6]);
+// bit1: dw += result (dw may be the gradient-arena slice).  workspace: etb_conv_wgrad_workspace_bytes(cp).
+extern "C" int etb_conv_wgrad(const void* x_bf16, const void* dy_bf16, float* dw_f32, const EtbConvParams* cp, int32_t flags, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  ETB_CHECK_ARG(x_bf16 && dy_bf16 && dw_f32 && cp && workspace);
   ETB_CHECK_ARG(cp->N > 0 && cp->H > 0 && cp->W > 0 && cp->Cin > 0 && cp->Cout > 0 && cp->Cin % 64 == 0);
   ETB_CHECK_ARG(cp->kh * cp->kw <= 12 && (cp->stride == 1 || cp->stride == 2));
   ETB_CHECK_ARG(cp->x_cstride % 8 == 0 && cp->y_cstride % 8 == 0 && (((uintptr_t)x_bf16) & 15) == 0 && (((uintptr_t)dy_bf16) & 15) == 0);
+  ETB_CHECK_ARG((((uintptr_t)workspace) & 15) == 0);
   PFN_tmapEncodeTiled enc = get_encode();
   if (!enc) {
     etb_set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
@@ -901,15 +964,11 @@ static int wgrad_impl(const void* x_bf16, const void* dy_bf16, float* dw_f32, co
   }
   const int Ho = (cp->H + 2 * cp->pad - cp->kh) / cp->stride + 1;
   const int Wo = (cp->W + 2 * cp->pad - cp->kw) / cp->stride + 1;
-  // tile configuration
-  // Measured on B200 (tools/conv_bench.py): with the split-K partials reduced by fp32 atomics the atomic volume is
-  // ~(#CTAs x tile area), so 256x256 tiles (4x the atomics, 4x the contention per address) lose more in the epilogue than
-  // they gain in L2 operand traffic: 128x128 tiles are the fastest configuration of this reduction scheme.
-  const int MT = 1;
-  const int BN = cp->Cin >= 128 ? 128 : 64;
-  const int KP = 128;
   WgradArgs wa;
   memset(&wa, 0, sizeof(wa));
+  int BN, KP, out_tiles, splitk;
+  wgrad_plan(cp, &BN, &KP, &wa.TW, &wa.TH, &wa.tiles_w, &wa.tiles_h, &wa.nimg, &out_tiles, &splitk);
+  wa.kpix = wa.TW * wa.TH;
   wa.ntaps = cp->kh * cp->kw;
   for (int kh = 0; kh < cp->kh; ++kh)
     for (int kw = 0; kw < cp->kw; ++kw) {
@@ -918,15 +977,19 @@ static int wgrad_impl(const void* x_bf16, const void* dy_bf16, float* dw_f32, co
     }
   wa.stride = cp->stride;
   wa.Cout = cp->Cout; wa.Cin = cp->Cin;
-  wa.dw = dw_f32;
+  const size_t dw_elems = (size_t)cp->Cout * wa.ntaps * cp->Cin;
+  if (workspace_bytes < (size_t)splitk * dw_elems * sizeof(float)) {
+    etb_set_error("etb_conv_wgrad: workspace too small (%zu < %zu)", workspace_bytes, (size_t)splitk * dw_elems * sizeof(float));
+    return ETB_ERR_NOMEM;
+  }
+  wa.dw = (float*)workspace;
+  wa.dw_split_stride = (long)dw_elems;
   const bool flat = (cp->kh == 1 && cp->kw == 1 && cp->stride == 1 && cp->pad == 0);
   cuuint64_t ddim[4], dstr[3], xdim[4], xstr[3];
   cuuint32_t dbox[4], xbox[4], one[4] = {1, 1, 1, 1}, xes[4];
   if (flat) {
     const long npix = (long)cp->N * cp->H * cp->W;
     ETB_CHECK_ARG(npix < (1l << 31));
-    wa.TW = KP; wa.TH = 1; wa.kpix = KP;
-    wa.tiles_w = (int)((npix + KP - 1) / KP); wa.tiles_h = 1; wa.nimg = 1;
     ddim[0] = cp->Cout; ddim[1] = (cuuint64_t)npix; ddim[2] = 1; ddim[3] = 1;
     dstr[0] = (cuuint64_t)cp->y_cstride * 2; dstr[1] = dstr[0] * (cuuint64_t)npix; dstr[2] = dstr[1];
     xdim[0] = cp->Cin; xdim[1] = (cuuint64_t)npix; xdim[2] = 1; xdim[3] = 1;
@@ -935,9 +998,6 @@ static int wgrad_impl(const void* x_bf16, const void* dy_bf16, float* dw_f32, co
     xbox[0] = 64; xbox[1] = KP; xbox[2] = 1; xbox[3] = 1;
     xes[0] = xes[1] = xes[2] = xes[3] = 1;
   } else {
-    pick_tile16(Wo, Ho, KP, &wa.TW, &wa.TH);
-    wa.kpix = wa.TW * wa.TH;
-    wa.tiles_w = (Wo + wa.TW - 1) / wa.TW; wa.tiles_h = (Ho + wa.TH - 1) / wa.TH; wa.nimg = cp->N;
     ddim[0] = cp->Cout; ddim[1] = Wo; ddim[2] = Ho; ddim[3] = cp->N;
     dstr[0] = (cuuint64_t)cp->y_cstride * 2; dstr[1] = dstr[0] * Wo; dstr[2] = dstr[1] * Ho;
     xdim[0] = cp->Cin; xdim[1] = cp->W; xdim[2] = cp->H; xdim[3] = cp->N;
@@ -955,54 +1015,22 @@ static int wgrad_impl(const void* x_bf16, const void* dy_bf16, float* dw_f32, co
           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { etb_set_error("cuTensorMapEncodeTiled(x) failed: %d", (int)r); return ETB_ERR_CUDA; }
   wa.flat = flat ? 1 : 0;
-  wa.co_tiles = (cp->Cout + 128 * MT - 1) / (128 * MT);
+  wa.co_tiles = (cp->Cout + 127) / 128;
   wa.ci_tiles = (cp->Cin + BN - 1) / BN;
-  const int out_tiles = wa.co_tiles * wa.ci_tiles * wa.ntaps;
-  const int total_kb = wa.nimg * wa.tiles_h * wa.tiles_w;
-  int splitk = (2 * etb_num_sms() + out_tiles - 1) / out_tiles;
-  if (splitk > total_kb) splitk = total_kb;
-  if (splitk < 1) splitk = 1;
-  if (accumulate && splitk < 2 && total_kb >= 2) splitk = 2;   // the atomic path is the accumulating one
-  // no empty slices: ceil-div chunking must leave the last slice non-empty
-  while (splitk > 1 && (long)(splitk - 1) * ((total_kb + splitk - 1) / splitk) >= total_kb) --splitk;
-  ETB_CHECK_ARG(!accumulate || splitk > 1);
   cudaStream_t st = (cudaStream_t)stream;
-  if (splitk > 1 && !accumulate) ETB_CHECK_CUDA(cudaMemsetAsync(dw_f32, 0, sizeof(float) * (size_t)cp->Cout * wa.ntaps * cp->Cin, st));
   dim3 grid((unsigned)out_tiles, (unsigned)splitk);
-  // 2x2 cluster with TMA multicast whenever both tile counts are even (Cout, Cin multiples of 256: the bulk of the trunk)
-  const bool cluster = (BN == 128) && (wa.co_tiles % 2 == 0) && (wa.ci_tiles % 2 == 0) && !getenv("ETB_WGRAD_NO_CLUSTER");
-  if (cluster) return launch_wgrad<1, 128, 128, 3, 1>(mDy, mX, wa, grid, st);
-  if (BN == 128) return launch_wgrad<1, 128, 128, 3, 0>(mDy, mX, wa, grid, st);
-  return launch_wgrad<1, 64, 128, 4, 0>(mDy, mX, wa, grid, st);
-}
-
-extern "C" int etb_conv_wgrad(const void* x_bf16, const void* dy_bf16, float* dw_f32, const EtbConvParams* cp, void* stream) {
-  return wgrad_impl(x_bf16, dy_bf16, dw_f32, cp, 0, stream);
-}
-// dw_f32 += dW (pointwise convs: dw has the parameter layout [Cout][Cin], so it can be the gradient arena slice itself)
-extern "C" int etb_conv_wgrad_acc(const void* x_bf16, const void* dy_bf16, float* dw_f32, const EtbConvParams* cp, void* stream) {
-  return wgrad_impl(x_bf16, dy_bf16, dw_f32, cp, 1, stream);
-}
-
-// dW [Cout][kh*kw][Cin] fp32 -> [Cout,Cin,kh,kw] fp32 (the nn.Parameter layout); stem: [Cout][128] -> [Cout,3,6,6]
-__global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restrict__ dw, float* __restrict__ o, int Cout, int Cin, int kk, int stem) {
-  // stem & 2: accumulate into o (the gradient arena) instead of overwriting
-  const int64_t total = (int64_t)Cout * Cin * kk;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int t = (int)(e % kk);
-    const int ci = (int)((e / kk) % Cin);
-    const int co = (int)(e / ((int64_t)kk * Cin));
-    const float v = (stem & 1) ? dw[(int64_t)co * 128 + t * 3 + ci] : dw[((int64_t)co * kk + t) * Cin + ci];
-    o[e] = (stem & 2) ? o[e] + v : v;
-  }
-}
-extern "C" int etb_unpack_wgrad(const float* dw_packed, float* w_oihw, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw, int32_t stem,
-                                void* stream) {
-  ETB_CHECK_ARG(dw_packed && w_oihw && Cout > 0 && Cin > 0 && kh > 0 && kw > 0);
-  const int64_t total = (int64_t)Cout * Cin * kh * kw;
-  int64_t blocks = (total + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  unpack_wgrad_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dw_packed, w_oihw, Cout, Cin, kh * kw, stem);
+  int rc;
+  const bool cluster = (BN == 128) && (wa.co_tiles % 2 == 0) && (wa.ci_tiles % 2 == 0) && getenv("ETB_WGRAD_CLUSTER");
+  if (cluster) rc = launch_wgrad<1, 128, 128, 3, 1>(mDy, mX, wa, grid, st);
+  else if (BN == 128) rc = launch_wgrad<1, 128, 128, 3, 0>(mDy, mX, wa, grid, st);
+  else rc = launch_wgrad<1, 64, 128, 4, 0>(mDy, mX, wa, grid, st);
+  if (rc != ETB_OK) return rc;
+  // rows co >= Cout of the last tile are never written: the reduce only reads [Cout] rows
+  const long n4 = (long)dw_elems / 4;
+  long blocks = (n4 + 255) / 256;
+  const long cap = (long)etb_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  wgrad_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>((const float*)workspace, (long)dw_elems, splitk, dw_f32, cp->Cout, cp->Cin, wa.ntaps, flags);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }

@@ -210,16 +210,14 @@ int etb_conv_dgrad(const void* dy_bf16, const void* wd_bf16, void* dx_bf16, cons
                    void* stream);
 
 /* weight gradient: dW[co][tap][ci] = sum_pixels dy * x(shifted): tcgen05 GEMM with the pixels as the
- * reduction dimension (MN-major operands straight from the NHWC tensors via TMA), split-K with fp32 atomics.
- * `cp` describes the FORWARD conv; cp->x_cstride is x's channel stride, cp->y_cstride dy's.  dw_f32 holds
- * Cout*kh*kw*Cin floats in [Cout][kh*kw][Cin] order; etb_unpack_wgrad converts to the parameter layout [Cout,Cin,kh,kw]
- * (stem != 0: dw is [Cout][128] in the etb_stem_im2col K order -> [Cout,3,6,6]). */
-int etb_conv_wgrad(const void* x_bf16, const void* dy_bf16, float* dw_f32, const EtbConvParams* cp, void* stream);
-/* same, but dw_f32 += dW (always through the split-K atomics): for pointwise convs dw has the parameter layout, so it can
- * be the gradient-arena slice itself.  etb_unpack_wgrad: stem bit0 = stem layout, bit1 = accumulate into w_oihw. */
-int etb_conv_wgrad_acc(const void* x_bf16, const void* dy_bf16, float* dw_f32, const EtbConvParams* cp, void* stream);
-int etb_unpack_wgrad(const float* dw_packed, float* w_oihw, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw, int32_t stem,
-                     void* stream);
+ * reduction dimension (MN-major operands straight from the NHWC tensors via TMA).  Two-stage split-K: every CTA stores its
+ * partial tile into its slice of `workspace`, then a reduce kernel sums the slices, converts to the parameter layout
+ * [Cout,Cin,kh,kw] and writes (flags bit1: adds into) dw_f32 -- which may be the gradient-arena slice of the parameter.
+ * `cp` describes the FORWARD conv; cp->x_cstride is x's channel stride, cp->y_cstride dy's.
+ * flags bit0: stem (cp = the K=128 pointwise GEMM over the etb_stem_im2col buffer; dw_f32 is [Cout,3,6,6]). */
+size_t etb_conv_wgrad_workspace_bytes(const EtbConvParams* cp);
+int etb_conv_wgrad(const void* x_bf16, const void* dy_bf16, float* dw_f32, const EtbConvParams* cp, int32_t flags,
+                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* training-mode BatchNorm2d (eps, momentum, batch statistics, running-stat update with the unbiased variance) + SiLU/ReLU
  * around the convolutions (models/backbone/common.py:480-481; utils/torch_utils.py:162-171), forward and backward.
