@@ -918,10 +918,16 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 }
 
 static void wgrad_plan(const EtbConvParams* cp, int* BN_, int* KP_, int* TW, int* TH, int* tiles_w, int* tiles_h, int* nimg, int* out_tiles,
-                       int* splitk) {
+                       int* splitk, int* MT_ = nullptr) {
   const int Ho = (cp->H + 2 * cp->pad - cp->kh) / cp->stride + 1;
   const int Wo = (cp->W + 2 * cp->pad - cp->kw) / cp->stride + 1;
-  const int BN = cp->Cin >= 128 ? 128 : 64, KP = 128;
+  int BN = cp->Cin >= 128 ? 128 : 64, KP = 128, MT = 1;
+  static int cfg_mode = -1;               // tuning override: ETB_WGRAD_CFG = 0 | 1: 128x256 | 2: 256x128 | 3: 256x256
+  if (cfg_mode < 0) { const char* e = getenv("ETB_WGRAD_CFG"); cfg_mode = e ? atoi(e) : 0; }
+  if (cfg_mode == 1 && cp->Cin >= 256) { BN = 256; KP = 64; }
+  if (cfg_mode == 2 && cp->Cout >= 256 && cp->Cin >= 128) { MT = 2; BN = 128; KP = 64; }
+  if (cfg_mode == 3 && cp->Cout >= 256 && cp->Cin >= 256) { MT = 2; BN = 256; KP = 64; }
+  if (MT_) *MT_ = MT;
   const bool flat = (cp->kh == 1 && cp->kw == 1 && cp->stride == 1 && cp->pad == 0);
   if (flat) {
     const long npix = (long)cp->N * cp->H * cp->W;
@@ -931,7 +937,7 @@ static void wgrad_plan(const EtbConvParams* cp, int* BN_, int* KP_, int* TW, int
     *tiles_w = (Wo + *TW - 1) / *TW; *tiles_h = (Ho + *TH - 1) / *TH; *nimg = cp->N;
   }
   const int ntaps = cp->kh * cp->kw;
-  *out_tiles = ((cp->Cout + 127) / 128) * ((cp->Cin + BN - 1) / BN) * ntaps;
+  *out_tiles = ((cp->Cout + 128 * MT - 1) / (128 * MT)) * ((cp->Cin + BN - 1) / BN) * ntaps;
   const int total_kb = *nimg * *tiles_h * *tiles_w;
   int sk = (2 * etb_num_sms() + *out_tiles - 1) / *out_tiles;   // ~2 waves of CTAs
   if (sk > total_kb) sk = total_kb;
@@ -966,8 +972,8 @@ extern "C" int etb_conv_wgrad(const void* x_bf16, const void* dy_bf16, float* dw
   const int Wo = (cp->W + 2 * cp->pad - cp->kw) / cp->stride + 1;
   WgradArgs wa;
   memset(&wa, 0, sizeof(wa));
-  int BN, KP, out_tiles, splitk;
-  wgrad_plan(cp, &BN, &KP, &wa.TW, &wa.TH, &wa.tiles_w, &wa.tiles_h, &wa.nimg, &out_tiles, &splitk);
+  int BN, KP, out_tiles, splitk, MT;
+  wgrad_plan(cp, &BN, &KP, &wa.TW, &wa.TH, &wa.tiles_w, &wa.tiles_h, &wa.nimg, &out_tiles, &splitk, &MT);
   wa.kpix = wa.TW * wa.TH;
   wa.ntaps = cp->kh * cp->kw;
   for (int kh = 0; kh < cp->kh; ++kh)
@@ -1015,13 +1021,16 @@ extern "C" int etb_conv_wgrad(const void* x_bf16, const void* dy_bf16, float* dw
           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { etb_set_error("cuTensorMapEncodeTiled(x) failed: %d", (int)r); return ETB_ERR_CUDA; }
   wa.flat = flat ? 1 : 0;
-  wa.co_tiles = (cp->Cout + 127) / 128;
+  wa.co_tiles = (cp->Cout + 128 * MT - 1) / (128 * MT);
   wa.ci_tiles = (cp->Cin + BN - 1) / BN;
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((unsigned)out_tiles, (unsigned)splitk);
   int rc;
-  const bool cluster = (BN == 128) && (wa.co_tiles % 2 == 0) && (wa.ci_tiles % 2 == 0) && getenv("ETB_WGRAD_CLUSTER");
+  const bool cluster = (MT == 1 && BN == 128) && (wa.co_tiles % 2 == 0) && (wa.ci_tiles % 2 == 0) && getenv("ETB_WGRAD_CLUSTER");
   if (cluster) rc = launch_wgrad<1, 128, 128, 3, 1>(mDy, mX, wa, grid, st);
+  else if (MT == 2 && BN == 256) rc = launch_wgrad<2, 256, 64, 3, 0>(mDy, mX, wa, grid, st);
+  else if (MT == 2) rc = launch_wgrad<2, 128, 64, 4, 0>(mDy, mX, wa, grid, st);
+  else if (BN == 256) rc = launch_wgrad<1, 256, 64, 4, 0>(mDy, mX, wa, grid, st);
   else if (BN == 128) rc = launch_wgrad<1, 128, 128, 3, 0>(mDy, mX, wa, grid, st);
   else rc = launch_wgrad<1, 64, 128, 4, 0>(mDy, mX, wa, grid, st);
   if (rc != ETB_OK) return rc;

@@ -21,6 +21,7 @@ from . import _lib
 from .ema import ModelEMA, CosineEMA, SemiSupModelEMA, update_ema_pair, next_pair_decays, ema_scalars
 from .loss import ComputeLoss
 from .model import Model
+from .optim import FusedSGD
 from .parallel import GradArena
 from .pseudo_label import FairPseudoLabel
 from .ssod_loss import ComputeStudentMatchLoss
@@ -84,7 +85,7 @@ class SSODTrainerStep:
                 g_bnw.append(v.weight)
             elif hasattr(v, 'weight') and isinstance(v.weight, nn.Parameter):
                 g_w.append(v.weight)
-        self.optimizer = torch.optim.SGD(g_b, lr=cfg.hyp.lr0, momentum=cfg.hyp.momentum, nesterov=True)
+        self.optimizer = FusedSGD(g_b, lr=cfg.hyp.lr0, momentum=cfg.hyp.momentum, nesterov=True)   # one launch, zeroes the grads
         self.optimizer.add_param_group({'params': g_w, 'weight_decay': weight_decay})
         self.optimizer.add_param_group({'params': g_bnw})
         if cfg.linear_lr:
@@ -120,8 +121,7 @@ class SSODTrainerStep:
                 if 'momentum' in x:
                     x['momentum'] = np.interp(ni, xi, [self.warmup_momentum, self.momentum])
         if ni - self.last_opt_step >= self.accumulate:
-            self.optimizer.step()
-            self._arena.zero()           # optimizer.zero_grad() keeping the arena views
+            self.optimizer.step(zero_grad=True)      # fused SGD-Nesterov; also performs optimizer.zero_grad() on the arena
             if self.semi_ema:
                 # == ema.update(model); semi_ema.update(ema.ema); inside a captured graph the decays come from device memory
                 update_ema_pair(self.ema, self.semi_ema, self.model, scalars_dev=self._ema_scalars_dev)
@@ -225,6 +225,7 @@ class SSODTrainerStep:
         d1, d2 = next_pair_decays(self.ema, self.semi_ema)
         # pageable source: the runtime stages the 16 bytes before returning, so the next step cannot overwrite them early
         self._ema_scalars_dev.copy_(torch.tensor(ema_scalars(d1, d2), dtype=torch.float32))
+        self.optimizer.refresh_hyper()       # lr / momentum of this step -> device memory read by the captured SGD kernel
         g["graph"].replay()
         if g["graph_b"] is not None:     # WORLD_SIZE > 1: [graph A: ... backward] -> NCCL all-reduce (eager) -> [graph B: SGD + EMA]
             self._allreduce_grads()

@@ -68,6 +68,22 @@ int etb_ema_update(const EtbEmaChunk* table_dev, int64_t n_chunks, float d, floa
 int etb_ema_update_dev(const EtbEmaChunk* table_dev, int64_t n_chunks, const float* scalars4_dev, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Fused SGD-Nesterov step over all parameters (replaces torch.optim.SGD.step + zero_grad behind
+ * trainer/ssod_trainer.py:481-484; groups/hyper-parameters as built in trainer/trainer.py:193-217):
+ *   g' = g + wd*p ; buf = momentum*buf + g' ; p -= lr*(g' + momentum*buf) ; (g = 0)
+ * chunk table like the EMA one (<= ETB_EMA_CHUNK elements per chunk); hyper_dev[4*group + {0,1,2}] = {lr, momentum, wd}
+ * lives in device memory so a captured CUDA graph follows the LR schedule.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct EtbSgdChunk {
+  float* p;
+  float* g;
+  float* buf;
+  int32_t n;
+  int32_t group;
+} EtbSgdChunk;
+int etb_sgd_step(const EtbSgdChunk* table_dev, int64_t n_chunks, const float* hyper_dev, int32_t zero_grad, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Detect eval-mode decode (models/head/yolov5_head.py:66-78): logits [B,na,ny,nx,no] of one level ->
  * rows of pred[B,P,no] at row offset `row0`:  sigmoid; xy=(2s-0.5+grid)*stride; wh=(2s)^2*anchor*stride.
  * ------------------------------------------------------------------------------------------- */

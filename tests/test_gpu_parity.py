@@ -293,3 +293,35 @@ def test_ema_large_unaligned_vs_two_rounding_formula():
     for k, v in ema.ema.state_dict().items():
         want = before[k] * np.float32(d) + np.float32(1.0 - d) * m.state_dict()[k]     # torch CUDA: mul, mul, add
         assert torch.equal(v, want), k
+
+
+# ------------------------------------------------------------------------------------------------ fused SGD
+def test_fused_sgd_matches_torch_sgd():
+    """FusedSGD (one launch, grads zeroed in the same pass) vs torch.optim.SGD(nesterov) with the reference's three
+    parameter groups (bias | conv weights + weight decay | BN weights), trainer/trainer.py:215-217."""
+    from efficientteacher_b200.optim import FusedSGD
+    torch.manual_seed(0)
+    shapes = [(255,), (64, 3, 6, 6), (128, 64, 3, 3), (1024, 1024, 1, 1), (513,), (7,)]
+    groups = [[0, 4], [1, 2, 3], [5]]
+    mk = lambda: [torch.nn.Parameter(torch.randn(s, generator=torch.Generator().manual_seed(i)).to(DEV)) for i, s in enumerate(shapes)]  # noqa: E731
+    pa, pb = mk(), mk()
+    oa = FusedSGD([pa[i] for i in groups[0]], lr=0.01, momentum=0.937, nesterov=True)
+    ob = torch.optim.SGD([pb[i] for i in groups[0]], lr=0.01, momentum=0.937, nesterov=True)
+    for o, ps in ((oa, pa), (ob, pb)):
+        o.add_param_group({'params': [ps[i] for i in groups[1]], 'weight_decay': 0.0005})
+        o.add_param_group({'params': [ps[i] for i in groups[2]]})
+    for step in range(3):
+        if step == 2:
+            for o in (oa, ob):
+                o.param_groups[1]['lr'] = 0.02       # schedule change is picked up
+        for i, (a, b) in enumerate(zip(pa, pb)):
+            gr = torch.randn(a.shape, generator=torch.Generator().manual_seed(100 * step + i)).to(DEV)
+            a.grad = gr.clone() if a.grad is None else a.grad.copy_(gr)
+            b.grad = gr.clone()
+        oa.step()
+        ob.step()
+        for a, b in zip(pa, pb):
+            torch.testing.assert_close(a.detach(), b.detach(), rtol=2e-6, atol=2e-7)
+            assert float(a.grad.abs().max()) == 0.0          # zeroed by the fused pass
+        for a, b in zip(pa, pb):
+            torch.testing.assert_close(oa.state[a]["momentum_buffer"], ob.state[b]["momentum_buffer"], rtol=2e-6, atol=2e-7)
