@@ -321,7 +321,7 @@ def test_fused_sgd_matches_torch_sgd():
         oa.step()
         ob.step()
         for a, b in zip(pa, pb):
-            torch.testing.assert_close(a.detach(), b.detach(), rtol=2e-6, atol=2e-7)
+            torch.testing.assert_close(a.detach(), b.detach(), rtol=2e-6, atol=1e-6)   # fma vs mul+add rounding
             assert float(a.grad.abs().max()) == 0.0          # zeroed by the fused pass
         for a, b in zip(pa, pb):
-            torch.testing.assert_close(oa.state[a]["momentum_buffer"], ob.state[b]["momentum_buffer"], rtol=2e-6, atol=2e-7)
+            torch.testing.assert_close(oa.state[a]["momentum_buffer"], ob.state[b]["momentum_buffer"], rtol=2e-6, atol=1e-6)
