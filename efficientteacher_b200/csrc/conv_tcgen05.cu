@@ -182,6 +182,105 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// Epilogue of one accumulator tile for one warp: columns [chalf*BN/2, (chalf+1)*BN/2) of the BN-wide tile starting at
+// output channel n0, for the output pixel `pix` of this thread's TMEM lane.  EPI is a compile-time tail selector so every
+// register array is statically indexed:
+//   EPI 0: raw bf16 store (+= existing when a.accumulate)       -- dgrad, training forward
+//   EPI 1: v*scale+bias (folded BN) -> SiLU/ReLU -> (+residual) -- teacher forward
+//   EPI 2: +bias, fp32 scatter into the Detect layout           -- head
+template <int BN, int EPI>
+__device__ __forceinline__ void conv_epilogue_cols(const ConvKArgs& a, uint32_t lane_addr, int n0, int chalf, bool row_ok, size_t pix) {
+  constexpr int HALF = BN / 2;
+#pragma unroll 1
+for (int cc = 0; cc < HALF; cc += 32) {
+  const int c0 = chalf * HALF + cc;
+  if (n0 + c0 >= a.Cout) break;  // warp-uniform
+  uint32_t v[32];
+  tmem_ld32(lane_addr + (uint32_t)c0, v);
+  if (!row_ok) continue;
+  const int gc0 = n0 + c0;
+  const bool full = gc0 + 32 <= a.Cout;
+  if (EPI == 2) {
+    // Detect train layout: y[img][anchor][oh][ow][o], channel c = anchor*no + o  (yolov5_head.py:66)
+    const size_t hw = (size_t)a.det_hw;
+    const size_t img_r = pix / hw, pin = pix - img_r * hw;   // pix is the global pixel index in both tilings
+    const int na = a.Cout / a.det_no;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int gc = gc0 + j;
+      if (gc < a.Cout) {
+        const int an = gc / a.det_no, o = gc - an * a.det_no;
+        a.y_f32[((img_r * na + an) * hw + pin) * a.det_no + o] = __uint_as_float(v[j]) + (a.bias ? __ldg(a.bias + gc) : 0.0f);
+      }
+    }
+    continue;
+  }
+  __nv_bfloat16* yp = a.y + pix * a.y_cstride + a.y_coffset + gc0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {         // 8 channels = one 16 B store
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[q * 8 + j]);
+    if (EPI == 1) {
+      float sc[8], bi[8];
+      if (full) {
+        const float4 s0 = a.scale ? __ldg(reinterpret_cast<const float4*>(a.scale + gc0) + 2 * q) : make_float4(1.f, 1.f, 1.f, 1.f);
+        const float4 s1 = a.scale ? __ldg(reinterpret_cast<const float4*>(a.scale + gc0) + 2 * q + 1) : make_float4(1.f, 1.f, 1.f, 1.f);
+        const float4 b0 = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + gc0) + 2 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 b1 = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + gc0) + 2 * q + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+        sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+        bi[0] = b0.x; bi[1] = b0.y; bi[2] = b0.z; bi[3] = b0.w; bi[4] = b1.x; bi[5] = b1.y; bi[6] = b1.z; bi[7] = b1.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int gc = gc0 + q * 8 + j;
+          sc[j] = (a.scale && gc < a.Cout) ? __ldg(a.scale + gc) : 1.0f;
+          bi[j] = (a.bias && gc < a.Cout) ? __ldg(a.bias + gc) : 0.0f;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float x = fmaf(f[j], sc[j], bi[j]);
+        if (a.act == 1) x = __fdividef(x, 1.0f + __expf(-x));
+        else if (a.act == 2) x = fmaxf(x, 0.0f);
+        f[j] = x;
+      }
+      if (a.residual && full) {
+        const uint4 rv = __ldg(reinterpret_cast<const uint4*>(a.residual + pix * a.res_cstride + a.res_coffset + gc0) + q);
+        const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 rf = __bfloat1622float2(r2[j]);
+          f[2 * j] += rf.x;
+          f[2 * j + 1] += rf.y;
+        }
+      }
+    }
+    if (full) {
+      if (EPI == 0 && a.accumulate) {
+        const uint4 pv = reinterpret_cast<const uint4*>(yp)[q];
+        const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&pv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 pf = __bfloat1622float2(p2[j]);
+          f[2 * j] += pf.x;
+          f[2 * j + 1] += pf.y;
+        }
+      }
+      uint4 ov;
+      __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+      reinterpret_cast<uint4*>(yp)[q] = ov;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (gc0 + q * 8 + j < a.Cout) yp[q * 8 + j] = __float2bfloat16(f[j]);
+    }
+  }
+}
+}
+
 // Persistent: gridDim.x CTAs walk the tile list (tile = blockIdx.x + i*gridDim.x; N tile fastest so the CTAs running
 // concurrently share A tiles in L2).  The smem ring and the two TMEM accumulators run across tile boundaries, so the
 // epilogue of tile i (tcgen05.ld -> BN/SiLU -> stores) overlaps the TMA/MMA main loop of tile i+1.
@@ -279,7 +378,6 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const int chalf = ew >> 2;
     const int row = 32 * quad + lane;
     const int th = row / a.TW, tw = row - th * a.TW;
-    constexpr int HALF = BN / 2;
     int lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
       const int acc = lt & 1;
@@ -294,94 +392,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       mbar_wait(&tmem_full[acc], (uint32_t)((lt >> 1) & 1));
       tc_fence_after();
       const uint32_t lane_addr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(32 * quad) << 16);
-#pragma unroll 1
-      for (int cc = 0; cc < HALF; cc += 32) {
-        const int c0 = chalf * HALF + cc;
-        if (n0 + c0 >= a.Cout) break;  // warp-uniform
-        uint32_t v[32];
-        tmem_ld32(lane_addr + (uint32_t)c0, v);
-        if (!row_ok) continue;
-        const int gc0 = n0 + c0;
-        const bool full = gc0 + 32 <= a.Cout;
-        if (EPI == 2) {
-          // Detect train layout: y[img][anchor][oh][ow][o], channel c = anchor*no + o  (yolov5_head.py:66)
-          const size_t hw = (size_t)a.det_hw;
-          const size_t img_r = pix / hw, pin = pix - img_r * hw;   // pix is the global pixel index in both tilings
-          const int na = a.Cout / a.det_no;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int gc = gc0 + j;
-            if (gc < a.Cout) {
-              const int an = gc / a.det_no, o = gc - an * a.det_no;
-              a.y_f32[((img_r * na + an) * hw + pin) * a.det_no + o] = __uint_as_float(v[j]) + (a.bias ? __ldg(a.bias + gc) : 0.0f);
-            }
-          }
-          continue;
-        }
-        __nv_bfloat16* yp = a.y + pix * a.y_cstride + a.y_coffset + gc0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {         // 8 channels = one 16 B store
-          float f[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[q * 8 + j]);
-          if (EPI == 1) {
-            float sc[8], bi[8];
-            if (full) {
-              const float4 s0 = a.scale ? __ldg(reinterpret_cast<const float4*>(a.scale + gc0) + 2 * q) : make_float4(1.f, 1.f, 1.f, 1.f);
-              const float4 s1 = a.scale ? __ldg(reinterpret_cast<const float4*>(a.scale + gc0) + 2 * q + 1) : make_float4(1.f, 1.f, 1.f, 1.f);
-              const float4 b0 = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + gc0) + 2 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-              const float4 b1 = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + gc0) + 2 * q + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-              sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
-              bi[0] = b0.x; bi[1] = b0.y; bi[2] = b0.z; bi[3] = b0.w; bi[4] = b1.x; bi[5] = b1.y; bi[6] = b1.z; bi[7] = b1.w;
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const int gc = gc0 + q * 8 + j;
-                sc[j] = (a.scale && gc < a.Cout) ? __ldg(a.scale + gc) : 1.0f;
-                bi[j] = (a.bias && gc < a.Cout) ? __ldg(a.bias + gc) : 0.0f;
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float x = fmaf(f[j], sc[j], bi[j]);
-              if (a.act == 1) x = __fdividef(x, 1.0f + __expf(-x));
-              else if (a.act == 2) x = fmaxf(x, 0.0f);
-              f[j] = x;
-            }
-            if (a.residual && full) {
-              const uint4 rv = __ldg(reinterpret_cast<const uint4*>(a.residual + pix * a.res_cstride + a.res_coffset + gc0) + q);
-              const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 rf = __bfloat1622float2(r2[j]);
-                f[2 * j] += rf.x;
-                f[2 * j + 1] += rf.y;
-              }
-            }
-          }
-          if (full) {
-            if (EPI == 0 && a.accumulate) {
-              const uint4 pv = reinterpret_cast<const uint4*>(yp)[q];
-              const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&pv);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 pf = __bfloat1622float2(p2[j]);
-                f[2 * j] += pf.x;
-                f[2 * j + 1] += pf.y;
-              }
-            }
-            uint4 ov;
-            __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-            reinterpret_cast<uint4*>(yp)[q] = ov;
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (gc0 + q * 8 + j < a.Cout) yp[q * 8 + j] = __float2bfloat16(f[j]);
-          }
-        }
-      }
+      conv_epilogue_cols<BN, EPI>(a, lane_addr, n0, chalf, row_ok, pix);
       // all tcgen05.ld of this warp have completed (wait::ld inside tmem_ld32): hand the accumulator back
       tc_fence_before();
       __syncwarp();
@@ -394,6 +405,213 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     tc_fence_after();
     tmem_dealloc(tmem_base, L::TMEM_COLS);
   }
+}
+
+// =====================================================================================================================
+// 2-SM variant (cta_group::2): a cluster of two CTAs owns a 256-pixel x 256-cout tile.  Each SM stages ONLY its own
+// 128-pixel A tile and HALF of the weight tile (128 of the 256 couts) -> 32 KB instead of 48 KB per K block and SM, which is
+// what bounds the 1-SM kernel (per-SM TMA->smem ingest).  The leader CTA (rank 0) issues
+// tcgen05.mma.cta_group::2 (M=256, N=256, K=16); each CTA's TMEM receives its own 128 rows x 256 columns and runs its own
+// epilogue.  Barriers: both producers complete_tx on the LEADER's full barrier (peer bit cleared in the address),
+// tcgen05.commit multicasts to both CTAs' empty / tmem_full barriers, both CTAs' epilogue warps arrive on the leader's
+// tmem_empty barrier.
+// =====================================================================================================================
+#define ETB_PEER_BIT_MASK 0xFEFFFFFFu
+
+__device__ __forceinline__ void tma_load_4d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & ETB_PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & ETB_PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+// arrive (no tx) on the LEADER CTA's copy of a barrier, from either CTA of the pair
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & ETB_PEER_BIT_MASK) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {   // arrive on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+template <int STAGES>
+struct Conv2Smem {
+  static constexpr int A_BYTES = CONV_BLOCK_M * 128;      // this CTA's 128 pixels
+  static constexpr int B_BYTES = 128 * 128;               // this CTA's half (128 couts) of the 256-wide weight tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+  static constexpr int TMEM_COLS = 512;                   // two 256-column accumulators per CTA
+};
+
+template <int STAGES, int EPI>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv_fwd2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const ConvKArgs a) {
+  constexpr int BN = 256;
+  using L = Conv2Smem<STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + L::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;     // [2]
+  uint64_t* tmem_empty = tmem_full + 2;     // [2]  (the leader's copies are the live ones)
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();           // 0 = leader
+  const int n_tiles = (a.Cout + BN - 1) / BN;
+  const int m_tiles = a.tiles_w * a.tiles_h * a.nimg;
+  const int m_pairs = (m_tiles + 1) / 2;
+  const int total_tiles = n_tiles * m_pairs;         // pair tiles: 256 pixels x 256 couts
+  const int kiters = a.ntaps * a.kblocks;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }
+    for (int q = 0; q < 2; ++q) { mbar_init(&tmem_full[q], 1); mbar_init(&tmem_empty[q], 16); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, L::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                // both CTAs' barriers + TMEM exist before any cross-CTA traffic
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs: own A tile, own half of B; bytes are accounted on the leader's full barrier) =====
+    if (lane == 0) {
+      const uint32_t a_bytes = (uint32_t)(a.TW * a.TH * 128);
+      int it = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+        const int n0 = (tile % n_tiles) * BN;
+        int t = (tile / n_tiles) * 2 + (int)rank;    // this CTA's m tile (may be == m_tiles for the odd tail: OOB -> zeros)
+        const int tw_i = t % a.tiles_w; t /= a.tiles_w;
+        const int th_i = t % a.tiles_h; t /= a.tiles_h;
+        const int img = t;
+        const int w0 = tw_i * a.TW, h0 = th_i * a.TH;
+        for (int tp = 0; tp < a.ntaps; ++tp)
+          for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+            mbar_wait(&empty[s], ph ^ 1u);           // my own smem stage is free (commit is multicast to both CTAs)
+            uint8_t* sa = smem + s * L::STAGE_BYTES;
+            uint8_t* sb = sa + L::A_BYTES;
+            if (rank == 0) mbar_expect_tx(&full[s], 2u * (a_bytes + (uint32_t)L::B_BYTES));
+            else mbar_arrive_leader(&full[s]);
+            tma_load_4d_2sm(&mapA, &full[s], sa, kb * CONV_BLOCK_K, w0 * a.stride + a.tap_dw[tp], h0 * a.stride + a.tap_dh[tp], img);
+            tma_load_2d_2sm(&mapB, &full[s], sb, (tp * a.kblocks + kb) * CONV_BLOCK_K, n0 + 128 * (int)rank);
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: leader CTA only, one thread, for the pair =====
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN);
+      int it = 0, lt = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++lt) {
+        const int acc = lt & 1;
+        mbar_wait(&tmem_empty[acc], (uint32_t)(((lt >> 1) & 1) ^ 1));   // both CTAs' epilogues drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int ki = 0; ki < kiters; ++ki, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint64_t adesc = make_kmajor_sw128_desc(sa);
+          const uint64_t bdesc = make_kmajor_sw128_desc(sa + L::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < CONV_BLOCK_K / 16; ++k)
+            umma_bf16_2sm(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ki | k) != 0 ? 1u : 0u);
+          umma_commit_2sm(&empty[s]);
+        }
+        umma_commit_2sm(&tmem_full[acc]);
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs, own 128 rows) =====
+    const int ew = warp - 2;
+    const int quad = warp & 3;
+    const int chalf = ew >> 2;
+    const int row = 32 * quad + lane;
+    const int th = row / a.TW, tw = row - th * a.TW;
+    int lt = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++lt) {
+      const int acc = lt & 1;
+      const int n0 = (tile % n_tiles) * BN;
+      const int mt = (tile / n_tiles) * 2 + (int)rank;
+      int t = mt;
+      const int tw_i = t % a.tiles_w; t /= a.tiles_w;
+      const int th_i = t % a.tiles_h; t /= a.tiles_h;
+      const int img = t;
+      const int oh = th_i * a.TH + th, ow = tw_i * a.TW + tw;
+      const bool row_ok = (mt < m_tiles) && (row < a.TW * a.TH) && (oh < a.Ho) && (ow < a.Wo);
+      const size_t pix = ((size_t)img * a.out_H + (size_t)(oh * a.out_os + a.out_ph)) * a.out_W + (size_t)(ow * a.out_os + a.out_pw);
+      mbar_wait(&tmem_full[acc], (uint32_t)((lt >> 1) & 1));
+      tc_fence_after();
+      const uint32_t lane_addr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(32 * quad) << 16);
+      conv_epilogue_cols<BN, EPI>(a, lane_addr, n0, chalf, row_ok, pix);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                // the peer may still signal / read until it is done too
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, L::TMEM_COLS);
+  }
+}
+
+template <int STAGES, int EPI>
+static int launch_conv2_e(const CUtensorMap& mA, const CUtensorMap& mB, const ConvKArgs& ka, dim3 grid, cudaStream_t st) {
+  using L = Conv2Smem<STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ETB_CHECK_CUDA(cudaFuncSetAttribute(conv_fwd2_kernel<STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(CONV_THREADS); cfg.dynamicSmemBytes = L::TOTAL; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  ETB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_fwd2_kernel<STAGES, EPI>, mA, mB, ka));
+  etb_count_launch();
+  return ETB_OK;
+}
+static int launch_conv2(const CUtensorMap& mA, const CUtensorMap& mB, const ConvKArgs& ka, dim3 grid, cudaStream_t st) {
+  if (ka.out_mode == 1) return launch_conv2_e<6, 2>(mA, mB, ka, grid, st);
+  if (ka.scale || ka.bias || ka.act || ka.residual) return launch_conv2_e<6, 1>(mA, mB, ka, grid, st);
+  return launch_conv2_e<6, 0>(mA, mB, ka, grid, st);
 }
 
 // ------------------------------------------------------------------------------------------------- host side
@@ -501,9 +719,13 @@ static int launch_gemm(const GemmGeom& g, ConvKArgs ka, cudaStream_t st) {
   }
   const long Ktot = (long)ka.ntaps * g.aC;
   const int BN = g.b_rows > 128 ? 256 : (g.b_rows > 64 ? 128 : 64);
+  static int two_sm = -1;                 // ETB_CONV_2SM=0 disables the cta_group::2 path
+  if (two_sm < 0) { const char* e = getenv("ETB_CONV_2SM"); two_sm = e ? atoi(e) : 1; }
+  const long m_tiles_all = (long)ka.tiles_w * ka.tiles_h * nimg;
+  const bool use2 = two_sm && BN == 256 && m_tiles_all >= 2;
   cuuint64_t wdim[2] = {(cuuint64_t)Ktot, (cuuint64_t)g.b_rows};
   cuuint64_t wstr[1] = {(cuuint64_t)Ktot * 2};
-  cuuint32_t wbox[2] = {64, (cuuint32_t)BN};
+  cuuint32_t wbox[2] = {64, (cuuint32_t)(use2 ? 128 : BN)};
   cuuint32_t westr[2] = {1, 1};
   r = enc(&mB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(g.b_ptr), wdim, wstr, wbox, westr, CU_TENSOR_MAP_INTERLEAVE_NONE,
           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -514,6 +736,12 @@ static int launch_gemm(const GemmGeom& g, ConvKArgs ka, cudaStream_t st) {
   ka.kblocks = g.aC / CONV_BLOCK_K;
   ka.Cout = g.b_rows;
   ka.nimg = nimg;
+  if (use2) {
+    const long pair_tiles = ((m_tiles_all + 1) / 2) * ((g.b_rows + BN - 1) / BN);
+    const long clusters = etb_num_sms() / 2;
+    dim3 grid2((unsigned)(2 * (pair_tiles < clusters ? pair_tiles : clusters)), 1);
+    return launch_conv2(mA, mB, ka, grid2, st);
+  }
   const long total_tiles = (long)ka.tiles_w * ka.tiles_h * nimg * ((g.b_rows + BN - 1) / BN);
   const long resident = (long)etb_num_sms();   // persistent: one CTA per SM; overlap comes from the 2 TMEM accumulators
   dim3 grid((unsigned)(total_tiles < resident ? total_tiles : resident), 1);
