@@ -1167,10 +1167,23 @@ static void wgrad_plan(const EtbConvParams* cp, int* BN_, int* KP_, int* TW, int
   const int ntaps = cp->kh * cp->kw;
   *out_tiles = ((cp->Cout + 128 * MT - 1) / (128 * MT)) * ((cp->Cin + BN - 1) / BN) * ntaps;
   const int total_kb = *nimg * *tiles_h * *tiles_w;
-  int sk = (2 * etb_num_sms() + *out_tiles - 1) / *out_tiles;   // ~2 waves of CTAs
-  if (sk > total_kb) sk = total_kb;
-  if (sk < 1) sk = 1;
-  while (sk > 1 && (long)(sk - 1) * ((total_kb + sk - 1) / sk) >= total_kb) --sk;   // no empty slices
+  // split-K: minimise  rounds(out_tiles*sk) * (K blocks per CTA * t_kb + t_fixed)  -- whole waves of 148 CTAs matter more
+  // than raw parallelism (measured: 2.2 waves cost 3 rounds).  t_kb ~ 512 MMA cycles per 128-pixel block, t_fixed ~ launch +
+  // TMEM alloc + pipeline fill + epilogue of one CTA.
+  const int sms = etb_num_sms();
+  const double t_kb = 0.27 * (double)(*TW * *TH) / 128.0, t_fixed = 6.0;
+  int sk = 1;
+  double best = 1e30;
+  const int sk_max = total_kb < 512 ? total_kb : 512;
+  for (int c = 1; c <= sk_max; ++c) {
+    const long ctas = (long)*out_tiles * c;
+    if (ctas > 8L * sms) break;
+    const long rounds = (ctas + sms - 1) / sms;
+    const int per = (total_kb + c - 1) / c;
+    if ((long)(c - 1) * per >= total_kb) continue;          // would leave an empty slice
+    const double cost = (double)rounds * (per * t_kb + t_fixed) + 0.002 * c;   // tiny bias towards fewer partials to reduce
+    if (cost < best) { best = cost; sk = c; }
+  }
   *splitk = sk; *BN_ = BN; *KP_ = KP;
 }
 
