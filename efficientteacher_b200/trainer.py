@@ -177,7 +177,7 @@ class SSODTrainerStep:
         self._mark("nms_pseudo_label")
         total_imgs = torch.cat([imgs, unlabeled_imgs], 0)
         with torch.autocast("cuda", dtype=self.amp_dtype):
-            total_pred, total_feature = self.model(total_imgs.contiguous(memory_format=torch.channels_last))
+            total_pred, total_feature = self.model(total_imgs)   # the native stem reads the NCHW image directly
         self._mark("student_forward")
         sup_pred, sup_feature, un_sup_pred, un_sup_feature = self.split_predict_and_feature(total_pred, total_feature, n_img)
         sup_loss, sup_loss_items = self.compute_loss(sup_pred, targets)
