@@ -20,7 +20,7 @@ import torch.nn as nn
 from . import _lib
 from .ema import ModelEMA, CosineEMA, SemiSupModelEMA, update_ema_pair, next_pair_decays, ema_scalars
 from .loss import ComputeLoss
-from .model import Model
+from .model import Model, SupModel
 from .optim import FusedSGD
 from .parallel import GradArena
 from .pseudo_label import FairPseudoLabel
@@ -288,3 +288,49 @@ class SSODTrainerStep:
         self.last_opt_step = saved_step
         self.profile = was_profile
         self._graph = st
+
+
+class SupTrainerStep:
+    """The supervised step (trainer/trainer.py:406-443 train_in_epoch body + :381-404 update_optimizer), BASELINE configs
+    #1/#2: student forward -> ComputeLoss -> backward -> [all-reduce] -> SGD-Nesterov -> ModelEMA.update, same native
+    kernels as the SSOD step minus the teacher / pseudo-label path."""
+
+    def __init__(self, cfg, device, rank=-1, world_size=1, epochs=None, batch_size=None, amp_dtype=torch.bfloat16):
+        self.cfg, self.device = cfg, device
+        self.RANK, self.WORLD_SIZE = rank, world_size
+        self.epochs = epochs if epochs is not None else cfg.epochs
+        self.batch_size = batch_size if batch_size is not None else cfg.Dataset.batch_size
+        self.amp_dtype = amp_dtype
+        self.model = SupModel(cfg).to(device)
+        self.ema = ModelEMA(self.model)          # the reference keeps it on rank 0/-1 only (trainer.py:157); harmless elsewhere
+        nbs = 64
+        self.accumulate = max(round(nbs / self.batch_size), 1)
+        weight_decay = cfg.hyp.weight_decay * self.batch_size * self.accumulate / nbs
+        g_bnw, g_w, g_b = [], [], []
+        for v in self.model.modules():
+            if hasattr(v, 'bias') and isinstance(v.bias, nn.Parameter):
+                g_b.append(v.bias)
+            if isinstance(v, nn.BatchNorm2d):
+                g_bnw.append(v.weight)
+            elif hasattr(v, 'weight') and isinstance(v.weight, nn.Parameter):
+                g_w.append(v.weight)
+        self.optimizer = FusedSGD(g_b, lr=cfg.hyp.lr0, momentum=cfg.hyp.momentum, nesterov=True)
+        self.optimizer.add_param_group({'params': g_w, 'weight_decay': weight_decay})
+        self.optimizer.add_param_group({'params': g_bnw})
+        self.compute_loss = ComputeLoss(self.model, cfg)
+        self._arena = None
+        self.last_opt_step = -1
+
+    def train_step(self, imgs, targets, ni):
+        with torch.autocast("cuda", dtype=self.amp_dtype):
+            pred = self.model(imgs)
+        loss, loss_items = self.compute_loss(pred, targets)
+        if self._arena is None:
+            self._arena = GradArena(self.model.parameters(), self.device)
+        loss.backward()
+        self._arena.all_reduce_sum(self.WORLD_SIZE)
+        if ni - self.last_opt_step >= 1:
+            self.optimizer.step(zero_grad=True)
+            self.ema.update(self.model)
+            self.last_opt_step = ni
+        return loss.detach()

@@ -190,3 +190,24 @@ def test_graphed_step_matches_eager_step():
     ra = torch.cat([out["eager"][1][k].flatten() for k in kr]); rb = torch.cat([out["graph"][1][k].flatten() for k in kr])
     rc = torch.cat([out["eager2"][1][k].flatten() for k in kr])
     assert ((ra - rb).norm() / ra.norm()).item() <= 3.0 * ((ra - rc).norm() / ra.norm()).item() + 5e-3
+
+
+def test_supervised_step_matches_cpu_reference():
+    """BASELINE config #1 shape of work (supervised step): loss of the native step vs the torch fp32 CPU restatement."""
+    from efficientteacher_b200.config import yolov5_sup_cfg
+    from efficientteacher_b200.trainer import SupTrainerStep
+    from oracle.trunk_ref import TrunkRef
+    from oracle import port
+    import synth
+    img, B = 256, 2
+    torch.manual_seed(0)
+    st = SupTrainerStep(yolov5_sup_cfg('l_shallow', batch_size=B, img_size=img), torch.device(DEV))
+    sd = {k: v.detach().cpu().clone() for k, v in st.model.state_dict().items()}
+    x = torch.rand(B, 3, img, img, generator=torch.Generator().manual_seed(3))
+    tg = synth.make_targets(5, 16, B)
+    raw, _ = TrunkRef(sd, (1, 2, 3, 1), 1).forward(x, train=True, with_features=False)
+    ref, _ = port.det_loss(raw, [port.build_targets(tg, synth.ANCHORS_GRID, synth.level_shapes(img))], [4.0, 1.0, 0.4], 0.05, 0.7, 0.3)
+    before = st.model.backbone.stage1.conv.weight.detach().clone()
+    loss = st.train_step(x.to(DEV), torch.from_numpy(tg).to(DEV), 0)
+    assert abs(loss.item() - ref.item()) <= 0.03 * abs(ref.item()), (loss.item(), ref.item())
+    assert not torch.equal(before, st.model.backbone.stage1.conv.weight.detach()) and st.ema.updates == 1
