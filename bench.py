@@ -372,7 +372,7 @@ def main():
                        "global_batch": imgs_per_step, "img_size": IMG, "parallelism": "dp%d" % world, "cuda_graph": use_graph,
                        "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
                        "native": "teacher trunk+head, student conv fwd/dgrad/wgrad (tcgen05) + BatchNorm(train)+SiLU fwd/bwd, weight packing, NMS/pseudo-label, assigners, losses fwd/bwd, EMA",
-                       "library_ops_left": "student cat / residual add / upsample / maxpool and their autograd, netD C->2 conv, domain focal loss (x0), SGD-Nesterov (torch foreach)",
+                       "library_ops_left": "student cat / residual add / upsample / maxpool and their autograd, netD C->2 conv, domain focal loss (x0)",
                        "pseudo_labels_last_step": n_pl, "nms_candidates_per_img_at_start": cand_per_img, "nms_detections_per_img_last_step": det_per_img},
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,

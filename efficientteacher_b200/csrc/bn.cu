@@ -102,10 +102,19 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, int M, int C,
   }
 }
 
-__device__ __forceinline__ float silu_f(float z) { return __fdividef(z, 1.0f + __expf(-z)); }
+// sigmoid through ONE MUFU op: s = 0.5*tanh(0.5 z) + 0.5 (tanh.approx.f32, rel. error ~2^-11: below bf16 resolution)
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float silu_f(float z) {          // z*sigmoid(z) = h + h*tanh(h), h = z/2
+  const float h = 0.5f * z;
+  return fmaf(h, tanh_approx(h), h);
+}
 // d silu(z)/dz = s*(1 + z*(1-s)),  s = sigmoid(z)
 __device__ __forceinline__ float dsilu_f(float z) {
-  const float s = __fdividef(1.0f, 1.0f + __expf(-z));
+  const float s = fmaf(0.5f, tanh_approx(0.5f * z), 0.5f);
   return s * fmaf(z, 1.0f - s, 1.0f);
 }
 
@@ -141,6 +150,8 @@ __global__ void __launch_bounds__(BN_THREADS) bn_act_bwd_reduce_kernel(const __n
   {
     const int g0 = threadIdx.x % (C >> 3);
     ldf8(scale + g0 * 8, sc); ldf8(shift + g0 * 8, sh); ldf8(mean + g0 * 8, mu); ldf8(invstd + g0 * 8, is);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mu[j] = -mu[j] * is[j];     // xhat = y*invstd + (-mean*invstd): one FMA per element
   }
   channel_reduce<2>(M, C, [&](int r, int g, float (*acc)[8]) {
     float fy[8], fd[8];
@@ -150,7 +161,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_act_bwd_reduce_kernel(const __n
     for (int j = 0; j < 8; ++j) {
       const float z = fmaf(fy[j], sc[j], sh[j]);
       const float dz = fd[j] * (act == 1 ? dsilu_f(z) : (act == 2 ? (z > 0.f ? 1.f : 0.f) : 1.f));
-      const float xh = (fy[j] - mu[j]) * is[j];
+      const float xh = fmaf(fy[j], is[j], mu[j]);
       acc[0][j] += dz;
       acc[1][j] = fmaf(dz, xh, acc[1][j]);
     }
@@ -186,8 +197,8 @@ __global__ void __launch_bounds__(BN_THREADS) bn_act_bwd_apply_kernel(const __nv
     for (int j = 0; j < 8; ++j) {
       const float z = fmaf(fy[j], sc[j], sh[j]);
       const float dz = fd[j] * (act == 1 ? dsilu_f(z) : (act == 2 ? (z > 0.f ? 1.f : 0.f) : 1.f));
-      const float xh = (fy[j] - mu[j]) * is[j];
-      fd[j] = sc[j] * (dz - s0[j] * invM - xh * s1[j] * invM);   // sc = gamma*invstd
+      const float xh = fmaf(fy[j], is[j], -mu[j] * is[j]);
+      fd[j] = sc[j] * fmaf(-xh, s1[j] * invM, fmaf(-s0[j], invM, dz));   // sc = gamma*invstd
     }
     store8(dy + r * ocs + g * 8, fd);
   }
