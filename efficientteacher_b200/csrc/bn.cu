@@ -10,6 +10,22 @@
 
 #define BN_THREADS 256
 
+__device__ __forceinline__ void unpack8(const uint4 v, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = __bfloat1622float2(h[j]);
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+struct Vec2 { uint4 a, b; };
+// streaming 16 B load; volatile so the UNROLL loads of a batch are issued back to back before the first use
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ void load8(const __nv_bfloat16* p, float* f) {
   const uint4 v = *reinterpret_cast<const uint4*>(p);
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
@@ -35,8 +51,8 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float* f) {
 // Per-channel reduction of up to two quantities.  Thread t owns channel group g = t % G (G = C/8 divides 256) and
 // pixel lane t / G; rows advance by (256/G)*gridDim.x so g never changes.  Block partials are combined through shared
 // memory, then one atomicAdd per channel per block.
-template <int NQ, typename F>
-__device__ __forceinline__ void channel_reduce(int M, int C, F&& per_row, float* __restrict__ out /*[NQ][C]*/) {
+template <int NQ, int UNROLL, typename D, typename L, typename F>
+__device__ __forceinline__ void channel_reduce(int M, int C, L&& load_row, F&& per_row, float* __restrict__ out /*[NQ][C]*/) {
   __shared__ float sh[NQ][BN_THREADS][8 + 1];
   const int G = C >> 3;
   const int g = threadIdx.x % G, pl = threadIdx.x / G, PL = BN_THREADS / G;
@@ -47,13 +63,14 @@ __device__ __forceinline__ void channel_reduce(int M, int C, F&& per_row, float*
     for (int j = 0; j < 8; ++j) acc[q][j] = 0.f;
   const int step = (int)gridDim.x * PL;
   int r = (int)blockIdx.x * PL + pl;
-  for (; r + 3 * step < M; r += 4 * step) {      // 4 independent rows in flight per thread
-    per_row(r, g, acc);
-    per_row(r + step, g, acc);
-    per_row(r + 2 * step, g, acc);
-    per_row(r + 3 * step, g, acc);
+  for (; r + (UNROLL - 1) * step < M; r += UNROLL * step) {      // UNROLL independent rows in flight per thread
+    D d[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) d[u] = load_row(r + u * step, g);
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) per_row(d[u], acc);
   }
-  for (; r < M; r += step) per_row(r, g, acc);
+  for (; r < M; r += step) per_row(load_row(r, g), acc);
 #pragma unroll
   for (int q = 0; q < NQ; ++q)
 #pragma unroll
@@ -71,9 +88,10 @@ __device__ __forceinline__ void channel_reduce(int M, int C, F&& per_row, float*
 
 // ---- forward statistics: sums[0][c] = sum y, sums[1][c] = sum y^2 ----
 __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const __nv_bfloat16* __restrict__ y, int M, int C, int cs, float* __restrict__ sums) {
-  channel_reduce<2>(M, C, [&](int r, int g, float (*acc)[8]) {
+  channel_reduce<2, 8, uint4>(M, C, [&](int r, int g) { return ldg_stream(y + (size_t)r * cs + g * 8); },
+                              [&](const uint4 v, float (*acc)[8]) {
     float f[8];
-    load8(y + (size_t)r * cs + g * 8, f);
+    unpack8(v, f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) { acc[0][j] += f[j]; acc[1][j] = fmaf(f[j], f[j], acc[1][j]); }
   }, sums);
@@ -119,24 +137,45 @@ __device__ __forceinline__ float dsilu_f(float z) {
 }
 
 // ---- forward apply: a = act(y*scale + shift) ----
+// The grid stride (gridDim.x*256 vectors) is a multiple of G = C/8 (a power of two <= 256), so a thread's channel group
+// never changes: its scale/shift live in registers for the whole kernel and the loop body is 2 independent 16 B loads,
+// 8 FMAs + SiLU, 2 stores.
 __global__ void __launch_bounds__(BN_THREADS) bn_act_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                                                                   const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, long M, int C,
                                                                   int ycs, int ocs, int act) {
   const int G = C >> 3;
   const int lg = 31 - __clz(G);            // G is a power of two (checked on the host): no 64-bit divisions
   const long total = M * G;
-  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-    const long r = e >> lg;
-    const int g = (int)(e & (G - 1));
-    float f[8], sc[8], sh[8];
-    load8(y + r * ycs + g * 8, f);
-    ldf8(scale + g * 8, sc); ldf8(shift + g * 8, sh);
+  const long stride = (long)gridDim.x * blockDim.x;
+  long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = (int)(e & (G - 1));
+  float sc[8], sh[8];
+  ldf8(scale + g * 8, sc); ldf8(shift + g * 8, sh);
+  y += g * 8;
+  out += g * 8;
+  auto body = [&](float* f) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float z = fmaf(f[j], sc[j], sh[j]);
       f[j] = act == 1 ? silu_f(z) : (act == 2 ? fmaxf(z, 0.f) : z);
     }
-    store8(out + r * ocs + g * 8, f);
+  };
+  for (; e + stride < total; e += 2 * stride) {
+    const long r0 = e >> lg, r1 = (e + stride) >> lg;
+    float f0[8], f1[8];
+    load8(y + r0 * ycs, f0);
+    load8(y + r1 * ycs, f1);
+    body(f0);
+    body(f1);
+    store8(out + r0 * ocs, f0);
+    store8(out + r1 * ocs, f1);
+  }
+  if (e < total) {
+    const long r0 = e >> lg;
+    float f0[8];
+    load8(y + r0 * ycs, f0);
+    body(f0);
+    store8(out + r0 * ocs, f0);
   }
 }
 
@@ -153,10 +192,15 @@ __global__ void __launch_bounds__(BN_THREADS) bn_act_bwd_reduce_kernel(const __n
 #pragma unroll
     for (int j = 0; j < 8; ++j) mu[j] = -mu[j] * is[j];     // xhat = y*invstd + (-mean*invstd): one FMA per element
   }
-  channel_reduce<2>(M, C, [&](int r, int g, float (*acc)[8]) {
+  channel_reduce<2, 4, Vec2>(M, C, [&](int r, int g) {
+    Vec2 v;
+    v.a = ldg_stream(y + (size_t)r * ycs + g * 8);
+    v.b = ldg_stream(da + (size_t)r * dacs + g * 8);
+    return v;
+  }, [&](const Vec2 v, float (*acc)[8]) {
     float fy[8], fd[8];
-    load8(y + (size_t)r * ycs + g * 8, fy);
-    load8(da + (size_t)r * dacs + g * 8, fd);
+    unpack8(v.a, fy);
+    unpack8(v.b, fd);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float z = fmaf(fy[j], sc[j], sh[j]);
@@ -169,7 +213,9 @@ __global__ void __launch_bounds__(BN_THREADS) bn_act_bwd_reduce_kernel(const __n
 }
 
 // ---- backward apply: dy = gamma*invstd * (dz - sum_dz/M - xhat*sum_dz_xhat/M); also writes dgamma, dbeta (block 0) ----
-__global__ void __launch_bounds__(BN_THREADS) bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ y,
+// Same fixed-channel-group structure as the forward apply: the six per-channel vectors are folded into five register
+// arrays once per thread.
+__global__ void __launch_bounds__(BN_THREADS, 3) bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ y,
                                                                       const float* __restrict__ scale, const float* __restrict__ shift,
                                                                       const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                       const float* __restrict__ sums, long M, int C, int dacs, int ycs, int ocs,
@@ -185,28 +231,72 @@ __global__ void __launch_bounds__(BN_THREADS) bn_act_bwd_apply_kernel(const __nv
       dgamma[c] = sums[C + c];
     }
   }
-  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-    const long r = e >> lg;
-    const int g = (int)(e & (G - 1));
-    float fy[8], fd[8], sc[8], sh[8], mu[8], is[8], s0[8], s1[8];
-    load8(y + r * ycs + g * 8, fy);
-    load8(da + r * dacs + g * 8, fd);
-    ldf8(scale + g * 8, sc); ldf8(shift + g * 8, sh); ldf8(mean + g * 8, mu); ldf8(invstd + g * 8, is);
-    ldf8(sums + g * 8, s0); ldf8(sums + C + g * 8, s1);
+  const long stride = (long)gridDim.x * blockDim.x;
+  long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = (int)(e & (G - 1));
+  // dy = sc*(dz - k0 - xhat*k1), xhat = y*invstd - mean*invstd  ==>  dy = sc*dz + y*P + Q with
+  // P = -sc*invstd*k1, Q = -sc*(k0 - mean*invstd*k1): four register arrays per thread instead of six
+  float sc[8], sh[8], P[8], Q[8];
+  {
+    float a1[8], mu[8], k0[8], k1[8];
+    ldf8(scale + g * 8, sc); ldf8(shift + g * 8, sh); ldf8(invstd + g * 8, a1); ldf8(mean + g * 8, mu);
+    ldf8(sums + g * 8, k0); ldf8(sums + C + g * 8, k1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float k1m = k1[j] * invM * a1[j];
+      P[j] = -sc[j] * k1m;
+      Q[j] = -sc[j] * fmaf(-mu[j], k1m, k0[j] * invM);
+    }
+  }
+  y += g * 8;
+  da += g * 8;
+  dy += g * 8;
+  auto body = [&](const float* fy, float* fd) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float z = fmaf(fy[j], sc[j], sh[j]);
       const float dz = fd[j] * (act == 1 ? dsilu_f(z) : (act == 2 ? (z > 0.f ? 1.f : 0.f) : 1.f));
-      const float xh = fmaf(fy[j], is[j], -mu[j] * is[j]);
-      fd[j] = sc[j] * fmaf(-xh, s1[j] * invM, fmaf(-s0[j], invM, dz));   // sc = gamma*invstd
+      fd[j] = fmaf(sc[j], dz, fmaf(fy[j], P[j], Q[j]));   // sc = gamma*invstd
     }
-    store8(dy + r * ocs + g * 8, fd);
+  };
+  for (; e + stride < total; e += 2 * stride) {
+    const long r0 = e >> lg, r1 = (e + stride) >> lg;
+    float y0[8], d0[8], y1[8], d1[8];
+    load8(y + r0 * ycs, y0);
+    load8(da + r0 * dacs, d0);
+    load8(y + r1 * ycs, y1);
+    load8(da + r1 * dacs, d1);
+    body(y0, d0);
+    body(y1, d1);
+    store8(dy + r0 * ocs, d0);
+    store8(dy + r1 * ocs, d1);
+  }
+  if (e < total) {
+    const long r0 = e >> lg;
+    float y0[8], d0[8];
+    load8(y + r0 * ycs, y0);
+    load8(da + r0 * dacs, d0);
+    body(y0, d0);
+    store8(dy + r0 * ocs, d0);
   }
 }
 
-static inline unsigned bn_grid(long work_threads) {
+// One full wave: grid = min(needed, SMs x resident blocks of THIS kernel) so a grid-stride loop never runs a partial
+// second wave (the reduce kernels hold 3-5 blocks per SM; a fixed 8-per-SM grid left the last wave 60% empty).
+template <typename K>
+static inline long bn_wave(K kernel) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BN_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+  return (long)etb_num_sms() * per_sm;
+}
+#define BN_WAVE(kernel)                           \
+  ([]() -> long {                                 \
+    static long w = 0;                            \
+    if (!w) w = bn_wave(kernel);                  \
+    return w;                                     \
+  }())
+static inline unsigned bn_grid(long work_threads, long cap) {
   long b = (work_threads + BN_THREADS - 1) / BN_THREADS;
-  const long cap = (long)etb_num_sms() * 8;
   return (unsigned)(b > cap ? cap : (b < 1 ? 1 : b));
 }
 static inline bool bn_c_ok(int C) { return C >= 8 && C % 8 == 0 && (C / 8) <= BN_THREADS && ((C / 8) & (C / 8 - 1)) == 0; }
@@ -218,7 +308,7 @@ extern "C" int etb_bn_stats(const void* y_bf16, int64_t M, int32_t C, int32_t y_
   ETB_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, st));
   const int PL = BN_THREADS / (C / 8);
   long blocks = (M + PL - 1) / PL;
-  const long cap = (long)etb_num_sms() * 8;
+  const long cap = BN_WAVE(bn_stats_kernel);
   if (blocks > cap) blocks = cap;
   bn_stats_kernel<<<(unsigned)blocks, BN_THREADS, 0, st>>>((const __nv_bfloat16*)y_bf16, (int)M, C, y_cstride, sums);
   ETB_CHECK_LAUNCH();
@@ -237,7 +327,7 @@ extern "C" int etb_bn_finalize(const float* sums, int64_t M, int32_t C, const fl
 extern "C" int etb_bn_act_apply(const void* y_bf16, const float* scale, const float* shift, void* out_bf16, int64_t M, int32_t C,
                                 int32_t y_cstride, int32_t out_cstride, int32_t act, void* stream) {
   ETB_CHECK_ARG(y_bf16 && scale && shift && out_bf16 && M > 0 && bn_c_ok(C) && y_cstride % 8 == 0 && out_cstride % 8 == 0);
-  bn_act_apply_kernel<<<bn_grid(M * (C / 8)), BN_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)y_bf16, scale, shift,
+  bn_act_apply_kernel<<<bn_grid(M * (C / 8), BN_WAVE(bn_act_apply_kernel)), BN_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)y_bf16, scale, shift,
                                                                                      (__nv_bfloat16*)out_bf16, (long)M, C, y_cstride, out_cstride, act);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
@@ -253,7 +343,7 @@ extern "C" int etb_bn_act_bwd_reduce(const void* da_bf16, const void* y_bf16, co
   ETB_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, st));
   const int PL = BN_THREADS / (C / 8);
   long blocks = (M + PL - 1) / PL;
-  const long cap = (long)etb_num_sms() * 8;
+  const long cap = BN_WAVE(bn_act_bwd_reduce_kernel);
   if (blocks > cap) blocks = cap;
   bn_act_bwd_reduce_kernel<<<(unsigned)blocks, BN_THREADS, 0, st>>>((const __nv_bfloat16*)da_bf16, (const __nv_bfloat16*)y_bf16, scale, shift, mean,
                                                                    invstd, (int)M, C, da_cstride, y_cstride, act, sums);
@@ -266,7 +356,7 @@ extern "C" int etb_bn_act_bwd_apply(const void* da_bf16, const void* y_bf16, con
                                     int32_t dy_cstride, int32_t act, void* dy_bf16, float* dgamma, float* dbeta, void* stream) {
   ETB_CHECK_ARG(da_bf16 && y_bf16 && scale && shift && mean && invstd && sums && dy_bf16 && dgamma && dbeta && M > 0 && bn_c_ok(C));
   ETB_CHECK_ARG(da_cstride % 8 == 0 && y_cstride % 8 == 0 && dy_cstride % 8 == 0);
-  bn_act_bwd_apply_kernel<<<bn_grid(M * (C / 8)), BN_THREADS, 0, (cudaStream_t)stream>>>(
+  bn_act_bwd_apply_kernel<<<bn_grid(M * (C / 8), BN_WAVE(bn_act_bwd_apply_kernel)), BN_THREADS, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)da_bf16, (const __nv_bfloat16*)y_bf16, scale, shift, mean, invstd, sums, (long)M, C, da_cstride, y_cstride, dy_cstride,
       act, (__nv_bfloat16*)dy_bf16, dgamma, dbeta);
   ETB_CHECK_LAUNCH();
