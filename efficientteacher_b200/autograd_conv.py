@@ -48,6 +48,109 @@ def _nhwc_of(t):
     return v
 
 
+class CatBuf:
+    """A concat buffer [N, Ct, H, W] (channels_last = NHWC in memory).  Producers write their outputs straight into
+    channel slices of `buf` (concat-by-offset, the training-side twin of engine.TrunkEngine's layout) and JoinFn turns
+    the filled buffer into the autograd node the consumer sees -- torch.cat and its backward copies never run.
+    Deliberately NOT a tensor: the Functions below receive it as an opaque argument, so the slice views they return
+    are plain tensors to autograd (no view/in-place bookkeeping; the kernels write through raw pointers)."""
+
+    def __init__(self, N, Ct, H, W, device):
+        self.buf = _empty_cl(N, Ct, H, W, device)
+        self.Ct = Ct
+
+    def slice(self, coff, C_):
+        return self.buf[:, coff:coff + C_]
+
+
+def _slice_nhwc(dest, coff, C_):
+    """(NHWC view of the channel slice, its pixel stride)"""
+    return dest.slice(coff, C_).permute(0, 2, 3, 1), dest.Ct
+
+
+class JoinFn(torch.autograd.Function):
+    """torch.cat(parts, 1) where the parts with copy flag False already live in their slices of dest.buf (written by
+    ConvBnActFn / UpsampleIntoFn); parts with flag True are copied in by one strided-copy kernel.  Backward hands every
+    part its channel slice of the incoming gradient as a view (no copies)."""
+
+    @staticmethod
+    def forward(ctx, dest, copy_flags, *parts):
+        off, splits = 0, []
+        for p, cp in zip(parts, copy_flags):
+            C_ = p.shape[1]
+            if cp:
+                pb, pcs = _as_nhwc(p, C_)
+                N, H, W, _ = pb.shape
+                co.copy_slice(pb, pcs, _slice_nhwc(dest, off, C_)[0], dest.Ct, N * H * W, C_)
+            splits.append(C_)
+            off += C_
+        assert off == dest.Ct
+        ctx.splits = splits
+        return dest.buf
+
+    @staticmethod
+    def backward(ctx, g):
+        outs, off = [], 0
+        for C_ in ctx.splits:
+            outs.append(g[:, off:off + C_])
+            off += C_
+        return (None, None, *outs)
+
+
+class UpsampleIntoFn(torch.autograd.Function):
+    """nn.Upsample(scale_factor=2, 'nearest') (models/neck/yolov5_neck.py:38,46) written into a CatBuf slice; backward =
+    2x2 block sums."""
+
+    @staticmethod
+    def forward(ctx, x, dest, coff):
+        N, C_, H, W = x.shape
+        xb, xcs = _as_nhwc(x, C_)
+        out, _ = _slice_nhwc(dest, coff, C_)
+        _lib.check(_lib.lib().etb_upsample2x_nhwc(_lib.ptr(xb), _lib.ptr(out), N, H, W, C_, xcs, 0, dest.Ct, 0, _lib.stream_ptr()),
+                   "etb_upsample2x_nhwc")
+        ctx.geom = (N, C_, H, W)
+        return dest.slice(coff, C_)
+
+    @staticmethod
+    def backward(ctx, g):
+        N, C_, H, W = ctx.geom
+        gb, gcs = _as_nhwc(g, C_)
+        dx = _empty_cl(N, C_, H, W, g.device)
+        co.upsample2x_bwd(gb, gcs, _nhwc_of(dx), C_)
+        return dx, None, None
+
+
+class SppfPoolFn(torch.autograd.Function):
+    """SPPF's three cascaded MaxPool2d(5,1,2) + concat (models/backbone/common.py:702-708): x already sits in slice 0 of
+    dest.buf (written by cv1); the pools fill slices 1..3 and keep their uint8 argmax; returns the whole buffer.
+    Backward runs the three pool backwards in gather form, each fused with the add of the next slice's gradient."""
+
+    @staticmethod
+    def forward(ctx, x, dest):
+        N, C_, H, W = x.shape
+        assert dest.Ct == 4 * C_
+        idx = torch.empty((3, N, H, W, C_), dtype=torch.uint8, device=x.device)
+        for k in range(3):
+            co.maxpool5_fwd(_slice_nhwc(dest, k * C_, C_)[0], C_, dest.Ct, _slice_nhwc(dest, (k + 1) * C_, C_)[0], dest.Ct, idx[k])
+        ctx.save_for_backward(idx)
+        ctx.geom = (N, C_, H, W)
+        return dest.buf
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        N, C_, H, W = ctx.geom
+        gb, gcs = _as_nhwc(g, 4 * C_)
+        gs = [gb[..., k * C_:(k + 1) * C_] for k in range(4)]
+        t2 = torch.empty((N, H, W, C_), dtype=torch.bfloat16, device=g.device)
+        co.maxpool5_bwd(gs[3], gcs, idx[2], gs[2], gcs, t2, C_, C_)
+        t1 = torch.empty((N, H, W, C_), dtype=torch.bfloat16, device=g.device)
+        co.maxpool5_bwd(t2, C_, idx[1], gs[1], gcs, t1, C_, C_)
+        dx = _empty_cl(N, C_, H, W, g.device)
+        co.maxpool5_bwd(t1, C_, idx[0], gs[0], gcs, _nhwc_of(dx), C_, C_)
+        return dx, None
+
+
 class ConvFn(torch.autograd.Function):
     """y = conv2d(x, w) (no bias, no activation), bf16 channels_last in / out."""
 
@@ -89,9 +192,12 @@ class ConvBnActFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, gamma, beta, running_mean, running_var, stride, pad, eps, momentum, act, is_stem,
-                wp=None, wd=None):
+                wp=None, wd=None, res=None, dest=None, coff=0):
+        """res: optional shortcut tensor added after the activation (Bottleneck, common.py:499); dest/coff: optional
+        CatBuf slice the activation is written into (the returned tensor is then that slice)."""
         Cout = weight.shape[0]
         ctx.wd = wd
+        ctx.has_res = res is not None
         if is_stem:
             xb = co.stem_im2col(x.float(), 1.0)               # [N,H/2,W/2,128]; saved instead of the image
             xcs, Cin, k, st, pd = 128, 128, 1, 1, 0
@@ -108,8 +214,15 @@ class ConvBnActFn(torch.autograd.Function):
             Ho, Wo = (H + 2 * pd - k) // st + 1, (W + 2 * pd - k) // st + 1
         y = torch.empty((N, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.device)
         co.conv_fwd(xb, wp, Cin, Cout, k, st, pd, None, None, None, x_cstride=xcs, out=y)
-        a = _empty_cl(N, Cout, Ho, Wo, x.device)
-        _, stats = co.bn_forward(y, Cout, gamma.detach(), beta.detach(), running_mean, running_var, eps, momentum, act, out=_nhwc_of(a))
+        if dest is None:
+            a = _empty_cl(N, Cout, Ho, Wo, x.device)
+            ab, acs = _nhwc_of(a), Cout
+        else:
+            a = dest.slice(coff, Cout)
+            ab, acs = _slice_nhwc(dest, coff, Cout)
+        rb, rcs = _as_nhwc(res, Cout) if res is not None else (None, None)
+        _, stats = co.bn_forward(y, Cout, gamma.detach(), beta.detach(), running_mean, running_var, eps, momentum, act, out=ab,
+                                 out_cstride=acs, res=rb, res_cstride=rcs)
         ctx.save_for_backward(xb if is_stem else x, weight, y, stats)
         ctx.meta = (stride, pad, act, is_stem)
         return a
@@ -138,7 +251,8 @@ class ConvBnActFn(torch.autograd.Function):
             dw = co.conv_wgrad(xb, dy, Cin, Cout, k, stride, pad, x_cstride=xcs, accumulate_into=tgt)
         if tgt is not None:
             dw = None
-        return dx, dw, dgamma, dbeta, None, None, None, None, None, None, None, None, None, None
+        return (dx, dw, dgamma, dbeta, None, None, None, None, None, None, None, None, None, None,
+                da if ctx.has_res else None, None, None)
 
 
 class StemFn(torch.autograd.Function):

@@ -167,8 +167,11 @@ def conv_wgrad(x, dy, Cin, Cout, k, stride, pad, x_coffset=0, dy_coffset=0, stem
 
 
 # ---- training-mode BatchNorm + activation around the convs (csrc/bn.cu) ----
-def bn_forward(y, C_, gamma, beta, running_mean, running_var, eps, momentum, act, y_cstride=None, out=None):
-    """y [N,H,W,*] bf16 raw conv output -> (a bf16 same geometry, stats [4,C] fp32 = scale, shift, mean, invstd)."""
+def bn_forward(y, C_, gamma, beta, running_mean, running_var, eps, momentum, act, y_cstride=None, out=None, out_cstride=None,
+               res=None, res_cstride=None):
+    """y [N,H,W,*] bf16 raw conv output -> (a bf16 same geometry, stats [4,C] fp32 = scale, shift, mean, invstd).
+    `out` may be a channel slice of a wider NHWC buffer (pass its pixel stride as out_cstride); `res` (same for
+    res_cstride) is added after the activation (Bottleneck shortcut)."""
     N, H, W, cs = y.shape
     if y_cstride is not None:
         cs = y_cstride
@@ -182,8 +185,10 @@ def bn_forward(y, C_, gamma, beta, running_mean, running_var, eps, momentum, act
                                    _lib.ptr(stats[2]), _lib.ptr(stats[3]), _lib.stream_ptr()), "etb_bn_finalize")
     if out is None:
         out = nhwc_empty(N, H, W, C_, y.device)
-    _lib.check(lib.etb_bn_act_apply(_lib.ptr(y), _lib.ptr(stats[0]), _lib.ptr(stats[1]), _lib.ptr(out), M, C_, cs, out.shape[3],
-                                    ACT[act], _lib.stream_ptr()), "etb_bn_act_apply")
+    ocs = out.shape[3] if out_cstride is None else out_cstride
+    _lib.check(lib.etb_bn_act_apply_res(_lib.ptr(y), _lib.ptr(stats[0]), _lib.ptr(stats[1]), None if res is None else _lib.ptr(res),
+                                        _lib.ptr(out), M, C_, cs, 0 if res is None else (res.shape[3] if res_cstride is None else res_cstride),
+                                        ocs, ACT[act], _lib.stream_ptr()), "etb_bn_act_apply_res")
     return out, stats
 
 
@@ -206,3 +211,30 @@ def bn_backward(da, y, C_, stats, act, da_cstride=None, y_cstride=None, out=None
                                         _lib.ptr(stats[3]), _lib.ptr(sums), M, C_, dacs, ycs, out.shape[3], ACT[act], _lib.ptr(out),
                                         _lib.ptr(dgb[0]), _lib.ptr(dgb[1]), _lib.stream_ptr()), "etb_bn_act_bwd_apply")
     return out, dgb[0], dgb[1]
+
+
+def maxpool5_fwd(x, C_, x_cstride, y, y_cstride, idx):
+    """5x5 s1 p2 max pool of the NHWC slice x (pixel stride x_cstride) into the slice y; idx [N,H,W,C] uint8 argmax."""
+    N, H, W, _ = x.shape
+    _lib.check(_lib.lib().etb_maxpool5_fwd(_lib.ptr(x), _lib.ptr(y), _lib.ptr(idx), N, H, W, C_, x_cstride, y_cstride, _lib.stream_ptr()),
+               "etb_maxpool5_fwd")
+
+
+def maxpool5_bwd(src, src_cstride, idx, add, add_cstride, out, out_cstride, C_):
+    """out = add + maxpool5-backward(src) through idx (gather form); add may be None."""
+    N, H, W, _ = src.shape
+    _lib.check(_lib.lib().etb_maxpool5_bwd(_lib.ptr(src), _lib.ptr(idx), None if add is None else _lib.ptr(add), _lib.ptr(out), N, H, W, C_,
+                                           src_cstride, add_cstride if add is not None else 8, out_cstride, _lib.stream_ptr()),
+               "etb_maxpool5_bwd")
+
+
+def upsample2x_bwd(dy, dy_cstride, dx, C_):
+    """dx [N,H,W,C] = 2x2 block sums of dy [N,2H,2W,*]."""
+    N, H, W, _ = dx.shape
+    _lib.check(_lib.lib().etb_upsample2x_bwd(_lib.ptr(dy), _lib.ptr(dx), N, H, W, C_, dy_cstride, dx.shape[3], _lib.stream_ptr()),
+               "etb_upsample2x_bwd")
+
+
+def copy_slice(x, x_cstride, y, y_cstride, M, C_):
+    _lib.check(_lib.lib().etb_copy_slice_nhwc(_lib.ptr(x), _lib.ptr(y), M, C_, x_cstride, y_cstride, _lib.stream_ptr()),
+               "etb_copy_slice_nhwc")

@@ -142,7 +142,7 @@ __device__ __forceinline__ float dsilu_f(float z) {
 // 8 FMAs + SiLU, 2 stores.
 __global__ void __launch_bounds__(BN_THREADS) bn_act_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                                                                   const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, long M, int C,
-                                                                  int ycs, int ocs, int act) {
+                                                                  int ycs, int ocs, int act, const __nv_bfloat16* __restrict__ res, int rcs) {
   const int G = C >> 3;
   const int lg = 31 - __clz(G);            // G is a power of two (checked on the host): no 64-bit divisions
   const long total = M * G;
@@ -153,11 +153,18 @@ __global__ void __launch_bounds__(BN_THREADS) bn_act_apply_kernel(const __nv_bfl
   ldf8(scale + g * 8, sc); ldf8(shift + g * 8, sh);
   y += g * 8;
   out += g * 8;
-  auto body = [&](float* f) {
+  if (res) res += g * 8;
+  auto body = [&](float* f, long r) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float z = fmaf(f[j], sc[j], sh[j]);
       f[j] = act == 1 ? silu_f(z) : (act == 2 ? fmaxf(z, 0.f) : z);
+    }
+    if (res) {      // Bottleneck shortcut (common.py:499): x + cv2(cv1(x)); the sum is rounded once, from fp32
+      float q[8];
+      load8(res + r * rcs, q);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += q[j];
     }
   };
   for (; e + stride < total; e += 2 * stride) {
@@ -165,8 +172,8 @@ __global__ void __launch_bounds__(BN_THREADS) bn_act_apply_kernel(const __nv_bfl
     float f0[8], f1[8];
     load8(y + r0 * ycs, f0);
     load8(y + r1 * ycs, f1);
-    body(f0);
-    body(f1);
+    body(f0, r0);
+    body(f1, r1);
     store8(out + r0 * ocs, f0);
     store8(out + r1 * ocs, f1);
   }
@@ -174,7 +181,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_act_apply_kernel(const __nv_bfl
     const long r0 = e >> lg;
     float f0[8];
     load8(y + r0 * ycs, f0);
-    body(f0);
+    body(f0, r0);
     store8(out + r0 * ocs, f0);
   }
 }
@@ -324,13 +331,20 @@ extern "C" int etb_bn_finalize(const float* sums, int64_t M, int32_t C, const fl
   return ETB_OK;
 }
 
-extern "C" int etb_bn_act_apply(const void* y_bf16, const float* scale, const float* shift, void* out_bf16, int64_t M, int32_t C,
-                                int32_t y_cstride, int32_t out_cstride, int32_t act, void* stream) {
+extern "C" int etb_bn_act_apply_res(const void* y_bf16, const float* scale, const float* shift, const void* res_bf16, void* out_bf16,
+                                    int64_t M, int32_t C, int32_t y_cstride, int32_t res_cstride, int32_t out_cstride, int32_t act,
+                                    void* stream) {
   ETB_CHECK_ARG(y_bf16 && scale && shift && out_bf16 && M > 0 && bn_c_ok(C) && y_cstride % 8 == 0 && out_cstride % 8 == 0);
-  bn_act_apply_kernel<<<bn_grid(M * (C / 8), BN_WAVE(bn_act_apply_kernel)), BN_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)y_bf16, scale, shift,
-                                                                                     (__nv_bfloat16*)out_bf16, (long)M, C, y_cstride, out_cstride, act);
+  ETB_CHECK_ARG(!res_bf16 || (res_cstride % 8 == 0 && res_cstride >= C));
+  bn_act_apply_kernel<<<bn_grid(M * (C / 8), BN_WAVE(bn_act_apply_kernel)), BN_THREADS, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)y_bf16, scale, shift, (__nv_bfloat16*)out_bf16, (long)M, C, y_cstride, out_cstride, act,
+      (const __nv_bfloat16*)res_bf16, res_cstride);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
+}
+extern "C" int etb_bn_act_apply(const void* y_bf16, const float* scale, const float* shift, void* out_bf16, int64_t M, int32_t C,
+                                int32_t y_cstride, int32_t out_cstride, int32_t act, void* stream) {
+  return etb_bn_act_apply_res(y_bf16, scale, shift, nullptr, out_bf16, M, C, y_cstride, 0, out_cstride, act, stream);
 }
 
 // sums: 2*C floats (zeroed here): [sum dz][sum dz*xhat]

@@ -1132,11 +1132,10 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       long dst;
-      if (flags & 1) {                       // stem: [Cout][128 = (kh*6+kw)*3+c] -> [Cout,3,6,6]
+      if (flags & 1) {                       // stem: [Cout][128 slots, k = (c*6+kh)*6+kw] -> [Cout,3,6,6] (same order)
         const int k = ci + j;
         if (k >= 108) continue;
-        const int c = k % 3, tt = k / 3;
-        dst = ((long)co * 3 + c) * 36 + tt;
+        dst = (long)co * 108 + k;
       } else {
         dst = ((long)co * Cin + ci + j) * kk + t;
       }

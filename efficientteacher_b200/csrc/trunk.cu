@@ -12,35 +12,60 @@ static inline unsigned grid_for(int64_t n, int threads) {
   return (unsigned)(b > cap ? cap : (b < 1 ? 1 : b));
 }
 
-// ---- stem im2col: one thread per (pixel, 8-element K group): 16 groups x 8 = 128 K slots (108 used) ----
+// ---- stem im2col (6x6 s2 p2, 3 channels -> K = 128 slots, 108 used) ----
+// K order k = (c*6 + kh)*6 + kw, i.e. exactly the [ci][kh][kw] order of the OIHW weight row, so the weight pack is a copy.
+// One block = 64 consecutive output pixels of one output row: the 18 (c,kh) input row segments (132 floats each) are
+// staged in shared memory with coalesced loads (zero-filled outside the image = the conv padding), then every thread
+// assembles 16 B chunks [pixel][8 k] so a warp writes 512 contiguous bytes.  HBM-bound: 12 B/pixel-channel read
+// (L2 serves the 3x row overlap), 256 B/pixel written.
+#define STEM_TP 64
+#define STEM_PITCH 133
 __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H, int W, float mul) {
+  __shared__ float sm[18 * STEM_PITCH];
   const int Ho = H / 2, Wo = W / 2;
-  const int64_t total = (int64_t)N * Ho * Wo * 16;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int g = (int)(e & 15);
-    const int64_t pix = e >> 4;
-    const int ow = (int)(pix % Wo), oh = (int)((pix / Wo) % Ho), n = (int)(pix / ((int64_t)Wo * Ho));
-    uint4 ov;
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(&ov);
+  const int tiles_w = (Wo + STEM_TP - 1) / STEM_TP;
+  const int tw = blockIdx.x % tiles_w;
+  const int oh = (blockIdx.x / tiles_w) % Ho;
+  const int n = blockIdx.x / (tiles_w * Ho);
+  const int ow0 = tw * STEM_TP;
+  const int iw0 = 2 * ow0 - 2, ih0 = 2 * oh - 2;
+  for (int i = threadIdx.x; i < 18 * 132; i += 256) {
+    const int row = i / 132, col = i - row * 132;
+    const int c = row / 6, kh = row - c * 6;
+    const int ih = ih0 + kh, iw = iw0 + col;
+    float v = 0.f;
+    if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = __fmul_rn(__ldg(x + (((int64_t)n * 3 + c) * H + ih) * W + iw), mul);
+    sm[row * STEM_PITCH + col] = v;
+  }
+  __syncthreads();
+  const int g = threadIdx.x & 15;          // the 8-element K group is fixed per thread
+  int off[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = g * 8 + j;
-      float v = 0.f;
-      if (k < 108) {
-        const int c = k % 3, t = k / 3, kw = t % 6, kh = t / 6;
-        const int ih = oh * 2 + kh - 2, iw = ow * 2 + kw - 2;
-        if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = __fmul_rn(__ldg(x + (((int64_t)n * 3 + c) * H + ih) * W + iw), mul);
-      }
-      o[j] = __float2bfloat16(v);
-    }
-    reinterpret_cast<uint4*>(y)[e] = ov;
+  for (int j = 0; j < 8; ++j) {
+    const int k = g * 8 + j;
+    off[j] = k < 108 ? (k / 6) * STEM_PITCH + (k % 6) : -1;
+  }
+  uint4* yo = reinterpret_cast<uint4*>(y) + (((int64_t)n * Ho + oh) * Wo + ow0) * 16;
+#pragma unroll
+  for (int q = threadIdx.x; q < STEM_TP * 16; q += 256) {
+    const int pp = q >> 4;
+    if (ow0 + pp >= Wo) break;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = off[j] >= 0 ? sm[off[j] + 2 * pp] : 0.f;
+    uint4 ov;
+    __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+    yo[q] = ov;
   }
 }
 
 extern "C" int etb_stem_im2col(const float* x, void* y_bf16, int32_t N, int32_t H, int32_t W, float mul, void* stream) {
   ETB_CHECK_ARG(x && y_bf16 && N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0);
-  const int64_t total = (int64_t)N * (H / 2) * (W / 2) * 16;
-  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y_bf16, N, H, W, mul);
+  const int64_t blocks = (int64_t)N * (H / 2) * ((W / 2 + STEM_TP - 1) / STEM_TP);
+  ETB_CHECK_ARG(blocks < (1ll << 31));
+  stem_im2col_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y_bf16, N, H, W, mul);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }
@@ -180,10 +205,7 @@ __global__ void pack_stem_weight_kernel(const float* __restrict__ w, __nv_bfloat
   if (e >= Cout * 128) return;
   const int k = e & 127, oc = e >> 7;
   float v = 0.f;
-  if (k < 108) {
-    const int c = k % 3, t = k / 3, kw = t % 6, kh = t / 6;
-    v = w[((oc * 3 + c) * 6 + kh) * 6 + kw];
-  }
+  if (k < 108) v = w[oc * 108 + k];          // K order (c,kh,kw) == the OIHW row
   o[e] = __float2bfloat16(v);
 }
 extern "C" int etb_pack_stem_weight(const float* w_oihw, void* w_bf16, int32_t Cout, void* stream) {
@@ -224,10 +246,7 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const EtbPackDesc* __re
     } else {
       const int k = (int)(e & 127), oc = (int)(e >> 7);
       v = 0.f;
-      if (k < 108) {
-        const int c = k % 3, t = k / 3, kw = t % 6, kh = t / 6;
-        v = w[((oc * 3 + c) * 6 + kh) * 6 + kw];
-      }
+      if (k < 108) v = w[oc * 108 + k];
     }
     o[dst] = __float2bfloat16(v);
   }

@@ -55,25 +55,39 @@ class Conv(nn.Module):
 
     NATIVE = True        # training convs on the tcgen05 fwd/dgrad/wgrad kernels (False: torch/cuDNN scaffold)
     FUSED_BN = True      # BatchNorm(train)+SiLU forward/backward on the fused kernels of csrc/bn.cu (False: torch ops)
+    FUSED_GLUE = True    # concat-by-offset / fused shortcut add / native pool+upsample (csrc/glue.cu) instead of torch ops
     is_stem = False
 
-    def forward(self, x):
+    def fused(self, x):
+        """True when this Conv runs as ONE ConvBnActFn (and can therefore write into a CatBuf slice / add a shortcut)."""
+        return Conv.NATIVE and Conv.FUSED_BN and x.is_cuda and self.training and isinstance(self.act, (nn.SiLU, nn.ReLU))
+
+    def glue(self, x):
+        return Conv.FUSED_GLUE and self.fused(x) and self.conv.out_channels % 8 == 0
+
+    def forward(self, x, res=None, dest=None, coff=0):
+        """res: shortcut added after the activation; dest/coff: autograd_conv.CatBuf slice to write the output into
+        (both only on the fused path -- callers check `glue(x)` first)."""
         if Conv.NATIVE and x.is_cuda:
             from .autograd_conv import ConvBnActFn, ConvFn, StemFn
             w = self.conv.weight
-            if Conv.FUSED_BN and self.training and isinstance(self.act, (nn.SiLU, nn.ReLU)):
+            if self.fused(x):
                 bn = self.bn
                 act = "silu" if isinstance(self.act, nn.SiLU) else "relu"
                 pc = getattr(self, "_packed", None)     # operands prepared by Model.pack_weights() (one launch per step)
                 return ConvBnActFn.apply(x, w, bn.weight, bn.bias, bn.running_mean, bn.running_var, self.conv.stride[0],
                                          self.conv.padding[0], bn.eps, bn.momentum, act, self.is_stem,
-                                         None if pc is None else pc.fwd, None if pc is None else pc.dgrad)
+                                         None if pc is None else pc.fwd, None if pc is None else pc.dgrad, res, dest, coff)
+            assert dest is None
             if self.is_stem:
                 y = StemFn.apply(x.float(), w)
             else:
                 y = ConvFn.apply(x, w, self.conv.stride[0], self.conv.padding[0])
-            return self.act(self.bn(y))
-        return self.act(self.bn(self.conv(x)))
+            y = self.act(self.bn(y))
+            return y if res is None else res + y
+        assert dest is None
+        y = self.act(self.bn(self.conv(x)))
+        return y if res is None else res + y
 
 
 class Bottleneck(nn.Module):
@@ -84,7 +98,10 @@ class Bottleneck(nn.Module):
         self.cv2 = Conv(c_, c2, k[1], 1, g=g, act=act)
         self.add = shortcut and c1 == c2
 
-    def forward(self, x):
+    def forward(self, x, dest=None, coff=0):
+        if self.cv2.glue(x):      # shortcut add fused into cv2's BN+SiLU apply; output optionally straight into a concat slice
+            return self.cv2(self.cv1(x), x if self.add else None, dest, coff)
+        assert dest is None
         return x + self.cv2(self.cv1(x)) if self.add else self.cv2(self.cv1(x))
 
 
@@ -98,6 +115,16 @@ class C3(nn.Module):
         self.m = nn.Sequential(*[Bottleneck(c_, c_, shortcut, g, e=1.0, act=act) for _ in range(n)])
 
     def forward(self, x):
+        if self.cv1.glue(x) and self.cv2.glue(x) and len(self.m) > 0:
+            from .autograd_conv import CatBuf, JoinFn
+            c_ = self.cv1.conv.out_channels
+            N, _, H, W = x.shape
+            cb = CatBuf(N, 2 * c_, H, W, x.device)          # [ m(cv1(x)) | cv2(x) ] written in place by their producers
+            a = self.cv1(x)
+            for i, b in enumerate(self.m):
+                a = b(a, cb, 0) if i == len(self.m) - 1 else b(a)
+            b2 = self.cv2(x, None, cb, c_)
+            return self.cv3(JoinFn.apply(cb, (False, False), a, b2))
         return self.cv3(torch.cat((self.m(self.cv1(x)), self.cv2(x)), dim=1))
 
 
@@ -110,6 +137,12 @@ class SPPF(nn.Module):
         self.m = nn.MaxPool2d(kernel_size=k, stride=1, padding=k // 2)
 
     def forward(self, x):
+        if self.cv1.glue(x) and self.m.kernel_size == 5:
+            from .autograd_conv import CatBuf, SppfPoolFn
+            c_ = self.cv1.conv.out_channels
+            N, _, H, W = x.shape
+            cb = CatBuf(N, 4 * c_, H, W, x.device)
+            return self.cv2(SppfPoolFn.apply(self.cv1(x, None, cb, 0), cb))
         x = self.cv1(x)
         y1 = self.m(x)
         y2 = self.m(y1)
@@ -180,9 +213,31 @@ class YoloV5Neck(nn.Module):
         self.C4 = C3(op4 + int(ip5 / 2), op5, d(3), False, 1, 0.5, act)
         self.concat = Concat()
 
+    def _up_cat(self, x, lateral):
+        """cat([upsample2x(x), lateral], 1) by offset: the upsample writes its slice, the lateral is copied into its own."""
+        from .autograd_conv import CatBuf, JoinFn, UpsampleIntoFn
+        N, C_, H, W = x.shape
+        cb = CatBuf(N, C_ + lateral.shape[1], 2 * H, 2 * W, x.device)
+        return JoinFn.apply(cb, (False, True), UpsampleIntoFn.apply(x, cb, 0), lateral)
+
+    def _down_cat(self, conv, x, lateral):
+        """cat([conv(x), lateral], 1): the stride-2 Conv writes its slice in place."""
+        from .autograd_conv import CatBuf, JoinFn
+        N, _, H, W = lateral.shape
+        C_ = conv.conv.out_channels
+        cb = CatBuf(N, C_ + lateral.shape[1], H, W, x.device)
+        return JoinFn.apply(cb, (False, True), conv(x, None, cb, 0), lateral)
+
     def forward(self, inputs):
         P3, P4, P5 = inputs
         xp_1 = self.conv1(P5)
+        if self.conv3.glue(P5) and all(t.shape[1] % 8 == 0 for t in (xp_1, P4, P3)):
+            x1 = self.C1(self._up_cat(xp_1, P4))
+            xp_2 = self.conv2(x1)
+            x2 = self.C2(self._up_cat(xp_2, P3))
+            x3 = self.C3(self._down_cat(self.conv3, x2, xp_2))
+            x4 = self.C4(self._down_cat(self.conv4, x3, xp_1))
+            return x2, x3, x4
         x1 = self.C1(self.concat([self.upsample1(xp_1), P4]))
         xp_2 = self.conv2(x1)
         x2 = self.C2(self.concat([self.upsample2(xp_2), P3]))

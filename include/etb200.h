@@ -247,6 +247,11 @@ int etb_bn_finalize(const float* sums, int64_t M, int32_t C, const float* gamma,
                     float* running_mean, float* running_var, float* scale, float* shift, float* mean, float* invstd, void* stream);
 int etb_bn_act_apply(const void* y_bf16, const float* scale, const float* shift, void* out_bf16, int64_t M, int32_t C,
                      int32_t y_cstride, int32_t out_cstride, int32_t act, void* stream);
+/* same + the Bottleneck shortcut (models/backbone/common.py:499 `x + cv2(cv1(x))`): out = act(y*scale+shift) + res
+ * (res may be NULL; res is NHWC bf16 with its own channel stride) */
+int etb_bn_act_apply_res(const void* y_bf16, const float* scale, const float* shift, const void* res_bf16, void* out_bf16,
+                         int64_t M, int32_t C, int32_t y_cstride, int32_t res_cstride, int32_t out_cstride, int32_t act,
+                         void* stream);
 int etb_bn_act_bwd_reduce(const void* da_bf16, const void* y_bf16, const float* scale, const float* shift, const float* mean,
                           const float* invstd, int64_t M, int32_t C, int32_t da_cstride, int32_t y_cstride, int32_t act,
                           float* sums, void* stream);
@@ -258,7 +263,7 @@ int etb_bn_act_bwd_apply(const void* da_bf16, const void* y_bf16, const float* s
 
 /* input prep + stem im2col (trainer/ssod_trainer.py:694-696 `.float()/255` fused with the 6x6 s2 p2 stem patch
  * gather of models/backbone/yolov5_backbone.py:56): x [N,3,H,W] fp32 NCHW -> y [N,H/2,W/2,128] bf16 with
- * K index (kh*6+kw)*3+c for K<108 and zeros above; `mul` scales the pixels (1/255 for uint8-range input, else 1). */
+ * K index (c*6+kh)*6+kw (the OIHW weight row order) for K<108 and zeros above; `mul` scales the pixels (1/255 for uint8-range input, else 1). */
 int etb_stem_im2col(const float* x, void* y_bf16, int32_t N, int32_t H, int32_t W, float mul, void* stream);
 /* NCHW fp32 <-> NHWC bf16 (channel stride / offset on the NHWC side) */
 int etb_nchw_f32_to_nhwc_bf16(const float* x, void* y, int32_t N, int32_t C, int32_t H, int32_t W,
@@ -271,6 +276,22 @@ int etb_sppf_pool(void* buf_bf16, int32_t N, int32_t H, int32_t W, int32_t C, in
 /* nn.Upsample(scale_factor=2, nearest) written into a channel slice of the concat buffer (yolov5_neck.py:92,97) */
 int etb_upsample2x_nhwc(const void* x_bf16, void* y_bf16, int32_t N, int32_t H, int32_t W, int32_t C,
                         int32_t x_cstride, int32_t x_coffset, int32_t y_cstride, int32_t y_coffset, void* stream);
+
+/* training-side glue between the student's convolutions (forward AND backward), all on channel slices of NHWC bf16
+ * buffers so torch.cat / nn.MaxPool2d / nn.Upsample and their autograd kernels drop out of the step:
+ *   etb_maxpool5_fwd : y = maxpool 5x5 s1 p2 (x), idx[N,H,W,C] u8 = argmax position (dy+2)*5+(dx+2), first max wins
+ *                      (SPPF, models/backbone/common.py:702-708)
+ *   etb_maxpool5_bwd : out = add + scatter of src through idx, in gather form (add may be NULL)
+ *   etb_upsample2x_bwd: dx[n,h,w,:] = sum of the 2x2 block of dy (models/neck/yolov5_neck.py:38,46 backward)
+ *   etb_copy_slice_nhwc: y[m,0:C] = x[m,0:C] (torch.cat of a tensor that was not produced in place) */
+int etb_maxpool5_fwd(const void* x_bf16, void* y_bf16, uint8_t* idx, int32_t N, int32_t H, int32_t W, int32_t C,
+                     int32_t x_cstride, int32_t y_cstride, void* stream);
+int etb_maxpool5_bwd(const void* src_bf16, const uint8_t* idx, const void* add_bf16, void* out_bf16, int32_t N, int32_t H,
+                     int32_t W, int32_t C, int32_t src_cstride, int32_t add_cstride, int32_t out_cstride, void* stream);
+int etb_upsample2x_bwd(const void* dy_bf16, void* dx_bf16, int32_t N, int32_t H, int32_t W, int32_t C, int32_t dy_cstride,
+                       int32_t dx_cstride, void* stream);
+int etb_copy_slice_nhwc(const void* x_bf16, void* y_bf16, int64_t M, int32_t C, int32_t x_cstride, int32_t y_cstride,
+                        void* stream);
 /* eval-mode BatchNorm folded to per-channel scale/bias: scale = g/sqrt(var+eps), bias = b - mean*scale */
 int etb_fold_bn(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
                 float* scale, float* bias, int32_t C, void* stream);

@@ -214,3 +214,120 @@ def test_conv_wgrad_accumulates_into_existing_grad(case):
     ref = base + torch.nn.grad.conv2d_weight(_bf(x), (Cout, Cin, k, k), _bf(dy), stride=s, padding=p)
     err = (g - ref).abs().max().item()
     assert err <= 2e-3 * max(ref.abs().max().item(), 1.0), err
+
+
+# ---------------------------------------------------------------- training-side glue (csrc/glue.cu)
+def _cl(t):
+    return t.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+
+
+def test_maxpool5_fwd_bwd_vs_torch():
+    from efficientteacher_b200 import convops as co
+    N, C_, H, W = 2, 64, 20, 20
+    x = _cl(_rand((N, C_, H, W), 11))
+    xb = x.permute(0, 2, 3, 1)
+    y = torch.empty((N, H, W, C_), dtype=torch.bfloat16, device=DEV)
+    idx = torch.empty((N, H, W, C_), dtype=torch.uint8, device=DEV)
+    co.maxpool5_fwd(xb, C_, C_, y, C_, idx)
+    xr = x.float().requires_grad_(True)
+    yr = F.max_pool2d(xr, 5, 1, 2)
+    assert torch.equal(y.permute(0, 3, 1, 2).float(), yr.detach())          # max of bf16 values is exact
+    g = _cl(_rand((N, C_, H, W), 12))
+    add = _cl(_rand((N, C_, H, W), 13))
+    yr.backward(g.float())
+    out = torch.empty((N, H, W, C_), dtype=torch.bfloat16, device=DEV)
+    co.maxpool5_bwd(g.permute(0, 2, 3, 1), C_, idx, add.permute(0, 2, 3, 1), C_, out, C_, C_)
+    want = xr.grad + add.float()
+    # ties inside a window (bf16 has few distinct values) are routed to the first maximum by both implementations
+    _check(out.permute(0, 3, 1, 2).float(), want, tol=1e-2)
+    out2 = torch.empty_like(out)
+    co.maxpool5_bwd(g.permute(0, 2, 3, 1), C_, idx, None, C_, out2, C_, C_)
+    _check(out2.permute(0, 3, 1, 2).float(), xr.grad, tol=1e-2)
+
+
+def test_upsample_bwd_and_slice_copy():
+    from efficientteacher_b200 import convops as co
+    N, C_, H, W = 2, 64, 10, 12
+    big = _cl(_rand((N, 2 * C_, 2 * H, 2 * W), 21))                       # dy lives in a channel slice of a wider gradient
+    gb = big.permute(0, 2, 3, 1)[..., C_:]
+    dx = torch.empty((N, H, W, C_), dtype=torch.bfloat16, device=DEV)
+    co.upsample2x_bwd(gb, 2 * C_, dx, C_)
+    want = F.avg_pool2d(big[:, C_:].float(), 2) * 4.0
+    _check(dx.permute(0, 3, 1, 2).float(), want, tol=1e-2)
+    dst = torch.zeros((N, 2 * H, 2 * W, 3 * C_), dtype=torch.bfloat16, device=DEV)
+    co.copy_slice(gb, 2 * C_, dst[..., C_:2 * C_], 3 * C_, N * 4 * H * W, C_)
+    assert torch.equal(dst[..., C_:2 * C_], gb) and float(dst[..., :C_].abs().max()) == 0 and float(dst[..., 2 * C_:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("n,shortcut", [(2, True), (1, False)])
+def test_c3_concat_by_offset_matches_torch_glue(n, shortcut):
+    """C3 with the fused glue (outputs written into concat slices, shortcut add inside the BN apply) against the same
+    native convs glued by torch.cat / torch add: outputs and every gradient must agree to bf16 rounding."""
+    from efficientteacher_b200.model import C3, Conv
+    torch.manual_seed(3)
+    m = C3(128, 128, n, shortcut, 1, 0.5, "silu").to(DEV).train()
+    x0 = _cl(_rand((2, 128, 20, 20), 31))
+    res = {}
+    for glue in (True, False):
+        Conv.FUSED_GLUE = glue
+        try:
+            m.zero_grad(set_to_none=True)
+            for mod in m.modules():
+                if isinstance(mod, torch.nn.BatchNorm2d):
+                    mod.reset_running_stats()
+            x = x0.clone().requires_grad_(True)
+            y = m(x)
+            (y.float() * torch.linspace(-1, 1, y.numel(), device=DEV).reshape(y.shape)).sum().backward()
+            res[glue] = (y.detach().float(), x.grad.float(), {k: p.grad.float().clone() for k, p in m.named_parameters()})
+        finally:
+            Conv.FUSED_GLUE = True
+    ya, xa, pa = res[True]
+    yb, xb_, pb = res[False]
+    _check(ya, yb, tol=2e-2)
+    cos = lambda a, b: float((a * b).sum() / (a.norm() * b.norm() + 1e-12))  # noqa: E731
+    assert cos(xa, xb_) > 0.999, cos(xa, xb_)
+    for k in pa:
+        assert cos(pa[k], pb[k]) > 0.995, (k, cos(pa[k], pb[k]))
+
+
+def test_sppf_and_neck_fused_glue_match_torch_glue():
+    """SPPF + neck with the fused glue vs the same native convs glued by torch ops.  Yardstick: the torch-glue path run
+    twice -- the BN statistics are summed with atomics, so two runs of the SAME path already differ by flipped bf16
+    roundings that compound over the neck's ~15 BN layers; the fused path must sit within 3x of that noise."""
+    from efficientteacher_b200.model import SPPF, Conv, YoloV5Neck
+    from efficientteacher_b200.config import yolov5_ssod_cfg
+    torch.manual_seed(5)
+    cos = lambda a, b: float((a * b).sum() / (a.norm() * b.norm() + 1e-12))  # noqa: E731
+    rel = lambda a, b: float((a - b).norm() / (b.norm() + 1e-12))  # noqa: E731
+    sp = SPPF(256, 256, 5, "silu").to(DEV).train()
+    neck = YoloV5Neck(yolov5_ssod_cfg("l_shallow")).to(DEV).train()
+    x0 = _cl(_rand((2, 256, 10, 10), 41))
+    feats0 = [_cl(_rand((4, 256, 32, 32), 42)), _cl(_rand((4, 512, 16, 16), 43)), _cl(_rand((4, 1024, 8, 8), 44))]
+    res = []
+    for glue in (True, False, False):
+        Conv.FUSED_GLUE = glue
+        try:
+            for mod in (sp, neck):
+                mod.zero_grad(set_to_none=True)
+            x = x0.clone().requires_grad_(True)
+            y = sp(x)
+            (y.float() * torch.linspace(-1, 1, y.numel(), device=DEV).reshape(y.shape)).sum().backward()
+            feats = [f.clone().requires_grad_(True) for f in feats0]
+            outs = neck(feats)
+            sum((o.float() * torch.linspace(-1, 1, o.numel(), device=DEV).reshape(o.shape)).sum() for o in outs).backward()
+            res.append(([y.detach().float()] + [o.detach().float() for o in outs], [x.grad.float()] + [f.grad.float() for f in feats],
+                        {("sp." if mod is sp else "neck.") + k: p.grad.float().clone() for mod in (sp, neck) for k, p in mod.named_parameters()}))
+        finally:
+            Conv.FUSED_GLUE = True
+    fused, t1, t2 = res
+    # SPPF forward has a single BN before the pools: tight
+    _check(fused[0][0], t1[0][0], tol=2e-2)
+    for i in range(len(fused[0])):
+        noise = rel(t2[0][i], t1[0][i])
+        assert rel(fused[0][i], t1[0][i]) <= max(3 * noise, 4e-3), (i, rel(fused[0][i], t1[0][i]), noise)
+    for i in range(len(fused[1])):
+        noise = 1 - cos(t2[1][i], t1[1][i])
+        assert 1 - cos(fused[1][i], t1[1][i]) <= max(3 * noise, 2e-3), (i, cos(fused[1][i], t1[1][i]), noise)
+    for k in fused[2]:
+        noise = 1 - cos(t2[2][k], t1[2][k])
+        assert 1 - cos(fused[2][k], t1[2][k]) <= max(3 * noise, 1e-2), (k, cos(fused[2][k], t1[2][k]), noise)
