@@ -146,6 +146,30 @@ def dominant_kernel_roofline(dev, peak_tflops, peak_kind):
             "peak_kind": peak_kind, "flops_per_launch": flops, "us_per_launch": ms * 1e3, "launches_timed": n}
 
 
+def kernel_table(step, ni, path, graph_ms):
+    """Per-kernel GPU time of 2 eager steps from CUPTI activity records (torch.profiler): low overhead, kernels not
+    serialised -- the shares are what the step really spends (unlike an ncu launch list)."""
+    from torch.profiler import ProfilerActivity, profile
+    nsteps = 2
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for i in range(nsteps):
+            step(ni + i)
+        torch.cuda.synchronize()
+    rows = {}
+    for ev in prof.events():
+        if ev.device_type is not None and "cuda" in str(ev.device_type).lower():
+            r = rows.setdefault(ev.name, [0, 0.0])
+            r[0] += 1
+            r[1] += ev.device_time_total if hasattr(ev, "device_time_total") else ev.cuda_time_total
+    tot = sum(v[1] for v in rows.values())
+    with open(path, "w") as f:
+        f.write("# per-kernel device time, eager step (CUPTI via torch.profiler), mean of %d steps; graph replay of the step: %.2f ms\n" % (nsteps, graph_ms))
+        f.write("# kernels/step %d, sum of kernel time/step %.2f ms\n" % (sum(v[0] for v in rows.values()) / nsteps, tot / nsteps / 1e3))
+        f.write("| kernel | launches/step | us/step | share |\n|---|---:|---:|---:|\n")
+        for name, (cnt, us) in sorted(rows.items(), key=lambda kv: -kv[1][1])[:60]:
+            f.write("| `%s` | %.1f | %.1f | %.1f%% |\n" % (name[:110], cnt / nsteps, us / nsteps, 100.0 * us / tot))
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU path of the step (oracle restatement; /root/reference cannot travel to the
     GPU box).  Rank 0 only.  Each step = one full SSOD step on a bounded sample (2 labeled + 2 unlabeled images)."""
@@ -218,6 +242,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end leg")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of replaying the captured CUDA graph of the step")
+    ap.add_argument("--kernel-table", default="", help="dev: write a per-kernel time table (torch.profiler/CUPTI, 2 eager steps) to this file")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -345,6 +370,9 @@ def main():
             step_e2e(ni); ni += 1
         ms_e2e = timed(step_e2e, args.steps, ni); ni += args.steps
     clocks = sampler.summary() if sampler else None
+    if args.kernel_table and rank == 0:
+        kernel_table(lambda i: st.train_instance(d_imgs, d_tg, d_us, d_uw, None, d_Ms, i), ni, args.kernel_table, ms / args.steps)
+        ni += 2
     n_pl = int(st.pseudo_label_creator.last_count_dev.item())
     det_per_img = float(st.pseudo_label_creator.last_det[1].float().mean().item())
 

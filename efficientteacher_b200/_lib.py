@@ -103,17 +103,19 @@ _SIGS = {
     "etb_conv_dgrad": (C.c_int, [vp, vp, vp, C.POINTER(EtbConvParams), C.c_int32, vp]),
     "etb_conv_wgrad_workspace_bytes": (C.c_size_t, [C.POINTER(EtbConvParams)]),
     "etb_conv_wgrad": (C.c_int, [vp, vp, vp, C.POINTER(EtbConvParams), C.c_int32, vp, C.c_size_t, vp]),
-    "etb_bn_stats": (C.c_int, [vp, C.c_int64, C.c_int32, C.c_int32, vp, vp]),
-    "etb_bn_finalize": (C.c_int, [vp, C.c_int64, C.c_int32, vp, vp, C.c_float, C.c_float, vp, vp, vp, vp, vp, vp, vp]),
+    "etb_bn_partial_rows": (C.c_int32, [C.c_int64, C.c_int32, C.c_int32]),
+    "etb_bn_stats": (C.c_int, [vp, C.c_int64, C.c_int32, C.c_int32, vp, C.c_int32, vp]),
+    "etb_bn_finalize": (C.c_int, [vp, C.c_int32, C.c_int64, C.c_int32, vp, vp, C.c_float, C.c_float, vp, vp, vp, vp, vp, vp, vp]),
     "etb_bn_act_apply": (C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
     "etb_bn_act_apply_res": (C.c_int, [vp, vp, vp, vp, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
     "etb_maxpool5_fwd": (C.c_int, [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
     "etb_maxpool5_bwd": (C.c_int, [vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
     "etb_upsample2x_bwd": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
     "etb_copy_slice_nhwc": (C.c_int, [vp, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, vp]),
-    "etb_bn_act_bwd_reduce": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp]),
+    "etb_bn_act_bwd_reduce": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int32, vp]),
+    "etb_bn_act_bwd_finalize": (C.c_int, [vp, C.c_int32, C.c_int32, vp, vp, vp, C.c_int32, vp]),
     "etb_bn_act_bwd_apply": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                                       vp, vp, vp, vp]),
+                                       vp, vp]),
     "etb_stem_im2col": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, vp]),
     "etb_nchw_f32_to_nhwc_bf16": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                             C.c_float, vp]),

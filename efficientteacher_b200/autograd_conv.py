@@ -225,6 +225,7 @@ class ConvBnActFn(torch.autograd.Function):
                                  out_cstride=acs, res=rb, res_cstride=rcs)
         ctx.save_for_backward(xb if is_stem else x, weight, y, stats)
         ctx.meta = (stride, pad, act, is_stem)
+        ctx.bn_params = (gamma, beta)        # for their .grad (gradient arena): dgamma / dbeta are accumulated in place
         return a
 
     @staticmethod
@@ -233,7 +234,12 @@ class ConvBnActFn(torch.autograd.Function):
         stride, pad, act, is_stem = ctx.meta
         Cout = weight.shape[0]
         dab, dacs = _as_nhwc(da, Cout)
-        dy, dgamma, dbeta = co.bn_backward(dab, y, Cout, stats, act, da_cstride=dacs)
+        gamma, beta = ctx.bn_params
+        gg, gb = gamma.grad, beta.grad
+        arena = (ACCUMULATE_INTO_GRAD and gg is not None and gb is not None and gg.dtype == torch.float32 and gb.dtype == torch.float32
+                 and gg.is_contiguous() and gb.is_contiguous())
+        dy, dgamma, dbeta = co.bn_backward(dab, y, Cout, stats, act, da_cstride=dacs, dgamma_into=gg if arena else None,
+                                           dbeta_into=gb if arena else None)
         dx = dw = None
         # gradient arena: when p.grad already exists (trainer.GradArena) the wgrad is added into it in place and autograd
         # gets None for the weight (no separate AccumulateGrad add pass, no temporary)

@@ -177,10 +177,11 @@ def bn_forward(y, C_, gamma, beta, running_mean, running_var, eps, momentum, act
         cs = y_cstride
     M = N * H * W
     lib = _lib.lib()
-    sums = torch.empty(2 * C_, dtype=torch.float32, device=y.device)
-    _lib.check(lib.etb_bn_stats(_lib.ptr(y), M, C_, cs, _lib.ptr(sums), _lib.stream_ptr()), "etb_bn_stats")
+    rows = int(lib.etb_bn_partial_rows(M, C_, 0))
+    partials = torch.empty((rows, 2, C_), dtype=torch.float32, device=y.device)
+    _lib.check(lib.etb_bn_stats(_lib.ptr(y), M, C_, cs, _lib.ptr(partials), rows, _lib.stream_ptr()), "etb_bn_stats")
     stats = torch.empty((4, C_), dtype=torch.float32, device=y.device)
-    _lib.check(lib.etb_bn_finalize(_lib.ptr(sums), M, C_, _lib.ptr(gamma), _lib.ptr(beta), float(eps), float(momentum),
+    _lib.check(lib.etb_bn_finalize(_lib.ptr(partials), rows, M, C_, _lib.ptr(gamma), _lib.ptr(beta), float(eps), float(momentum),
                                    _lib.ptr(running_mean), _lib.ptr(running_var), _lib.ptr(stats[0]), _lib.ptr(stats[1]),
                                    _lib.ptr(stats[2]), _lib.ptr(stats[3]), _lib.stream_ptr()), "etb_bn_finalize")
     if out is None:
@@ -192,25 +193,33 @@ def bn_forward(y, C_, gamma, beta, running_mean, running_var, eps, momentum, act
     return out, stats
 
 
-def bn_backward(da, y, C_, stats, act, da_cstride=None, y_cstride=None, out=None):
-    """da, y [N,H,W,*] bf16 -> (dy_raw bf16 [N,H,W,C], dgamma [C], dbeta [C])."""
+def bn_backward(da, y, C_, stats, act, da_cstride=None, y_cstride=None, out=None, dgamma_into=None, dbeta_into=None):
+    """da, y [N,H,W,*] bf16 -> (dy_raw bf16 [N,H,W,C], dgamma [C], dbeta [C]).  With dgamma_into / dbeta_into (the
+    parameters' fp32 .grad in the gradient arena) the two sums are ADDED in place by the finalize kernel and
+    (dy, None, None) is returned -- no AccumulateGrad add kernels."""
     N, H, W, ycs = y.shape
     if y_cstride is not None:
         ycs = y_cstride
     dacs = da.shape[3] if da_cstride is None else da_cstride
     M = N * H * W
     lib = _lib.lib()
-    sums = torch.empty(2 * C_, dtype=torch.float32, device=y.device)
+    rows = int(lib.etb_bn_partial_rows(M, C_, 1))
+    partials = torch.empty((rows, 2, C_), dtype=torch.float32, device=y.device)
     _lib.check(lib.etb_bn_act_bwd_reduce(_lib.ptr(da), _lib.ptr(y), _lib.ptr(stats[0]), _lib.ptr(stats[1]), _lib.ptr(stats[2]),
-                                         _lib.ptr(stats[3]), M, C_, dacs, ycs, ACT[act], _lib.ptr(sums), _lib.stream_ptr()),
+                                         _lib.ptr(stats[3]), M, C_, dacs, ycs, ACT[act], _lib.ptr(partials), rows, _lib.stream_ptr()),
                "etb_bn_act_bwd_reduce")
+    sums = torch.empty(2 * C_, dtype=torch.float32, device=y.device)
+    acc = dgamma_into is not None and dbeta_into is not None
+    dgb = None if acc else torch.empty((2, C_), dtype=torch.float32, device=y.device)
+    _lib.check(lib.etb_bn_act_bwd_finalize(_lib.ptr(partials), rows, C_, _lib.ptr(sums), _lib.ptr(dgamma_into if acc else dgb[0]),
+                                           _lib.ptr(dbeta_into if acc else dgb[1]), 1 if acc else 0, _lib.stream_ptr()),
+               "etb_bn_act_bwd_finalize")
     if out is None:
         out = nhwc_empty(N, H, W, C_, y.device)
-    dgb = torch.empty((2, C_), dtype=torch.float32, device=y.device)
     _lib.check(lib.etb_bn_act_bwd_apply(_lib.ptr(da), _lib.ptr(y), _lib.ptr(stats[0]), _lib.ptr(stats[1]), _lib.ptr(stats[2]),
                                         _lib.ptr(stats[3]), _lib.ptr(sums), M, C_, dacs, ycs, out.shape[3], ACT[act], _lib.ptr(out),
-                                        _lib.ptr(dgb[0]), _lib.ptr(dgb[1]), _lib.stream_ptr()), "etb_bn_act_bwd_apply")
-    return out, dgb[0], dgb[1]
+                                        _lib.stream_ptr()), "etb_bn_act_bwd_apply")
+    return (out, None, None) if acc else (out, dgb[0], dgb[1])
 
 
 def maxpool5_fwd(x, C_, x_cstride, y, y_cstride, idx):

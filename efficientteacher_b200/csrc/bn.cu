@@ -50,7 +50,8 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float* f) {
 
 // Per-channel reduction of up to two quantities.  Thread t owns channel group g = t % G (G = C/8 divides 256) and
 // pixel lane t / G; rows advance by (256/G)*gridDim.x so g never changes.  Block partials are combined through shared
-// memory, then one atomicAdd per channel per block.
+// memory and written to out[blockIdx.x][NQ][C]: no atomics, no memset, and the second stage (reduce_partials) sums the
+// rows in a fixed order, so the statistics are bit-reproducible run to run.
 template <int NQ, int UNROLL, typename D, typename L, typename F>
 __device__ __forceinline__ void channel_reduce(int M, int C, L&& load_row, F&& per_row, float* __restrict__ out /*[NQ][C]*/) {
   __shared__ float sh[NQ][BN_THREADS][8 + 1];
@@ -82,7 +83,49 @@ __device__ __forceinline__ void channel_reduce(int M, int C, L&& load_row, F&& p
     const int cg = c >> 3, cj = c & 7;
     float s = 0.f;
     for (int p = 0; p < PL; ++p) s += sh[q][p * G + cg][cj];
-    atomicAdd(out + (size_t)q * C + c, s);
+    out[(size_t)blockIdx.x * NQ * C + idx] = s;
+  }
+}
+
+// Second stage: block (32 channels x 32 row groups); v[q] = sum over the nb partial rows of channel c, fixed order.
+// Returns the totals to the threads with threadIdx.y == 0.
+// CH x GR = 1024 threads: 32 x 32 for wide layers, 8 x 128 for C <= 256 (more blocks, shorter serial chains).
+template <int BNR_CH, int BNR_GR>
+__device__ __forceinline__ void reduce_partials(const float* __restrict__ partials, int nb, int C, int c, float* v0, float* v1) {
+  __shared__ float red[2][BNR_GR][BNR_CH + 1];
+  float a0 = 0.f, a1 = 0.f;
+  if (c < C) {
+    int b = threadIdx.y;
+    for (; b + 3 * BNR_GR < nb; b += 4 * BNR_GR) {
+      const float* p = partials + (size_t)b * 2 * C + c;
+      const size_t st = (size_t)BNR_GR * 2 * C;
+      const float x0 = __ldg(p), x1 = __ldg(p + st), x2 = __ldg(p + 2 * st), x3 = __ldg(p + 3 * st);
+      const float y0 = __ldg(p + C), y1 = __ldg(p + st + C), y2 = __ldg(p + 2 * st + C), y3 = __ldg(p + 3 * st + C);
+      a0 += (x0 + x1) + (x2 + x3);
+      a1 += (y0 + y1) + (y2 + y3);
+    }
+    for (; b < nb; b += BNR_GR) {
+      a0 += __ldg(partials + (size_t)b * 2 * C + c);
+      a1 += __ldg(partials + (size_t)b * 2 * C + C + c);
+    }
+  }
+  red[0][threadIdx.y][threadIdx.x] = a0;
+  red[1][threadIdx.y][threadIdx.x] = a1;
+  __syncthreads();
+#pragma unroll
+  for (int s = BNR_GR / 2; s >= 8; s >>= 1) {     // fixed-shape tree: deterministic
+    if ((int)threadIdx.y < s) {
+      red[0][threadIdx.y][threadIdx.x] += red[0][threadIdx.y + s][threadIdx.x];
+      red[1][threadIdx.y][threadIdx.x] += red[1][threadIdx.y + s][threadIdx.x];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.y == 0) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) { s0 += red[0][g][threadIdx.x]; s1 += red[1][g][threadIdx.x]; }
+    *v0 = s0;
+    *v1 = s1;
   }
 }
 
@@ -98,14 +141,20 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const __nv_bfloat1
 }
 
 // ---- finalize: batch mean / biased var -> scale, shift; running stats with the unbiased variance (torch semantics) ----
-__global__ void bn_finalize_kernel(const float* __restrict__ sums, int M, int C, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   float eps, float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
-                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out, float* __restrict__ invstd_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+template <int BNR_CH, int BNR_GR>
+__global__ void __launch_bounds__(BNR_CH * BNR_GR) bn_finalize_kernel(const float* __restrict__ partials, int nb, int M, int C,
+                                                                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                                       float momentum, float* __restrict__ running_mean,
+                                                                       float* __restrict__ running_var, float* __restrict__ scale,
+                                                                       float* __restrict__ shift, float* __restrict__ mean_out,
+                                                                       float* __restrict__ invstd_out) {
+  const int c = blockIdx.x * BNR_CH + threadIdx.x;
+  float sum = 0.f, sumsq = 0.f;
+  reduce_partials<BNR_CH, BNR_GR>(partials, nb, C, c, &sum, &sumsq);
+  if (c >= C || threadIdx.y != 0) return;
   const float inv = 1.0f / (float)M;
-  const float mean = sums[c] * inv;
-  float var = fmaf(-mean, mean, sums[C + c] * inv);
+  const float mean = sum * inv;
+  float var = fmaf(-mean, mean, sumsq * inv);
   var = fmaxf(var, 0.0f);
   const float invstd = rsqrtf(var + eps);
   const float sc = gamma[c] * invstd;
@@ -219,25 +268,37 @@ __global__ void __launch_bounds__(BN_THREADS) bn_act_bwd_reduce_kernel(const __n
   }, sums);
 }
 
-// ---- backward apply: dy = gamma*invstd * (dz - sum_dz/M - xhat*sum_dz_xhat/M); also writes dgamma, dbeta (block 0) ----
+// ---- backward finalize: sums[2C] = totals of the partial rows; dbeta / dgamma written or accumulated (gradient arena) ----
+template <int BNR_CH, int BNR_GR>
+__global__ void __launch_bounds__(BNR_CH * BNR_GR) bn_bwd_finalize_kernel(const float* __restrict__ partials, int nb, int C, float* __restrict__ sums,
+                                                                           float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
+  const int c = blockIdx.x * BNR_CH + threadIdx.x;
+  float s0 = 0.f, s1 = 0.f;
+  reduce_partials<BNR_CH, BNR_GR>(partials, nb, C, c, &s0, &s1);
+  if (c >= C || threadIdx.y != 0) return;
+  sums[c] = s0;
+  sums[C + c] = s1;
+  if (accumulate) {
+    dbeta[c] += s0;
+    dgamma[c] += s1;
+  } else {
+    dbeta[c] = s0;
+    dgamma[c] = s1;
+  }
+}
+
+// ---- backward apply: dy = gamma*invstd * (dz - sum_dz/M - xhat*sum_dz_xhat/M) ----
 // Same fixed-channel-group structure as the forward apply: the six per-channel vectors are folded into five register
 // arrays once per thread.
 __global__ void __launch_bounds__(BN_THREADS, 3) bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ y,
                                                                       const float* __restrict__ scale, const float* __restrict__ shift,
                                                                       const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                       const float* __restrict__ sums, long M, int C, int dacs, int ycs, int ocs,
-                                                                      int act, __nv_bfloat16* __restrict__ dy, float* __restrict__ dgamma,
-                                                                      float* __restrict__ dbeta) {
+                                                                      int act, __nv_bfloat16* __restrict__ dy) {
   const int G = C >> 3;
   const int lg = 31 - __clz(G);
   const long total = M * G;
   const float invM = 1.0f / (float)M;
-  if (blockIdx.x == 0) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      dbeta[c] = sums[c];
-      dgamma[c] = sums[C + c];
-    }
-  }
   const long stride = (long)gridDim.x * blockDim.x;
   long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int g = (int)(e & (G - 1));
@@ -308,25 +369,41 @@ static inline unsigned bn_grid(long work_threads, long cap) {
 }
 static inline bool bn_c_ok(int C) { return C >= 8 && C % 8 == 0 && (C / 8) <= BN_THREADS && ((C / 8) & (C / 8 - 1)) == 0; }
 
-// sums must hold 2*C floats (zeroed here).  y [M][y_cstride] bf16.
-extern "C" int etb_bn_stats(const void* y_bf16, int64_t M, int32_t C, int32_t y_cstride, float* sums, void* stream) {
-  ETB_CHECK_ARG(y_bf16 && sums && M > 0 && M < (1ll << 31) && bn_c_ok(C) && y_cstride % 8 == 0 && y_cstride >= C);
-  cudaStream_t st = (cudaStream_t)stream;
-  ETB_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, st));
+static inline long bn_reduce_blocks(long M, int C, long wave) {
   const int PL = BN_THREADS / (C / 8);
   long blocks = (M + PL - 1) / PL;
-  const long cap = BN_WAVE(bn_stats_kernel);
-  if (blocks > cap) blocks = cap;
-  bn_stats_kernel<<<(unsigned)blocks, BN_THREADS, 0, st>>>((const __nv_bfloat16*)y_bf16, (int)M, C, y_cstride, sums);
+  // at least ~64 KB of activation per block so the partial-row count stays small for the second stage
+  const long by_bytes = (M * C * 2 + 65535) / 65536;
+  if (blocks > by_bytes) blocks = by_bytes;
+  if (blocks > wave) blocks = wave;
+  return blocks < 1 ? 1 : blocks;
+}
+
+// rows of the partial-sum buffer ([rows][2][C] floats) the reduction kernels need: which = 0 forward stats, 1 backward reduce
+extern "C" int32_t etb_bn_partial_rows(int64_t M, int32_t C, int32_t which) {
+  if (M <= 0 || !bn_c_ok(C)) return 0;
+  return (int32_t)bn_reduce_blocks((long)M, C, which ? BN_WAVE(bn_act_bwd_reduce_kernel) : BN_WAVE(bn_stats_kernel));
+}
+
+// partials: [rows = etb_bn_partial_rows(M,C,0)][2][C] floats, fully overwritten.  y [M][y_cstride] bf16.
+extern "C" int etb_bn_stats(const void* y_bf16, int64_t M, int32_t C, int32_t y_cstride, float* partials, int32_t rows, void* stream) {
+  ETB_CHECK_ARG(y_bf16 && partials && M > 0 && M < (1ll << 31) && bn_c_ok(C) && y_cstride % 8 == 0 && y_cstride >= C);
+  ETB_CHECK_ARG(rows == etb_bn_partial_rows(M, C, 0));
+  bn_stats_kernel<<<(unsigned)rows, BN_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)y_bf16, (int)M, C, y_cstride, partials);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }
 
-extern "C" int etb_bn_finalize(const float* sums, int64_t M, int32_t C, const float* gamma, const float* beta, float eps, float momentum,
-                               float* running_mean, float* running_var, float* scale, float* shift, float* mean, float* invstd, void* stream) {
-  ETB_CHECK_ARG(sums && gamma && beta && scale && shift && mean && invstd && M > 0 && C > 0);
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, (int)M, C, gamma, beta, eps, momentum, running_mean, running_var, scale,
-                                                                       shift, mean, invstd);
+extern "C" int etb_bn_finalize(const float* partials, int32_t rows, int64_t M, int32_t C, const float* gamma, const float* beta, float eps,
+                               float momentum, float* running_mean, float* running_var, float* scale, float* shift, float* mean, float* invstd,
+                               void* stream) {
+  ETB_CHECK_ARG(partials && rows > 0 && gamma && beta && scale && shift && mean && invstd && M > 0 && C > 0);
+  if (C <= 256)
+    bn_finalize_kernel<8, 128><<<(C + 7) / 8, dim3(8, 128), 0, (cudaStream_t)stream>>>(partials, rows, (int)M, C, gamma, beta, eps, momentum, running_mean,
+                                                                                      running_var, scale, shift, mean, invstd);
+  else
+    bn_finalize_kernel<32, 32><<<(C + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(partials, rows, (int)M, C, gamma, beta, eps, momentum, running_mean,
+                                                                                        running_var, scale, shift, mean, invstd);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }
@@ -347,32 +424,39 @@ extern "C" int etb_bn_act_apply(const void* y_bf16, const float* scale, const fl
   return etb_bn_act_apply_res(y_bf16, scale, shift, nullptr, out_bf16, M, C, y_cstride, 0, out_cstride, act, stream);
 }
 
-// sums: 2*C floats (zeroed here): [sum dz][sum dz*xhat]
+// partials: [rows = etb_bn_partial_rows(M,C,1)][2][C] floats: per-block [sum dz][sum dz*xhat], fully overwritten
 extern "C" int etb_bn_act_bwd_reduce(const void* da_bf16, const void* y_bf16, const float* scale, const float* shift, const float* mean,
                                      const float* invstd, int64_t M, int32_t C, int32_t da_cstride, int32_t y_cstride, int32_t act,
-                                     float* sums, void* stream) {
-  ETB_CHECK_ARG(da_bf16 && y_bf16 && scale && shift && mean && invstd && sums && M > 0 && M < (1ll << 31) && bn_c_ok(C));
-  ETB_CHECK_ARG(da_cstride % 8 == 0 && y_cstride % 8 == 0);
-  cudaStream_t st = (cudaStream_t)stream;
-  ETB_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, st));
-  const int PL = BN_THREADS / (C / 8);
-  long blocks = (M + PL - 1) / PL;
-  const long cap = BN_WAVE(bn_act_bwd_reduce_kernel);
-  if (blocks > cap) blocks = cap;
-  bn_act_bwd_reduce_kernel<<<(unsigned)blocks, BN_THREADS, 0, st>>>((const __nv_bfloat16*)da_bf16, (const __nv_bfloat16*)y_bf16, scale, shift, mean,
-                                                                   invstd, (int)M, C, da_cstride, y_cstride, act, sums);
+                                     float* partials, int32_t rows, void* stream) {
+  ETB_CHECK_ARG(da_bf16 && y_bf16 && scale && shift && mean && invstd && partials && M > 0 && M < (1ll << 31) && bn_c_ok(C));
+  ETB_CHECK_ARG(da_cstride % 8 == 0 && y_cstride % 8 == 0 && rows == etb_bn_partial_rows(M, C, 1));
+  bn_act_bwd_reduce_kernel<<<(unsigned)rows, BN_THREADS, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)da_bf16, (const __nv_bfloat16*)y_bf16, scale, shift, mean, invstd, (int)M, C, da_cstride, y_cstride, act, partials);
+  ETB_CHECK_LAUNCH();
+  return ETB_OK;
+}
+
+// sums[2C] = column totals of partials; dbeta = sum dz, dgamma = sum dz*xhat, written (accumulate = 0) or added in place
+// (accumulate = 1: dgamma / dbeta are the parameters' .grad in the gradient arena)
+extern "C" int etb_bn_act_bwd_finalize(const float* partials, int32_t rows, int32_t C, float* sums, float* dgamma, float* dbeta,
+                                       int32_t accumulate, void* stream) {
+  ETB_CHECK_ARG(partials && rows > 0 && C > 0 && sums && dgamma && dbeta);
+  if (C <= 256)
+    bn_bwd_finalize_kernel<8, 128><<<(C + 7) / 8, dim3(8, 128), 0, (cudaStream_t)stream>>>(partials, rows, C, sums, dgamma, dbeta, accumulate);
+  else
+    bn_bwd_finalize_kernel<32, 32><<<(C + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(partials, rows, C, sums, dgamma, dbeta, accumulate);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }
 
 extern "C" int etb_bn_act_bwd_apply(const void* da_bf16, const void* y_bf16, const float* scale, const float* shift, const float* mean,
                                     const float* invstd, const float* sums, int64_t M, int32_t C, int32_t da_cstride, int32_t y_cstride,
-                                    int32_t dy_cstride, int32_t act, void* dy_bf16, float* dgamma, float* dbeta, void* stream) {
-  ETB_CHECK_ARG(da_bf16 && y_bf16 && scale && shift && mean && invstd && sums && dy_bf16 && dgamma && dbeta && M > 0 && bn_c_ok(C));
+                                    int32_t dy_cstride, int32_t act, void* dy_bf16, void* stream) {
+  ETB_CHECK_ARG(da_bf16 && y_bf16 && scale && shift && mean && invstd && sums && dy_bf16 && M > 0 && bn_c_ok(C));
   ETB_CHECK_ARG(da_cstride % 8 == 0 && y_cstride % 8 == 0 && dy_cstride % 8 == 0);
   bn_act_bwd_apply_kernel<<<bn_grid(M * (C / 8), BN_WAVE(bn_act_bwd_apply_kernel)), BN_THREADS, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)da_bf16, (const __nv_bfloat16*)y_bf16, scale, shift, mean, invstd, sums, (long)M, C, da_cstride, y_cstride, dy_cstride,
-      act, (__nv_bfloat16*)dy_bf16, dgamma, dbeta);
+      act, (__nv_bfloat16*)dy_bf16);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }

@@ -1113,35 +1113,105 @@ static int launch_wgrad(const CUtensorMap& mDy, const CUtensorMap& mX, const Wgr
 }
 
 // ---- second stage of the split-K: sum the slices, emit the parameter layout, optionally accumulate ----
-// thread = 4 consecutive ci of one (co, tap): coalesced float4 reads of every slice.
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, long slice, int splitk, float* __restrict__ out, int Cout,
-                                                           int Cin, int kk, int flags) {
+// block = 32 lanes (each 4 consecutive ci of one (co, tap): coalesced float4 reads of every slice) x SG slice groups;
+// group g sums slices g, g+SG, ... (4 independent loads in flight), the groups are combined through shared memory in a
+// fixed order (deterministic).  SG grows with the split count so a 148-way split of a small layer is not one serial chain.
+template <int SG>
+__global__ void __launch_bounds__(32 * SG) wgrad_reduce_kernel(const float* __restrict__ ws, long slice, int splitk, float* __restrict__ out, int Cout,
+                                                               int Cin, int kk, int flags) {
+  __shared__ float4 red[SG][32];
   const long n4 = (long)Cout * kk * Cin / 4;
-  for (long e4 = (long)blockIdx.x * blockDim.x + threadIdx.x; e4 < n4; e4 += (long)gridDim.x * blockDim.x) {
-    const float4* p = reinterpret_cast<const float4*>(ws) + e4;
-    float4 acc = __ldg(p);
-    for (int s = 1; s < splitk; ++s) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(ws + (size_t)s * slice) + e4);
+  const int lane = threadIdx.x, sg = threadIdx.y;
+  for (long e4 = (long)blockIdx.x * 32 + lane; e4 - lane < n4; e4 += (long)gridDim.x * 32) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e4 < n4) {
+      const float4* p = reinterpret_cast<const float4*>(ws) + e4;
+      const size_t st4 = (size_t)slice / 4;
+      int sidx = sg;
+      for (; sidx + 3 * SG < splitk; sidx += 4 * SG) {
+        const float4 v0 = __ldg(p + (size_t)sidx * st4), v1 = __ldg(p + (size_t)(sidx + SG) * st4);
+        const float4 v2 = __ldg(p + (size_t)(sidx + 2 * SG) * st4), v3 = __ldg(p + (size_t)(sidx + 3 * SG) * st4);
+        acc.x += (v0.x + v1.x) + (v2.x + v3.x); acc.y += (v0.y + v1.y) + (v2.y + v3.y);
+        acc.z += (v0.z + v1.z) + (v2.z + v3.z); acc.w += (v0.w + v1.w) + (v2.w + v3.w);
+      }
+      for (; sidx < splitk; sidx += SG) {
+        const float4 v = __ldg(p + (size_t)sidx * st4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+    if (SG > 1) {
+      red[sg][lane] = acc;
+      __syncthreads();
+      if (sg == 0) {
+#pragma unroll
+        for (int g = 1; g < SG; ++g) {
+          const float4 v = red[g][lane];
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+      }
+    }
+    if (sg == 0 && e4 < n4) {
+      const long e = e4 * 4;
+      const int ci = (int)(e % Cin);
+      const long t2 = e / Cin;
+      const int t = (int)(t2 % kk), co = (int)(t2 / kk);
+      const float vals[4] = {acc.x, acc.y, acc.z, acc.w};
+      if (kk == 1 && !(flags & 1) && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {   // pointwise: the GEMM layout IS the parameter layout
+        float4* o = reinterpret_cast<float4*>(out + e);
+        if (flags & 2) { const float4 q = *o; acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w; }
+        *o = acc;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          long dst;
+          if (flags & 1) {                       // stem: [Cout][128 slots, k = (c*6+kh)*6+kw] -> [Cout,3,6,6] (same order)
+            const int k = ci + j;
+            if (k >= 108) continue;
+            dst = (long)co * 108 + k;
+          } else {
+            dst = ((long)co * Cin + ci + j) * kk + t;
+          }
+          out[dst] = (flags & 2) ? out[dst] + vals[j] : vals[j];
+        }
+      }
+    }
+    if (SG > 1) __syncthreads();
+  }
+}
+
+// kk > 1 (3x3 ...): the GEMM layout [co][tap][ci] has to become the parameter layout [co][ci][tap].  One block = one co
+// and 64 consecutive ci: unit (tap, lane) sums its float4 over the slices (coalesced along ci), the [64][kk] patch is
+// transposed through shared memory and written (or accumulated) as ONE contiguous run of 64*kk floats -- the naive
+// scatter cost 8x sector amplification on both the read-modify-write and the store (60 us per 3x3 layer).
+__global__ void __launch_bounds__(256) wgrad_reduce_taps_kernel(const float* __restrict__ ws, long slice, int splitk, float* __restrict__ out, int Cin,
+                                                                int kk, int flags) {
+  __shared__ float sm[64 * 12];
+  const int chunks = Cin >> 6;
+  const int co = blockIdx.x / chunks, ci0 = (blockIdx.x - co * chunks) << 6;
+  const size_t st4 = (size_t)slice / 4;
+  for (int u = threadIdx.x; u < kk * 16; u += 256) {
+    const int t = u >> 4, lane = u & 15;
+    const float4* p = reinterpret_cast<const float4*>(ws + ((size_t)co * kk + t) * Cin + ci0) + lane;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int sidx = 0;
+    for (; sidx + 3 < splitk; sidx += 4) {
+      const float4 v0 = __ldg(p + (size_t)sidx * st4), v1 = __ldg(p + (size_t)(sidx + 1) * st4);
+      const float4 v2 = __ldg(p + (size_t)(sidx + 2) * st4), v3 = __ldg(p + (size_t)(sidx + 3) * st4);
+      acc.x += (v0.x + v1.x) + (v2.x + v3.x); acc.y += (v0.y + v1.y) + (v2.y + v3.y);
+      acc.z += (v0.z + v1.z) + (v2.z + v3.z); acc.w += (v0.w + v1.w) + (v2.w + v3.w);
+    }
+    for (; sidx < splitk; ++sidx) {
+      const float4 v = __ldg(p + (size_t)sidx * st4);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
-    const long e = e4 * 4;
-    const int ci = (int)(e % Cin);
-    const long t2 = e / Cin;
-    const int t = (int)(t2 % kk), co = (int)(t2 / kk);
-    const float vals[4] = {acc.x, acc.y, acc.z, acc.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      long dst;
-      if (flags & 1) {                       // stem: [Cout][128 slots, k = (c*6+kh)*6+kw] -> [Cout,3,6,6] (same order)
-        const int k = ci + j;
-        if (k >= 108) continue;
-        dst = (long)co * 108 + k;
-      } else {
-        dst = ((long)co * Cin + ci + j) * kk + t;
-      }
-      out[dst] = (flags & 2) ? out[dst] + vals[j] : vals[j];
-    }
+    sm[(4 * lane + 0) * kk + t] = acc.x;
+    sm[(4 * lane + 1) * kk + t] = acc.y;
+    sm[(4 * lane + 2) * kk + t] = acc.z;
+    sm[(4 * lane + 3) * kk + t] = acc.w;
   }
+  __syncthreads();
+  float* o = out + ((size_t)co * Cin + ci0) * kk;
+  for (int i = threadIdx.x; i < 64 * kk; i += 256) o[i] = (flags & 2) ? o[i] + sm[i] : sm[i];
 }
 
 static void wgrad_plan(const EtbConvParams* cp, int* BN_, int* KP_, int* TW, int* TH, int* tiles_w, int* tiles_h, int* nimg, int* out_tiles,
@@ -1276,10 +1346,18 @@ extern "C" int etb_conv_wgrad(const void* x_bf16, const void* dy_bf16, float* dw
   if (rc != ETB_OK) return rc;
   // rows co >= Cout of the last tile are never written: the reduce only reads [Cout] rows
   const long n4 = (long)dw_elems / 4;
-  long blocks = (n4 + 255) / 256;
-  const long cap = (long)etb_num_sms() * 8;
+  long blocks = (n4 + 31) / 32;
+  const long cap = (long)etb_num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  wgrad_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>((const float*)workspace, (long)dw_elems, splitk, dw_f32, cp->Cout, cp->Cin, wa.ntaps, flags);
+  if (wa.ntaps > 1 && !(flags & 1))
+    wgrad_reduce_taps_kernel<<<(unsigned)(cp->Cout * (cp->Cin >> 6)), 256, 0, st>>>((const float*)workspace, (long)dw_elems, splitk, dw_f32, cp->Cin, wa.ntaps,
+                                                                                  flags);
+  else if (splitk >= 32)
+    wgrad_reduce_kernel<16><<<(unsigned)blocks, dim3(32, 16), 0, st>>>((const float*)workspace, (long)dw_elems, splitk, dw_f32, cp->Cout, cp->Cin, wa.ntaps, flags);
+  else if (splitk >= 6)
+    wgrad_reduce_kernel<4><<<(unsigned)blocks, dim3(32, 4), 0, st>>>((const float*)workspace, (long)dw_elems, splitk, dw_f32, cp->Cout, cp->Cin, wa.ntaps, flags);
+  else
+    wgrad_reduce_kernel<1><<<(unsigned)blocks, dim3(32, 1), 0, st>>>((const float*)workspace, (long)dw_elems, splitk, dw_f32, cp->Cout, cp->Cin, wa.ntaps, flags);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }

@@ -10,28 +10,35 @@ import torch
 
 
 class GradArena:
-    """All gradients of `params` as views of one contiguous fp32 buffer."""
+    """All gradients of `params` as views of one contiguous fp32 buffer.  Every view starts on a 16-byte boundary (the
+    wgrad / BN-backward kernels accumulate into the views with float4 accesses); the pad floats stay zero."""
+
+    ALIGN = 4   # floats
+
+    @classmethod
+    def _offsets(cls, params):
+        offs, o = [], 0
+        for p in params:
+            offs.append(o)
+            o += (p.numel() + cls.ALIGN - 1) // cls.ALIGN * cls.ALIGN
+        return offs, o
 
     def __init__(self, params, device=None):
         self.params = [p for p in params if p.requires_grad]
-        n = sum(p.numel() for p in self.params)
+        self.offsets, n = self._offsets(self.params)
         dev = device if device is not None else self.params[0].device
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
-        o = 0
-        for p in self.params:
+        for p, o in zip(self.params, self.offsets):
             p.grad = self.flat[o:o + p.numel()].view_as(p)
-            o += p.numel()
 
     def zero(self):
         self.flat.zero_()
 
     def check_views(self):
         """True while every p.grad still aliases the arena (optimizer.zero_grad(set_to_none=True) would break it)."""
-        o = 0
-        for p in self.params:
+        for p, o in zip(self.params, self.offsets):
             if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + 4 * o:
                 return False
-            o += p.numel()
         return True
 
     def all_reduce_sum(self, world_size, group=None):

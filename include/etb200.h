@@ -238,13 +238,18 @@ int etb_conv_wgrad(const void* x_bf16, const void* dy_bf16, float* dw_f32, const
 /* training-mode BatchNorm2d (eps, momentum, batch statistics, running-stat update with the unbiased variance) + SiLU/ReLU
  * around the convolutions (models/backbone/common.py:480-481; utils/torch_utils.py:162-171), forward and backward.
  * y / da / dy / out are NHWC bf16 [M][cstride] with M = N*H*W; per-channel vectors are fp32.  act: 0 none, 1 SiLU, 2 ReLU.
- *   forward : etb_bn_stats (sums[2C] = sum y, sum y^2) -> etb_bn_finalize (scale, shift, mean, invstd, running stats)
+ *   forward : etb_bn_stats (per-block partial rows [rows][2][C] = sum y, sum y^2; rows = etb_bn_partial_rows(M,C,0))
+ *             -> etb_bn_finalize (fixed-order sum of the rows -> scale, shift, mean, invstd, running stats)
  *             -> etb_bn_act_apply (a = act(y*scale+shift))
- *   backward: etb_bn_act_bwd_reduce (sums[2C] = sum dz, sum dz*xhat; dz = da*act'(z)) -> etb_bn_act_bwd_apply
- *             (dy = gamma*invstd*(dz - sum_dz/M - xhat*sum_dz_xhat/M), dgamma, dbeta) */
-int etb_bn_stats(const void* y_bf16, int64_t M, int32_t C, int32_t y_cstride, float* sums, void* stream);
-int etb_bn_finalize(const float* sums, int64_t M, int32_t C, const float* gamma, const float* beta, float eps, float momentum,
-                    float* running_mean, float* running_var, float* scale, float* shift, float* mean, float* invstd, void* stream);
+ *   backward: etb_bn_act_bwd_reduce (partial rows of sum dz, sum dz*xhat; dz = da*act'(z); rows = etb_bn_partial_rows(M,C,1))
+ *             -> etb_bn_act_bwd_finalize (sums[2C]; dbeta, dgamma written or accumulated into the parameters' .grad)
+ *             -> etb_bn_act_bwd_apply (dy = gamma*invstd*(dz - sum_dz/M - xhat*sum_dz_xhat/M))
+ * No atomics and no memsets: the statistics are bit-reproducible run to run. */
+int32_t etb_bn_partial_rows(int64_t M, int32_t C, int32_t which /* 0 forward stats, 1 backward reduce */);
+int etb_bn_stats(const void* y_bf16, int64_t M, int32_t C, int32_t y_cstride, float* partials, int32_t rows, void* stream);
+int etb_bn_finalize(const float* partials, int32_t rows, int64_t M, int32_t C, const float* gamma, const float* beta, float eps,
+                    float momentum, float* running_mean, float* running_var, float* scale, float* shift, float* mean,
+                    float* invstd, void* stream);
 int etb_bn_act_apply(const void* y_bf16, const float* scale, const float* shift, void* out_bf16, int64_t M, int32_t C,
                      int32_t y_cstride, int32_t out_cstride, int32_t act, void* stream);
 /* same + the Bottleneck shortcut (models/backbone/common.py:499 `x + cv2(cv1(x))`): out = act(y*scale+shift) + res
@@ -254,10 +259,12 @@ int etb_bn_act_apply_res(const void* y_bf16, const float* scale, const float* sh
                          void* stream);
 int etb_bn_act_bwd_reduce(const void* da_bf16, const void* y_bf16, const float* scale, const float* shift, const float* mean,
                           const float* invstd, int64_t M, int32_t C, int32_t da_cstride, int32_t y_cstride, int32_t act,
-                          float* sums, void* stream);
+                          float* partials, int32_t rows, void* stream);
+int etb_bn_act_bwd_finalize(const float* partials, int32_t rows, int32_t C, float* sums, float* dgamma, float* dbeta,
+                            int32_t accumulate, void* stream);
 int etb_bn_act_bwd_apply(const void* da_bf16, const void* y_bf16, const float* scale, const float* shift, const float* mean,
                          const float* invstd, const float* sums, int64_t M, int32_t C, int32_t da_cstride, int32_t y_cstride,
-                         int32_t dy_cstride, int32_t act, void* dy_bf16, float* dgamma, float* dbeta, void* stream);
+                         int32_t dy_cstride, int32_t act, void* dy_bf16, void* stream);
 
 /* small layout / elementwise helpers of the trunk (all HBM-bound, coalesced 16 B vectors) */
 

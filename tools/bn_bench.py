@@ -26,14 +26,15 @@ def main():
         rm = torch.zeros(C_, device=dev); rv = torch.ones(C_, device=dev)
         out = torch.empty_like(y)
         a, stats = co.bn_forward(y, C_, gamma, beta, rm, rv, 1e-3, 0.03, "silu", out=out)
-        sums = torch.empty(2 * C_, dtype=torch.float32, device=dev)
-        dgb = torch.empty(2, C_, device=dev)
+        sums = torch.zeros(2 * C_, dtype=torch.float32, device=dev)
+        rows0, rows1 = int(lib.etb_bn_partial_rows(M, C_, 0)), int(lib.etb_bn_partial_rows(M, C_, 1))
+        part = torch.empty(max(rows0, rows1), 2, C_, device=dev)
         nb = M * C_ * 2
         r = {}
-        r["stats(1R)"] = (timeit(lambda: lib.etb_bn_stats(_lib.ptr(y), M, C_, C_, _lib.ptr(sums), _lib.stream_ptr())), 1)
+        r["stats(1R)"] = (timeit(lambda: lib.etb_bn_stats(_lib.ptr(y), M, C_, C_, _lib.ptr(part), rows0, _lib.stream_ptr())), 1)
         r["apply(1R1W)"] = (timeit(lambda: lib.etb_bn_act_apply(_lib.ptr(y), _lib.ptr(stats[0]), _lib.ptr(stats[1]), _lib.ptr(out), M, C_, C_, C_, 1, _lib.stream_ptr())), 2)
-        r["bwd_reduce(2R)"] = (timeit(lambda: lib.etb_bn_act_bwd_reduce(_lib.ptr(da), _lib.ptr(y), _lib.ptr(stats[0]), _lib.ptr(stats[1]), _lib.ptr(stats[2]), _lib.ptr(stats[3]), M, C_, C_, C_, 1, _lib.ptr(sums), _lib.stream_ptr())), 2)
-        r["bwd_apply(2R1W)"] = (timeit(lambda: lib.etb_bn_act_bwd_apply(_lib.ptr(da), _lib.ptr(y), _lib.ptr(stats[0]), _lib.ptr(stats[1]), _lib.ptr(stats[2]), _lib.ptr(stats[3]), _lib.ptr(sums), M, C_, C_, C_, C_, 1, _lib.ptr(out), _lib.ptr(dgb[0]), _lib.ptr(dgb[1]), _lib.stream_ptr())), 3)
+        r["bwd_reduce(2R)"] = (timeit(lambda: lib.etb_bn_act_bwd_reduce(_lib.ptr(da), _lib.ptr(y), _lib.ptr(stats[0]), _lib.ptr(stats[1]), _lib.ptr(stats[2]), _lib.ptr(stats[3]), M, C_, C_, C_, 1, _lib.ptr(part), rows1, _lib.stream_ptr())), 2)
+        r["bwd_apply(2R1W)"] = (timeit(lambda: lib.etb_bn_act_bwd_apply(_lib.ptr(da), _lib.ptr(y), _lib.ptr(stats[0]), _lib.ptr(stats[1]), _lib.ptr(stats[2]), _lib.ptr(stats[3]), _lib.ptr(sums), M, C_, C_, C_, C_, 1, _lib.ptr(out), _lib.stream_ptr())), 3)
         print("M=%8d C=%4d (%6.1f MB/pass): " % (M, C_, nb / 1e6) + "  ".join("%s %6.1fus %4.0fGB/s(%.2f)" % (k, ms * 1e3, p * nb / ms / 1e6, p * nb / ms / 1e6 / pk) for k, (ms, p) in r.items()), flush=True)
 
 

@@ -101,6 +101,12 @@ def main():
             ms = timeit(lambda: co.conv_fwd(x, wp, Cin, Cout, k, s, p, sc, bi, "silu", out=y))
             row["fwd_us"], row["fwd_tflops"] = ms * 1e3, flops / ms / 1e9
             tot["fwd"][0] += ms * cnt; tot["fwd"][1] += flops * cnt
+        if "raw" in tot:        # the student's training forward: raw bf16 conv output (BN statistics come next)
+            wp = co.pack_weight(w)
+            y = torch.empty(N, Ho, Ho, cpad, dtype=torch.bfloat16, device=dev)
+            ms = timeit(lambda: co.conv_fwd(x, wp, Cin, Cout, k, s, p, None, None, None, out=y))
+            row["raw_us"], row["raw_tflops"] = ms * 1e3, flops / ms / 1e9
+            tot["raw"][0] += ms * cnt; tot["raw"][1] += flops * cnt
         if "dgrad" in tot and Cout % 64 == 0:
             wd = co.pack_weight_dgrad(w, s, p)
             dx = torch.empty(N, H, H, Cin, dtype=torch.bfloat16, device=dev)
@@ -111,7 +117,10 @@ def main():
             ms = timeit(lambda: co.conv_wgrad(x, dy, Cin, Cout, k, s, p))
             row["wgrad_us"], row["wgrad_tflops"] = ms * 1e3, flops / ms / 1e9
             tot["wgrad"][0] += ms * cnt; tot["wgrad"][1] += flops * cnt
-        print(json.dumps(row), flush=True)
+        # floors: HBM (read x + write y, bf16) at 6.5 TB/s vs tensor pipe at the sustained bf16 peak (1443 TF/s)
+        row["floor_us"] = max((N * H * H * Cin + N * Ho * Ho * Cout) * 2 / 6.5e6, flops / 1443.6e6)
+        print("%-22s x%-2d %6.1fGF floor %6.1fus | " % (name, cnt, flops / 1e9, row["floor_us"]) +
+              " ".join("%s %6.1fus" % (m, row[m + "_us"]) for m in tot if m + "_us" in row), flush=True)
         res.append(row)
         del x, dy
     summ = {m: dict(ms=v[0], tflops=v[1] / v[0] / 1e9 if v[0] else None) for m, v in tot.items()}
