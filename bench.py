@@ -116,34 +116,44 @@ def conv_flops_teacher(engine_model, n_img, img):
 
 
 def dominant_kernel_roofline(dev, peak_tflops, peak_kind):
-    """conv_fwd_kernel (tcgen05 implicit GEMM) on the shape family that carries 57% of the trunk FLOPs (3x3 s1 C->C
-    Bottleneck conv; here 256->256 on 40x40 maps, batch 32 = the student's batch), 30 back-to-back launches timed with CUDA
-    events on the launching stream.  Algorithmic FLOPs = 2*N*H*W*Cout*Cin*9; DRAM traffic from the committed ncu capture
-    (profiles/r1_kernel_metrics.md)."""
+    """The step's top kernel by GPU time (profiles/r1_step_kernel_table.md): conv_fwd2_kernel<6,0> -- the cta_group::2
+    tcgen05 implicit GEMM with the raw bf16 epilogue that runs the student's training forward AND (with transposed taps)
+    its dgrad -- on the shape family that carries 57% of the trunk FLOPs (3x3 s1 C->C Bottleneck conv; here 256->256 on
+    40x40 maps, batch 32 = the student's batch).  30 launches timed with CUDA events on the launching stream, rotating
+    over 6 input/output buffer sets (315 MB > the 126 MB L2) so no launch finds its input in L2.
+    Algorithmic FLOPs = 2*N*H*W*Cout*Cin*9; DRAM traffic from the committed ncu capture (profiles/r1_kernel_metrics.md)."""
     from efficientteacher_b200 import convops as co
     N, H, C_ = 32, 40, 256
-    x = torch.randn(N, H, H, C_, device=dev).to(torch.bfloat16)
+    nbuf = 6
+    xs = [torch.randn(N, H, H, C_, device=dev).to(torch.bfloat16) for _ in range(nbuf)]
+    ys = [torch.empty(N, H, H, C_, dtype=torch.bfloat16, device=dev) for _ in range(nbuf)]
     w = co.pack_weight(torch.randn(C_, C_, 3, 3, device=dev) * (C_ * 9) ** -0.5)
-    sc, bi = torch.ones(C_, device=dev), torch.zeros(C_, device=dev)
-    y = torch.empty(N, H, H, C_, dtype=torch.bfloat16, device=dev)
-    f = lambda: co.conv_fwd(x, w, C_, C_, 3, 1, 1, sc, bi, "silu", out=y)  # noqa: E731
-    for _ in range(5):
-        f()
+    f = lambda i: co.conv_fwd(xs[i % nbuf], w, C_, C_, 3, 1, 1, None, None, None, out=ys[i % nbuf])  # noqa: E731
+    for i in range(nbuf):
+        f(i)
     torch.cuda.synchronize()
     n = 30
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    for _ in range(n):
-        f()
+    for i in range(n):
+        f(i)
     e.record()
     torch.cuda.synchronize()
     ms = s.elapsed_time(e) / n
     flops = 2.0 * N * H * H * C_ * C_ * 9
     ach = flops / ms / 1e9
-    return {"bound": "tensor", "kernel": "conv_fwd_kernel<256,4,1> (tcgen05 implicit GEMM, TMA-fed, folded BN+SiLU epilogue), 3x3 s1 256->256 @40x40, batch 32",
+    return {"bound": "tensor", "kernel": "conv_fwd2_kernel<6,0> (cta_group::2 tcgen05 implicit GEMM, TMA-fed, raw bf16 epilogue: student forward + dgrad), 3x3 s1 256->256 @40x40, batch 32",
             "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops,
-            "traffic": 27.44e6 + 8.45e6, "traffic_note": "dram__bytes_read+write per launch from ncu --set full (profiles/prof_conv_fwd_3x3_256.ncu-rep); algorithmic bytes 26.2 MB in + 1.2 MB weights + 26.2 MB out (output still L2-resident at kernel end)",
-            "peak_kind": peak_kind, "flops_per_launch": flops, "us_per_launch": ms * 1e3, "launches_timed": n}
+            "traffic": DOMINANT_TRAFFIC, "traffic_note": DOMINANT_TRAFFIC_NOTE,
+            "peak_kind": peak_kind, "flops_per_launch": flops, "us_per_launch": ms * 1e3, "launches_timed": n,
+            "l2": "rotating 6 buffer sets (315 MB) > L2"}
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full capture
+DOMINANT_TRAFFIC = 27.42e6 + 13.82e6
+DOMINANT_TRAFFIC_NOTE = ("dram__bytes_read+write per launch from ncu --set full (profiles/prof_conv_fwd2_raw_3x3_256.ncu-rep, mean of 2 "
+                         "launches: 27.42 MB read, 12.5-15.1 MB written); algorithmic bytes 26.2 MB in + 1.2 MB weights + 26.2 MB out "
+                         "(the rest of the output is still L2-resident at kernel end): no re-reads")
 
 
 def kernel_table(step, ni, path, graph_ms):
@@ -242,6 +252,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end leg")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of replaying the captured CUDA graph of the step")
+    ap.add_argument("--nvtx-step", action="store_true", help="dev: wrap ONE extra eager step in the NVTX range 'etb_step' (ncu --nvtx --nvtx-include etb_step)")
     ap.add_argument("--kernel-table", default="", help="dev: write a per-kernel time table (torch.profiler/CUPTI, 2 eager steps) to this file")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -370,6 +381,12 @@ def main():
             step_e2e(ni); ni += 1
         ms_e2e = timed(step_e2e, args.steps, ni); ni += args.steps
     clocks = sampler.summary() if sampler else None
+    if args.nvtx_step and rank == 0:
+        torch.cuda.synchronize()
+        rid = torch.cuda.nvtx.range_start("etb_step")     # start/end range: process-wide (backward runs on autograd's thread)
+        st.train_instance(d_imgs, d_tg, d_us, d_uw, None, d_Ms, ni); ni += 1
+        torch.cuda.synchronize()
+        torch.cuda.nvtx.range_end(rid)
     if args.kernel_table and rank == 0:
         kernel_table(lambda i: st.train_instance(d_imgs, d_tg, d_us, d_uw, None, d_Ms, i), ni, args.kernel_table, ms / args.steps)
         ni += 2
@@ -400,7 +417,7 @@ def main():
                        "global_batch": imgs_per_step, "img_size": IMG, "parallelism": "dp%d" % world, "cuda_graph": use_graph,
                        "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
                        "native": "teacher trunk+head, student conv fwd/dgrad/wgrad (tcgen05) + BatchNorm(train)+SiLU fwd/bwd, weight packing, NMS/pseudo-label, assigners, losses fwd/bwd, EMA",
-                       "library_ops_left": "student cat / residual add / upsample / maxpool and their autograd, netD C->2 conv, domain focal loss (x0)",
+                       "library_ops_left": "autograd's gradient fan-in adds where a FanIn does not apply, Detect backward layout ops, netD C->2 conv, domain focal loss (x0)",
                        "pseudo_labels_last_step": n_pl, "nms_candidates_per_img_at_start": cand_per_img, "nms_detections_per_img_last_step": det_per_img},
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,

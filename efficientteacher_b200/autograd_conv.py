@@ -63,6 +63,63 @@ class CatBuf:
         return self.buf[:, coff:coff + C_]
 
 
+class FanIn:
+    """Gradient fan-in of an activation that has several native consumers (C3 input -> cv1 and cv2; Bottleneck input ->
+    cv1 and the shortcut; backbone feature -> next stage and the neck's concat).  Autograd would sum the consumers'
+    gradients with one ATen add per extra consumer (3 passes over the tensor each).  Instead every participating
+    consumer registers in forward (`n`), and in backward the first contribution becomes the accumulation buffer, later
+    convolutions ADD their dgrad into it in the kernel epilogue (etb_conv_dgrad accumulate: 1 extra read), and only the
+    last participant hands the buffer to autograd -- the others return None.  Consumers that do not participate (torch
+    ops) are still summed by the engine, so the result is exact in every mix."""
+    __slots__ = ("n", "k", "buf")
+
+    def __init__(self):
+        self.n, self.k, self.buf = 0, 0, None
+
+    @staticmethod
+    def of(x):
+        """the FanIn attached to tensor x by its producer module (None if x has a single consumer)"""
+        return getattr(x, "_etb_fan", None) if x.requires_grad else None
+
+    def done(self):
+        self.k += 1
+        if self.k < self.n:
+            return None
+        buf, self.buf = self.buf, None
+        return buf
+
+    def put(self, g):
+        """pass-through contribution (shortcut / concat slice): g becomes, or is added to, the buffer"""
+        self.buf = g if self.buf is None else self.buf + g
+        return self.done()
+
+    def add_dgrad(self, run, N, C_, H, W, device):
+        """convolution contribution: run(out_nhwc, out_cstride, accumulate) launches the dgrad"""
+        if self.buf is None:
+            self.buf = _empty_cl(N, C_, H, W, device)
+            run(_nhwc_of(self.buf), C_, False)
+        else:
+            v = _inplace_nhwc(self.buf, C_)
+            if v is None:                      # layout the kernel cannot address in place: out-of-place fallback
+                dx = _empty_cl(N, C_, H, W, device)
+                run(_nhwc_of(dx), C_, False)
+                self.buf = self.buf + dx
+            else:
+                run(v[0], v[1], True)
+        return self.done()
+
+
+def _inplace_nhwc(t, C_):
+    """(NHWC view, pixel stride) of a bf16 NCHW-shaped tensor that is physically NHWC (possibly a channel slice), else None"""
+    N, C2, H, W = t.shape
+    if t.dtype != torch.bfloat16 or C2 != C_:
+        return None
+    sN, sC, sH, sW = t.stride()
+    if sC == 1 and sW >= C_ and sW % 8 == 0 and sH == W * sW and sN == H * W * sW and t.data_ptr() % 16 == 0:
+        return t.permute(0, 2, 3, 1), sW
+    return None
+
+
 def _slice_nhwc(dest, coff, C_):
     """(NHWC view of the channel slice, its pixel stride)"""
     return dest.slice(coff, C_).permute(0, 2, 3, 1), dest.Ct
@@ -76,7 +133,12 @@ class JoinFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, dest, copy_flags, *parts):
         off, splits = 0, []
+        ctx.fans = []
         for p, cp in zip(parts, copy_flags):
+            fan = FanIn.of(p) if cp else None      # a copied-in part (backbone feature, lateral) may have other consumers
+            if fan is not None:
+                fan.n += 1
+            ctx.fans.append(fan)
             C_ = p.shape[1]
             if cp:
                 pb, pcs = _as_nhwc(p, C_)
@@ -91,8 +153,9 @@ class JoinFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         outs, off = [], 0
-        for C_ in ctx.splits:
-            outs.append(g[:, off:off + C_])
+        for C_, fan in zip(ctx.splits, ctx.fans):
+            gs = g[:, off:off + C_]
+            outs.append(gs if fan is None else fan.put(gs))
             off += C_
         return (None, None, *outs)
 
@@ -198,6 +261,11 @@ class ConvBnActFn(torch.autograd.Function):
         Cout = weight.shape[0]
         ctx.wd = wd
         ctx.has_res = res is not None
+        ctx.fan = None if is_stem else FanIn.of(x)
+        ctx.res_fan = FanIn.of(res) if res is not None else None
+        for f in (ctx.fan, ctx.res_fan):
+            if f is not None:
+                f.n += 1
         if is_stem:
             xb = co.stem_im2col(x.float(), 1.0)               # [N,H/2,W/2,128]; saved instead of the image
             xcs, Cin, k, st, pd = 128, 128, 1, 1, 0
@@ -250,15 +318,21 @@ class ConvBnActFn(torch.autograd.Function):
             Cin, k = weight.shape[1], weight.shape[2]
             N, _, H, W = xs.shape
             if ctx.needs_input_grad[0]:
-                dx = _empty_cl(N, Cin, H, W, da.device)
                 wd = ctx.wd if ctx.wd is not None else co.pack_weight_dgrad(weight, stride, pad)
-                co.conv_dgrad(dy, wd, N, H, W, Cin, Cout, k, stride, pad, out=_nhwc_of(dx))
+                if ctx.fan is None:
+                    dx = _empty_cl(N, Cin, H, W, da.device)
+                    co.conv_dgrad(dy, wd, N, H, W, Cin, Cout, k, stride, pad, out=_nhwc_of(dx))
+                else:
+                    dx = ctx.fan.add_dgrad(lambda o, ocs, acc: co.conv_dgrad(dy, wd, N, H, W, Cin, Cout, k, stride, pad, out=o,
+                                                                             out_cstride=ocs, accumulate=acc), N, Cin, H, W, da.device)
             xb, xcs = _as_nhwc(xs, Cin)
             dw = co.conv_wgrad(xb, dy, Cin, Cout, k, stride, pad, x_cstride=xcs, accumulate_into=tgt)
         if tgt is not None:
             dw = None
-        return (dx, dw, dgamma, dbeta, None, None, None, None, None, None, None, None, None, None,
-                da if ctx.has_res else None, None, None)
+        dres = None
+        if ctx.has_res:
+            dres = da if ctx.res_fan is None else ctx.res_fan.put(da)
+        return (dx, dw, dgamma, dbeta, None, None, None, None, None, None, None, None, None, None, dres, None, None)
 
 
 class StemFn(torch.autograd.Function):

@@ -124,7 +124,7 @@ def pack_weight_dgrad(w_oihw, stride, pad):
 
 
 def conv_dgrad(dy, wd_packed, N, H, W, Cin, Cout, k, stride, pad, out=None, out_coffset=0, dy_coffset=0, accumulate=False,
-               dy_cstride=None):
+               dy_cstride=None, out_cstride=None):
     """dy: [N,Ho,Wo,Cs] bf16 NHWC (channels [dy_coffset, +Cout)) -> dx [N,H,W,*] bf16 at channel offset out_coffset."""
     _lib.require_cuda(dy, wd_packed)
     cp = EtbConvParams()
@@ -134,7 +134,7 @@ def conv_dgrad(dy, wd_packed, N, H, W, Cin, Cout, k, stride, pad, out=None, out_
     cp.x_cstride = dy.shape[3] if dy_cstride is None else dy_cstride
     if out is None:
         out = nhwc_empty(N, H, W, Cin, dy.device)
-    cp.y_cstride, cp.y_coffset = out.shape[3], out_coffset
+    cp.y_cstride, cp.y_coffset = (out.shape[3] if out_cstride is None else out_cstride), out_coffset
     _lib.check(_lib.lib().etb_conv_dgrad(C.c_void_p(dy.data_ptr() + 2 * dy_coffset), _lib.ptr(wd_packed), _lib.ptr(out), C.byref(cp),
                                          int(accumulate), _lib.stream_ptr()), "etb_conv_dgrad")
     return out

@@ -188,16 +188,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 //   EPI 0: raw bf16 store (+= existing when a.accumulate)       -- dgrad, training forward
 //   EPI 1: v*scale+bias (folded BN) -> SiLU/ReLU -> (+residual) -- teacher forward
 //   EPI 2: +bias, fp32 scatter into the Detect layout           -- head
+// One 32-column chunk; returns false when the chunk starts beyond Cout (warp-uniform).  pre: the 4 x 16 B of the existing
+// output this chunk adds to (EPI 0 accumulate), loaded by the caller BEFORE it waited for the accumulator.
 template <int BN, int EPI>
-__device__ __forceinline__ void conv_epilogue_cols(const ConvKArgs& a, uint32_t lane_addr, int n0, int chalf, bool row_ok, size_t pix) {
+__device__ __forceinline__ bool conv_epilogue_chunk(const ConvKArgs& a, uint32_t lane_addr, int n0, int chalf, bool row_ok, size_t pix, int cc,
+                                                    const uint4* pre) {
   constexpr int HALF = BN / 2;
-#pragma unroll 1
-for (int cc = 0; cc < HALF; cc += 32) {
+{
   const int c0 = chalf * HALF + cc;
-  if (n0 + c0 >= a.Cout) break;  // warp-uniform
+  if (n0 + c0 >= a.Cout) return false;  // warp-uniform
   uint32_t v[32];
   tmem_ld32(lane_addr + (uint32_t)c0, v);
-  if (!row_ok) continue;
+  if (!row_ok) return true;
   const int gc0 = n0 + c0;
   const bool full = gc0 + 32 <= a.Cout;
   if (EPI == 2) {
@@ -213,7 +215,7 @@ for (int cc = 0; cc < HALF; cc += 32) {
         a.y_f32[((img_r * na + an) * hw + pin) * a.det_no + o] = __uint_as_float(v[j]) + (a.bias ? __ldg(a.bias + gc) : 0.0f);
       }
     }
-    continue;
+    return true;
   }
   __nv_bfloat16* yp = a.y + pix * a.y_cstride + a.y_coffset + gc0;
 #pragma unroll
@@ -258,7 +260,7 @@ for (int cc = 0; cc < HALF; cc += 32) {
     }
     if (full) {
       if (EPI == 0 && a.accumulate) {
-        const uint4 pv = reinterpret_cast<const uint4*>(yp)[q];
+        const uint4 pv = pre[q];
         const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&pv);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -279,6 +281,42 @@ for (int cc = 0; cc < HALF; cc += 32) {
     }
   }
 }
+  return true;
+}
+
+// EPI 0 accumulate (dx += dgrad: gradient fan-in): the existing output of this thread's pixel row (HALF channels) is
+// fetched into registers by epilogue_preload() at the top of the tile, i.e. while the MMAs of the tile are still running,
+// so its latency is off the epilogue's critical path (a dependent load per chunk cost +40 % on the pointwise dgrads).
+template <int BN, int EPI>
+struct EpiPre { uint4 v[EPI == 0 ? BN / 16 : 1]; };
+
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_preload(const ConvKArgs& a, int n0, int chalf, bool row_ok, size_t pix, EpiPre<BN, EPI>& pre) {
+  if (EPI == 0) {
+    if (a.accumulate && row_ok) {
+      constexpr int HALF = BN / 2;
+      const int gc = n0 + chalf * HALF;
+      const uint4* yp4 = reinterpret_cast<const uint4*>(a.y + pix * a.y_cstride + a.y_coffset + gc);
+#pragma unroll
+      for (int i = 0; i < BN / 16; ++i)
+        if (gc + i * 8 + 8 <= a.Cout) pre.v[i] = yp4[i];
+    }
+  }
+}
+
+template <int BN, int EPI>
+__device__ __forceinline__ void conv_epilogue_cols(const ConvKArgs& a, uint32_t lane_addr, int n0, int chalf, bool row_ok, size_t pix,
+                                                   const EpiPre<BN, EPI>& pre) {
+  constexpr int HALF = BN / 2;
+  if (EPI == 0) {
+#pragma unroll
+    for (int cc = 0; cc < HALF; cc += 32)
+      if (!conv_epilogue_chunk<BN, EPI>(a, lane_addr, n0, chalf, row_ok, pix, cc, pre.v + cc / 8)) break;
+  } else {
+#pragma unroll 1
+    for (int cc = 0; cc < HALF; cc += 32)
+      if (!conv_epilogue_chunk<BN, EPI>(a, lane_addr, n0, chalf, row_ok, pix, cc, pre.v)) break;
+  }
 }
 
 // Persistent: gridDim.x CTAs walk the tile list (tile = blockIdx.x + i*gridDim.x; N tile fastest so the CTAs running
@@ -389,10 +427,12 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       const int oh = th_i * a.TH + th, ow = tw_i * a.TW + tw;
       const bool row_ok = (row < a.TW * a.TH) && (oh < a.Ho) && (ow < a.Wo);
       const size_t pix = ((size_t)img * a.out_H + (size_t)(oh * a.out_os + a.out_ph)) * a.out_W + (size_t)(ow * a.out_os + a.out_pw);
+      EpiPre<BN, EPI> pre;
+      epilogue_preload<BN, EPI>(a, n0, chalf, row_ok, pix, pre);
       mbar_wait(&tmem_full[acc], (uint32_t)((lt >> 1) & 1));
       tc_fence_after();
       const uint32_t lane_addr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(32 * quad) << 16);
-      conv_epilogue_cols<BN, EPI>(a, lane_addr, n0, chalf, row_ok, pix);
+      conv_epilogue_cols<BN, EPI>(a, lane_addr, n0, chalf, row_ok, pix, pre);
       // all tcgen05.ld of this warp have completed (wait::ld inside tmem_ld32): hand the accumulator back
       tc_fence_before();
       __syncwarp();
@@ -572,10 +612,12 @@ conv_fwd2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       const int oh = th_i * a.TH + th, ow = tw_i * a.TW + tw;
       const bool row_ok = (mt < m_tiles) && (row < a.TW * a.TH) && (oh < a.Ho) && (ow < a.Wo);
       const size_t pix = ((size_t)img * a.out_H + (size_t)(oh * a.out_os + a.out_ph)) * a.out_W + (size_t)(ow * a.out_os + a.out_pw);
+      EpiPre<BN, EPI> pre;
+      epilogue_preload<BN, EPI>(a, n0, chalf, row_ok, pix, pre);
       mbar_wait(&tmem_full[acc], (uint32_t)((lt >> 1) & 1));
       tc_fence_after();
       const uint32_t lane_addr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(32 * quad) << 16);
-      conv_epilogue_cols<BN, EPI>(a, lane_addr, n0, chalf, row_ok, pix);
+      conv_epilogue_cols<BN, EPI>(a, lane_addr, n0, chalf, row_ok, pix, pre);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);

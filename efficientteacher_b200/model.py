@@ -6,9 +6,10 @@ so reference checkpoints / EMA deep copies / optimizer param grouping keep worki
 Execution:
   * eval / no-grad forward (the teacher-EMA pass of trainer/ssod_trainer.py:595-599) runs on the native engine
     (engine.TrunkEngine: tcgen05 implicit-GEMM convs, NHWC bf16, BN folded, concat-by-offset, fused Detect).
-  * training forward/backward of the trunk currently goes through torch autograd with bf16 autocast and
-    channels_last (library kernels) -- stated in DESIGN.md as the remaining scaffold; every other step of the
-    training path (losses, assigners, pseudo labels, EMA) is native.
+  * training forward/backward: torch autograd only sequences the graph; every node is a native Function
+    (autograd_conv.ConvBnActFn = tcgen05 conv + fused BatchNorm(train)+SiLU(+shortcut), JoinFn / SppfPoolFn /
+    UpsampleIntoFn = concat-by-offset glue of csrc/glue.cu, DetectConvFn), tensors stay NHWC bf16 and are exposed to
+    torch as channels_last views.
 There is no CPU path: forward raises without a CUDA device + libetb200.so.
 """
 import math
@@ -56,6 +57,7 @@ class Conv(nn.Module):
     NATIVE = True        # training convs on the tcgen05 fwd/dgrad/wgrad kernels (False: torch/cuDNN scaffold)
     FUSED_BN = True      # BatchNorm(train)+SiLU forward/backward on the fused kernels of csrc/bn.cu (False: torch ops)
     FUSED_GLUE = True    # concat-by-offset / fused shortcut add / native pool+upsample (csrc/glue.cu) instead of torch ops
+    FUSED_FANIN = True   # gradient fan-in (C3 input, shortcut, backbone feature) accumulated in the dgrad epilogue
     is_stem = False
 
     def fused(self, x):
@@ -90,6 +92,15 @@ class Conv(nn.Module):
         return y if res is None else res + y
 
 
+def _fan_out(x):
+    """Mark activation x as having several native consumers (autograd_conv.FanIn): their gradients are accumulated inside
+    the dgrad epilogues instead of by autograd's add kernels.  No-op when x needs no gradient or is already marked."""
+    if Conv.FUSED_FANIN and x.requires_grad and getattr(x, "_etb_fan", None) is None:
+        from .autograd_conv import FanIn
+        x._etb_fan = FanIn()
+    return x
+
+
 class Bottleneck(nn.Module):
     def __init__(self, c1, c2, shortcut=True, g=1, k=(1, 3), e=0.5, act=True):
         super().__init__()
@@ -100,6 +111,8 @@ class Bottleneck(nn.Module):
 
     def forward(self, x, dest=None, coff=0):
         if self.cv2.glue(x):      # shortcut add fused into cv2's BN+SiLU apply; output optionally straight into a concat slice
+            if self.add:
+                _fan_out(x)       # x feeds cv1 and the shortcut: their gradients meet in cv1's dgrad epilogue, not in an ATen add
             return self.cv2(self.cv1(x), x if self.add else None, dest, coff)
         assert dest is None
         return x + self.cv2(self.cv1(x)) if self.add else self.cv2(self.cv1(x))
@@ -120,6 +133,7 @@ class C3(nn.Module):
             c_ = self.cv1.conv.out_channels
             N, _, H, W = x.shape
             cb = CatBuf(N, 2 * c_, H, W, x.device)          # [ m(cv1(x)) | cv2(x) ] written in place by their producers
+            _fan_out(x)                                     # x feeds cv1 and cv2: the second dgrad accumulates into the first's output
             a = self.cv1(x)
             for i, b in enumerate(self.m):
                 a = b(a, cb, 0) if i == len(self.m) - 1 else b(a)
@@ -184,7 +198,11 @@ class YoloV5BackBone(nn.Module):
     def forward(self, x):
         x = self.stage2_2(self.stage2_1(self.stage1(x)))
         c3 = self.stage3_2(self.stage3_1(x))
+        if self.stage4_1.glue(c3):
+            _fan_out(c3)          # consumed by stage4_1 and by the neck's concat (JoinFn lateral)
         c4 = self.stage4_2(self.stage4_1(c3))
+        if self.stage5_1.glue(c4):
+            _fan_out(c4)
         return c3, c4, self.sppf(self.stage5_2(self.stage5_1(c4)))
 
 

@@ -331,3 +331,29 @@ def test_sppf_and_neck_fused_glue_match_torch_glue():
     for k in fused[2]:
         noise = 1 - cos(t2[2][k], t1[2][k])
         assert 1 - cos(fused[2][k], t1[2][k]) <= max(3 * noise, 1e-2), (k, cos(fused[2][k], t1[2][k]), noise)
+
+
+def test_fanin_epilogue_accumulation_matches_autograd_adds():
+    """Gradient fan-in (C3 input -> cv1 + cv2, Bottleneck input -> cv1 + shortcut) accumulated inside the dgrad epilogue
+    vs autograd's add kernels: same forward, so the input gradient may differ only by bf16 rounding of the partial sums."""
+    from efficientteacher_b200.model import C3, Conv
+    torch.manual_seed(7)
+    m = C3(128, 128, 3, True, 1, 0.5, "silu").to(DEV).train()
+    x0 = _cl(_rand((2, 128, 24, 24), 51))
+    res = {}
+    for fan in (True, False):
+        Conv.FUSED_FANIN = fan
+        try:
+            m.zero_grad(set_to_none=True)
+            x = x0.clone().requires_grad_(True)
+            y = m(x)
+            (y.float() * torch.linspace(-1, 1, y.numel(), device=DEV).reshape(y.shape)).sum().backward()
+            res[fan] = (y.detach().float(), x.grad.float(), {k: p.grad.float().clone() for k, p in m.named_parameters()})
+        finally:
+            Conv.FUSED_FANIN = True
+    assert torch.equal(res[True][0], res[False][0])          # forward is untouched (and deterministic)
+    cos = lambda a, b: float((a * b).sum() / (a.norm() * b.norm() + 1e-12))  # noqa: E731
+    assert cos(res[True][1], res[False][1]) > 0.9995
+    _check(res[True][1], res[False][1], tol=3e-2)
+    for k in res[True][2]:
+        assert cos(res[True][2][k], res[False][2][k]) > 0.999, (k, cos(res[True][2][k], res[False][2][k]))
