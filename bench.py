@@ -116,7 +116,7 @@ def conv_flops_teacher(engine_model, n_img, img):
 
 
 def dominant_kernel_roofline(dev, peak_tflops, peak_kind):
-    """The step's top kernel by GPU time (profiles/r1_step_kernel_table.md): conv_fwd2_kernel<6,0> -- the cta_group::2
+    """The step's top kernel by GPU time (profiles/r1_step_kernel_table.md): conv_fwd2_kernel<256,6,0> -- the cta_group::2
     tcgen05 implicit GEMM with the raw bf16 epilogue that runs the student's training forward AND (with transposed taps)
     its dgrad -- on the shape family that carries 57% of the trunk FLOPs (3x3 s1 C->C Bottleneck conv; here 256->256 on
     40x40 maps, batch 32 = the student's batch).  30 launches timed with CUDA events on the launching stream, rotating
@@ -142,7 +142,7 @@ def dominant_kernel_roofline(dev, peak_tflops, peak_kind):
     ms = s.elapsed_time(e) / n
     flops = 2.0 * N * H * H * C_ * C_ * 9
     ach = flops / ms / 1e9
-    return {"bound": "tensor", "kernel": "conv_fwd2_kernel<6,0> (cta_group::2 tcgen05 implicit GEMM, TMA-fed, raw bf16 epilogue: student forward + dgrad), 3x3 s1 256->256 @40x40, batch 32",
+    return {"bound": "tensor", "kernel": "conv_fwd2_kernel<256,6,0> (cta_group::2 tcgen05 implicit GEMM, TMA-fed, raw bf16 epilogue: student forward + dgrad), 3x3 s1 256->256 @40x40, batch 32",
             "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops,
             "traffic": DOMINANT_TRAFFIC, "traffic_note": DOMINANT_TRAFFIC_NOTE,
             "peak_kind": peak_kind, "flops_per_launch": flops, "us_per_launch": ms * 1e3, "launches_timed": n,

@@ -495,21 +495,20 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {   // arrive on 
                : "memory");
 }
 
-template <int STAGES>
+template <int BN, int STAGES>
 struct Conv2Smem {
   static constexpr int A_BYTES = CONV_BLOCK_M * 128;      // this CTA's 128 pixels
-  static constexpr int B_BYTES = 128 * 128;               // this CTA's half (128 couts) of the 256-wide weight tile
+  static constexpr int B_BYTES = (BN / 2) * 128;          // this CTA's half (BN/2 couts) of the BN-wide weight tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;
-  static constexpr int TMEM_COLS = 512;                   // two 256-column accumulators per CTA
+  static constexpr int TMEM_COLS = 2 * BN;                // two BN-column accumulators per CTA
 };
 
-template <int STAGES, int EPI>
+template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_fwd2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const ConvKArgs a) {
-  constexpr int BN = 256;
-  using L = Conv2Smem<STAGES>;
+  using L = Conv2Smem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = (uint64_t*)(smem + L::BAR_OFF);
@@ -563,7 +562,7 @@ conv_fwd2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             if (rank == 0) mbar_expect_tx(&full[s], 2u * (a_bytes + (uint32_t)L::B_BYTES));
             else mbar_arrive_leader(&full[s]);
             tma_load_4d_2sm(&mapA, &full[s], sa, kb * CONV_BLOCK_K, w0 * a.stride + a.tap_dw[tp], h0 * a.stride + a.tap_dh[tp], img);
-            tma_load_2d_2sm(&mapB, &full[s], sb, (tp * a.kblocks + kb) * CONV_BLOCK_K, n0 + 128 * (int)rank);
+            tma_load_2d_2sm(&mapB, &full[s], sb, (tp * a.kblocks + kb) * CONV_BLOCK_K, n0 + (BN / 2) * (int)rank);
           }
       }
     }
@@ -632,12 +631,12 @@ conv_fwd2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   }
 }
 
-template <int STAGES, int EPI>
+template <int BN, int STAGES, int EPI>
 static int launch_conv2_e(const CUtensorMap& mA, const CUtensorMap& mB, const ConvKArgs& ka, dim3 grid, cudaStream_t st) {
-  using L = Conv2Smem<STAGES>;
+  using L = Conv2Smem<BN, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
-    ETB_CHECK_CUDA(cudaFuncSetAttribute(conv_fwd2_kernel<STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    ETB_CHECK_CUDA(cudaFuncSetAttribute(conv_fwd2_kernel<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
@@ -646,14 +645,15 @@ static int launch_conv2_e(const CUtensorMap& mA, const CUtensorMap& mB, const Co
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  ETB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_fwd2_kernel<STAGES, EPI>, mA, mB, ka));
+  ETB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_fwd2_kernel<BN, STAGES, EPI>, mA, mB, ka));
   etb_count_launch();
   return ETB_OK;
 }
+template <int BN, int STAGES>
 static int launch_conv2(const CUtensorMap& mA, const CUtensorMap& mB, const ConvKArgs& ka, dim3 grid, cudaStream_t st) {
-  if (ka.out_mode == 1) return launch_conv2_e<6, 2>(mA, mB, ka, grid, st);
-  if (ka.scale || ka.bias || ka.act || ka.residual) return launch_conv2_e<6, 1>(mA, mB, ka, grid, st);
-  return launch_conv2_e<6, 0>(mA, mB, ka, grid, st);
+  if (ka.out_mode == 1) return launch_conv2_e<BN, STAGES, 2>(mA, mB, ka, grid, st);
+  if (ka.scale || ka.bias || ka.act || ka.residual) return launch_conv2_e<BN, STAGES, 1>(mA, mB, ka, grid, st);
+  return launch_conv2_e<BN, STAGES, 0>(mA, mB, ka, grid, st);
 }
 
 // ------------------------------------------------------------------------------------------------- host side
@@ -764,10 +764,11 @@ static int launch_gemm(const GemmGeom& g, ConvKArgs ka, cudaStream_t st) {
   static int two_sm = -1;                 // ETB_CONV_2SM=0 disables the cta_group::2 path
   if (two_sm < 0) { const char* e = getenv("ETB_CONV_2SM"); two_sm = e ? atoi(e) : 1; }
   const long m_tiles_all = (long)ka.tiles_w * ka.tiles_h * nimg;
-  const bool use2 = two_sm && BN == 256 && m_tiles_all >= 2;
+  // cta_group::2 for the 256- and 128-wide tiles (two_sm & 1 / & 2): the pair halves each SM's weight ingest
+  const bool use2 = ((BN == 256 && (two_sm & 1)) || (BN == 128 && (two_sm & 2))) && m_tiles_all >= 2;
   cuuint64_t wdim[2] = {(cuuint64_t)Ktot, (cuuint64_t)g.b_rows};
   cuuint64_t wstr[1] = {(cuuint64_t)Ktot * 2};
-  cuuint32_t wbox[2] = {64, (cuuint32_t)(use2 ? 128 : BN)};
+  cuuint32_t wbox[2] = {64, (cuuint32_t)(use2 ? BN / 2 : BN)};
   cuuint32_t westr[2] = {1, 1};
   r = enc(&mB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(g.b_ptr), wdim, wstr, wbox, westr, CU_TENSOR_MAP_INTERLEAVE_NONE,
           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -782,7 +783,7 @@ static int launch_gemm(const GemmGeom& g, ConvKArgs ka, cudaStream_t st) {
     const long pair_tiles = ((m_tiles_all + 1) / 2) * ((g.b_rows + BN - 1) / BN);
     const long clusters = etb_num_sms() / 2;
     dim3 grid2((unsigned)(2 * (pair_tiles < clusters ? pair_tiles : clusters)), 1);
-    return launch_conv2(mA, mB, ka, grid2, st);
+    return BN == 256 ? launch_conv2<256, 6>(mA, mB, ka, grid2, st) : launch_conv2<128, 8>(mA, mB, ka, grid2, st);
   }
   const long total_tiles = (long)ka.tiles_w * ka.tiles_h * nimg * ((g.b_rows + BN - 1) / BN);
   const long resident = (long)etb_num_sms();   // persistent: one CTA per SM; overlap comes from the 2 TMEM accumulators
