@@ -36,7 +36,7 @@ def to_nchw_f32(x_nhwc, C_=None, coffset=0):
 def pack_weight(w_oihw, cin_pad=None):
     w = w_oihw.detach().float().contiguous()
     Cout, Cin, kh, kw = w.shape
-    cp = Cin if cin_pad is None else cin_pad
+    cp = (Cin + 63) // 64 * 64 if cin_pad is None else cin_pad     # every tap padded to the 64-channel K block
     out = torch.empty((Cout, kh * kw * cp), dtype=torch.bfloat16, device=w.device)
     _lib.check(_lib.lib().etb_pack_weight(_lib.ptr(w), _lib.ptr(out), Cout, Cin, kh, kw, cp, _lib.stream_ptr()), "etb_pack_weight")
     return out

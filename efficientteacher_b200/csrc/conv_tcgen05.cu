@@ -721,7 +721,10 @@ static int launch_gemm(const GemmGeom& g, ConvKArgs ka, cudaStream_t st) {
     etb_set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
     return ETB_ERR_CUDA;
   }
-  ETB_CHECK_ARG(g.aC % CONV_BLOCK_K == 0 && g.a_cstride >= g.aC && g.a_cstride % 8 == 0);
+  // aC need not be a multiple of the 64-channel K block: the A box is clipped by TMA (zero fill beyond aC) and the B operand is
+  // packed with every tap padded to aCp = ceil64(aC) zero columns (etb_pack_weight Cin_pad / dgrad out_ld)
+  ETB_CHECK_ARG(g.aC % 8 == 0 && g.aC > 0 && g.a_cstride >= g.aC && g.a_cstride % 8 == 0);
+  const int aCp = (g.aC + CONV_BLOCK_K - 1) / CONV_BLOCK_K * CONV_BLOCK_K;
   ETB_CHECK_ARG((((uintptr_t)g.a_ptr) & 15) == 0 && (((uintptr_t)g.b_ptr) & 15) == 0);
   ETB_CHECK_ARG(ka.ntaps >= 1 && ka.ntaps <= 12);
   cuuint64_t gdim[4], gstr[3];
@@ -759,7 +762,7 @@ static int launch_gemm(const GemmGeom& g, ConvKArgs ka, cudaStream_t st) {
     etb_set_error("cuTensorMapEncodeTiled(A) failed: %d", (int)r);
     return ETB_ERR_CUDA;
   }
-  const long Ktot = (long)ka.ntaps * g.aC;
+  const long Ktot = (long)ka.ntaps * aCp;
   const int BN = g.b_rows > 128 ? 256 : (g.b_rows > 64 ? 128 : 64);
   static int two_sm = -1;                 // ETB_CONV_2SM=0 disables the cta_group::2 path
   if (two_sm < 0) { const char* e = getenv("ETB_CONV_2SM"); two_sm = e ? atoi(e) : 1; }
@@ -776,7 +779,7 @@ static int launch_gemm(const GemmGeom& g, ConvKArgs ka, cudaStream_t st) {
     etb_set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r);
     return ETB_ERR_CUDA;
   }
-  ka.kblocks = g.aC / CONV_BLOCK_K;
+  ka.kblocks = aCp / CONV_BLOCK_K;
   ka.Cout = g.b_rows;
   ka.nimg = nimg;
   if (use2) {
@@ -858,21 +861,22 @@ static int dgrad_taps(int k, int s, int pad, int ph, int pw, signed char* kh_l, 
 
 extern "C" int64_t etb_dgrad_weight_elems(int32_t Cout, int32_t Cin, int32_t k, int32_t stride) {
   (void)stride;
-  return (int64_t)Cin * k * k * Cout;   // all parity classes together visit every tap exactly once
+  const int64_t Coutp = (Cout + CONV_BLOCK_K - 1) / CONV_BLOCK_K * CONV_BLOCK_K;   // every tap padded to the 64-channel K block
+  return (int64_t)Cin * k * k * Coutp;   // all parity classes together visit every tap exactly once
 }
 
 struct TapTable { signed char v[24]; };
-__global__ void __launch_bounds__(256) pack_weight_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o, int Cout, int Cin, int k, int ntaps, TapTable tt) {
-  const int64_t total = (int64_t)Cin * ntaps * Cout;
+__global__ void __launch_bounds__(256) pack_weight_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o, int Cout, int Coutp, int Cin, int k, int ntaps, TapTable tt) {
+  const int64_t total = (int64_t)Cin * ntaps * Coutp;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int co = (int)(e % Cout);
-    const int t = (int)((e / Cout) % ntaps);
-    const int ci = (int)(e / ((int64_t)Cout * ntaps));
-    o[e] = __float2bfloat16(w[(((int64_t)co * Cin + ci) * k + tt.v[t]) * k + tt.v[12 + t]]);
+    const int co = (int)(e % Coutp);
+    const int t = (int)((e / Coutp) % ntaps);
+    const int ci = (int)(e / ((int64_t)Coutp * ntaps));
+    o[e] = __float2bfloat16(co < Cout ? w[(((int64_t)co * Cin + ci) * k + tt.v[t]) * k + tt.v[12 + t]] : 0.f);
   }
 }
 
-// w [Cout,Cin,k,k] fp32 -> for each parity class c (row-major ph,pw) a [Cin][ntaps_c*Cout] bf16 block, blocks concatenated
+// w [Cout,Cin,k,k] fp32 -> for each parity class c (row-major ph,pw) a [Cin][ntaps_c*ceil64(Cout)] bf16 block (zero padded), blocks concatenated
 extern "C" int etb_pack_weight_dgrad(const float* w_oihw, void* out_bf16, int32_t Cout, int32_t Cin, int32_t k, int32_t stride,
                                      int32_t pad, void* stream) {
   ETB_CHECK_ARG(w_oihw && out_bf16 && Cout > 0 && Cin > 0 && k >= 1 && k * k <= 12 && (stride == 1 || stride == 2));
@@ -883,10 +887,11 @@ extern "C" int etb_pack_weight_dgrad(const float* w_oihw, void* out_bf16, int32_
       signed char dh[12], dw[12];
       const int nt = dgrad_taps(k, stride, pad, ph, pw, tt.v, tt.v + 12, dh, dw);
       if (nt == 0) continue;
-      const int64_t total = (int64_t)Cin * nt * Cout;
+      const int Coutp = (Cout + CONV_BLOCK_K - 1) / CONV_BLOCK_K * CONV_BLOCK_K;
+      const int64_t total = (int64_t)Cin * nt * Coutp;
       int64_t blocks = (total + 255) / 256;
       if (blocks > 148 * 16) blocks = 148 * 16;
-      pack_weight_dgrad_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, o, Cout, Cin, k, nt, tt);
+      pack_weight_dgrad_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, o, Cout, Coutp, Cin, k, nt, tt);
       ETB_CHECK_LAUNCH();
       o += total;
     }
@@ -900,7 +905,8 @@ extern "C" int etb_conv_dgrad(const void* dy_bf16, const void* wd_bf16, void* dx
                               void* stream) {
   ETB_CHECK_ARG(dy_bf16 && wd_bf16 && dx_bf16 && cp);
   ETB_CHECK_ARG(cp->kh == cp->kw && cp->kh * cp->kw <= 12 && (cp->stride == 1 || cp->stride == 2));
-  ETB_CHECK_ARG(cp->Cout % CONV_BLOCK_K == 0 && cp->y_cstride % 8 == 0 && cp->y_coffset % 8 == 0 && cp->y_cstride >= cp->y_coffset + cp->Cin);
+  ETB_CHECK_ARG(cp->Cout % 8 == 0 && cp->y_cstride % 8 == 0 && cp->y_coffset % 8 == 0 && cp->y_cstride >= cp->y_coffset + cp->Cin);
+  const int Coutp = (cp->Cout + CONV_BLOCK_K - 1) / CONV_BLOCK_K * CONV_BLOCK_K;   // row pitch of one tap in the packed operand
   const int k = cp->kh, s = cp->stride, pad = cp->pad;
   const int Ho = (cp->H + 2 * pad - k) / s + 1, Wo = (cp->W + 2 * pad - k) / s + 1;
   const __nv_bfloat16* wd = (const __nv_bfloat16*)wd_bf16;
@@ -926,7 +932,7 @@ extern "C" int etb_conv_dgrad(const void* dy_bf16, const void* wd_bf16, void* dx
       ka.y = (__nv_bfloat16*)dx_bf16;
       int rc = launch_gemm(g, ka, (cudaStream_t)stream);
       if (rc != ETB_OK) return rc;
-      wd += (size_t)cp->Cin * nt * cp->Cout;
+      wd += (size_t)cp->Cin * nt * Coutp;
     }
   return ETB_OK;
 }
@@ -1229,11 +1235,13 @@ __global__ void __launch_bounds__(32 * SG) wgrad_reduce_kernel(const float* __re
 __global__ void __launch_bounds__(256) wgrad_reduce_taps_kernel(const float* __restrict__ ws, long slice, int splitk, float* __restrict__ out, int Cin,
                                                                 int kk, int flags) {
   __shared__ float sm[64 * 12];
-  const int chunks = Cin >> 6;
-  const int co = blockIdx.x / chunks, ci0 = (blockIdx.x - co * chunks) << 6;
+  const int CW = Cin < 64 ? Cin : 64;            // channels per block (Cin is a multiple of 64, or smaller than 64 and of 8)
+  const int L4 = CW >> 2;                        // float4 lanes per tap
+  const int chunks = Cin / CW;
+  const int co = blockIdx.x / chunks, ci0 = (blockIdx.x - co * chunks) * CW;
   const size_t st4 = (size_t)slice / 4;
-  for (int u = threadIdx.x; u < kk * 16; u += 256) {
-    const int t = u >> 4, lane = u & 15;
+  for (int u = threadIdx.x; u < kk * L4; u += 256) {
+    const int t = u / L4, lane = u - t * L4;
     const float4* p = reinterpret_cast<const float4*>(ws + ((size_t)co * kk + t) * Cin + ci0) + lane;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int sidx = 0;
@@ -1254,7 +1262,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_taps_kernel(const float* __r
   }
   __syncthreads();
   float* o = out + ((size_t)co * Cin + ci0) * kk;
-  for (int i = threadIdx.x; i < 64 * kk; i += 256) o[i] = (flags & 2) ? o[i] + sm[i] : sm[i];
+  for (int i = threadIdx.x; i < CW * kk; i += 256) o[i] = (flags & 2) ? o[i] + sm[i] : sm[i];
 }
 
 static void wgrad_plan(const EtbConvParams* cp, int* BN_, int* KP_, int* TW, int* TH, int* tiles_w, int* tiles_h, int* nimg, int* out_tiles,
@@ -1312,7 +1320,7 @@ extern "C" size_t etb_conv_wgrad_workspace_bytes(const EtbConvParams* cp) {
 extern "C" int etb_conv_wgrad(const void* x_bf16, const void* dy_bf16, float* dw_f32, const EtbConvParams* cp, int32_t flags, void* workspace,
                               size_t workspace_bytes, void* stream) {
   ETB_CHECK_ARG(x_bf16 && dy_bf16 && dw_f32 && cp && workspace);
-  ETB_CHECK_ARG(cp->N > 0 && cp->H > 0 && cp->W > 0 && cp->Cin > 0 && cp->Cout > 0 && cp->Cin % 64 == 0);
+  ETB_CHECK_ARG(cp->N > 0 && cp->H > 0 && cp->W > 0 && cp->Cin > 0 && cp->Cout > 0 && cp->Cin % 8 == 0 && (cp->Cin % 64 == 0 || cp->Cin < 64));
   ETB_CHECK_ARG(cp->kh * cp->kw <= 12 && (cp->stride == 1 || cp->stride == 2));
   ETB_CHECK_ARG(cp->x_cstride % 8 == 0 && cp->y_cstride % 8 == 0 && (((uintptr_t)x_bf16) & 15) == 0 && (((uintptr_t)dy_bf16) & 15) == 0);
   ETB_CHECK_ARG((((uintptr_t)workspace) & 15) == 0);
@@ -1393,7 +1401,7 @@ extern "C" int etb_conv_wgrad(const void* x_bf16, const void* dy_bf16, float* dw
   const long cap = (long)etb_num_sms() * 16;
   if (blocks > cap) blocks = cap;
   if (wa.ntaps > 1 && !(flags & 1))
-    wgrad_reduce_taps_kernel<<<(unsigned)(cp->Cout * (cp->Cin >> 6)), 256, 0, st>>>((const float*)workspace, (long)dw_elems, splitk, dw_f32, cp->Cin, wa.ntaps,
+    wgrad_reduce_taps_kernel<<<(unsigned)(cp->Cout * (cp->Cin < 64 ? 1 : cp->Cin >> 6)), 256, 0, st>>>((const float*)workspace, (long)dw_elems, splitk, dw_f32, cp->Cin, wa.ntaps,
                                                                                   flags);
   else if (splitk >= 32)
     wgrad_reduce_kernel<16><<<(unsigned)blocks, dim3(32, 16), 0, st>>>((const float*)workspace, (long)dw_elems, splitk, dw_f32, cp->Cout, cp->Cin, wa.ntaps, flags);

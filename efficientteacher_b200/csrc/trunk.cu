@@ -216,7 +216,7 @@ extern "C" int etb_pack_stem_weight(const float* w_oihw, void* w_bf16, int32_t C
 }
 
 // ---- multi-tensor weight packing / BN folding: ONE launch for all ~104 convs of the trunk (replaces ~440 tiny launches/step) ----
-// mode 0: fwd  [Cout][kh][kw][Cin]   <- w[co][ci][kh][kw]        (dst index e: ci fastest)
+// mode 0: fwd  [Cout][kh][kw][Cin or out_ld]   <- w[co][ci][kh][kw]        (dst index e: ci fastest; out_ld > Cin pads every tap)
 // mode 1: dgrad class  [Cin][ntaps][out_ld>=Cout] <- w[co][ci][kh_t][kw_t]   (dst: co fastest; row pitch out_ld per tap)
 // mode 2: stem [Cout][128] in the etb_stem_im2col K order
 __global__ void __launch_bounds__(256) pack_multi_kernel(const EtbPackDesc* __restrict__ descs, const int2* __restrict__ chunks) {
@@ -237,6 +237,7 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const EtbPackDesc* __re
       const int64_t t2 = e / d.Cin;
       const int t = (int)(t2 % kk), co = (int)(t2 / kk);
       v = w[((int64_t)co * d.Cin + ci) * kk + t];
+      if (d.out_ld > d.Cin) dst = ((int64_t)co * kk + t) * d.out_ld + ci;   // every tap padded to out_ld = ceil64(Cin) (pad stays zero)
     } else if (d.mode == 1) {
       const int co = (int)(e % d.Cout);
       const int64_t t2 = e / d.Cout;

@@ -59,8 +59,8 @@ class TrunkEngine:
             for d in ("det_8", "det_16", "det_32"):
                 self.params[d + ".conv1"].act = "relu"
         for q in self.params.values():
-            if q.Cin % 64 != 0 and not q.stem:
-                raise NotImplementedError("tcgen05 conv path needs Cin %% 64 == 0 (got %d)" % q.Cin)
+            if q.Cin % 8 != 0 and not q.stem:
+                raise NotImplementedError("tcgen05 conv path needs Cin %% 8 == 0 (16 B rows; got %d)" % q.Cin)
         self.launches = 0
         self.packer = None
 

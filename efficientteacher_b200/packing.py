@@ -14,6 +14,10 @@ from . import _lib
 from ._lib import EtbFoldDesc, EtbPackDesc, ETB_PACK_CHUNK
 
 
+def _ceil64(c):
+    return (c + 63) // 64 * 64
+
+
 def dgrad_classes(k, s, pad):
     """[(kh list, kw list)] per output-parity class in the order etb_conv_dgrad visits them (ph outer, pw inner)."""
     out = []
@@ -48,10 +52,11 @@ class WeightPacker:
         Cout, Cin, k, _ = weight.shape
         pc = PackedConv()
         pc.Cin, pc.Cout, pc.k, pc.s, pc.p = (128 if stem else Cin), Cout, (1 if stem else k), (1 if stem else stride), (0 if stem else pad)
-        pc.fwd = torch.empty((Cout, 128 if stem else k * k * Cin), dtype=torch.bfloat16, device=self.device)
+        # every tap is padded to a multiple of the 64-channel K block (YOLOv5s widths: 32-channel layers); pads stay zero
+        pc.fwd = torch.zeros((Cout, 128 if stem else k * k * _ceil64(Cin)), dtype=torch.bfloat16, device=self.device)
         pc.dgrad = None
         if want_dgrad and not stem:
-            ld = Cout if dgrad_cout_pad is None else dgrad_cout_pad
+            ld = _ceil64(Cout) if dgrad_cout_pad is None else dgrad_cout_pad
             pc.dgrad = torch.zeros(Cin * k * k * ld, dtype=torch.bfloat16, device=self.device)
         pc.scale = pc.bias = None
         self.items.append((weight, pc, "stem" if stem else "conv", dgrad_cout_pad))
@@ -83,9 +88,9 @@ class WeightPacker:
             if kind == "stem":
                 push(w, pc.fwd.data_ptr(), Cout * 128, Cout, 3, 6, 2)
                 continue
-            push(w, pc.fwd.data_ptr(), Cout * k * k * Cin, Cout, Cin, k, 0)
+            push(w, pc.fwd.data_ptr(), Cout * k * k * Cin, Cout, Cin, k, 0, out_ld=_ceil64(Cin))
             if pc.dgrad is not None:
-                ld = Cout if cpad is None else cpad
+                ld = _ceil64(Cout) if cpad is None else cpad
                 off = 0
                 for khs, kws in dgrad_classes(k, pc.s, pc.p):
                     nt = len(khs)

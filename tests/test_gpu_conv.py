@@ -41,6 +41,11 @@ CASES = [
     (1, 128, 40, 40, 256, 3, 1, 1),    # 3x3 s1 40x40, BN=256
     (2, 64, 32, 32, 128, 3, 2, 1),     # 3x3 s2 (TMA element strides)
     (1, 128, 40, 40, 128, 3, 2, 1),    # 3x3 s2 -> 20x20
+    # YOLOv5s widths: channel counts that are not a multiple of the 64-channel K block (TMA clips the box, packs are padded)
+    (2, 32, 16, 16, 64, 3, 2, 1),      # Cin = 32, stride 2 (stage2_1 of v5s)
+    (2, 32, 20, 20, 32, 3, 1, 1),      # Cin = Cout = 32 (Bottleneck of the first C3)
+    (2, 64, 20, 20, 32, 1, 1, 0),      # pointwise to 32 channels
+    (2, 96, 16, 16, 32, 1, 1, 0),      # Cin = 96: 1.5 K blocks
 ]
 
 
@@ -117,6 +122,9 @@ DGRAD_CASES = [
     (1, 64, 40, 40, 128, 3, 1, 1),
     (2, 64, 32, 32, 128, 3, 2, 1),     # stride 2: four parity-class launches
     (1, 128, 40, 40, 256, 3, 2, 1),
+    (2, 32, 16, 16, 64, 3, 2, 1),      # v5s: dgrad K = Cout = 64, 32 output channels
+    (2, 32, 20, 20, 32, 3, 1, 1),      # v5s: K = 32 (half a K block, zero-filled by TMA)
+    (2, 64, 20, 20, 32, 1, 1, 0),
 ]
 
 
@@ -145,6 +153,10 @@ WGRAD_CASES = [
     (2, 128, 20, 20, 128, 3, 1, 1),    # 20x20: K tiles with out-of-image rows
     (2, 64, 32, 32, 128, 3, 2, 1),     # stride 2
     (8, 256, 40, 40, 256, 3, 1, 1),    # split-K with atomics
+    (2, 32, 16, 16, 64, 3, 2, 1),      # v5s: Cin = 32 (half-filled ci tile), 9 taps
+    (2, 32, 20, 20, 32, 3, 1, 1),
+    (2, 64, 20, 20, 32, 1, 1, 0),
+    (2, 32, 20, 20, 64, 1, 1, 0),
 ]
 
 

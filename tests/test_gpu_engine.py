@@ -35,7 +35,7 @@ def _rel(a, b):
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-6)).item()
 
 
-@pytest.mark.parametrize("size,img,B", [("l_shallow", 256, 2), ("l", 320, 1)])
+@pytest.mark.parametrize("size,img,B", [("l_shallow", 256, 2), ("l", 320, 1), ("s", 320, 2)])
 def test_teacher_forward_vs_torch_fp32(size, img, B):
     from oracle.trunk_ref import TrunkRef
     from oracle import port
@@ -192,16 +192,18 @@ def test_graphed_step_matches_eager_step():
     assert ((ra - rb).norm() / ra.norm()).item() <= 3.0 * ((ra - rc).norm() / ra.norm()).item() + 5e-3
 
 
-def test_supervised_step_matches_cpu_reference():
-    """BASELINE config #1 shape of work (supervised step): loss of the native step vs the torch fp32 CPU restatement."""
+@pytest.mark.parametrize("size,img", [("l_shallow", 256), ("s", 640)])
+def test_supervised_step_matches_cpu_reference(size, img):
+    """Supervised step (BASELINE configs[1] shape of work on the shallow YOLOv5l; configs[0] itself = YOLOv5s 640 batch 2,
+    whose 32-channel layers exercise the clipped-K-block path): loss of the native step vs the torch fp32 CPU restatement."""
     from efficientteacher_b200.config import yolov5_sup_cfg
     from efficientteacher_b200.trainer import SupTrainerStep
     from oracle.trunk_ref import TrunkRef
     from oracle import port
     import synth
-    img, B = 256, 2
+    B = 2
     torch.manual_seed(0)
-    st = SupTrainerStep(yolov5_sup_cfg('l_shallow', batch_size=B, img_size=img), torch.device(DEV))
+    st = SupTrainerStep(yolov5_sup_cfg(size, batch_size=B, img_size=img), torch.device(DEV))
     sd = {k: v.detach().cpu().clone() for k, v in st.model.state_dict().items()}
     x = torch.rand(B, 3, img, img, generator=torch.Generator().manual_seed(3))
     tg = synth.make_targets(5, 16, B)
