@@ -58,12 +58,12 @@ def test_teacher_forward_vs_torch_fp32(size, img, B):
     torch.testing.assert_close(pred.cpu(), want, rtol=1e-5, atol=1e-4)
 
 
-def test_full_ssod_step_runs_and_matches_cpu_step():
+@pytest.mark.parametrize("img,bl,bu", [(256, 2, 2), (1280, 1, 1)])      # 1280: BASELINE configs[4] geometry (102,000 predictions/img)
+def test_full_ssod_step_runs_and_matches_cpu_step(img, bl, bu):
     from efficientteacher_b200.config import yolov5_ssod_cfg
     from efficientteacher_b200.trainer import SSODTrainerStep
     from oracle.step_ref import CpuSSODStep
     import synth
-    img, bl, bu = 256, 2, 2
     torch.manual_seed(0)
     cfg = yolov5_ssod_cfg('l_shallow', batch_size=bl + bu, img_size=img)   # full width (Cin % 64 == 0), depth 0.33
     st = SSODTrainerStep(cfg, torch.device(DEV), epochs=300, amp_dtype=torch.bfloat16)

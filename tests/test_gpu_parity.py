@@ -126,6 +126,18 @@ def test_nms_no_candidates_and_properties_full_size():
     assert len(d2) == len(b0)
 
 
+def test_nms_1280_geometry_vs_oracle():
+    """BASELINE configs[4]: 1280x1280 -> 102,000 predictions per image; keep-sets and rows bit-exact vs the oracle."""
+    from efficientteacher_b200 import nms as N
+    pred = synth.make_teacher_pred(11, 3, 102000, img=1280)
+    dets = N.non_max_suppression_ssod(torch.from_numpy(pred).to(DEV), 0.1, 0.65)
+    want = port.nms_ssod(pred, 0.1, 0.65)
+    for b, d in enumerate(dets):
+        d = d.cpu().numpy()
+        assert np.array_equal(d, want[b])
+        assert len(d) <= 300 and np.all(np.diff(d[:, 4]) <= 0)
+
+
 # ------------------------------------------------------------------------------------------------ select_targets
 def _ssod_loss_obj(model_like=None):
     from efficientteacher_b200.ssod_loss import ComputeStudentMatchLoss
