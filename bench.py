@@ -325,13 +325,20 @@ def main():
             return st.train_instance_graphed(d_imgs, d_tg, d_us, d_uw, None, d_Ms, i)
         return st.train_instance(d_imgs, d_tg, d_us, d_uw, None, d_Ms, i)
 
+    from efficientteacher_b200.trainer import DevicePrefetcher
+    pf = DevicePrefetcher(dev)
+    host_batch = {k: host[k] for k in ("imgs", "u_strong", "u_weak", "targets", "Ms")}
+
     def step_e2e(i):
-        imgs = host["imgs"].to(dev, non_blocking=True).float() / 255.0
-        us = host["u_strong"].to(dev, non_blocking=True).float() / 255.0
-        uw = host["u_weak"].to(dev, non_blocking=True).float() / 255.0
-        tg = host["targets"].to(dev, non_blocking=True)
-        Ms = host["Ms"].to(dev, non_blocking=True)
-        loss = (st.train_instance_graphed if use_graph else st.train_instance)(imgs, tg, us, uw, None, Ms, i)
+        # every step: H2D of this step's uint8 batch from pinned memory (staged on a side stream, so the copy of step i+1
+        # overlaps the kernels of step i), uint8 -> float/255 on the compute stream, the step, D2H read of the loss
+        if pf.pending == 0:
+            pf.put(host_batch)
+        b = pf.get()
+        imgs, us, uw = b["imgs"].float() / 255.0, b["u_strong"].float() / 255.0, b["u_weak"].float() / 255.0
+        loss = (st.train_instance_graphed if use_graph else st.train_instance)(imgs, b["targets"], us, uw, None, b["Ms"], i)
+        pf.release()
+        pf.put(host_batch)                   # next step's inputs start moving now
         return float(loss.item())            # D2H read of the step's result
 
     def barrier():

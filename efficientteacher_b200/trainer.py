@@ -334,3 +334,49 @@ class SupTrainerStep:
             self.ema.update(self.model)
             self.last_opt_step = ni
         return loss.detach()
+
+
+class DevicePrefetcher:
+    """Double-buffered host -> device staging of a batch on a side stream, so the H2D copy of step i+1 overlaps the kernels
+    of step i (the reference's loop copies on the compute stream: `imgs.to(device, non_blocking=True)`,
+    trainer/ssod_trainer.py:694-696).  put(batch of pinned host tensors) enqueues the copies into the next slot;
+    get() makes the current stream wait for the oldest slot and returns its device tensors.  A slot is reused two put()s
+    later, i.e. after the step that consumed it has been enqueued on the compute stream -- put() makes the copy stream wait
+    for that point before overwriting."""
+
+    def __init__(self, device, slots=2):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+        self.slots = [dict(buf=None, ready=torch.cuda.Event(), free=None) for _ in range(slots)]
+        self.head = self.tail = 0          # next slot to fill / next slot to hand out
+        self.pending = 0
+
+    def put(self, batch):
+        assert self.pending < len(self.slots), "prefetcher full: call get() first"
+        sl = self.slots[self.head]
+        if sl["buf"] is None:
+            sl["buf"] = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in batch.items()}
+        if sl["free"] is not None:
+            self.stream.wait_event(sl["free"])          # the consumer of this slot's previous contents has been enqueued and finished
+        with torch.cuda.stream(self.stream):
+            for k, v in batch.items():
+                sl["buf"][k].copy_(v, non_blocking=True)
+            sl["ready"].record(self.stream)
+        self.head = (self.head + 1) % len(self.slots)
+        self.pending += 1
+
+    def get(self):
+        assert self.pending > 0, "prefetcher empty: call put() first"
+        sl = self.slots[self.tail]
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(sl["ready"])
+        self._last = sl
+        self.tail = (self.tail + 1) % len(self.slots)
+        self.pending -= 1
+        return sl["buf"]
+
+    def release(self):
+        """call after the kernels that read the last get()'s tensors have been enqueued on the current stream"""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._last["free"] = ev
