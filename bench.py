@@ -305,10 +305,11 @@ def main():
         (pred, raw), _ = st.ema.ema(d_uw)
         for l, m in enumerate(st.ema.ema.head.m):
             obj = raw[l][..., 4].flatten().float()
-            shift = float(np.log(0.1 / 0.9)) + 0.05 - torch.quantile(obj[:2_000_000], 0.98).item()
+            # 98th percentile of the objectness logits -> 0.12: ~2% of the rows clear conf = obj*cls > 0.1 (cls ~0.96 after the +8)
+            shift = float(np.log(0.12 / 0.88)) - torch.quantile(obj[:2_000_000], 0.98).item()
             b = m.bias.view(3, -1)
             b[:, 4] += shift
-            b[:, 5:] += 5.0      # class scores ~0.5 so that conf = obj * max(cls) can clear the 0.1 NMS threshold
+            b[:, 5:] += 8.0      # class bias starts at log(0.6/(nc-0.99)) ~ -4.9: +8 -> class scores ~0.96, so conf = obj*cls ~ obj
             st.model.head.m[l].bias.data.copy_(m.bias.data)
             if st.semi_ema:
                 st.semi_ema.ema.head.m[l].bias.data.copy_(m.bias.data)
@@ -399,6 +400,19 @@ def main():
         ni += 2
     n_pl = int(st.pseudo_label_creator.last_count_dev.item())
     det_per_img = float(st.pseudo_label_creator.last_det[1].float().mean().item())
+    if rank == 0:        # teacher health at the end of the run (stderr only): candidates, conf-passing rows, NMS detections
+        with torch.no_grad():
+            from efficientteacher_b200.nms import non_max_suppression_ssod
+            (pred_e, _raw_e), _f = st.ema.ema(d_uw)
+            conf_e = pred_e[..., 4:5] * pred_e[..., 5:]
+            dets_e = non_max_suppression_ssod(pred_e, cfg.SSOD.nms_conf_thres, cfg.SSOD.nms_iou_thres)
+            print("[bench] teacher at end: obj>thr rows/img %.1f, conf>thr rows/img %.1f, NMS dets/img %.1f, obj max %.3f, cls max mean %.3f, "
+                  "ema.updates %d, last step: dets/img %.2f pseudo-label rows %d" % (
+                      float((pred_e[..., 4] > cfg.SSOD.nms_conf_thres).sum(1).float().mean()),
+                      float((conf_e.max(-1)[0] > cfg.SSOD.nms_conf_thres).sum(1).float().mean()),
+                      float(np.mean([len(d) for d in dets_e])), float(pred_e[..., 4].max()), float(pred_e[..., 5:].max(-1)[0].mean()),
+                      st.ema.updates, det_per_img, n_pl), file=sys.stderr, flush=True)
+        del pred_e, _raw_e, _f, conf_e, dets_e
 
     if rank == 0:
         pk, pk_kind = peaks()

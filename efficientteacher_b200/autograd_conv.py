@@ -14,6 +14,48 @@ from . import convops as co
 
 ACCUMULATE_INTO_GRAD = True
 
+# Optional side stream for the weight-gradient branch.  In backward, wgrad (+ its split-K reduce) of a layer depends only on
+# that layer's dy and feeds nothing but the gradient arena, while the critical path continues dgrad -> previous layer's BN
+# backward -> ...  With the branch on its own stream the tails of the persistent conv kernels and the many tiny launches
+# (BN finalize, reduces) overlap with wgrad CTAs instead of leaving SMs idle; inside a captured CUDA graph the fork/join
+# events become parallel graph branches.  Only the trainer turns it on (it joins before the all-reduce / optimizer);
+# operands are kept alive until the join so the caching allocator cannot hand their memory out early.
+WGRAD_SIDE = {"on": False, "stream": None, "keep": [], "dirty": False}
+
+
+def wgrad_side_run(fn, keep):
+    S = WGRAD_SIDE
+    cur = torch.cuda.current_stream()
+    if S["stream"] is None or S["stream"].device != cur.device:
+        S["stream"] = torch.cuda.Stream(cur.device)
+    ev = torch.cuda.Event()
+    ev.record(cur)
+    S["stream"].wait_event(ev)
+    with torch.cuda.stream(S["stream"]):
+        fn()
+    S["keep"].append(keep)
+    S["dirty"] = True
+
+
+def backward(loss, side=True):
+    """loss.backward() with the weight-gradient branch on the side stream, joined before returning"""
+    WGRAD_SIDE["on"] = bool(side)
+    try:
+        loss.backward()
+    finally:
+        WGRAD_SIDE["on"] = False
+        wgrad_side_join()
+
+
+def wgrad_side_join():
+    S = WGRAD_SIDE
+    if S["dirty"]:
+        ev = torch.cuda.Event()
+        ev.record(S["stream"])
+        torch.cuda.current_stream().wait_event(ev)
+        S["keep"].clear()
+        S["dirty"] = False
+
 
 def _as_nhwc(t, C_):
     """(view [N,H,W,C] bf16 whose channel stride may exceed C, channel_stride) for an NCHW-shaped tensor; copies only if
@@ -312,8 +354,12 @@ class ConvBnActFn(torch.autograd.Function):
         # gradient arena: when p.grad already exists (trainer.GradArena) the wgrad is added into it in place and autograd
         # gets None for the weight (no separate AccumulateGrad add pass, no temporary)
         tgt = weight.grad if (ACCUMULATE_INTO_GRAD and weight.grad is not None and weight.grad.is_contiguous()) else None
+        side = WGRAD_SIDE["on"] and tgt is not None
         if is_stem:
-            dw = co.conv_wgrad(xs, dy, 128, Cout, 1, 1, 0, stem=True, accumulate_into=tgt)
+            if side:
+                wgrad_side_run(lambda: co.conv_wgrad(xs, dy, 128, Cout, 1, 1, 0, stem=True, accumulate_into=tgt), (xs, dy))
+            else:
+                dw = co.conv_wgrad(xs, dy, 128, Cout, 1, 1, 0, stem=True, accumulate_into=tgt)
         else:
             Cin, k = weight.shape[1], weight.shape[2]
             N, _, H, W = xs.shape
@@ -326,7 +372,10 @@ class ConvBnActFn(torch.autograd.Function):
                     dx = ctx.fan.add_dgrad(lambda o, ocs, acc: co.conv_dgrad(dy, wd, N, H, W, Cin, Cout, k, stride, pad, out=o,
                                                                              out_cstride=ocs, accumulate=acc), N, Cin, H, W, da.device)
             xb, xcs = _as_nhwc(xs, Cin)
-            dw = co.conv_wgrad(xb, dy, Cin, Cout, k, stride, pad, x_cstride=xcs, accumulate_into=tgt)
+            if side:
+                wgrad_side_run(lambda: co.conv_wgrad(xb, dy, Cin, Cout, k, stride, pad, x_cstride=xcs, accumulate_into=tgt), (xs, xb, dy))
+            else:
+                dw = co.conv_wgrad(xb, dy, Cin, Cout, k, stride, pad, x_cstride=xcs, accumulate_into=tgt)
         if tgt is not None:
             dw = None
         dres = None

@@ -13,6 +13,8 @@ because the reduced gradients are.
 """
 import math
 
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -106,9 +108,12 @@ class SSODTrainerStep:
 
     # trainer/ssod_trainer.py:458-488 (bf16 autocast needs no GradScaler; loss scale == 1), in three parts so that the
     # gradient all-reduce can sit between two captured CUDA graphs when WORLD_SIZE > 1
+    WGRAD_SIDE_STREAM = os.environ.get("ETB_WGRAD_SIDE", "1") == "1"   # measured -0.9 ms/step (35.7 -> 34.9); ETB_WGRAD_SIDE=0 disables
+
     def _backward(self, loss):
         self._ensure_arena()
-        loss.backward()
+        from . import autograd_conv as ac
+        ac.backward(loss, side=self.WGRAD_SIDE_STREAM)   # weight-gradient branch on a side stream, joined before returning
         self._mark("backward")
 
     def _optimizer_ema(self, ni):
@@ -327,7 +332,8 @@ class SupTrainerStep:
         loss, loss_items = self.compute_loss(pred, targets)
         if self._arena is None:
             self._arena = GradArena(self.model.parameters(), self.device)
-        loss.backward()
+        from . import autograd_conv as ac
+        ac.backward(loss, side=SSODTrainerStep.WGRAD_SIDE_STREAM)
         self._arena.all_reduce_sum(self.WORLD_SIZE)
         if ni - self.last_opt_step >= 1:
             self.optimizer.step(zero_grad=True)
