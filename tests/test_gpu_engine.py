@@ -234,3 +234,43 @@ def test_device_prefetcher_roundtrip():
         want = batches[i]["a"].float().sum() + batches[i]["b"].sum()
         assert abs(x.item() - want.item()) <= 1e-3 * abs(want.item())
         assert torch.equal(got["a"].cpu(), batches[i]["a"]) or True   # slot may already be refilled: value check above is the contract
+
+
+@pytest.mark.xfail(strict=False, reason="open issue (DESIGN.md section 7, item 0): in bench.py the EMA teacher's features collapse within ~15 "
+                                        "steps although decay = 0.9999; not yet reproduced / root-caused at test scale")
+def test_teacher_is_stable_under_high_ema_decay():
+    """With ema.updates = 100000 the decay is 0.9999: over 12 steps the teacher moves by <= 0.12 % of the student-teacher gap,
+    so its logits on a fixed input must stay where they were (a CPU fp32 emulation of the same 12 steps with the reference's
+    hyper-parameters moves BN scales by ~0.03/step and running variances by ~2 %/step: nothing explodes)."""
+    from efficientteacher_b200.config import yolov5_ssod_cfg
+    from efficientteacher_b200.trainer import SSODTrainerStep
+    import synth
+    img, bl, bu = 256, 4, 4
+    r = np.random.RandomState(5)
+    imgs = torch.from_numpy(r.rand(bl, 3, img, img).astype(np.float32)).to(DEV)
+    uw = torch.from_numpy(r.rand(bu, 3, img, img).astype(np.float32)).to(DEV)
+    us = uw.flip(3).contiguous()
+    tg = torch.from_numpy(synth.make_targets(7, 8 * bl, bl)).to(DEV)
+    Ms = torch.from_numpy(synth.make_Ms(9, bu, img)).to(DEV)
+    torch.manual_seed(0)
+    st = SSODTrainerStep(yolov5_ssod_cfg('l_shallow', batch_size=bl + bu, img_size=img), torch.device(DEV), epochs=300)
+    st.ema.updates = 100000
+    with torch.no_grad():
+        for mm in (st.model, st.ema.ema, st.semi_ema.ema):
+            for h in mm.head.m:
+                h.bias.view(3, -1)[:, 4] += 6.5
+                h.bias.view(3, -1)[:, 5:] += 5.0
+        (_, raw0), _ = st.ema.ema(uw)
+        raw0 = [t.clone() for t in raw0]
+    for mode, n in (("eager", 6), ("graph", 6)):
+        for i in range(n):
+            f = st.train_instance_graphed if mode == "graph" else st.train_instance
+            loss = f(imgs, tg, us, uw, None, Ms, i)
+            assert torch.isfinite(loss).all()
+        with torch.no_grad():
+            (_, raw1), _ = st.ema.ema(uw)
+        for a, b in zip(raw1, raw0):
+            rel = float((a - b).norm() / b.norm())
+            assert rel < 0.02, (mode, rel)
+    bn_var = max(float(q.running_var.max()) for q in st.model.modules() if isinstance(q, torch.nn.BatchNorm2d))
+    assert bn_var < 1e3, bn_var
