@@ -27,6 +27,12 @@ def bn_ext(mod):
             max(float(q.weight.abs().max()) for q in bb), max(float(q.bias.abs().max()) for q in bb))
 
 
+def bn_top(mod, k=3):
+    rows = [(float(q.running_var.max()), float(q.weight.abs().max()), n) for n, q in mod.named_modules() if isinstance(q, torch.nn.BatchNorm2d)]
+    rows.sort(reverse=True)
+    return " ".join("%s(var %.3g,|g| %.3g)" % (n, v, g) for v, g, n in rows[:k])
+
+
 def run(variant, args):
     import synth
     from efficientteacher_b200 import autograd_conv as ac
@@ -88,6 +94,9 @@ def run(variant, args):
         drift = max(float((a - b).norm() / b.norm()) for a, b in zip(raw1, raw0))
         print("step %2d loss %.4f teacher drift %.4f | student BN (var,|mean|,|g|,|b|) %s | teacher %s | max|grad| bias/w/bnw %s" % (
             i, float(loss), drift, "%.3g %.3g %.3g %.3g" % bn_ext(st.model), "%.3g %.3g %.3g %.3g" % bn_ext(st.ema.ema), gmax), flush=True)
+        if i in (0, args.steps - 1) or drift > 0.05:
+            wmax = max((float(p.abs().max()), n) for n, p in st.model.named_parameters() if p.dim() == 4)
+            print("        student top BN: %s | largest conv weight %.3g (%s)" % (bn_top(st.model), wmax[0], wmax[1]), flush=True)
 
 
 def main():
