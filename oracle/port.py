@@ -97,6 +97,39 @@ def nms_ssod(pred, conf_thres, iou_thres, max_det=300, max_nms=30000, max_wh=768
     return out
 
 
+def nms_val(pred, conf_thres, iou_thres, multi_label=True, agnostic=False, max_det=300, max_nms=30000, max_wh=7680.0):
+    """The validation-time NMS (general.py:994-1098; val.py:149-465 calls it with conf 0.001, multi_label=True):
+    pred [B,P,5+nc] fp32 -> list of [k,6] fp32 arrays [x1,y1,x2,y2,conf,cls].
+    multi_label: every (row, class) pair with obj*cls > conf is a detection (row-major order of torch.nonzero, :1052);
+    more than max_nms detections: the max_nms best by confidence (:1071-1072); then class-offset greedy NMS, max_det."""
+    pred = np.asarray(pred, dtype=F32)
+    thr = F32(conf_thres)
+    out = []
+    for x in pred:
+        nc = x.shape[1] - 5
+        x = x[(x[:, 4] > thr) & (x[:, 5:].max(1) > thr)]               # :1005 candidates
+        if not len(x):
+            out.append(np.zeros((0, 6), F32)); continue
+        cls = x[:, 5:] * x[:, 4:5]                                     # :1040 conf = obj_conf * cls_conf
+        half_w, half_h = x[:, 2] / F32(2), x[:, 3] / F32(2)            # xywh2xyxy :630-637
+        box = np.stack([x[:, 0] - half_w, x[:, 1] - half_h, x[:, 0] + half_w, x[:, 1] + half_h], 1)
+        if multi_label and nc > 1:                                     # :1051-1053
+            i, j = np.nonzero(cls > thr)
+            rows = np.concatenate([box[i], cls[i, j][:, None], j[:, None].astype(F32)], 1)
+        else:                                                          # :1054-1056 best class only
+            j = cls.argmax(1)
+            conf = cls[np.arange(len(cls)), j]
+            rows = np.concatenate([box, conf[:, None], j[:, None].astype(F32)], 1)[conf > thr]
+        if not len(rows):
+            out.append(np.zeros((0, 6), F32)); continue
+        if len(rows) > max_nms:                                        # :1071-1072
+            rows = rows[np.argsort(-rows[:, 4], kind="stable")[:max_nms]]
+        c = rows[:, 5:6] * F32(0.0 if agnostic else max_wh)            # :1076
+        keep = greedy_nms(rows[:, :4] + c, rows[:, 4], iou_thres)[:max_det]   # :1080-1082
+        out.append(rows[keep].astype(F32))
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------
 # pseudo-label rows -- utils/plots.py:485-491 ; utils/self_supervised_utils.py:207-232, 414-454, 316-321
 # ---------------------------------------------------------------------------------------------------------

@@ -38,8 +38,27 @@ def sample_idx(n, k, seed):
     return np.random.RandomState(seed).randint(0, n, k)
 
 
+def gen_val_nms(ns):
+    """val.py-path NMS (general.py:994-1098): multi_label at conf 0.001 (the 30000-cap path) and at 0.25, best-class twin."""
+    cases = (("ml_cap", 41, 2, 2000, 0.3, 0.001, 0.6, True), ("ml_few", 42, 3, 4000, 0.05, 0.25, 0.45, True),
+             ("best", 43, 2, 4000, 0.05, 0.001, 0.6, False))
+    out = {}
+    for name, seed, B, P, frac, conf, iou, ml in cases:
+        pred = synth.make_teacher_pred(seed, B, P, cand_frac=frac)
+        dets = ns.non_max_suppression(torch.from_numpy(pred).clone(), conf_thres=conf, iou_thres=iou, multi_label=ml)
+        out[name + "_meta"] = np.array([seed, B, P, frac, conf, iou, float(ml)], dtype=np.float64)
+        for b in range(B):
+            out[f"{name}_det{b}"] = dets[b].numpy().reshape(-1, 6)
+        print("val nms", name, [len(d) for d in dets])
+    np.savez_compressed(os.path.join(HERE, "nms_val.npz"), **out)
+
+
 def main():
     ns = ref_harness.load_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "--only-val-nms":      # adds one fixture without touching the others
+        torch.set_num_threads(8)
+        gen_val_nms(ns)
+        return
     torch.set_num_threads(8)
     cfg = ref_harness.make_cfg(SSOD_YAML, SMALL)
     torch.manual_seed(0)

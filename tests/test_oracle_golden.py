@@ -132,3 +132,18 @@ def test_ema(golden):
             assert np.array_equal(ema[k], g[f"ema{step}_{k}"]), k       # bit-exact
             assert np.array_equal(semi[k], g[f"semi{step}_{k}"]), k
             assert np.array_equal(ssup[k], g[f"ssup{step}_{k}"]), k
+
+
+@pytest.mark.parametrize("name", ["ml_cap", "ml_few", "best"])
+def test_val_path_nms_multi_label(golden, name):
+    """non_max_suppression(multi_label=True, conf 0.001) including the 30 000-cap path.
+    The oracle restatement is pinned here against the live reference; the CUDA kernel for it is the next widening step."""
+    g = golden("nms_val")
+    seed, B, P, frac, conf, iou, ml = g[name + "_meta"]
+    pred = synth.make_teacher_pred(int(seed), int(B), int(P), cand_frac=float(frac))
+    got = port.nms_val(pred, float(conf), float(iou), multi_label=bool(ml))
+    for b in range(int(B)):
+        want = g[f"{name}_det{b}"]
+        assert got[b].shape == want.shape, (name, b, got[b].shape, want.shape)
+        assert np.array_equal(got[b][:, 5], want[:, 5])                       # classes / order exact
+        np.testing.assert_array_equal(got[b], want)                           # boxes and scores bit-exact
