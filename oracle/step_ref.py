@@ -23,7 +23,11 @@ def domain_focal(feature, label):
 
 class CpuSSODStep:
     def __init__(self, state_dict, depth, neck_depth, lr=0.01, momentum=0.937, weight_decay=0.0005, batch_size=32,
-                 ema_updates=0, semi_decay=0.999, teacher_loss_weight=3.0):
+                 ema_updates=0, semi_decay=0.999, teacher_loss_weight=3.0, bn_momentum=0.0, warmup=None):
+        """bn_momentum > 0: the student's running statistics are updated like nn.BatchNorm2d(momentum) does (needed for
+        multi-step trajectories; the single-step parity tests leave it 0).  warmup = (nw, warmup_bias_lr, warmup_momentum):
+        apply the reference's per-iteration warm-up (trainer/trainer.py:388-395: group index 2 gets warmup_bias_lr)."""
+        self.bn_momentum, self.warmup, self.lr0, self.momentum0, self.ni = bn_momentum, warmup, lr, momentum, 0
         self.student = {k: v.detach().clone().float() for k, v in state_dict.items()}
         self.teacher = {k: v.detach().clone() for k, v in self.student.items()}
         self.semi = {k: v.detach().clone() for k, v in self.student.items()}
@@ -54,7 +58,7 @@ class CpuSSODStep:
         dets = port.nms_ssod(pred, conf_thres, iou_thres)
         rows = port.pseudo_label_rows(dets, Ms, H, W)
         n_img = imgs.shape[0]
-        raw, feat = TrunkRef(self.student, self.depth, self.neck_depth).forward(torch.cat([imgs, u_strong], 0), train=True)
+        raw, feat = TrunkRef(self.student, self.depth, self.neck_depth, bn_momentum=self.bn_momentum).forward(torch.cat([imgs, u_strong], 0), train=True)
         sup_p, un_p = [r[:n_img] for r in raw], [r[n_img:] for r in raw]
         sup_loss, _ = port.det_loss(sup_p, [port.build_targets(np.asarray(targets), ANCHORS_GRID, shapes)], [4.0, 1.0, 0.4], 0.05, 0.7, 0.3)
         sup_loss = sup_loss + domain_focal([f[:n_img] for f in feat], 0) * 0 + domain_focal([f[n_img:] for f in feat], 1) * 0
@@ -65,6 +69,12 @@ class CpuSSODStep:
         else:
             un_loss = torch.zeros(1)
         loss = sup_loss + un_loss * self.tlw
+        if self.warmup is not None and self.ni <= self.warmup[0]:
+            xi = [0, self.warmup[0]]
+            for j, pg in enumerate(self.opt.param_groups):
+                pg['lr'] = float(np.interp(self.ni, xi, [self.warmup[1] if j == 2 else 0.0, self.lr0]))
+                pg['momentum'] = float(np.interp(self.ni, xi, [self.warmup[2], self.momentum0]))
+        self.ni += 1
         self.opt.zero_grad()
         loss.backward()
         self.opt.step()

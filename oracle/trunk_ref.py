@@ -2,15 +2,17 @@
 state_dict with the reference's key names (models/backbone/yolov5_backbone.py:76-88, models/neck/yolov5_neck.py:88-109,
 models/head/yolov5_head.py:47-87, models/detector/yolo_ssod.py:105-118, models/backbone/common.py Conv/Bottleneck/C3/SPPF).
 It is the torch reference the tcgen05 trunk is compared with, and the trunk of the CPU baseline in bench.py.
-Works on any device; train=True uses batch statistics (and does NOT update running stats)."""
+Works on any device; train=True uses batch statistics and, with bn_momentum > 0, updates the running statistics in the
+state_dict in place like nn.BatchNorm2d does (default 0: leaves them alone)."""
 import torch
 import torch.nn.functional as F
 
 
 class TrunkRef:
-    def __init__(self, state_dict, depth=(3, 6, 9, 3), neck_depth=3, bn_eps=1e-3):
+    def __init__(self, state_dict, depth=(3, 6, 9, 3), neck_depth=3, bn_eps=1e-3, bn_momentum=0.0):
         self.sd = state_dict
         self.eps = bn_eps
+        self.momentum = bn_momentum
         self.depth, self.neck_depth = depth, neck_depth
 
     @classmethod
@@ -22,7 +24,10 @@ class TrunkRef:
     def conv(self, p, x, k, s, train, act=True):
         sd = self.sd
         y = F.conv2d(x, sd[p + ".conv.weight"], None, s, k // 2 if k != 6 else 2)
-        if train:
+        if train and self.momentum > 0:
+            y = F.batch_norm(y, sd[p + ".bn.running_mean"], sd[p + ".bn.running_var"], sd[p + ".bn.weight"], sd[p + ".bn.bias"], True,
+                             self.momentum, self.eps)
+        elif train:
             y = F.batch_norm(y, None, None, sd[p + ".bn.weight"], sd[p + ".bn.bias"], True, 0.0, self.eps)
         else:
             y = F.batch_norm(y, sd[p + ".bn.running_mean"], sd[p + ".bn.running_var"], sd[p + ".bn.weight"], sd[p + ".bn.bias"],

@@ -239,19 +239,23 @@ def test_device_prefetcher_roundtrip():
 @pytest.mark.xfail(strict=False, reason="open issue (DESIGN.md section 7, item 0): in bench.py the EMA teacher's features collapse within ~15 "
                                         "steps although decay = 0.9999; not yet reproduced / root-caused at test scale")
 def test_teacher_is_stable_under_high_ema_decay():
-    """With ema.updates = 100000 the decay is 0.9999: over 12 steps the teacher moves by <= 0.12 % of the student-teacher gap,
-    so its logits on a fixed input must stay where they were (a CPU fp32 emulation of the same 12 steps with the reference's
-    hyper-parameters moves BN scales by ~0.03/step and running variances by ~2 %/step: nothing explodes)."""
+    """With ema.updates = 100000 the decay is 0.9999: over 12 steps the teacher moves by <= 0.12 % of the student-teacher gap.
+    The CPU fp32 restatement of the same steps (oracle/step_ref.py with BN running statistics and the reference's warm-up)
+    measures a teacher-logit drift of 6e-5 after 12 steps and a loss falling 52.2 -> 39.1; the native path must stay within
+    2 % drift and follow the CPU loss trajectory."""
     from efficientteacher_b200.config import yolov5_ssod_cfg
     from efficientteacher_b200.trainer import SSODTrainerStep
+    from oracle.step_ref import CpuSSODStep
     import synth
     img, bl, bu = 256, 4, 4
     r = np.random.RandomState(5)
-    imgs = torch.from_numpy(r.rand(bl, 3, img, img).astype(np.float32)).to(DEV)
-    uw = torch.from_numpy(r.rand(bu, 3, img, img).astype(np.float32)).to(DEV)
-    us = uw.flip(3).contiguous()
-    tg = torch.from_numpy(synth.make_targets(7, 8 * bl, bl)).to(DEV)
-    Ms = torch.from_numpy(synth.make_Ms(9, bu, img)).to(DEV)
+    imgs_c = torch.from_numpy(r.rand(bl, 3, img, img).astype(np.float32))
+    uw_c = torch.from_numpy(r.rand(bu, 3, img, img).astype(np.float32))
+    us_c = uw_c.flip(3).contiguous()
+    tg_c = synth.make_targets(7, 8 * bl, bl)
+    Ms_c = synth.make_Ms(9, bu, img)
+    imgs, uw, us = imgs_c.to(DEV), uw_c.to(DEV), us_c.to(DEV)
+    tg, Ms = torch.from_numpy(tg_c).to(DEV), torch.from_numpy(Ms_c).to(DEV)
     torch.manual_seed(0)
     st = SSODTrainerStep(yolov5_ssod_cfg('l_shallow', batch_size=bl + bu, img_size=img), torch.device(DEV), epochs=300)
     st.ema.updates = 100000
@@ -262,11 +266,18 @@ def test_teacher_is_stable_under_high_ema_decay():
                 h.bias.view(3, -1)[:, 5:] += 5.0
         (_, raw0), _ = st.ema.ema(uw)
         raw0 = [t.clone() for t in raw0]
+    cpu = CpuSSODStep({k: v.cpu() for k, v in st.model.state_dict().items()}, (1, 2, 3, 1), 1, batch_size=bl + bu, ema_updates=100000,
+                      bn_momentum=0.03, warmup=(st.nw, st.warmup_bias_lr, st.warmup_momentum))
+    step = 0
     for mode, n in (("eager", 6), ("graph", 6)):
         for i in range(n):
             f = st.train_instance_graphed if mode == "graph" else st.train_instance
-            loss = f(imgs, tg, us, uw, None, Ms, i)
+            loss = f(imgs, tg, us, uw, None, Ms, step)
             assert torch.isfinite(loss).all()
+            if mode == "eager":
+                ref, _ = cpu.step(imgs_c, tg_c, us_c, uw_c, Ms_c)
+                assert abs(loss.item() - ref) <= 0.08 * abs(ref), (step, loss.item(), ref)
+            step += 1
         with torch.no_grad():
             (_, raw1), _ = st.ema.ema(uw)
         for a, b in zip(raw1, raw0):
