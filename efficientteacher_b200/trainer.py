@@ -43,7 +43,10 @@ def domain_focal_loss(feature, label, gamma=2.0):
 
 
 class SSODTrainerStep:
-    def __init__(self, cfg, device, rank=-1, world_size=1, epochs=None, batch_size=None, amp_dtype=torch.bfloat16):
+    def __init__(self, cfg, device, rank=-1, world_size=1, epochs=None, batch_size=None, amp_dtype=torch.bfloat16,
+                 pseudo_label_stats=None):
+        """pseudo_label_stats (LabelMatch only): dict(target_data_len, label_num_per_image, cls_ratio_gt) that the reference
+        derives from its datasets (ssod_trainer.py:71)."""
         self.cfg, self.device = cfg, device
         self.RANK, self.WORLD_SIZE = rank, world_size
         self.epochs = epochs if epochs is not None else cfg.epochs
@@ -63,7 +66,14 @@ class SSODTrainerStep:
         self.build_optimizer(cfg)
         self.compute_loss = ComputeLoss(self.model, cfg)
         self.compute_un_sup_loss = ComputeStudentMatchLoss(self.model, cfg)
-        self.pseudo_label_creator = FairPseudoLabel(cfg)
+        if getattr(cfg.SSOD, "pseudo_label_type", "FairPseudoLabel") == "LabelMatch":      # ssod_trainer.py:69-71
+            from .labelmatch import LabelMatch
+            ps = pseudo_label_stats or {}
+            nc = cfg.Dataset.nc
+            self.pseudo_label_creator = LabelMatch(cfg, int(ps.get("target_data_len", 0) / max(world_size, 1)), ps.get("label_num_per_image", 7.0),
+                                                   ps.get("cls_ratio_gt", np.full(nc, 1.0 / nc)))
+        else:
+            self.pseudo_label_creator = FairPseudoLabel(cfg)
         self.da_loss_weights = cfg.SSOD.da_loss_weights
         self.last_opt_step = -1
         self.nw = 0          # warm-up iterations (the bench runs past warm-up)
@@ -169,6 +179,10 @@ class SSODTrainerStep:
         with torch.no_grad():
             (teacher_pred, train_out), teacher_feature = self.ema.ema(unlabeled_imgs_ori, augment=False)
         self._mark("teacher_forward")
+        if hasattr(self.pseudo_label_creator, "update_device"):      # LabelMatch: ssod_trainer.py:616-617 (labeled-target histogram)
+            self.pseudo_label_creator.update_device(targets)
+            self.pseudo_label_creator.count += imgs.shape[0]
+            self.pseudo_label_creator.pse_count += unlabeled_imgs.shape[0]
         if host_pseudo_labels:   # the reference's return contract: CPU float64 rows + flag (one D2H sync)
             unlabeled_targets, invalid_target_shape = self.pseudo_label_creator.create_pseudo_label_online_with_gt(
                 teacher_pred, unlabeled_imgs, unlabeled_M, unlabeled_imgs_ori, unlabeled_gt, self.RANK)
@@ -236,7 +250,19 @@ class SSODTrainerStep:
             self._allreduce_grads()
             g["graph_b"].replay()
         self.last_opt_step = ni
+        if hasattr(self.pseudo_label_creator, "stage_detections"):   # LabelMatch: the captured step cannot stage its detections itself
+            self.pseudo_label_creator.stage_detections()
         return g["loss"]
+
+    def after_epoch(self, epoch, start_epoch=0):
+        """ssod_trainer.py:319-323: LabelMatch re-estimates the per-class thresholds once per epoch; the unsupervised loss
+        picks them up (and a captured step has to be re-captured because the thresholds are device constants of the graph)."""
+        c = self.pseudo_label_creator
+        if hasattr(c, "update_epoch_cls_thr") and epoch >= getattr(self.cfg.SSOD, "dynamic_thres_epoch", 0):
+            c.update_epoch_cls_thr(epoch - start_epoch)
+            self.compute_un_sup_loss.ignore_thres_high = list(c.cls_thr_high)
+            self.compute_un_sup_loss.ignore_thres_low = list(c.cls_thr_low)
+            self.reset_graph()
 
     def reset_graph(self):
         self._graph = None

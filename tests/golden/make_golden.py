@@ -53,11 +53,53 @@ def gen_val_nms(ns):
     np.savez_compressed(os.path.join(HERE, "nms_val.npz"), **out)
 
 
+def gen_labelmatch(ns):
+    """utils/labelmatch.py: the LabelMatch pseudo-label creator over two batches + the per-epoch threshold update (GMM)."""
+    import importlib
+    lm = importlib.import_module("utils.labelmatch")
+    cfg = ref_harness.make_cfg(SSOD_YAML, SMALL)
+    nc = 80
+    torch.manual_seed(0)
+    np.random.seed(0)
+    creator = lm.LabelMatch(cfg, 1000, 7.0, np.full(nc, 1.0 / nc))
+    fpl = ns.FairPseudoLabel(cfg)
+    out = dict(nms_conf_thres=creator.nms_conf_thres, nms_iou_thres=creator.nms_iou_thres,
+               resample_high_percent=cfg.SSOD.resample_high_percent, resample_low_percent=cfg.SSOD.resample_low_percent,
+               ignore_thres_high=cfg.SSOD.ignore_thres_high, ignore_thres_low=cfg.SSOD.ignore_thres_low)
+    for bi, (seed, B, P, frac) in enumerate(((51, 4, 25200, 0.02), (52, 4, 25200, 0.03))):
+        pred = synth.make_teacher_pred(seed, B, P, cand_frac=frac)
+        Ms = synth.make_Ms(seed + 100, B)
+        imgs = torch.zeros(B, 3, 640, 640)
+        rows, invalid = creator.create_pseudo_label_online_with_gt(torch.from_numpy(pred).clone(), imgs, torch.from_numpy(Ms), imgs.clone())
+        rows = rows.numpy() if isinstance(rows, torch.Tensor) else np.zeros((0, 9))
+        rows_f, _ = fpl.create_pseudo_label_online_with_gt(torch.from_numpy(pred).clone(), imgs, torch.from_numpy(Ms), imgs.clone())
+        rows_f = rows_f.numpy() if isinstance(rows_f, torch.Tensor) else np.zeros((0, 9))
+        print("labelmatch batch", bi, rows.shape, "identical to FairPseudoLabel rows:", rows.shape == rows_f.shape and np.array_equal(rows, rows_f))
+        out[f"b{bi}_meta"] = np.array([seed, B, P, frac], dtype=np.float64)
+        out[f"b{bi}_rows"] = rows
+        out[f"b{bi}_same_as_fair"] = np.array(rows.shape == rows_f.shape and np.array_equal(rows, rows_f))
+        creator.update(rows, n=B, pse_n=B)
+    lens = np.array([len(c) for c in creator.score_list_epoch], dtype=np.int64)
+    out["epoch_score_lens"] = lens
+    out["epoch_scores"] = np.array([v for c in creator.score_list_epoch for v in c], dtype=np.float64)
+    out["cls_tmp"] = creator.cls_tmp.copy()
+    creator.update_epoch_cls_thr(0)
+    out["thr_high_e0"] = np.array(creator.cls_thr_high, dtype=np.float64)
+    out["thr_low_e0"] = np.array(creator.cls_thr_low, dtype=np.float64)
+    out["cls_num_total_e0"] = creator.cls_num_total.copy()
+    np.savez_compressed(os.path.join(HERE, "labelmatch.npz"), **out)
+    print("labelmatch thr_high[:8]", out["thr_high_e0"][:8], "thr_low[:8]", out["thr_low_e0"][:8])
+
+
 def main():
     ns = ref_harness.load_reference()
     if len(sys.argv) > 1 and sys.argv[1] == "--only-val-nms":      # adds one fixture without touching the others
         torch.set_num_threads(8)
         gen_val_nms(ns)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "--only-labelmatch":
+        torch.set_num_threads(8)
+        gen_labelmatch(ns)
         return
     torch.set_num_threads(8)
     cfg = ref_harness.make_cfg(SSOD_YAML, SMALL)

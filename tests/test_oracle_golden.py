@@ -147,3 +147,37 @@ def test_val_path_nms_multi_label(golden, name):
         assert got[b].shape == want.shape, (name, b, got[b].shape, want.shape)
         assert np.array_equal(got[b][:, 5], want[:, 5])                       # classes / order exact
         np.testing.assert_array_equal(got[b], want)                           # boxes and scores bit-exact
+
+
+def test_labelmatch_bookkeeping_and_epoch_thresholds(golden):
+    """the LabelMatch creator.  Its rows equal FairPseudoLabel's (asserted when the fixture was made), so
+    the device pipeline is shared; here the host side of the mirror (score lists per class, per-epoch thresholds incl. the
+    GMM split) is checked against the live reference, fed with the oracle's detections for the same seeded inputs."""
+    from types import SimpleNamespace as NS
+    from efficientteacher_b200.labelmatch import LabelMatch
+    g = golden("labelmatch")
+    assert bool(g["b0_same_as_fair"]) and bool(g["b1_same_as_fair"])
+    cfg = NS(SSOD=NS(nms_conf_thres=float(g["nms_conf_thres"]), nms_iou_thres=float(g["nms_iou_thres"]), debug=False, multi_label=False,
+                     ignore_thres_low=float(g["ignore_thres_low"]), ignore_thres_high=float(g["ignore_thres_high"]),
+                     resample_high_percent=float(g["resample_high_percent"]), resample_low_percent=float(g["resample_low_percent"])),
+             Dataset=NS(names=[str(i) for i in range(80)], np=0))
+    lm = LabelMatch(cfg, 1000, 7.0, np.full(80, 1.0 / 80))
+    for bi in range(2):
+        seed, B, P, frac = g[f"b{bi}_meta"]
+        pred = synth.make_teacher_pred(int(seed), int(B), int(P), cand_frac=float(frac))
+        dets = port.nms_ssod(pred, lm.nms_conf_thres, lm.nms_iou_thres)
+        det = np.zeros((int(B), 300, 8), np.float32)
+        for b, d in enumerate(dets):
+            det[b, :len(d)] = d
+        lm.record_detections(det, np.array([len(d) for d in dets]))
+        rows = port.pseudo_label_rows(dets, synth.make_Ms(int(seed) + 100, int(B)), 640, 640)
+        np.testing.assert_allclose(rows, g[f"b{bi}_rows"], rtol=1e-9, atol=1e-9)
+        lm.update(rows, n=int(B), pse_n=int(B))
+    lens = np.array([len(c) for c in lm.score_list_epoch])
+    assert np.array_equal(lens, g["epoch_score_lens"])
+    assert np.array_equal(np.array([v for c in lm.score_list_epoch for v in c]), g["epoch_scores"])      # same values, same order
+    assert np.array_equal(lm.cls_tmp, g["cls_tmp"])
+    lm.update_epoch_cls_thr(0)
+    np.testing.assert_allclose(np.array(lm.cls_thr_low), g["thr_low_e0"], rtol=0, atol=0)
+    np.testing.assert_allclose(np.array(lm.cls_thr_high), g["thr_high_e0"], rtol=1e-9, atol=1e-12)
+    assert np.array_equal(lm.cls_num_total, g["cls_num_total_e0"]) and all(len(c) == 0 for c in lm.score_list_epoch)
