@@ -337,3 +337,34 @@ def test_fused_sgd_matches_torch_sgd():
             assert float(a.grad.abs().max()) == 0.0          # zeroed by the fused pass
         for a, b in zip(pa, pb):
             torch.testing.assert_close(oa.state[a]["momentum_buffer"], ob.state[b]["momentum_buffer"], rtol=2e-6, atol=1e-6)
+
+
+def test_labelmatch_device_path_matches_reference(golden):
+    """LabelMatch on the device pipeline: rows, the per-class score lists (async pinned copy + flush) and the epoch thresholds
+    against the live-reference fixture (tests/golden/labelmatch.npz)."""
+    from types import SimpleNamespace as NS
+    from efficientteacher_b200.labelmatch import LabelMatch
+    g = golden("labelmatch")
+    cfg = NS(SSOD=NS(nms_conf_thres=float(g["nms_conf_thres"]), nms_iou_thres=float(g["nms_iou_thres"]), debug=False, multi_label=False,
+                     ignore_thres_low=float(g["ignore_thres_low"]), ignore_thres_high=float(g["ignore_thres_high"]),
+                     resample_high_percent=float(g["resample_high_percent"]), resample_low_percent=float(g["resample_low_percent"])),
+             Dataset=NS(names=[str(i) for i in range(80)], np=0))
+    lm = LabelMatch(cfg, 1000, 7.0, np.full(80, 1.0 / 80))
+    for bi in range(2):
+        seed, B, P, frac = g[f"b{bi}_meta"]
+        pred = torch.from_numpy(synth.make_teacher_pred(int(seed), int(B), int(P), cand_frac=float(frac))).to(DEV)
+        Ms = torch.from_numpy(synth.make_Ms(int(seed) + 100, int(B))).to(DEV)
+        imgs = torch.zeros(int(B), 3, 640, 640, device=DEV)
+        rows, invalid = lm.create_pseudo_label_online_with_gt(pred, imgs, Ms, imgs)
+        assert not invalid
+        rows = rows.numpy()
+        want = g[f"b{bi}_rows"]
+        assert rows.shape == want.shape and np.array_equal(rows[:, :2], want[:, :2])
+        np.testing.assert_allclose(rows, want, rtol=1e-9, atol=1e-9)
+        lm.update(rows, n=int(B), pse_n=int(B))
+    lm.flush()
+    assert np.array_equal(np.array([len(c) for c in lm.score_list_epoch]), g["epoch_score_lens"])
+    assert np.array_equal(np.array([v for c in lm.score_list_epoch for v in c]), g["epoch_scores"])
+    lm.update_epoch_cls_thr(0)
+    np.testing.assert_allclose(np.array(lm.cls_thr_low), g["thr_low_e0"], rtol=0, atol=0)
+    np.testing.assert_allclose(np.array(lm.cls_thr_high), g["thr_high_e0"], rtol=1e-9, atol=1e-12)
