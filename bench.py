@@ -409,24 +409,27 @@ def main():
     n_pl = int(st.pseudo_label_creator.last_count_dev.item())
     det_per_img = float(st.pseudo_label_creator.last_det[1].float().mean().item())
     if rank == 0:        # teacher health at the end of the run (stderr only): candidates, conf-passing rows, NMS detections
-        with torch.no_grad():
-            from efficientteacher_b200.nms import non_max_suppression_ssod
-            (pred_e, _raw_e), _f = st.ema.ema(d_uw)
-            conf_e = pred_e[..., 4:5] * pred_e[..., 5:]
-            dets_e = non_max_suppression_ssod(pred_e, cfg.SSOD.nms_conf_thres, cfg.SSOD.nms_iou_thres)
-            def _bnmax(mod):
-                bb = [q for q in mod.modules() if isinstance(q, torch.nn.BatchNorm2d)]
-                return (max(float(q.running_var.max()) for q in bb), max(float(q.running_mean.abs().max()) for q in bb),
-                        max(float(q.weight.abs().max()) for q in bb), max(float(q.bias.abs().max()) for q in bb))
-            print("[bench] BN max (running_var, |running_mean|, |gamma|, |beta|): student %s teacher %s" % (
-                "%.3g %.3g %.3g %.3g" % _bnmax(st.model), "%.3g %.3g %.3g %.3g" % _bnmax(st.ema.ema)), file=sys.stderr, flush=True)
-            print("[bench] teacher at end: obj>thr rows/img %.1f, conf>thr rows/img %.1f, NMS dets/img %.1f, obj max %.3f, cls max mean %.3f, "
-                  "ema.updates %d, last step: dets/img %.2f pseudo-label rows %d" % (
-                      float((pred_e[..., 4] > cfg.SSOD.nms_conf_thres).sum(1).float().mean()),
-                      float((conf_e.max(-1)[0] > cfg.SSOD.nms_conf_thres).sum(1).float().mean()),
-                      float(np.mean([len(d) for d in dets_e])), float(pred_e[..., 4].max()), float(pred_e[..., 5:].max(-1)[0].mean()),
-                      st.ema.updates, det_per_img, n_pl), file=sys.stderr, flush=True)
-        del pred_e, _raw_e, _f, conf_e, dets_e
+        try:
+            with torch.no_grad():
+                from efficientteacher_b200.nms import non_max_suppression_ssod
+                (pred_e, _raw_e), _f = st.ema.ema(d_uw)
+                conf_e = pred_e[..., 4:5] * pred_e[..., 5:]
+                dets_e = non_max_suppression_ssod(pred_e, cfg.SSOD.nms_conf_thres, cfg.SSOD.nms_iou_thres)
+                def _bnmax(mod):
+                    bb = [q for q in mod.modules() if isinstance(q, torch.nn.BatchNorm2d)]
+                    return (max(float(q.running_var.max()) for q in bb), max(float(q.running_mean.abs().max()) for q in bb),
+                            max(float(q.weight.abs().max()) for q in bb), max(float(q.bias.abs().max()) for q in bb))
+                print("[bench] BN max (running_var, |running_mean|, |gamma|, |beta|): student %s teacher %s" % (
+                    "%.3g %.3g %.3g %.3g" % _bnmax(st.model), "%.3g %.3g %.3g %.3g" % _bnmax(st.ema.ema)), file=sys.stderr, flush=True)
+                print("[bench] teacher at end: obj>thr rows/img %.1f, conf>thr rows/img %.1f, NMS dets/img %.1f, obj max %.3f, cls max mean %.3f, "
+                      "ema.updates %d, last step: dets/img %.2f pseudo-label rows %d" % (
+                          float((pred_e[..., 4] > cfg.SSOD.nms_conf_thres).sum(1).float().mean()),
+                          float((conf_e.max(-1)[0] > cfg.SSOD.nms_conf_thres).sum(1).float().mean()),
+                          float(np.mean([len(d) for d in dets_e])), float(pred_e[..., 4].max()), float(pred_e[..., 5:].max(-1)[0].mean()),
+                          st.ema.updates, det_per_img, n_pl), file=sys.stderr, flush=True)
+            del pred_e, _raw_e, _f, conf_e, dets_e
+        except Exception as exc:      # diagnostics only: never let them take the bench line down
+            print("[bench] teacher health check failed: %r" % (exc,), file=sys.stderr, flush=True)
 
     if rank == 0:
         pk, pk_kind = peaks()
