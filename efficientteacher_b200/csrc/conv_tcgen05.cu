@@ -945,8 +945,9 @@ extern "C" int etb_conv_dgrad(const void* dy_bf16, const void* wd_bf16, void* dx
 // image, fetched for both operands by 4-D TMA boxes {64 ch, TW, TH, 1} (x with the tap shift / element strides, zero
 // padding = OOB fill) into 128B-swizzled smem = the canonical MN-major UMMA layout:
 //   64-channel group = kpix rows x 128 B;  8-row K atoms 1024 B apart (SBO);  channel groups one region apart (LBO).
-// One CTA owns one (co tile, ci tile, tap) and a contiguous slice of the K blocks (split-K across gridDim.y); partial
-// tiles are reduced with fp32 atomics (red.global.add.f32) into dW, which the entry point zeroes first.
+// One CTA owns one (co tile, ci tile, tap) and a contiguous slice of the K blocks (split-K across gridDim.y); every CTA
+// stores its partial tile into its own slice of the workspace (plain coalesced stores, no atomics, no memset) and a second
+// kernel (wgrad_reduce_kernel / wgrad_reduce_taps_kernel) sums the slices in a fixed order into the parameter layout.
 // =====================================================================================================================
 struct WgradArgs {
   int ntaps;
