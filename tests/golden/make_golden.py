@@ -40,13 +40,15 @@ def sample_idx(n, k, seed):
 
 def gen_val_nms(ns):
     """val.py-path NMS (general.py:994-1098): multi_label at conf 0.001 (the 30000-cap path) and at 0.25, best-class twin."""
-    cases = (("ml_cap", 41, 2, 2000, 0.3, 0.001, 0.6, True), ("ml_few", 42, 3, 4000, 0.05, 0.25, 0.45, True),
-             ("best", 43, 2, 4000, 0.05, 0.001, 0.6, False))
+    cases = (("ml_cap", 41, 2, 2000, 0.3, 0.001, 0.6, True, False), ("ml_few", 42, 3, 4000, 0.05, 0.25, 0.45, True, False),
+             ("best", 43, 2, 4000, 0.05, 0.001, 0.6, False, False), ("ml_agn", 44, 3, 1500, 0.1, 0.05, 0.5, True, True))
     out = {}
-    for name, seed, B, P, frac, conf, iou, ml in cases:
+    for name, seed, B, P, frac, conf, iou, ml, agn in cases:
         pred = synth.make_teacher_pred(seed, B, P, cand_frac=frac)
-        dets = ns.non_max_suppression(torch.from_numpy(pred).clone(), conf_thres=conf, iou_thres=iou, multi_label=ml)
-        out[name + "_meta"] = np.array([seed, B, P, frac, conf, iou, float(ml)], dtype=np.float64)
+        if name == "ml_agn":
+            pred[1, :, 4] = 0.0            # an image without candidates
+        dets = ns.non_max_suppression(torch.from_numpy(pred).clone(), conf_thres=conf, iou_thres=iou, multi_label=ml, agnostic=agn)
+        out[name + "_meta"] = np.array([seed, B, P, frac, conf, iou, float(ml), float(agn)], dtype=np.float64)
         for b in range(B):
             out[f"{name}_det{b}"] = dets[b].numpy().reshape(-1, 6)
         print("val nms", name, [len(d) for d in dets])

@@ -134,14 +134,16 @@ def test_ema(golden):
             assert np.array_equal(ssup[k], g[f"ssup{step}_{k}"]), k
 
 
-@pytest.mark.parametrize("name", ["ml_cap", "ml_few", "best"])
+@pytest.mark.parametrize("name", ["ml_cap", "ml_few", "best", "ml_agn"])
 def test_val_path_nms_multi_label(golden, name):
     """non_max_suppression(multi_label=True, conf 0.001) including the 30 000-cap path.
     The oracle restatement is pinned here against the live reference; the CUDA kernel for it is the next widening step."""
     g = golden("nms_val")
-    seed, B, P, frac, conf, iou, ml = g[name + "_meta"]
+    seed, B, P, frac, conf, iou, ml, agn = g[name + "_meta"]
     pred = synth.make_teacher_pred(int(seed), int(B), int(P), cand_frac=float(frac))
-    got = port.nms_val(pred, float(conf), float(iou), multi_label=bool(ml))
+    if name == "ml_agn":
+        pred[1, :, 4] = 0.0                # an image without candidates (class-agnostic case)
+    got = port.nms_val(pred, float(conf), float(iou), multi_label=bool(ml), agnostic=bool(agn))
     for b in range(int(B)):
         want = g[f"{name}_det{b}"]
         assert got[b].shape == want.shape, (name, b, got[b].shape, want.shape)
