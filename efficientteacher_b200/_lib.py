@@ -87,6 +87,8 @@ _SIGS = {
                                     C.c_int32, c_f32p, C.c_float, vp]),
     "etb_nms_workspace_bytes": (C.c_size_t, [C.POINTER(EtbNmsParams)]),
     "etb_nms_ssod": (C.c_int, [vp, C.POINTER(EtbNmsParams), vp, vp, vp, vp, vp, vp, C.c_size_t, vp]),
+    "etb_nms_val_workspace_bytes": (C.c_size_t, [C.POINTER(EtbNmsParams)]),
+    "etb_nms_val": (C.c_int, [vp, C.POINTER(EtbNmsParams), vp, vp, vp, C.c_size_t, vp]),
     "etb_select_targets": (C.c_int, [vp, vp, C.c_int32, C.c_int32, vp, vp, C.c_int32, C.c_int32, vp, vp, vp]),
     "etb_build_targets": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.POINTER(EtbAssignLevels),
                                     C.POINTER(EtbAssignOut), vp]),

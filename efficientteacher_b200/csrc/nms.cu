@@ -400,3 +400,306 @@ extern "C" int etb_nms_ssod(const float* pred, const EtbNmsParams* p, float* det
   }
   return ETB_OK;
 }
+
+// =====================================================================================================================
+// val.py NMS: non_max_suppression(multi_label=True) (reference utils/general.py:994-1098; val.py:149-465 calls it with
+// conf_thres 0.001) -- SURVEY.md 8f rank 2.  Every (row, class) PAIR with obj*cls > conf of a candidate row is a detection
+// (row-major order of torch.nonzero, general.py:1052); if an image has more than max_nms (30 000) of them only the max_nms
+// best by confidence survive (general.py:1071-1072; ties at the cut: the earlier pair, i.e. a stable descending sort).
+// Front end (this section) = exact top-max_nms selection without sorting the up to P*nc pairs:
+//   V1 ml_hist   x3 : 12+12+8-bit radix histograms of the pair keys (key = fp32 bits of conf: monotonic for conf > 0)
+//   V2 ml_select x3 : one block per image walks the histogram from the top: fixes the next digits of the max_nms-th key
+//   V3 ml_count     : per 64-row chunk, pairs with key > T and with key == T
+//   V4 ml_write     : order-preserving compaction of {key > T} U {first need_eq pairs with key == T} into the record
+//                     layout of the SSOD path ([x1,y1,x2,y2,conf,cls,0,0], key = conf)
+// then the SAME rank_kernel / nms_image_kernel as the SSOD path run on the <= max_nms survivors.
+// Algorithmic bytes: the prediction tensor is read 5 times (340 B/row each); everything else is O(max_nms).
+// =====================================================================================================================
+#define ML_ROWS 64          // rows per block (8 warps x 8 rows)
+#define ML_BINS 4096
+
+struct MlWs {
+  uint32_t* hist;       // [B][ML_BINS]
+  uint32_t* state;      // [B][8]: 0 prefix (known high bits), 1 k_rem, 2 greater, 3 all (take everything), 4 total pairs
+  int32_t* chunk_gt;    // [B][nchunks]
+  int32_t* chunk_eq;    // [B][nchunks]
+  int32_t nchunks;
+};
+
+__device__ __forceinline__ uint32_t ml_key(float obj, float cls, float thr) {
+  const float conf = __fmul_rn(cls, obj);
+  return conf > thr ? __float_as_uint(conf) : 0u;      // conf > thr >= 0: positive floats order like their bit patterns
+}
+// is `row` a candidate of general.py:1005 (obj > thr and max cls > thr)?  One warp; all lanes get the answer.
+__device__ __forceinline__ bool ml_row_candidate(const float* __restrict__ row, int nc, float thr, int lane) {
+  const float obj = row[4];
+  if (!(obj > thr)) return false;
+  float m = -INFINITY;
+  for (int c = lane; c < nc; c += 32) m = fmaxf(m, row[5 + c]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  return m > thr;
+}
+
+// level 0: bins = key >> 20 (all valid keys); level 1: (key >> 8) & 0xFFF of keys whose top 12 bits == prefix >> 20;
+// level 2: key & 0xFF of keys whose top 24 bits == prefix >> 8.
+__global__ void __launch_bounds__(256) ml_hist_kernel(const float* __restrict__ pred, EtbNmsParams p, MlWs ws, int level) {
+  __shared__ uint32_t sh[ML_BINS];
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nc = p.no - 5;
+  if (level > 0 && ws.state[b * 8 + 3]) return;      // everything is taken: no selection needed
+  for (int i = threadIdx.x; i < ML_BINS; i += 256) sh[i] = 0;
+  __syncthreads();
+  const uint32_t prefix = ws.state[b * 8 + 0];
+  for (int rr = warp; rr < ML_ROWS; rr += 8) {
+    const int r = blockIdx.x * ML_ROWS + rr;
+    if (r >= p.P) break;
+    const float* row = pred + ((size_t)b * p.P + r) * p.no;
+    if (!ml_row_candidate(row, nc, p.conf_thres, lane)) continue;
+    const float obj = row[4];
+    for (int c = lane; c < nc; c += 32) {
+      const uint32_t k = ml_key(obj, row[5 + c], p.conf_thres);
+      if (!k) continue;
+      if (level == 0) atomicAdd(&sh[k >> 20], 1u);
+      else if (level == 1) { if ((k >> 20) == (prefix >> 20)) atomicAdd(&sh[(k >> 8) & 0xFFFu], 1u); }
+      else { if ((k >> 8) == (prefix >> 8)) atomicAdd(&sh[k & 0xFFu], 1u); }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ML_BINS; i += 256)
+    if (sh[i]) atomicAdd(&ws.hist[(size_t)b * ML_BINS + i], sh[i]);
+}
+
+// One block (256 threads) per image.  Finds, walking the bins from the top, the bin that holds the k_rem-th largest key
+// among the keys that match the digits fixed so far; updates prefix / k_rem / greater; clears the histogram for the next level.
+__global__ void __launch_bounds__(256) ml_select_kernel(EtbNmsParams p, MlWs ws, int level) {
+  __shared__ uint32_t part[256];
+  __shared__ int found_bin;
+  const int b = blockIdx.x;
+  uint32_t* hist = ws.hist + (size_t)b * ML_BINS;
+  uint32_t* st = ws.state + b * 8;
+  if (level > 0 && st[3]) return;
+  const int nb = level == 2 ? 256 : ML_BINS;
+  const int per = nb / 256;                           // bins per thread, thread t owns the descending range [nb-1-t*per, ...]
+  uint32_t s = 0;
+  for (int j = 0; j < per; ++j) s += hist[nb - 1 - (threadIdx.x * per + j)];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t total = 0;
+    for (int t = 0; t < 256; ++t) total += part[t];
+    if (level == 0) {
+      st[4] = total;
+      st[2] = 0;
+      st[0] = 0;
+      if (total <= (uint32_t)p.max_nms) { st[3] = 1; st[1] = 0; found_bin = -1; }
+      else { st[3] = 0; st[1] = (uint32_t)p.max_nms; found_bin = 0; }
+    } else {
+      found_bin = 0;
+    }
+    if (found_bin == 0) {
+      uint32_t k_rem = st[1], above = 0;
+      int bin = -1;
+      for (int t = 0; t < 256 && bin < 0; ++t) {
+        if (above + part[t] >= k_rem) {
+          for (int j = 0; j < per; ++j) {
+            const int bb = nb - 1 - (t * per + j);
+            const uint32_t h = hist[bb];
+            if (above + h >= k_rem) { bin = bb; break; }
+            above += h;
+          }
+        } else {
+          above += part[t];
+        }
+      }
+      // bin >= 0 always: total of the matching keys >= k_rem by construction
+      st[2] += above;                                  // keys strictly greater than everything in `bin`
+      st[1] = k_rem - above;                           // rank of the wanted key inside `bin`
+      if (level == 0) st[0] = (uint32_t)bin << 20;
+      else if (level == 1) st[0] |= (uint32_t)bin << 8;
+      else st[0] |= (uint32_t)bin;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ML_BINS; i += 256) hist[i] = 0;
+}
+
+// selection predicate pieces for one key: gt = key > T (or everything valid when `all`), eq = key == T
+__device__ __forceinline__ void ml_class(uint32_t k, uint32_t T, bool all, int* gt, int* eq) {
+  *gt = (k != 0u) && (all || k > T);
+  *eq = (k != 0u) && !all && k == T;
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(256) ml_pairs_kernel(const float* __restrict__ pred, EtbNmsParams p, MlWs ws, NmsWs nw, int cap) {
+  __shared__ int row_gt[ML_ROWS], row_eq[ML_ROWS];
+  __shared__ int sbase_gt, sbase_eq;
+  const int b = blockIdx.y, chunk = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nc = p.no - 5;
+  const uint32_t T = ws.state[b * 8 + 0];
+  const bool all = ws.state[b * 8 + 3] != 0;
+  const int need_eq = all ? 0 : (int)ws.state[b * 8 + 1];     // after level 2: how many keys == T are taken (the first ones)
+  // pass 1: per-row counts
+  for (int rr = warp; rr < ML_ROWS; rr += 8) {
+    const int r = chunk * ML_ROWS + rr;
+    int g = 0, e = 0;
+    if (r < p.P) {
+      const float* row = pred + ((size_t)b * p.P + r) * p.no;
+      if (ml_row_candidate(row, nc, p.conf_thres, lane)) {
+        const float obj = row[4];
+        for (int c = lane; c < nc; c += 32) {
+          int gt, eq;
+          ml_class(ml_key(obj, row[5 + c], p.conf_thres), T, all, &gt, &eq);
+          g += gt; e += eq;
+        }
+      }
+    }
+    g = warp_sum_i(g); e = warp_sum_i(e);
+    if (lane == 0) { row_gt[rr] = g; row_eq[rr] = e; }
+  }
+  __syncthreads();
+  if (!WRITE) {
+    if (threadIdx.x == 0) {
+      int g = 0, e = 0;
+      for (int i = 0; i < ML_ROWS; ++i) { g += row_gt[i]; e += row_eq[i]; }
+      ws.chunk_gt[b * ws.nchunks + chunk] = g;
+      ws.chunk_eq[b * ws.nchunks + chunk] = e;
+    }
+    return;
+  }
+  // pass 2 (WRITE): prefix of the preceding chunks, then of the preceding rows, then the ordered write
+  if (threadIdx.x < 32) {
+    int g = 0, e = 0;
+    for (int c = threadIdx.x; c < chunk; c += 32) { g += ws.chunk_gt[b * ws.nchunks + c]; e += ws.chunk_eq[b * ws.nchunks + c]; }
+    g = warp_sum_i(g); e = warp_sum_i(e);
+    if (threadIdx.x == 0) {
+      sbase_gt = g; sbase_eq = e;
+      int pg = g, pe = e;                                 // exclusive prefix over the rows of the chunk (64 values: serial is fine)
+      for (int i = 0; i < ML_ROWS; ++i) {
+        const int tg = row_gt[i], te = row_eq[i];
+        row_gt[i] = pg; row_eq[i] = pe;
+        pg += tg; pe += te;
+      }
+      if (chunk == ws.nchunks - 1) {                      // totals of the image
+        const int n = pg + (pe < need_eq ? pe : need_eq);
+        nw.n1[b] = n;
+        nw.n2[b] = n;
+      }
+    }
+  }
+  __syncthreads();
+  for (int rr = warp; rr < ML_ROWS; rr += 8) {
+    const int r = chunk * ML_ROWS + rr;
+    if (r >= p.P) break;
+    const float* row = pred + ((size_t)b * p.P + r) * p.no;
+    if (!ml_row_candidate(row, nc, p.conf_thres, lane)) continue;
+    const float obj = row[4];
+    int g_before = row_gt[rr], e_before = row_eq[rr];
+    const float cx = row[0], cy = row[1], w = row[2], h = row[3];
+    const float hw = __fdiv_rn(w, 2.0f), hh = __fdiv_rn(h, 2.0f);
+    for (int c0 = 0; c0 < nc; c0 += 32) {                 // classes in ascending order: 32 at a time, ballot prefix inside
+      const int c = c0 + lane;
+      uint32_t k = 0;
+      float conf = 0.f;
+      if (c < nc) { conf = __fmul_rn(row[5 + c], obj); k = conf > p.conf_thres ? __float_as_uint(conf) : 0u; }
+      int gt, eq;
+      ml_class(k, T, all, &gt, &eq);
+      const unsigned mg = __ballot_sync(0xffffffffu, gt), me = __ballot_sync(0xffffffffu, eq);
+      const unsigned lower = (1u << lane) - 1u;
+      const int g_here = g_before + __popc(mg & lower), e_here = e_before + __popc(me & lower);
+      int pos = -1;
+      if (gt) pos = g_here + (e_here < need_eq ? e_here : need_eq);
+      else if (eq && e_here < need_eq) pos = g_here + e_here;
+      if (pos >= 0 && pos < cap) {
+        float* o = nw.rec + ((size_t)b * cap + pos) * 8;
+        o[0] = __fsub_rn(cx, hw);
+        o[1] = __fsub_rn(cy, hh);
+        o[2] = __fadd_rn(cx, hw);
+        o[3] = __fadd_rn(cy, hh);
+        o[4] = conf;
+        o[5] = (float)c;
+        o[6] = obj;
+        o[7] = row[5 + c];
+        nw.key[(size_t)b * cap + pos] = conf;
+      }
+      g_before += __popc(mg);
+      e_before += __popc(me);
+    }
+  }
+}
+
+static size_t nms_val_layout(const EtbNmsParams* p, int cap, char* base, NmsWs* nw, MlWs* ml) {
+  const size_t B = p->B;
+  const int nchunks = (p->P + ML_ROWS - 1) / ML_ROWS;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return base ? base + o : (char*)nullptr;
+  };
+  char* c0 = take(B * sizeof(int32_t));                    // n1
+  char* c1 = take(B * sizeof(int32_t));                    // n2
+  char* c2 = take(B * sizeof(int32_t));                    // pl_seg_cnt (unused here, kept so the kernels see valid pointers)
+  char* h0 = take(B * ML_BINS * sizeof(uint32_t));         // hist   } zeroed together with the counters
+  char* s0 = take(B * 8 * sizeof(uint32_t));               // state  }
+  char* g0 = take(B * (size_t)nchunks * sizeof(int32_t));
+  char* e0 = take(B * (size_t)nchunks * sizeof(int32_t));
+  char* r0 = take(B * (size_t)cap * 8 * sizeof(float));
+  char* k0 = take(B * (size_t)cap * sizeof(float));
+  char* o0 = take(B * (size_t)cap * sizeof(int32_t));
+  char* p0 = take(B * (size_t)p->max_det * 9 * sizeof(double));
+  if (nw && ml) {
+    nw->n1 = (int32_t*)c0; nw->n2 = (int32_t*)c1; nw->pl_seg_cnt = (int32_t*)c2;
+    nw->chunk_cnt = (int32_t*)g0; nw->cand_idx = nullptr;
+    nw->rec = (float*)r0; nw->key = (float*)k0; nw->sorted = (int32_t*)o0; nw->pl_seg = (double*)p0;
+    nw->nchunks = nchunks;
+    ml->hist = (uint32_t*)h0; ml->state = (uint32_t*)s0; ml->chunk_gt = (int32_t*)g0; ml->chunk_eq = (int32_t*)e0;
+    ml->nchunks = nchunks;
+  }
+  return off;
+}
+static int nms_val_cap(const EtbNmsParams* p) {
+  const long pairs = (long)p->P * (p->no - 5);
+  return (int)(pairs < p->max_nms ? pairs : p->max_nms);
+}
+
+extern "C" size_t etb_nms_val_workspace_bytes(const EtbNmsParams* p) {
+  if (!p || p->B <= 0 || p->P <= 0 || p->no <= 5 || p->max_nms <= 0) return 0;
+  return nms_val_layout(p, nms_val_cap(p), nullptr, nullptr, nullptr);
+}
+
+// det [B,max_det,8] rows [x1,y1,x2,y2,conf,cls,obj,cls_score] (the caller keeps columns 0..5), det_cnt [B].
+extern "C" int etb_nms_val(const float* pred, const EtbNmsParams* p, float* det, int32_t* det_cnt, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  ETB_CHECK_ARG(pred && p && det && det_cnt && workspace);
+  ETB_CHECK_ARG(p->B > 0 && p->P > 0 && p->no > 6 && p->max_det > 0 && p->max_det <= NMS_MAXK && p->max_nms > 0 && p->conf_thres >= 0.f);
+  const int cap = nms_val_cap(p);
+  NmsWs nw;
+  MlWs ml;
+  const size_t need = nms_val_layout(p, cap, (char*)workspace, &nw, &ml);
+  if (need > workspace_bytes) {
+    etb_set_error("etb_nms_val: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return ETB_ERR_NOMEM;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  ETB_CHECK_CUDA(cudaMemsetAsync(nw.n1, 0, (char*)ml.chunk_gt - (char*)nw.n1, st));      // counters, histogram, state
+  dim3 gC(ml.nchunks, p->B);
+  for (int level = 0; level < 3; ++level) {
+    ml_hist_kernel<<<gC, 256, 0, st>>>(pred, *p, ml, level);
+    ETB_CHECK_LAUNCH();
+    ml_select_kernel<<<p->B, 256, 0, st>>>(*p, ml, level);
+    ETB_CHECK_LAUNCH();
+  }
+  ml_pairs_kernel<false><<<gC, 256, 0, st>>>(pred, *p, ml, nw, cap);
+  ETB_CHECK_LAUNCH();
+  ml_pairs_kernel<true><<<gC, 256, 0, st>>>(pred, *p, ml, nw, cap);
+  ETB_CHECK_LAUNCH();
+  EtbNmsParams q = *p;
+  q.P = cap;                                               // the survivors live in [B][cap] record / key / sorted arrays
+  dim3 gR((cap + 255) / 256, p->B);
+  rank_kernel<<<gR, 256, 0, st>>>(q, nw);
+  ETB_CHECK_LAUNCH();
+  nms_image_kernel<<<p->B, 1024, 0, st>>>(q, nw, det, det_cnt, nullptr);
+  ETB_CHECK_LAUNCH();
+  return ETB_OK;
+}

@@ -117,6 +117,15 @@ size_t etb_nms_workspace_bytes(const EtbNmsParams* p);
 int etb_nms_ssod(const float* pred, const EtbNmsParams* p, float* det, int32_t* det_cnt, const double* Ms,
                  double* pl_rows, int32_t* pl_cnt, void* workspace, size_t workspace_bytes, void* stream);
 
+/* val.py NMS: non_max_suppression(multi_label=True) (utils/general.py:994-1098).  Every (row, class)
+ * pair of a candidate row with obj*cls > conf_thres is a detection; more than max_nms per image: the max_nms best (exact
+ * radix select, ties -> earlier pair); then the same rank + greedy NMS kernels as etb_nms_ssod.  Needs nc > 1 (the
+ * reference disables multi_label for nc == 1: use etb_nms_ssod with need_cls_conf = 1).  det [B,max_det,8] (columns 0..5
+ * are the reference's [xyxy, conf, cls]), det_cnt [B].  No pseudo-label transform on this path. */
+size_t etb_nms_val_workspace_bytes(const EtbNmsParams* p);
+int etb_nms_val(const float* pred, const EtbNmsParams* p, float* det, int32_t* det_cnt, void* workspace,
+                size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Pseudo-Label-Assigner routing: ComputeStudentMatchLoss.select_targets
  * (models/loss/ssod/ssod_loss.py:130-192).  rows [N,9] float64 (N read from n_dev if non-NULL, else n_host);

@@ -368,3 +368,23 @@ def test_labelmatch_device_path_matches_reference(golden):
     lm.update_epoch_cls_thr(0)
     np.testing.assert_allclose(np.array(lm.cls_thr_low), g["thr_low_e0"], rtol=0, atol=0)
     np.testing.assert_allclose(np.array(lm.cls_thr_high), g["thr_high_e0"], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.xfail(strict=False, reason="etb_nms_val was written after the round's GPU minutes were spent: first GPU run pending "
+                                        "(the oracle it is compared with is pinned bit-exactly to the live reference)")
+@pytest.mark.parametrize("name", ["ml_cap", "ml_few", "ml_agn"])
+def test_val_nms_multi_label_vs_reference_golden(golden, name):
+    """val.py path: non_max_suppression(multi_label=True) on the device (radix top-30000 + shared NMS kernels) against the
+    live-reference fixture: keep-sets, order, boxes and scores bit-exact."""
+    from efficientteacher_b200 import nms as N
+    g = golden("nms_val")
+    seed, B, P, frac, conf, iou, ml, agn = g[name + "_meta"]
+    pred = synth.make_teacher_pred(int(seed), int(B), int(P), cand_frac=float(frac))
+    if name == "ml_agn":
+        pred[1, :, 4] = 0.0
+    dets = N.non_max_suppression(torch.from_numpy(pred).to(DEV), float(conf), float(iou), multi_label=True, agnostic=bool(agn))
+    for b in range(int(B)):
+        want = g[f"{name}_det{b}"]
+        got = dets[b].cpu().numpy()
+        assert got.shape == want.shape, (name, b, got.shape, want.shape)
+        np.testing.assert_array_equal(got, want)
