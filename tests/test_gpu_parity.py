@@ -339,6 +339,8 @@ def test_fused_sgd_matches_torch_sgd():
             torch.testing.assert_close(oa.state[a]["momentum_buffer"], ob.state[b]["momentum_buffer"], rtol=2e-6, atol=1e-6)
 
 
+@pytest.mark.xfail(strict=False, reason="written after the round's GPU minutes were spent: first GPU run pending (the host logic it "
+                                        "adds is pinned to the live reference on the CPU, the device pipeline is FairPseudoLabel's)")
 def test_labelmatch_device_path_matches_reference(golden):
     """LabelMatch on the device pipeline: rows, the per-class score lists (async pinned copy + flush) and the epoch thresholds
     against the live-reference fixture (tests/golden/labelmatch.npz)."""
