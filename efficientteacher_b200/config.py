@@ -32,7 +32,7 @@ def _ssod():
               ignore_thres_high=0.6, uncertain_aug=True, use_ota=False, multi_label=False, ignore_obj=False,
               pseudo_label_with_obj=True, pseudo_label_with_bbox=True, pseudo_label_with_cls=False, with_da_loss=False,
               da_loss_weights=0.01, epoch_adaptor=True, ema_rate=0.999, cosine_ema=True, imitate_teacher=False,
-              focal_loss=0.0, pseudo_label_type='FairPseudoLabel', debug=False, fixed_accumulate=True,
+              focal_loss=0.0, pseudo_label_type='FairPseudoLabel', debug=False, fixed_accumulate=False,
               extra_teachers=[], multi_step_lr=False)
 
 

@@ -256,6 +256,11 @@ __device__ __forceinline__ bool conv_epilogue_chunk(const ConvKArgs& a, uint32_t
           f[2 * j] += rf.x;
           f[2 * j + 1] += rf.y;
         }
+      } else if (a.residual) {       // last, partial 32-channel chunk (Cout % 32 != 0: YOLOv5m / custom widths)
+        const __nv_bfloat16* rp = a.residual + pix * a.res_cstride + a.res_coffset + gc0 + q * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (gc0 + q * 8 + j < a.Cout) f[j] += __bfloat162float(rp[j]);
       }
     }
     if (full) {
@@ -275,9 +280,15 @@ __device__ __forceinline__ bool conv_epilogue_chunk(const ConvKArgs& a, uint32_t
       for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
       reinterpret_cast<uint4*>(yp)[q] = ov;
     } else {
+      // partial chunk: scalar stores; the fan-in accumulate (dx += dgrad) reads the existing value here (the preload only
+      // covers whole 32-channel chunks)
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        if (gc0 + q * 8 + j < a.Cout) yp[q * 8 + j] = __float2bfloat16(f[j]);
+        if (gc0 + q * 8 + j < a.Cout) {
+          float o = f[j];
+          if (EPI == 0 && a.accumulate) o += __bfloat162float(yp[q * 8 + j]);
+          yp[q * 8 + j] = __float2bfloat16(o);
+        }
     }
   }
 }

@@ -71,6 +71,23 @@ class FusedSGD(torch.optim.Optimizer):
         _lib.check(_lib.lib().etb_sgd_step(_lib.ptr(self._table), self._n, _lib.ptr(self._hyper), int(zero_grad), _lib.stream_ptr()),
                    "etb_sgd_step")
 
+    def load_state_dict(self, state_dict):
+        """torch's load_state_dict replaces state[p]['momentum_buffer'] by fresh tensors; copy them into the flat buffer the
+        kernel reads (and keep the per-parameter views), so a resumed run really continues with the restored momentum
+        (trainer/trainer.py:251: `self.optimizer.load_state_dict(ckpt['optimizer'])`)."""
+        super().load_state_dict(state_dict)
+        if self._table is not None:
+            with torch.no_grad():
+                o = 0
+                for _, p in self._ps:
+                    view = self._flat[o:o + p.numel()].view_as(p)
+                    loaded = self.state[p].get("momentum_buffer")
+                    if loaded is not None and loaded.data_ptr() != view.data_ptr():
+                        view.copy_(loaded)
+                    self.state[p]["momentum_buffer"] = view
+                    o += p.numel()
+        self._hyper_host = None      # force the next step to push lr / momentum / weight_decay again
+
     def refresh_hyper(self):
         """Push the current lr / momentum / weight_decay of the param groups to device memory (call before replaying a
         captured graph that contains step())."""

@@ -44,9 +44,10 @@ def domain_focal_loss(feature, label, gamma=2.0):
 
 class SSODTrainerStep:
     def __init__(self, cfg, device, rank=-1, world_size=1, epochs=None, batch_size=None, amp_dtype=torch.bfloat16,
-                 pseudo_label_stats=None):
+                 pseudo_label_stats=None, nb=None, start_epoch=0):
         """pseudo_label_stats (LabelMatch only): dict(target_data_len, label_num_per_image, cls_ratio_gt) that the reference
-        derives from its datasets (ssod_trainer.py:71)."""
+        derives from its datasets (ssod_trainer.py:71).  nb = batches per epoch (len(train_loader)); it only sizes the
+        warm-up window exactly like trainer/trainer.py:372-376 (nb=None: the 1000-iteration floor)."""
         self.cfg, self.device = cfg, device
         self.RANK, self.WORLD_SIZE = rank, world_size
         self.epochs = epochs if epochs is not None else cfg.epochs
@@ -76,7 +77,14 @@ class SSODTrainerStep:
             self.pseudo_label_creator = FairPseudoLabel(cfg)
         self.da_loss_weights = cfg.SSOD.da_loss_weights
         self.last_opt_step = -1
-        self.nw = 0          # warm-up iterations (the bench runs past warm-up)
+        # trainer/trainer.py:372-376: number of warm-up iterations = max(warmup_epochs * nb, 1000), capped at half the run
+        self.nb = nb
+        if cfg.hyp.warmup_epochs > 0:
+            self.nw = max(round(cfg.hyp.warmup_epochs * (nb or 0)), 1000)
+            if nb:
+                self.nw = min(self.nw, (self.epochs - start_epoch) / 2 * nb)
+        else:
+            self.nw = -1
         self._arena = None
         self.last = {}
         self.profile = False     # record CUDA events at the phase boundaries of train_instance
@@ -126,22 +134,31 @@ class SSODTrainerStep:
         ac.backward(loss, side=self.WGRAD_SIDE_STREAM)   # weight-gradient branch on a side stream, joined before returning
         self._mark("backward")
 
-    def _optimizer_ema(self, ni):
+    def _warmup(self, ni):
+        """ssod_trainer.py:462-478: accumulate + per-iteration warm-up of lr / momentum (host scalars only; the fused SGD
+        kernel reads them from device memory, so this also serves the captured step).  Group 2 -- the BatchNorm weights in
+        the reference's group order (trainer.py:215-217) -- is the one that falls from warmup_bias_lr."""
         self.accumulate = 1 if self.fixed_accumulate else max(round(64 / self.batch_size), 1)
         if ni <= self.nw:
             xi = [0, self.nw]
             self.accumulate = max(1, np.interp(ni, xi, [1, 1 if self.fixed_accumulate else 64 / self.batch_size]).round())
             for j, x in enumerate(self.optimizer.param_groups):
-                x['lr'] = np.interp(ni, xi, [self.warmup_bias_lr if j == 2 else 0.0, x['initial_lr'] * self.lf(self.epoch)])
+                x['lr'] = float(np.interp(ni, xi, [self.warmup_bias_lr if j == 2 else 0.0, x['initial_lr'] * self.lf(self.epoch)]))
                 if 'momentum' in x:
-                    x['momentum'] = np.interp(ni, xi, [self.warmup_momentum, self.momentum])
-        if ni - self.last_opt_step >= self.accumulate:
-            self.optimizer.step(zero_grad=True)      # fused SGD-Nesterov; also performs optimizer.zero_grad() on the arena
-            if self.semi_ema:
-                # == ema.update(model); semi_ema.update(ema.ema); inside a captured graph the decays come from device memory
-                update_ema_pair(self.ema, self.semi_ema, self.model, scalars_dev=self._ema_scalars_dev)
-            else:
-                self.ema.update(self.model)
+                    x['momentum'] = float(np.interp(ni, xi, [self.warmup_momentum, self.momentum]))
+        return ni - self.last_opt_step >= self.accumulate
+
+    def _step_and_ema(self, capturing=False):
+        self.optimizer.step(zero_grad=True)      # fused SGD-Nesterov; also performs optimizer.zero_grad() on the arena
+        if self.semi_ema:
+            # == ema.update(model); semi_ema.update(ema.ema); inside a captured graph the decays come from device memory
+            update_ema_pair(self.ema, self.semi_ema, self.model, scalars_dev=self._ema_scalars_dev if capturing else None)
+        else:
+            self.ema.update(self.model)
+
+    def _optimizer_ema(self, ni):
+        if self._warmup(ni):
+            self._step_and_ema()
             self.last_opt_step = ni
 
     def update_optimizer(self, loss, ni):
@@ -219,15 +236,21 @@ class SSODTrainerStep:
             return loss.detach()
         self.update_optimizer(loss, ni)
         self._mark("optimizer_ema")
-        self.last = dict(loss=loss.detach(), sup=sup_loss_items, unsup=un_sup_loss_items)
+        # logging values only -- detached, so that no reference to this step's autograd graph (and to the AccumulateGrad
+        # nodes of the parameters, which are tied to the stream they were created on) survives the step
+        det = lambda d: {k: (v.detach() if torch.is_tensor(v) else v) for k, v in d.items()}  # noqa: E731
+        self.last = dict(loss=loss.detach(), sup=det(sup_loss_items), unsup=det(un_sup_loss_items))
         return loss.detach()
 
-    # ---- the whole step as ONE CUDA graph ---------------------------------------------------------------------------
+    # ---- the whole step as CUDA graphs ------------------------------------------------------------------------------
     def train_instance_graphed(self, imgs, targets, unlabeled_imgs, unlabeled_imgs_ori, unlabeled_gt, unlabeled_M, ni):
         """train_instance captured once (static shapes, device-resident pseudo labels, no host sync anywhere in the step)
-        and replayed: ~1.5k kernel launches + the autograd traversal collapse into one cudaGraphLaunch.  Inputs are copied
-        into static buffers; the EMA decays of this step are written to device memory before the replay; the learning
-        rate is baked at capture time, so call `reset_graph()` whenever the scheduler / warm-up changes it."""
+        and replayed as two graphs: A = teacher forward ... backward (gradients accumulate in the arena), B = SGD-Nesterov +
+        both EMA updates.  B is replayed on the iterations the reference's cadence steps the optimizer
+        (ssod_trainer.py:462-488: `accumulate`, warm-up); for WORLD_SIZE > 1 the NCCL all-reduce sits between A and B.  The
+        ~1.5k kernel launches + the autograd traversal collapse into two cudaGraphLaunch calls.  Inputs are copied into
+        static buffers; learning rate / momentum (warm-up, scheduler) and the EMA decays of the step are host scalars
+        written to device memory before B is replayed, so the schedule needs no re-capture."""
         if self.semi_ema is None:
             raise NotImplementedError("graphed step needs the fused ema/semi_ema pair (burn_epochs == 0)")
         shapes = (tuple(imgs.shape), tuple(targets.shape), tuple(unlabeled_imgs.shape), tuple(unlabeled_M.shape))
@@ -241,15 +264,15 @@ class SSODTrainerStep:
         g["us"].copy_(unlabeled_imgs, non_blocking=True)
         g["uw"].copy_(unlabeled_imgs_ori, non_blocking=True)
         g["Ms"].copy_(unlabeled_M, non_blocking=True)
-        d1, d2 = next_pair_decays(self.ema, self.semi_ema)
-        # pageable source: the runtime stages the 16 bytes before returning, so the next step cannot overwrite them early
-        self._ema_scalars_dev.copy_(torch.tensor(ema_scalars(d1, d2), dtype=torch.float32))
-        self.optimizer.refresh_hyper()       # lr / momentum of this step -> device memory read by the captured SGD kernel
         g["graph"].replay()
-        if g["graph_b"] is not None:     # WORLD_SIZE > 1: [graph A: ... backward] -> NCCL all-reduce (eager) -> [graph B: SGD + EMA]
-            self._allreduce_grads()
+        if self._warmup(ni):                 # host: accumulate / lr / momentum of iteration ni
+            self._allreduce_grads()          # WORLD_SIZE > 1: one SUM all-reduce of the arena (no-op otherwise)
+            d1, d2 = next_pair_decays(self.ema, self.semi_ema)
+            # pageable source: the runtime stages the 16 bytes before returning, so the next step cannot overwrite them early
+            self._ema_scalars_dev.copy_(torch.tensor(ema_scalars(d1, d2), dtype=torch.float32))
+            self.optimizer.refresh_hyper()   # lr / momentum of this step -> device memory read by the captured SGD kernel
             g["graph_b"].replay()
-        self.last_opt_step = ni
+            self.last_opt_step = ni
         if hasattr(self.pseudo_label_creator, "stage_detections"):   # LabelMatch: the captured step cannot stage its detections itself
             self.pseudo_label_creator.stage_detections()
         return g["loss"]
@@ -271,41 +294,43 @@ class SSODTrainerStep:
     def _capture(self, imgs, targets, us, uw, Ms, ni, shapes):
         dev = self.device
         st = dict(shapes=shapes, imgs=imgs.clone(), targets=targets.clone(), us=us.clone(), uw=uw.clone(),
-                  Ms=Ms.to(dev, torch.float64).clone(), sc_host=torch.zeros(4, dtype=torch.float32).pin_memory())
+                  Ms=Ms.to(dev, torch.float64).clone())
         self._ema_scalars_dev = torch.zeros(4, dtype=torch.float32, device=dev)
         was_profile, self.profile = self.profile, False
-        d1, d2 = next_pair_decays(self.ema, self.semi_ema, advance=False)
-        self._ema_scalars_dev.copy_(torch.tensor(ema_scalars(d1, d2), dtype=torch.float32))
+        self.last = {}
         # the warm-up steps below really train: snapshot every piece of state they touch and restore it afterwards
+        self._ensure_arena()
         had_momentum = any(len(self.optimizer.state[p]) for g_ in self.optimizer.param_groups for p in g_["params"])
         tensors = [t for m in (self.model, self.ema.ema, self.semi_ema.ema) for t in m.state_dict().values()]
         if had_momentum:
             tensors += [self.optimizer.state[p]["momentum_buffer"] for g_ in self.optimizer.param_groups for p in g_["params"]
                         if self.optimizer.state[p].get("momentum_buffer") is not None]
+        tensors.append(self._arena.flat)     # gradients already accumulated towards the next optimizer step (accumulate > 1)
         snap = [t.clone() for t in tensors]
-        saved_step = self.last_opt_step
+        saved = (self.last_opt_step, self.ema.updates, self.semi_ema.updates, self.accumulate,
+                 [(x['lr'], x.get('momentum')) for x in self.optimizer.param_groups])
+        lm_state = None
+        if hasattr(self.pseudo_label_creator, "count"):
+            lm_state = (self.pseudo_label_creator.count, self.pseudo_label_creator.pse_count)
         # warm-up on a side stream (allocator + lazily-created state: momentum buffers, chunk tables, workspaces, TMA/func attrs)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(2):
-                self.last_opt_step = ni - 10**6      # the optimizer + EMA branch must be taken (and captured) every time
-                self.train_instance(st["imgs"], st["targets"], st["us"], st["uw"], None, st["Ms"], ni)
-        split = self.WORLD_SIZE > 1
+                self.train_instance(st["imgs"], st["targets"], st["us"], st["uw"], None, st["Ms"], ni, _stop_after_backward=True)
+                self._allreduce_grads()
+                self._warmup(ni)
+                self._step_and_ema()          # the optimizer + EMA branch is exercised (and later captured) unconditionally
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
-        self.last_opt_step = ni - 10**6
         with torch.cuda.graph(graph):
-            st["loss"] = self.train_instance(st["imgs"], st["targets"], st["us"], st["uw"], None, st["Ms"], ni, _stop_after_backward=split)
+            st["loss"] = self.train_instance(st["imgs"], st["targets"], st["us"], st["uw"], None, st["Ms"], ni, _stop_after_backward=True)
         st["graph"] = graph
-        st["graph_b"] = None
-        if split:
-            gb = torch.cuda.CUDAGraph()
-            self.last_opt_step = ni - 10**6
-            with torch.cuda.graph(gb, pool=graph.pool()):
-                self._optimizer_ema(ni)
-            st["graph_b"] = gb
+        gb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gb, pool=graph.pool()):
+            self._step_and_ema(capturing=True)
+        st["graph_b"] = gb
         with torch.no_grad():
             for t, c in zip(tensors, snap):
                 t.copy_(c)
@@ -315,8 +340,13 @@ class SSODTrainerStep:
                         b = self.optimizer.state[p].get("momentum_buffer")
                         if b is not None:
                             b.zero_()
-            self._arena.zero()
-        self.last_opt_step = saved_step
+        self.last_opt_step, self.ema.updates, self.semi_ema.updates, self.accumulate, hyp = saved
+        for x, (lr, mom) in zip(self.optimizer.param_groups, hyp):
+            x['lr'] = lr
+            if mom is not None:
+                x['momentum'] = mom
+        if lm_state is not None:
+            self.pseudo_label_creator.count, self.pseudo_label_creator.pse_count = lm_state
         self.profile = was_profile
         self._graph = st
 
@@ -324,48 +354,91 @@ class SSODTrainerStep:
 class SupTrainerStep:
     """The supervised step (trainer/trainer.py:406-443 train_in_epoch body + :381-404 update_optimizer), BASELINE configs
     #1/#2: student forward -> ComputeLoss -> backward -> [all-reduce] -> SGD-Nesterov -> ModelEMA.update, same native
-    kernels as the SSOD step minus the teacher / pseudo-label path."""
+    kernels as the SSOD step minus the teacher / pseudo-label path.  The optimizer cadence is the reference's:
+    accumulate = max(round(64 / batch_size), 1) iterations per optimizer step (gradients add up in the arena in between)
+    and the per-iteration warm-up of lr / momentum / accumulate while ni <= nw (trainer.py:372-376, 385-395)."""
 
-    def __init__(self, cfg, device, rank=-1, world_size=1, epochs=None, batch_size=None, amp_dtype=torch.bfloat16):
+    def __init__(self, cfg, device, rank=-1, world_size=1, epochs=None, batch_size=None, amp_dtype=torch.bfloat16, nb=None,
+                 start_epoch=0):
         self.cfg, self.device = cfg, device
         self.RANK, self.WORLD_SIZE = rank, world_size
         self.epochs = epochs if epochs is not None else cfg.epochs
+        self.epoch = 0
         self.batch_size = batch_size if batch_size is not None else cfg.Dataset.batch_size
         self.amp_dtype = amp_dtype
         self.model = SupModel(cfg).to(device)
         self.ema = ModelEMA(self.model)          # the reference keeps it on rank 0/-1 only (trainer.py:157); harmless elsewhere
-        nbs = 64
-        self.accumulate = max(round(nbs / self.batch_size), 1)
-        weight_decay = cfg.hyp.weight_decay * self.batch_size * self.accumulate / nbs
-        g_bnw, g_w, g_b = [], [], []
-        for v in self.model.modules():
-            if hasattr(v, 'bias') and isinstance(v.bias, nn.Parameter):
-                g_b.append(v.bias)
-            if isinstance(v, nn.BatchNorm2d):
-                g_bnw.append(v.weight)
-            elif hasattr(v, 'weight') and isinstance(v.weight, nn.Parameter):
-                g_w.append(v.weight)
-        self.optimizer = FusedSGD(g_b, lr=cfg.hyp.lr0, momentum=cfg.hyp.momentum, nesterov=True)
-        self.optimizer.add_param_group({'params': g_w, 'weight_decay': weight_decay})
-        self.optimizer.add_param_group({'params': g_bnw})
+        self.semi_ema = None
+        self.fixed_accumulate = False            # trainer/trainer.py has no such switch
+        SSODTrainerStep.build_optimizer(self, cfg)
         self.compute_loss = ComputeLoss(self.model, cfg)
         self._arena = None
         self.last_opt_step = -1
+        if cfg.hyp.warmup_epochs > 0:
+            self.nw = max(round(cfg.hyp.warmup_epochs * (nb or 0)), 1000)
+            if nb:
+                self.nw = min(self.nw, (self.epochs - start_epoch) / 2 * nb)
+        else:
+            self.nw = -1
+        self._graph = None
 
-    def train_step(self, imgs, targets, ni):
+    _warmup = SSODTrainerStep._warmup
+    _ensure_arena = SSODTrainerStep._ensure_arena
+
+    def _forward_backward(self, imgs, targets):
         with torch.autocast("cuda", dtype=self.amp_dtype):
             pred = self.model(imgs)
         loss, loss_items = self.compute_loss(pred, targets)
-        if self._arena is None:
-            self._arena = GradArena(self.model.parameters(), self.device)
+        self._ensure_arena()
         from . import autograd_conv as ac
         ac.backward(loss, side=SSODTrainerStep.WGRAD_SIDE_STREAM)
-        self._arena.all_reduce_sum(self.WORLD_SIZE)
-        if ni - self.last_opt_step >= 1:
-            self.optimizer.step(zero_grad=True)
-            self.ema.update(self.model)
-            self.last_opt_step = ni
         return loss.detach()
+
+    def _step_and_ema(self):
+        self.optimizer.step(zero_grad=True)
+        self.ema.update(self.model)
+
+    def train_step(self, imgs, targets, ni):
+        loss = self._forward_backward(imgs, targets)
+        if self._warmup(ni):
+            self._arena.all_reduce_sum(self.WORLD_SIZE)
+            self._step_and_ema()
+            self.last_opt_step = ni
+        return loss
+
+    def train_step_graphed(self, imgs, targets, ni):
+        """train_step with forward + loss + backward replayed from one captured CUDA graph (static shapes); the optimizer /
+        EMA launches (2 kernels, host-side decay) stay eager on the iterations the cadence asks for."""
+        shapes = (tuple(imgs.shape), tuple(targets.shape))
+        if self._graph is None or self._graph["shapes"] != shapes:
+            self._ensure_arena()
+            st = dict(shapes=shapes, imgs=imgs.clone(), targets=targets.clone())
+            tensors = [t for t in self.model.state_dict().values()] + [self._arena.flat]
+            snap = [t.clone() for t in tensors]
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self._forward_backward(st["imgs"], st["targets"])
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                st["loss"] = self._forward_backward(st["imgs"], st["targets"])
+            st["graph"] = graph
+            with torch.no_grad():
+                for t, c in zip(tensors, snap):       # BN running statistics / num_batches_tracked / the arena
+                    t.copy_(c)
+            self._graph = st
+        g = self._graph
+        g["imgs"].copy_(imgs, non_blocking=True)
+        g["targets"].copy_(targets, non_blocking=True)
+        g["graph"].replay()
+        if self._warmup(ni):
+            self._arena.all_reduce_sum(self.WORLD_SIZE)
+            self._step_and_ema()
+            self.last_opt_step = ni
+        return g["loss"]
 
 
 class DevicePrefetcher:

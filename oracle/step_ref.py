@@ -23,11 +23,12 @@ def domain_focal(feature, label):
 
 class CpuSSODStep:
     def __init__(self, state_dict, depth, neck_depth, lr=0.01, momentum=0.937, weight_decay=0.0005, batch_size=32,
-                 ema_updates=0, semi_decay=0.999, teacher_loss_weight=3.0, bn_momentum=0.0, warmup=None):
+                 ema_updates=0, semi_decay=0.999, teacher_loss_weight=3.0, bn_momentum=0.0, warmup=None, fixed_accumulate=True):
         """bn_momentum > 0: the student's running statistics are updated like nn.BatchNorm2d(momentum) does (needed for
         multi-step trajectories; the single-step parity tests leave it 0).  warmup = (nw, warmup_bias_lr, warmup_momentum):
         apply the reference's per-iteration warm-up (trainer/trainer.py:388-395: group index 2 gets warmup_bias_lr)."""
         self.bn_momentum, self.warmup, self.lr0, self.momentum0, self.ni = bn_momentum, warmup, lr, momentum, 0
+        self.fixed_accumulate, self.batch_size, self.last_opt_step = fixed_accumulate, batch_size, -1
         self.student = {k: v.detach().clone().float() for k, v in state_dict.items()}
         self.teacher = {k: v.detach().clone() for k, v in self.student.items()}
         self.semi = {k: v.detach().clone() for k, v in self.student.items()}
@@ -69,15 +70,21 @@ class CpuSSODStep:
         else:
             un_loss = torch.zeros(1)
         loss = sup_loss + un_loss * self.tlw
+        # ssod_trainer.py:458-488: backward (gradients accumulate), accumulate / warm-up, optimizer + EMA when due
+        loss.backward()
+        accumulate = 1 if self.fixed_accumulate else max(round(64 / self.batch_size), 1)
         if self.warmup is not None and self.ni <= self.warmup[0]:
             xi = [0, self.warmup[0]]
+            accumulate = max(1, np.interp(self.ni, xi, [1, 1 if self.fixed_accumulate else 64 / self.batch_size]).round())
             for j, pg in enumerate(self.opt.param_groups):
                 pg['lr'] = float(np.interp(self.ni, xi, [self.warmup[1] if j == 2 else 0.0, self.lr0]))
                 pg['momentum'] = float(np.interp(self.ni, xi, [self.warmup[2], self.momentum0]))
-        self.ni += 1
-        self.opt.zero_grad()
-        loss.backward()
+        ni, self.ni = self.ni, self.ni + 1
+        if ni - self.last_opt_step < accumulate:
+            return float(loss.detach()), len(rows)
+        self.last_opt_step = ni
         self.opt.step()
+        self.opt.zero_grad()
         self.ema_updates += 1
         d = 0.9999 * (1 - math.exp(-self.ema_updates / 2000))
         with torch.no_grad():
@@ -86,4 +93,4 @@ class CpuSSODStep:
                     v.mul_(d).add_((1.0 - d) * self.student[k].detach())
                     s = self.semi[k]
                     s.mul_(self.semi_decay).add_((1.0 - self.semi_decay) * v)
-        return float(loss), len(rows)
+        return float(loss.detach()), len(rows)

@@ -46,6 +46,13 @@ CASES = [
     (2, 32, 20, 20, 32, 3, 1, 1),      # Cin = Cout = 32 (Bottleneck of the first C3)
     (2, 64, 20, 20, 32, 1, 1, 0),      # pointwise to 32 channels
     (2, 96, 16, 16, 32, 1, 1, 0),      # Cin = 96: 1.5 K blocks
+    # YOLOv5m widths (48 / 96 / 192 ...): the last 32-channel epilogue chunk is partial
+    (2, 48, 20, 20, 48, 3, 1, 1),
+    (2, 96, 16, 16, 192, 1, 1, 0),
+    # real YOLOv5l shapes at the bench batch
+    (32, 64, 160, 160, 64, 3, 1, 1),   # first C3's Bottleneck conv: 160x160 maps, batch 32
+    (32, 2048, 20, 20, 1024, 1, 1, 0), # SPPF cv2: K = 2048
+    (32, 128, 160, 160, 256, 3, 2, 1), # stage3_1
 ]
 
 
@@ -78,6 +85,16 @@ def test_conv_residual_and_concat_slices():
     got = co.to_nchw_f32(buf, C_, 128)
     _check(got, F.silu(F.conv2d(_bf(x), _bf(w), None, 1, 1)) + _bf(r))
     assert torch.equal(co.to_nchw_f32(buf, C_, 64), _bf(x))       # neighbours untouched
+
+
+def test_conv_residual_partial_chunk():
+    """Cout = 48 (YOLOv5m Bottleneck width): the shortcut must also be added in the last, partial 32-channel chunk."""
+    from efficientteacher_b200 import convops as co
+    N, C_, H, W = 2, 48, 20, 20
+    x, r = _rand((N, C_, H, W), 3), _rand((N, C_, H, W), 4)
+    w = _rand((C_, C_, 3, 3), 5, scale=(C_ * 9) ** -0.5)
+    y = co.conv_fwd(co.to_nhwc_bf16(x), co.pack_weight(w), C_, C_, 3, 1, 1, None, None, act="silu", residual=co.to_nhwc_bf16(r))
+    _check(co.to_nchw_f32(y), F.silu(F.conv2d(_bf(x), _bf(w), None, 1, 1)) + _bf(r))
 
 
 def test_detect_head_layout():
@@ -125,6 +142,14 @@ DGRAD_CASES = [
     (2, 32, 16, 16, 64, 3, 2, 1),      # v5s: dgrad K = Cout = 64, 32 output channels
     (2, 32, 20, 20, 32, 3, 1, 1),      # v5s: K = 32 (half a K block, zero-filled by TMA)
     (2, 64, 20, 20, 32, 1, 1, 0),
+    # YOLOv5m widths: Cin (= dgrad output channels) not a multiple of 32 -> partial epilogue chunk, incl. the fan-in accumulate
+    (2, 48, 16, 16, 96, 1, 1, 0),
+    (2, 96, 20, 20, 48, 3, 1, 1),
+    (2, 48, 20, 20, 48, 3, 1, 1),
+    # real YOLOv5l shapes at the bench batch
+    (32, 64, 160, 160, 64, 3, 1, 1),
+    (32, 2048, 20, 20, 1024, 1, 1, 0),
+    (32, 128, 160, 160, 256, 3, 2, 1),
 ]
 
 
@@ -157,6 +182,11 @@ WGRAD_CASES = [
     (2, 32, 20, 20, 32, 3, 1, 1),
     (2, 64, 20, 20, 32, 1, 1, 0),
     (2, 32, 20, 20, 64, 1, 1, 0),
+    # real YOLOv5l shapes at the bench batch (deep split-K)
+    (32, 64, 160, 160, 64, 3, 1, 1),   # 819,200 pixels reduced per tap
+    (32, 2048, 20, 20, 1024, 1, 1, 0),
+    (32, 256, 40, 40, 256, 3, 1, 1),
+    (32, 128, 160, 160, 256, 3, 2, 1),
 ]
 
 

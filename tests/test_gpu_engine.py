@@ -236,52 +236,113 @@ def test_device_prefetcher_roundtrip():
         assert torch.equal(got["a"].cpu(), batches[i]["a"]) or True   # slot may already be refilled: value check above is the contract
 
 
-@pytest.mark.xfail(strict=False, reason="open issue (DESIGN.md section 7, item 0): in bench.py the EMA teacher's features collapse within ~15 "
-                                        "steps although decay = 0.9999; not yet reproduced / root-caused at test scale")
-def test_teacher_is_stable_under_high_ema_decay():
-    """With ema.updates = 100000 the decay is 0.9999: over 12 steps the teacher moves by <= 0.12 % of the student-teacher gap.
-    The CPU fp32 restatement of the same steps (oracle/step_ref.py with BN running statistics and the reference's warm-up)
-    measures a teacher-logit drift of 6e-5 after 12 steps and a loss falling 52.2 -> 39.1; the native path must stay within
-    2 % drift and follow the CPU loss trajectory."""
-    from efficientteacher_b200.config import yolov5_ssod_cfg
-    from efficientteacher_b200.trainer import SSODTrainerStep
-    from oracle.step_ref import CpuSSODStep
+def _traj_inputs(img, bl, bu):
     import synth
-    img, bl, bu = 256, 4, 4
     r = np.random.RandomState(5)
     imgs_c = torch.from_numpy(r.rand(bl, 3, img, img).astype(np.float32))
     uw_c = torch.from_numpy(r.rand(bu, 3, img, img).astype(np.float32))
     us_c = uw_c.flip(3).contiguous()
-    tg_c = synth.make_targets(7, 8 * bl, bl)
-    Ms_c = synth.make_Ms(9, bu, img)
+    return imgs_c, uw_c, us_c, synth.make_targets(7, 8 * bl, bl), synth.make_Ms(9, bu, img)
+
+
+def _bn_ext(named_tensors):
+    """(max running_var, max |gamma|) over an iterable of (key, tensor)"""
+    rv = g = 0.0
+    for k, v in named_tensors:
+        if k.endswith("running_var"):
+            rv = max(rv, float(v.max()))
+        elif k.endswith("bn.weight"):
+            g = max(g, float(v.abs().max()))
+    return rv, g
+
+
+def _run_native_trajectory(size, img, bl, bu, steps_eager, steps_graph, native=True):
+    """steps of the SSOD step from the seeded random init in the reference's warm-up regime (ni = 0.., nw = 1000: weight lr
+    ramps from 0, BN-weight lr falls from 0.1 -- trainer/trainer.py:372-395); returns the per-step rows
+    (loss, pseudo-label rows, max running_var, max |gamma|) and the teacher-logit drift at the end."""
+    from efficientteacher_b200 import model as M
+    from efficientteacher_b200.config import yolov5_ssod_cfg
+    from efficientteacher_b200.trainer import SSODTrainerStep
+    imgs_c, uw_c, us_c, tg_c, Ms_c = _traj_inputs(img, bl, bu)
     imgs, uw, us = imgs_c.to(DEV), uw_c.to(DEV), us_c.to(DEV)
     tg, Ms = torch.from_numpy(tg_c).to(DEV), torch.from_numpy(Ms_c).to(DEV)
     torch.manual_seed(0)
-    st = SSODTrainerStep(yolov5_ssod_cfg('l_shallow', batch_size=bl + bu, img_size=img), torch.device(DEV), epochs=300)
-    st.ema.updates = 100000
-    with torch.no_grad():
-        for mm in (st.model, st.ema.ema, st.semi_ema.ema):
-            for h in mm.head.m:
-                h.bias.view(3, -1)[:, 4] += 6.5
-                h.bias.view(3, -1)[:, 5:] += 5.0
-        (_, raw0), _ = st.ema.ema(uw)
-        raw0 = [t.clone() for t in raw0]
-    cpu = CpuSSODStep({k: v.cpu() for k, v in st.model.state_dict().items()}, (1, 2, 3, 1), 1, batch_size=bl + bu, ema_updates=100000,
-                      bn_momentum=0.03, warmup=(st.nw, st.warmup_bias_lr, st.warmup_momentum))
-    step = 0
-    for mode, n in (("eager", 6), ("graph", 6)):
-        for i in range(n):
-            f = st.train_instance_graphed if mode == "graph" else st.train_instance
-            loss = f(imgs, tg, us, uw, None, Ms, step)
-            assert torch.isfinite(loss).all()
-            if mode == "eager":
-                ref, _ = cpu.step(imgs_c, tg_c, us_c, uw_c, Ms_c)
-                assert abs(loss.item() - ref) <= 0.08 * abs(ref), (step, loss.item(), ref)
-            step += 1
+    cfg = yolov5_ssod_cfg(size, batch_size=bl + bu, img_size=img)
+    cfg.SSOD.fixed_accumulate = True
+    M.Conv.NATIVE = native
+    try:
+        st = SSODTrainerStep(cfg, torch.device(DEV), epochs=300)
+        st.ema.updates = 100000
+        with torch.no_grad():
+            for mm in (st.model, st.ema.ema, st.semi_ema.ema):
+                for h in mm.head.m:
+                    h.bias.view(3, -1)[:, 4] += 6.5
+                    h.bias.view(3, -1)[:, 5:] += 5.0
+            sd0 = {k: v.detach().cpu().clone() for k, v in st.model.state_dict().items()}
+            (_, raw0), _ = st.ema.ema(uw)
+            raw0 = [t.clone() for t in raw0]
+        rows = []
+        for i in range(steps_eager + steps_graph):
+            f = st.train_instance if i < steps_eager else st.train_instance_graphed
+            loss = f(imgs, tg, us, uw, None, Ms, i)
+            assert torch.isfinite(loss).all(), i
+            rv, g = _bn_ext(st.model.state_dict().items())
+            rows.append((float(loss), int(st.pseudo_label_creator.last_count_dev.item()), rv, g))
         with torch.no_grad():
             (_, raw1), _ = st.ema.ema(uw)
-        for a, b in zip(raw1, raw0):
-            rel = float((a - b).norm() / b.norm())
-            assert rel < 0.02, (mode, rel)
-    bn_var = max(float(q.running_var.max()) for q in st.model.modules() if isinstance(q, torch.nn.BatchNorm2d))
-    assert bn_var < 1e3, bn_var
+        drift = max(float((a - b).norm() / b.norm()) for a, b in zip(raw1, raw0))
+        assert st.ema.updates == 100000 + steps_eager + steps_graph
+    finally:
+        M.Conv.NATIVE = True
+    return rows, drift, sd0, st
+
+
+def test_multi_step_trajectory_tracks_cpu_oracle():
+    """N1 (multi-iteration parity of the state a step hands to the next one): 12 consecutive SSOD steps (6 eager launches,
+    then 6 replays of the captured graphs) from a seeded random init in the reference's warm-up regime, against the fp32 CPU
+    restatement of the same 12 steps (oracle/step_ref.py: running statistics, warm-up, SGD-Nesterov, both EMAs).  Per step:
+    loss within 3 %, pseudo-label rows within 10 %, max BN running_var within 15 %, max |gamma| within 3 %; at the end the
+    teacher logits have moved by < 0.5 % (decay 0.9999) and the student's BN state is finite and bounded."""
+    from oracle.step_ref import CpuSSODStep
+    img, bl, bu = 256, 4, 4
+    rows, drift, sd0, st = _run_native_trajectory('l_shallow', img, bl, bu, 6, 6)
+    imgs_c, uw_c, us_c, tg_c, Ms_c = _traj_inputs(img, bl, bu)
+    cpu = CpuSSODStep(sd0, (1, 2, 3, 1), 1, batch_size=bl + bu, ema_updates=100000, bn_momentum=0.03,
+                      warmup=(st.nw, st.warmup_bias_lr, st.warmup_momentum))
+    ref = []
+    for i in range(len(rows)):
+        loss, n = cpu.step(imgs_c, tg_c, us_c, uw_c, Ms_c)
+        ref.append((loss, n) + _bn_ext(cpu.student.items()))
+    msg = "\n".join("step %2d native loss %.4f rows %4d rv %.4g g %.4g | cpu loss %.4f rows %4d rv %.4g g %.4g" % (i, *a, *b)
+                    for i, (a, b) in enumerate(zip(rows, ref)))
+    print(msg)
+    for i, (a, b) in enumerate(zip(rows, ref)):
+        assert abs(a[0] - b[0]) <= 0.03 * abs(b[0]), (i, msg)
+        assert abs(a[1] - b[1]) <= max(5, 0.10 * b[1]), (i, msg)
+        assert abs(a[2] - b[2]) <= 0.15 * b[2], (i, msg)
+        assert abs(a[3] - b[3]) <= 0.03 * b[3], (i, msg)
+    assert ref[-1][0] < ref[0][0] and rows[-1][0] < rows[0][0], msg       # both arms are learning
+    assert drift < 5e-3, drift
+    # teacher state vs the oracle's teacher after the 12 EMA updates (fp32 state, bf16 student trajectory)
+    t_nat = torch.cat([v.flatten().float().cpu() for k, v in st.ema.ema.state_dict().items() if v.dtype.is_floating_point and "running" not in k])
+    t_cpu = torch.cat([v.flatten() for k, v in cpu.teacher.items() if v.dtype.is_floating_point and "running" not in k])
+    assert float((t_nat - t_cpu).norm() / t_cpu.norm()) < 1e-3
+
+
+def test_multi_step_trajectory_full_yolov5l():
+    """30 consecutive steps of the full-depth YOLOv5l at 320 (2+2 images), all through the captured graphs after 2 eager
+    steps, against the torch-bf16 / cuDNN arm (Conv.NATIVE = False: same model, same trainer, library kernels) of the same
+    trajectory: the native path must stay as close to it as bf16 allows and keep a live teacher (pseudo labels at the last
+    step within 10 % of the first)."""
+    img, bl, bu = 320, 2, 2
+    rows, drift, _, _ = _run_native_trajectory('l', img, bl, bu, 2, 28)
+    lib_rows, lib_drift, _, _ = _run_native_trajectory('l', img, bl, bu, 30, 0, native=False)
+    msg = "\n".join("step %2d native loss %.4f rows %4d rv %.4g g %.4g | torch-bf16 loss %.4f rows %4d rv %.4g g %.4g" % (i, *a, *b)
+                    for i, (a, b) in enumerate(zip(rows, lib_rows)))
+    print(msg)
+    for i, (a, b) in enumerate(zip(rows, lib_rows)):
+        assert abs(a[0] - b[0]) <= 0.04 * abs(b[0]), (i, msg)
+        assert abs(a[2] - b[2]) <= 0.2 * b[2], (i, msg)
+        assert abs(a[3] - b[3]) <= 0.04 * b[3], (i, msg)
+    assert rows[0][1] > 0 and abs(rows[-1][1] - rows[0][1]) <= 0.1 * rows[0][1], msg
+    assert drift < 1e-2 and lib_drift < 1e-2, (drift, lib_drift)

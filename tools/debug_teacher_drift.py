@@ -59,7 +59,11 @@ def run(variant, args):
             graph = False
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
-    st = SSODTrainerStep(yolov5_ssod_cfg(args.size, batch_size=args.bl + args.bu, img_size=args.img), dev, epochs=300)
+    cfg = yolov5_ssod_cfg(args.size, batch_size=args.bl + args.bu, img_size=args.img)
+    cfg.SSOD.fixed_accumulate = True
+    st = SSODTrainerStep(cfg, dev, epochs=300)
+    if args.nw is not None:
+        st.nw = args.nw           # 0 = the round-1 regime (full lr on a random init), default = the reference's warm-up (1000)
     st.ema.updates = args.updates
     r = np.random.RandomState(3)
     imgs = torch.from_numpy(r.rand(args.bl, 3, args.img, args.img).astype(np.float32)).to(dev)
@@ -71,9 +75,13 @@ def run(variant, args):
         bns = [m for m in st.model.modules() if isinstance(m, torch.nn.BatchNorm2d)]
         for m in bns:
             m.momentum = 1.0
-        st.model(torch.cat([imgs, us], 0).contiguous(memory_format=torch.channels_last))
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            st.model(torch.cat([imgs, us], 0).contiguous(memory_format=torch.channels_last))
         for m in bns:
             m.momentum = 0.03
+        for h in st.model.head.m:           # candidates for the pseudo-label path (objectness ~0.5, class scores ~0.5)
+            h.bias.view(3, -1)[:, 4] += 6.5
+            h.bias.view(3, -1)[:, 5:] += 5.0
         st.ema.ema.load_state_dict(st.model.state_dict())
         st.semi_ema.ema.load_state_dict(st.model.state_dict())
         (_, raw0), _ = st.ema.ema(uw)
@@ -92,8 +100,8 @@ def run(variant, args):
         with torch.no_grad():
             (_, raw1), _ = st.ema.ema(uw)
         drift = max(float((a - b).norm() / b.norm()) for a, b in zip(raw1, raw0))
-        print("step %2d loss %.4f teacher drift %.4f | student BN (var,|mean|,|g|,|b|) %s | teacher %s | max|grad| bias/w/bnw %s" % (
-            i, float(loss), drift, "%.3g %.3g %.3g %.3g" % bn_ext(st.model), "%.3g %.3g %.3g %.3g" % bn_ext(st.ema.ema), gmax), flush=True)
+        print("step %2d loss %.4f rows %d teacher drift %.5f | student BN (var,|mean|,|g|,|b|) %s | teacher %s | max|grad| bias/w/bnw %s" % (
+            i, float(loss), int(st.pseudo_label_creator.last_count_dev.item()), drift, "%.3g %.3g %.3g %.3g" % bn_ext(st.model), "%.3g %.3g %.3g %.3g" % bn_ext(st.ema.ema), gmax), flush=True)
         if i in (0, args.steps - 1) or drift > 0.05:
             wmax = max((float(p.abs().max()), n) for n, p in st.model.named_parameters() if p.dim() == 4)
             print("        student top BN: %s | largest conv weight %.3g (%s)" % (bn_top(st.model), wmax[0], wmax[1]), flush=True)
@@ -107,6 +115,7 @@ def main():
     ap.add_argument("--bu", type=int, default=4)
     ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--updates", type=int, default=100000)
+    ap.add_argument("--nw", type=int, default=None)
     ap.add_argument("--variants", default="base,eager,noside,nofanin,noglue,torchbn")
     args = ap.parse_args()
     import __graft_entry__ as g
