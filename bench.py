@@ -33,6 +33,16 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 B_L, B_U, IMG = 16, 16, 640
 METRIC = "images/sec YOLOv5l SSOD step @640 bs32 (16 labeled + 16 unlabeled per GPU)"
+NB = 369     # batches per epoch of the reference's COCO 10 % recipe (11,829 labeled images / 32): sizes the warm-up window (nw = 1107)
+# --config: the headline (default) and the two other single-GPU configurations of BASELINE.json
+CONFIGS = {
+    "ssod640": dict(kind="ssod", bl=16, bu=16, img=640, metric=METRIC,
+                    workload="YOLOv5l SSOD 640: 16 labeled + 16 unlabeled per GPU (BASELINE configs[2] per-GPU batch), optimizer+2xEMA every step"),
+    "ssod1280": dict(kind="ssod", bl=8, bu=8, img=1280, metric="images/sec YOLOv5l SSOD step @1280 bs16 (8 labeled + 8 unlabeled per GPU)",
+                     workload="YOLOv5l SSOD 1280: 8 labeled + 8 unlabeled per GPU (BASELINE configs[4]), optimizer+2xEMA every step"),
+    "sup32": dict(kind="sup", bl=32, bu=0, img=640, metric="images/sec YOLOv5l supervised step @640 bs32",
+                  workload="YOLOv5l supervised 640, batch 32 on one GPU (BASELINE configs[1]); optimizer cadence of the reference (accumulate=2 past warm-up, 1 inside it)"),
+}
 
 
 def peaks():
@@ -76,15 +86,15 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
-def synth_batch(rank, device=None, pinned=False):
+def synth_batch(rank, device=None, pinned=False, bl=B_L, bu=B_U, img=IMG):
     """Per-rank seeded synthetic batch (SURVEY.md 8d, config #3): uint8 images like the loaders produce, 8 targets/img."""
     import synth
     r = np.random.RandomState(1 + rank)
-    mk = lambda n: torch.from_numpy(r.randint(0, 256, (n, 3, IMG, IMG), dtype=np.uint8))  # noqa: E731
-    imgs, u_weak = mk(B_L), mk(B_U)
+    mk = lambda n: torch.from_numpy(r.randint(0, 256, (n, 3, img, img), dtype=np.uint8))  # noqa: E731
+    imgs, u_weak = mk(bl), mk(max(bu, 1))
     u_strong = u_weak.flip(3).contiguous()
-    targets = torch.from_numpy(synth.make_targets(100 + rank, 8 * B_L, B_L))
-    Ms = torch.from_numpy(synth.make_Ms(200 + rank, B_U, IMG))
+    targets = torch.from_numpy(synth.make_targets(100 + rank, 8 * bl, bl))
+    Ms = torch.from_numpy(synth.make_Ms(200 + rank, max(bu, 1), img))
     out = dict(imgs=imgs, u_weak=u_weak, u_strong=u_strong, targets=targets, Ms=Ms)
     if pinned:
         out = {k: v.pin_memory() for k, v in out.items()}
@@ -180,67 +190,144 @@ def kernel_table(step, ni, path, graph_ms):
             f.write("| `%s` | %.1f | %.1f | %.1f%% |\n" % (name[:110], cnt / nsteps, us / nsteps, 100.0 * us / tot))
 
 
-def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU path of the step (oracle restatement; /root/reference cannot travel to the
-    GPU box).  Rank 0 only.  Each step = one full SSOD step on a bounded sample (2 labeled + 2 unlabeled images)."""
-    if rank != 0:
-        return
+def _cpu_step_sample(threads, bl, bu, steps, img=IMG):
+    """`steps` full SSOD steps of the oracle's CPU restatement (oracle/step_ref.py: torch fp32 trunk + port) on bl+bu images
+    with `threads` host threads; returns the per-step seconds (the first step is a warm-up and is not returned)."""
     from oracle.step_ref import CpuSSODStep
     from efficientteacher_b200.config import yolov5_ssod_cfg
     from efficientteacher_b200.model import Model
     import synth
-    torch.set_num_threads(min(os.cpu_count(), 16))
+    torch.set_num_threads(threads)
     torch.manual_seed(0)
     model = Model(yolov5_ssod_cfg('l'))
-    bl = bu = 1
-    step = CpuSSODStep(model.state_dict(), (3, 6, 9, 3), 3, batch_size=B_L + B_U, ema_updates=100000)
+    step = CpuSSODStep(model.state_dict(), (3, 6, 9, 3), 3, batch_size=B_L + B_U, ema_updates=100000, bn_momentum=0.03,
+                       warmup=(max(round(3 * NB), 1000), 0.1, 0.8))
     r = np.random.RandomState(1)
-    imgs = torch.from_numpy(r.rand(bl, 3, IMG, IMG).astype(np.float32))
-    uw = torch.from_numpy(r.rand(bu, 3, IMG, IMG).astype(np.float32))
+    imgs = torch.from_numpy(r.rand(bl, 3, img, img).astype(np.float32))
+    uw = torch.from_numpy(r.rand(bu, 3, img, img).astype(np.float32))
     tg = synth.make_targets(100, 8 * bl, bl)
-    Ms = synth.make_Ms(200, bu, IMG)
+    Ms = synth.make_Ms(200, bu, img)
     ts = []
-    for i in range(args.warmup + args.steps):
+    for i in range(steps + 1):
         t0 = time.perf_counter()
         step.step(imgs, tg, uw.flip(3), uw, Ms)
-        if i >= args.warmup:
+        if i > 0:
             ts.append(time.perf_counter() - t0)
+    return ts
+
+
+def _best_threads(bl, bu):
+    """torch's CPU convolutions stop scaling well before 100+ threads: probe {all cores, 32} with one step each (after
+    one warm-up step) and keep the fastest setting -- the baseline gets the thread count it is fastest with."""
+    ncpu = os.cpu_count() or 1
+    cands = sorted({c for c in (ncpu, 32) if c <= ncpu}, reverse=True)
+    best = None
+    for c in cands:
+        t = _cpu_step_sample(c, bl, bu, 1)[0]
+        if best is None or t < best[1]:
+            best = (c, t)
+    return best[0], {c: None for c in cands}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path of the step (oracle restatement; /root/reference cannot travel to the
+    GPU box).  Rank 0 only.  Each step = one full SSOD step on a bounded sample (2 labeled + 2 unlabeled images), fp32, with
+    the host thread count torch is fastest at (probed: all cores / 32)."""
+    if rank != 0:
+        return
+    bl = bu = 2
+    threads, _ = _best_threads(bl, bu)
+    ts = _cpu_step_sample(threads, bl, bu, args.warmup + args.steps)[args.warmup:]
     sec = float(np.mean(ts))
     val = (bl + bu) / sec
-    sample = "full SSOD step (teacher fwd, NMS+pseudo-label, student fwd/bwd, both losses, SGD, 2x EMA) on 1 labeled + 1 unlabeled 640x640 images, fp32 torch CPU, %d threads" % torch.get_num_threads()
+    sample = ("full SSOD step (teacher fwd, NMS+pseudo-label, student fwd/bwd, both losses, SGD, 2x EMA) on 2 labeled + 2 unlabeled 640x640 images, "
+              "fp32 torch CPU, %d threads (fastest of all-cores/32 on this host; %d cores present)" % (threads, os.cpu_count()))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": "YOLOv5l SSOD 640, CPU bounded sample 1+1 images/step"},
-        "cpu_baseline": {"value": val, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "dtype": "f32", "data": "synthetic", "config": {"workload": "YOLOv5l SSOD 640, CPU bounded sample 2+2 images/step"},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
 
 
 def cpu_baseline_quick():
-    from oracle.step_ref import CpuSSODStep
-    from efficientteacher_b200.config import yolov5_ssod_cfg
-    from efficientteacher_b200.model import Model
-    import synth
-    nthr = min(os.cpu_count(), 16)     # torch CPU convs stop scaling (and collapse when oversubscribed) beyond ~16 threads
-    torch.set_num_threads(nthr)
-    torch.manual_seed(0)
-    model = Model(yolov5_ssod_cfg('l'))
-    step = CpuSSODStep(model.state_dict(), (3, 6, 9, 3), 3, batch_size=B_L + B_U, ema_updates=100000)
-    r = np.random.RandomState(1)
-    bl = bu = 1
-    imgs = torch.from_numpy(r.rand(bl, 3, IMG, IMG).astype(np.float32))
-    uw = torch.from_numpy(r.rand(bu, 3, IMG, IMG).astype(np.float32))
-    tg = synth.make_targets(100, 8 * bl, bl)
-    Ms = synth.make_Ms(200, bu, IMG)
-    ts = []
+    bl = bu = 2
     t_all = time.perf_counter()
-    while len(ts) < 3 and time.perf_counter() - t_all < 20:   # first iteration doubles as warm-up when the box is slow
-        t0 = time.perf_counter()
-        step.step(imgs, tg, uw.flip(3), uw, Ms)
-        ts.append(time.perf_counter() - t0)
-    sec = float(np.min(ts))
-    return {"value": (bl + bu) / sec, "unit": "images/s", "cores": nthr, "kind": "port",
-            "sample": "%d full SSOD steps on 1 labeled + 1 unlabeled 640x640 images (oracle/step_ref.py, torch fp32 CPU, %d threads), min step time %.2f s" % (len(ts), nthr, sec)}
+    threads, _ = _best_threads(bl, bu)
+    ts = _cpu_step_sample(threads, bl, bu, 2)
+    sec = float(np.mean(ts))
+    return {"value": (bl + bu) / sec, "unit": "images/s", "cores": threads, "kind": "port",
+            "sample": "2 full SSOD steps (after 1 warm-up) on 2 labeled + 2 unlabeled 640x640 images (oracle/step_ref.py, torch fp32 CPU) with %d threads "
+                      "= the fastest of all-cores/32 on this %d-core host; mean step %.2f s; whole probe %.0f s" % (
+                          threads, os.cpu_count(), sec, time.perf_counter() - t_all)}
+
+
+def nms_pseudo_label_full_load(creator, dev):
+    """The metric's second half: NMS + pseudo-label transform, ms/batch at FULL candidate load, on synthetic decoded teacher
+    predictions (SURVEY.md 8d recipe: 2 % of the rows are candidates): 16 x 25,200 (640) and 8 x 100,800 (1280).  CUDA events
+    around 20 calls of FairPseudoLabel.create_pseudo_label_device (candidate filter -> rank -> batched greedy NMS -> affine
+    pseudo-label transform; no host sync), after 3 warm-up calls."""
+    import synth
+    out = {}
+    g = torch.Generator(device=dev).manual_seed(0)
+    for name, B, P, img in (("16x25200_img640", 16, 25200, 640), ("8x100800_img1280", 8, 100800, 1280)):
+        x = torch.empty((B, P, 85), dtype=torch.float32, device=dev)
+        x[..., 0:2] = torch.rand((B, P, 2), generator=g, device=dev) * img
+        x[..., 2:4] = torch.rand((B, P, 2), generator=g, device=dev) * 192 + 4
+        hot = torch.rand((B, P), generator=g, device=dev) < 0.02
+        x[..., 4] = torch.where(hot, torch.rand((B, P), generator=g, device=dev) * 0.9 + 0.1, torch.rand((B, P), generator=g, device=dev) * 0.05)
+        x[..., 5:] = torch.rand((B, P, 80), generator=g, device=dev) ** 4
+        Ms = torch.from_numpy(synth.make_Ms(200, B, img)).to(dev)
+        for _ in range(3):
+            creator.create_pseudo_label_device(x, Ms, img, img)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 20
+        s.record()
+        for _ in range(n):
+            rows, cnt = creator.create_pseudo_label_device(x, Ms, img, img)
+        e.record()
+        torch.cuda.synchronize()
+        out[name] = {"ms_per_batch": s.elapsed_time(e) / n, "candidates_per_img": float((x[..., 4] > 0.1).sum(1).float().mean()),
+                     "detections_per_img": float(creator.last_det[1].float().mean()), "pseudo_label_rows": int(cnt.item())}
+        del x
+    return out
+
+
+def gpu_eager_baseline(st, host, cfg_b, dev, steps=5, warmup=3):
+    """The same step with stock PyTorch on this GPU (oracle/eager_ref.py: ATen / cuDNN / torchvision eager under bf16 autocast,
+    channels_last, cudnn.benchmark, torch.optim.SGD, per-tensor EMA loops, per-image torchvision NMS, host-side pseudo-label
+    transform -- the way the reference executes it), started from the native step's CURRENT state (same weights, same batch).
+    SURVEY.md 2.1 / 8(d): "the kernel-level bar to beat on the same box"."""
+    from oracle.eager_ref import EagerSSODStep
+    import synth
+    torch.backends.cudnn.benchmark = True        # the reference: init_seeds(1 + RANK) -> cudnn.benchmark = True (utils/general.py)
+    depth = tuple(len(getattr(st.model.backbone, n).m) for n in ("stage2_2", "stage3_2", "stage4_2", "stage5_2"))
+    sd = {k: v.detach().clone() for k, v in st.model.state_dict().items()}
+    eg = EagerSSODStep(sd, depth, len(st.model.neck.C1.m), dev, synth.ANCHORS_GRID, amp_dtype=torch.bfloat16, batch_size=cfg_b["bl"] + cfg_b["bu"],
+                       ema_updates=st.ema.updates, warmup=(st.nw, st.warmup_bias_lr, st.warmup_momentum))
+    eg.teacher = {k: v.detach().clone() for k, v in st.ema.ema.state_dict().items()}
+    eg.ni = 30
+    f01 = lambda t: t.to(dev).float() / 255.0  # noqa: E731
+    imgs, uw, us = f01(host["imgs"]), f01(host["u_weak"]), f01(host["u_strong"])
+    tg, Ms = host["targets"].to(dev), host["Ms"].to(dev)
+    for _ in range(warmup):
+        eg.step(imgs, tg, us, uw, Ms)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(steps):
+        loss = eg.step(imgs, tg, us, uw, Ms)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / steps
+    out = {"value": (cfg_b["bl"] + cfg_b["bu"]) / (ms / 1e3), "unit": "images/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
+           "pseudo_label_rows_last_step": int(eg.n_pseudo), "loss_last_step": float(loss),
+           "what": "oracle/eager_ref.EagerSSODStep: PyTorch %s eager (cuDNN/ATen/torchvision), bf16 autocast, channels_last, cudnn.benchmark, same weights/batch as the native step, "
+                   "inputs resident in HBM" % torch.__version__}
+    del eg
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -249,9 +336,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--config", default="ssod640", choices=sorted(CONFIGS), help="ssod640 = the headline (BASELINE.json metric); ssod1280 / sup32 = configs[4] / configs[1]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end leg")
-    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of replaying the captured CUDA graph of the step")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of replaying the captured CUDA graphs of the step")
     ap.add_argument("--nvtx-step", action="store_true", help="dev: wrap ONE extra eager step in the NVTX range 'etb_step' (ncu --nvtx --nvtx-include etb_step)")
     ap.add_argument("--kernel-table", default="", help="dev: write a per-kernel time table (torch.profiler/CUPTI, 2 eager steps) to this file")
     args = ap.parse_args()
@@ -263,6 +352,8 @@ def main():
         return
     assert world == args.gpus, "launch with torch.distributed.run --nproc-per-node %d" % args.gpus
     assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+    cb = CONFIGS[args.config]
+    bl, bu, img, ssod = cb["bl"], cb["bu"], cb["img"], cb["kind"] == "ssod"
     import __graft_entry__ as g
     if rank == 0:
         g.build()
@@ -273,70 +364,83 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
         dist.barrier()
     from efficientteacher_b200 import _lib
-    from efficientteacher_b200.config import yolov5_ssod_cfg
-    from efficientteacher_b200.trainer import SSODTrainerStep
+    from efficientteacher_b200.config import yolov5_ssod_cfg, yolov5_sup_cfg
+    from efficientteacher_b200.trainer import SSODTrainerStep, SupTrainerStep
     lib = _lib.lib()
 
     torch.manual_seed(0)                       # identical initial student on every rank (DDP broadcasts rank 0's)
-    cfg = yolov5_ssod_cfg('l', batch_size=(B_L + B_U) * world, img_size=IMG)
-    st = SSODTrainerStep(cfg, dev, rank=rank if world > 1 else -1, world_size=world, epochs=300)
-    st.ema.updates = 100000                    # steady-state decay (0.9999): the teacher does not collapse onto the student
-    host = synth_batch(rank, pinned=True)
+    host = synth_batch(rank, pinned=True, bl=bl, bu=bu, img=img)
     f01 = lambda t: t.to(dev).float() / 255.0  # noqa: E731  trainer/ssod_trainer.py:694-696
     d_imgs, d_uw, d_us = f01(host["imgs"]), f01(host["u_weak"]), f01(host["u_strong"])
     d_tg, d_Ms = host["targets"].to(dev), host["Ms"].to(dev)
+    if ssod:
+        cfg = yolov5_ssod_cfg('l', batch_size=(bl + bu) * world, img_size=img)
+        cfg.SSOD.fixed_accumulate = True       # optimizer step + both EMA updates EVERY iteration
+        st = SSODTrainerStep(cfg, dev, rank=rank if world > 1 else -1, world_size=world, epochs=300, nb=NB)
+        # Synthetic steady state.  lr / momentum follow the reference's schedule from ni = 0 (warm-up, trainer.py:372-395:
+        # conv-weight lr ramps up from 0 over nw = 1107 iterations) -- the state a from-scratch run is in, and the one in
+        # which a random-init model is well conditioned (at full lr a random init blows its BN statistics up in ~10 steps
+        # under ANY bf16 implementation: tools/debug_teacher_drift.py --nw 0).  The EMA decay is the
+        # steady-state 0.9999 (ema.updates = 100000) so the calibrated teacher stays put over the run.
+        st.ema.updates = 100000
+    else:
+        cfg = yolov5_sup_cfg('l', batch_size=bl * world, img_size=img)
+        st = SupTrainerStep(cfg, dev, rank=rank if world > 1 else -1, world_size=world, epochs=300, nb=NB)
 
     # Synthetic steady state: random-init weights make an eval-mode teacher degenerate (default running
     # statistics -> constant outputs) and give no confident boxes.  (1) set every BN's running statistics to the batch
     # statistics of the synthetic data (one train-mode pass with momentum 1) and start teacher = student; (2) rescale / shift
-    # the Detect head's objectness rows and biases so ~2% of the 25,200 predictions/img have obj > 0.3 (robustly above the 0.1
+    # the Detect head's objectness rows and biases so ~2% of the predictions/img have obj > 0.3 (robustly above the 0.1
     # NMS threshold) and class scores are ~0.96.  Everything else stays random-init.
+    cand_per_img = det_per_img0 = None
     with torch.no_grad():
         bns = [m for m in st.model.modules() if isinstance(m, torch.nn.BatchNorm2d)]
         for m in bns:
             m.momentum = 1.0
         with torch.autocast("cuda", dtype=torch.bfloat16):
-            st.model(torch.cat([d_imgs, d_us], 0).contiguous(memory_format=torch.channels_last))
+            st.model((torch.cat([d_imgs, d_us], 0) if ssod else d_imgs).contiguous(memory_format=torch.channels_last))
         for m in bns:
             m.momentum = 0.03
         st.ema.ema.load_state_dict(st.model.state_dict())
-        if st.semi_ema:
+        if ssod:
             st.semi_ema.ema.load_state_dict(st.model.state_dict())
-        (pred, raw), _ = st.ema.ema(d_uw)
-        for l, m in enumerate(st.ema.ema.head.m):
-            # A random-init head gives objectness logits with std ~0.15: a bias shift alone puts the top rows a hair above the
-            # threshold and the first 50 EMA updates (which drag the teacher after a student whose objectness is being trained
-            # down) remove every candidate.  So (2a) widen the objectness logits to std 3 by scaling the three objectness rows
-            # of the 1x1 head conv, (2b) set the bias so the 98th percentile is obj = 0.3, (2c) class bias +8 (it starts at
-            # log(0.6/(nc-0.99)) ~ -4.9) so class scores are ~0.96 and conf = obj*cls ~ obj.
-            b = m.bias.view(3, -1)
-            w = m.weight.view(3, -1, m.weight.shape[1])
-            lin = (raw[l][..., 4].float() - b[:, 4].float().view(1, 3, 1, 1)).flatten()
-            sc = 3.0 / max(float(lin.std()), 1e-6)
-            q98 = torch.quantile(sc * lin[:2_000_000], 0.98).item()
-            w[:, 4] *= sc
-            b[:, 4] = float(np.log(0.3 / 0.7)) - q98
-            b[:, 5:] += 8.0
-            for other in (st.model, st.semi_ema.ema if st.semi_ema else None):
-                if other is not None:
+            (pred, raw), _ = st.ema.ema(d_uw)
+            for l, m in enumerate(st.ema.ema.head.m):
+                # A random-init head gives objectness logits with std ~0.15: (2a) widen them to std 3 by scaling the three
+                # objectness rows of the 1x1 head conv, (2b) set the bias so the 98th percentile is obj = 0.3, (2c) class bias
+                # +8 (it starts at log(0.6/(nc-0.99)) ~ -4.9) so class scores are ~0.96 and conf = obj*cls ~ obj.
+                b = m.bias.view(3, -1)
+                w = m.weight.view(3, -1, m.weight.shape[1])
+                lin = (raw[l][..., 4].float() - b[:, 4].float().view(1, 3, 1, 1)).flatten()
+                sc = 3.0 / max(float(lin.std()), 1e-6)
+                q98 = torch.quantile(sc * lin[:2_000_000], 0.98).item()
+                w[:, 4] *= sc
+                b[:, 4] = float(np.log(0.3 / 0.7)) - q98
+                b[:, 5:] += 8.0
+                for other in (st.model, st.semi_ema.ema):
                     other.head.m[l].bias.data.copy_(m.bias.data)
                     other.head.m[l].weight.data.copy_(m.weight.data)
-
-    with torch.no_grad():
-        (pred, raw), _ = st.ema.ema(d_uw)
-        cand_per_img = float((pred[..., 4] > cfg.SSOD.nms_conf_thres).sum(1).float().mean().item())
-    del pred, raw
+            (pred, raw), _ = st.ema.ema(d_uw)
+            cand_per_img = float((pred[..., 4] > cfg.SSOD.nms_conf_thres).sum(1).float().mean().item())
+            del pred, raw
 
     use_graph = not args.no_graph
 
     def step_resident(i):
-        if use_graph:
-            return st.train_instance_graphed(d_imgs, d_tg, d_us, d_uw, None, d_Ms, i)
-        return st.train_instance(d_imgs, d_tg, d_us, d_uw, None, d_Ms, i)
+        if ssod:
+            f = st.train_instance_graphed if use_graph else st.train_instance
+            return f(d_imgs, d_tg, d_us, d_uw, None, d_Ms, i)
+        return (st.train_step_graphed if use_graph else st.train_step)(d_imgs, d_tg, i)
+
+    def step_eager(i):
+        if ssod:
+            return st.train_instance(d_imgs, d_tg, d_us, d_uw, None, d_Ms, i)
+        return st.train_step(d_imgs, d_tg, i)
 
     from efficientteacher_b200.trainer import DevicePrefetcher
     pf = DevicePrefetcher(dev)
-    host_batch = {k: host[k] for k in ("imgs", "u_strong", "u_weak", "targets", "Ms")}
+    keys = ("imgs", "u_strong", "u_weak", "targets", "Ms") if ssod else ("imgs", "targets")
+    host_batch = {k: host[k] for k in keys}
 
     def step_e2e(i):
         # every step: H2D of this step's uint8 batch from pinned memory (staged on a side stream, so the copy of step i+1
@@ -344,8 +448,11 @@ def main():
         if pf.pending == 0:
             pf.put(host_batch)
         b = pf.get()
-        imgs, us, uw = b["imgs"].float() / 255.0, b["u_strong"].float() / 255.0, b["u_weak"].float() / 255.0
-        loss = (st.train_instance_graphed if use_graph else st.train_instance)(imgs, b["targets"], us, uw, None, b["Ms"], i)
+        if ssod:
+            imgs, us, uw = b["imgs"].float() / 255.0, b["u_strong"].float() / 255.0, b["u_weak"].float() / 255.0
+            loss = (st.train_instance_graphed if use_graph else st.train_instance)(imgs, b["targets"], us, uw, None, b["Ms"], i)
+        else:
+            loss = (st.train_step_graphed if use_graph else st.train_step)(b["imgs"].float() / 255.0, b["targets"], i)
         pf.release()
         pf.put(host_batch)                   # next step's inputs start moving now
         return float(loss.item())            # D2H read of the step's result
@@ -370,25 +477,34 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    def pl_state():
+        c = st.pseudo_label_creator
+        return int(c.last_count_dev.item()), float(c.last_det[1].float().mean().item())
+
     ni = 0
     for _ in range(args.warmup):
         step_resident(ni); ni += 1
     torch.cuda.synchronize()
+    if ssod:
+        n_pl0, det_per_img0 = pl_state()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
     ms = timed(step_resident, args.steps, ni); ni += args.steps
+    if ssod:
+        n_pl_timed, det_timed = pl_state()       # pseudo-label load at the LAST TIMED step
     # kernel-launch count and per-phase CUDA-event times come from an eager (un-graphed) pass of the same step
-    st.train_instance(d_imgs, d_tg, d_us, d_uw, None, d_Ms, ni); ni += 1     # one eager step first: lazy one-time work
+    step_eager(ni); ni += 1     # one eager step first: lazy one-time work
     torch.cuda.synchronize()
-    st.profile, st.phase_events = True, []
+    if ssod:
+        st.profile, st.phase_events = True, []
     l0 = lib.etb_launch_count()
     nprof = 3
     for _ in range(nprof):
-        st.train_instance(d_imgs, d_tg, d_us, d_uw, None, d_Ms, ni); ni += 1
+        step_eager(ni); ni += 1
     torch.cuda.synchronize()
     launches = (lib.etb_launch_count() - l0) / nprof
-    phases = {k: v / nprof for k, v in st.phase_times_ms().items()}
+    phases = {k: v / nprof for k, v in st.phase_times_ms().items()} if ssod else {}
     st.profile = False
     if args.no_e2e:
         ms_e2e = float("nan")
@@ -400,69 +516,82 @@ def main():
     if args.nvtx_step and rank == 0:
         torch.cuda.synchronize()
         rid = torch.cuda.nvtx.range_start("etb_step")     # start/end range: process-wide (backward runs on autograd's thread)
-        st.train_instance(d_imgs, d_tg, d_us, d_uw, None, d_Ms, ni); ni += 1
+        step_eager(ni); ni += 1
         torch.cuda.synchronize()
         torch.cuda.nvtx.range_end(rid)
     if args.kernel_table and rank == 0:
-        kernel_table(lambda i: st.train_instance(d_imgs, d_tg, d_us, d_uw, None, d_Ms, i), ni, args.kernel_table, ms / args.steps)
+        kernel_table(step_eager, ni, args.kernel_table, ms / args.steps)
         ni += 2
-    n_pl = int(st.pseudo_label_creator.last_count_dev.item())
-    det_per_img = float(st.pseudo_label_creator.last_det[1].float().mean().item())
-    if rank == 0:        # teacher health at the end of the run (stderr only): candidates, conf-passing rows, NMS detections
-        try:
-            with torch.no_grad():
-                from efficientteacher_b200.nms import non_max_suppression_ssod
-                (pred_e, _raw_e), _f = st.ema.ema(d_uw)
-                conf_e = pred_e[..., 4:5] * pred_e[..., 5:]
-                dets_e = non_max_suppression_ssod(pred_e, cfg.SSOD.nms_conf_thres, cfg.SSOD.nms_iou_thres)
-                def _bnmax(mod):
-                    bb = [q for q in mod.modules() if isinstance(q, torch.nn.BatchNorm2d)]
-                    return (max(float(q.running_var.max()) for q in bb), max(float(q.running_mean.abs().max()) for q in bb),
-                            max(float(q.weight.abs().max()) for q in bb), max(float(q.bias.abs().max()) for q in bb))
-                print("[bench] BN max (running_var, |running_mean|, |gamma|, |beta|): student %s teacher %s" % (
-                    "%.3g %.3g %.3g %.3g" % _bnmax(st.model), "%.3g %.3g %.3g %.3g" % _bnmax(st.ema.ema)), file=sys.stderr, flush=True)
-                print("[bench] teacher at end: obj>thr rows/img %.1f, conf>thr rows/img %.1f, NMS dets/img %.1f, obj max %.3f, cls max mean %.3f, "
-                      "ema.updates %d, last step: dets/img %.2f pseudo-label rows %d" % (
-                          float((pred_e[..., 4] > cfg.SSOD.nms_conf_thres).sum(1).float().mean()),
-                          float((conf_e.max(-1)[0] > cfg.SSOD.nms_conf_thres).sum(1).float().mean()),
-                          float(np.mean([len(d) for d in dets_e])), float(pred_e[..., 4].max()), float(pred_e[..., 5:].max(-1)[0].mean()),
-                          st.ema.updates, det_per_img, n_pl), file=sys.stderr, flush=True)
-            del pred_e, _raw_e, _f, conf_e, dets_e
-        except Exception as exc:      # diagnostics only: never let them take the bench line down
-            print("[bench] teacher health check failed: %r" % (exc,), file=sys.stderr, flush=True)
+
+    # ---- self-check: the run is only a measurement if the whole step really ran at load --------------------------------
+    health = {}
+    if ssod:
+        n_pl_end, det_end = pl_state()
+        with torch.no_grad():
+            (pred_e, _raw_e), _f = st.ema.ema(d_uw)
+            cand_end = float((pred_e[..., 4] > cfg.SSOD.nms_conf_thres).sum(1).float().mean())
+            del pred_e, _raw_e, _f
+
+        def _bnmax(mod):
+            bb = [q for q in mod.modules() if isinstance(q, torch.nn.BatchNorm2d)]
+            return [max(float(q.running_var.max()) for q in bb), max(float(q.running_mean.abs().max()) for q in bb),
+                    max(float(q.weight.abs().max()) for q in bb), max(float(q.bias.abs().max()) for q in bb)]
+        health = {"nms_candidates_per_img_at_start": cand_per_img, "nms_candidates_per_img_at_end": cand_end,
+                  "nms_detections_per_img_first_timed_step": det_per_img0, "nms_detections_per_img_last_timed_step": det_timed,
+                  "pseudo_label_rows_first_timed_step": n_pl0, "pseudo_label_rows_last_timed_step": n_pl_timed,
+                  "pseudo_label_rows_end_of_run": n_pl_end,
+                  "student_bn_max[running_var,|running_mean|,|gamma|,|beta|]": _bnmax(st.model),
+                  "teacher_bn_max[running_var,|running_mean|,|gamma|,|beta|]": _bnmax(st.ema.ema), "steps_total": ni}
+        ok = (n_pl_timed > 0 and n_pl_end > 0 and cand_per_img > 0 and 0.5 * cand_per_img <= cand_end <= 2.0 * cand_per_img
+              and 0.5 * n_pl0 <= n_pl_timed <= 2.0 * n_pl0 and all(np.isfinite(health["student_bn_max[running_var,|running_mean|,|gamma|,|beta|]"])))
+        flags = torch.tensor([0 if ok else 1], device=dev)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(flags, op=dist.ReduceOp.MAX)
+        if int(flags.item()):
+            print("[bench] INVALID RUN (rank %d): the pseudo-label branch did not stay loaded / the state diverged: %s" % (rank, json.dumps(health)),
+                  file=sys.stderr, flush=True)
+            sys.exit(3)
 
     if rank == 0:
         pk, pk_kind = peaks()
-        imgs_per_step = (B_L + B_U) * world
+        imgs_per_step = (bl + bu) * world
         value = imgs_per_step * args.steps / (ms / 1e3)
         e2e_val = imgs_per_step * args.steps / (ms_e2e / 1e3)
-        t_flops = conv_flops_teacher(st.ema.ema, B_U, IMG)
+        f_img = conv_flops_teacher(st.ema.ema, 1, img)
         t_ms = phases.get("teacher_forward", float("nan"))
         peak = pk["bf16_tflops_sustained"]
         # conv FLOPs of the whole step: teacher fwd (B_U) + student fwd/dgrad/wgrad (B_L+B_U; the stem has no dgrad)
-        f_img = t_flops / B_U
-        step_flops = f_img * (B_U + 3 * (B_L + B_U))
+        step_flops = f_img * (bu + 3 * (bl + bu))
         roof = dominant_kernel_roofline(dev, peak, pk_kind + " bf16_tflops_sustained")
         roof["step_level"] = {"conv_flops_per_step": step_flops, "achieved_tflops": step_flops / (ms / args.steps / 1e3) / 1e12,
                               "frac_of_peak": step_flops / (ms / args.steps / 1e3) / 1e12 / peak,
-                              "teacher_forward_phase_tflops": t_flops / (t_ms / 1e3) / 1e12}
-        h2d = sum(host[k].numel() * host[k].element_size() for k in host)
+                              "teacher_forward_phase_tflops": f_img * bu / (t_ms / 1e3) / 1e12 if ssod else None}
+        h2d = sum(host[k].numel() * host[k].element_size() for k in keys)
         out = {
-            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": cb["metric"], "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic (seeded uint8 images, 8 gt boxes/img, random-init YOLOv5l; teacher objectness bias calibrated to ~2% NMS candidates)",
-            "config": {"workload": "YOLOv5l SSOD 640: 16 labeled + 16 unlabeled per GPU (BASELINE configs[2] per-GPU batch), optimizer+2xEMA every step",
-                       "global_batch": imgs_per_step, "img_size": IMG, "parallelism": "dp%d" % world, "cuda_graph": use_graph,
+            "dtype": "bf16", "data": "synthetic (seeded uint8 images, 8 gt boxes/img, random-init YOLOv5l with BN statistics calibrated on the batch; teacher objectness calibrated to ~2% NMS candidates)",
+            "config": {"workload": cb["workload"], "config_name": args.config,
+                       "global_batch": imgs_per_step, "img_size": img, "parallelism": "dp%d" % world, "cuda_graph": use_graph,
+                       "schedule": "reference warm-up from ni=0 (nw=%s, nb=%d): lr/momentum change every step (device-resident hyper-parameters)" % (st.nw, NB),
                        "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
-                       "native": "teacher trunk+head, student conv fwd/dgrad/wgrad (tcgen05) + BatchNorm(train)+SiLU fwd/bwd, weight packing, NMS/pseudo-label, assigners, losses fwd/bwd, EMA",
-                       "library_ops_left": "autograd's gradient fan-in adds where a FanIn does not apply, Detect backward layout ops, netD C->2 conv, domain focal loss (x0)",
-                       "pseudo_labels_last_step": n_pl, "pseudo_label_note": "random-noise data + the reference hyper-parameters make the student's BN statistics diverge; the EMA teacher's candidates decay from the value at start to ~0 within the run (DESIGN.md section 6); NMS+pseudo-label at full load: 0.20 ms/batch", "nms_candidates_per_img_at_start": cand_per_img, "nms_detections_per_img_last_step": det_per_img},
+                       "native": "teacher trunk+head, student conv fwd/dgrad/wgrad (tcgen05) + BatchNorm(train)+SiLU fwd/bwd, weight packing, NMS/pseudo-label, assigners, losses fwd/bwd, SGD, EMA",
+                       "self_check": health},
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
             "phases_ms": phases,
             "roofline": roof,
             "clocks": clocks,
         }
+        if ssod:
+            out["nms_pseudo_label_ms_per_batch"] = nms_pseudo_label_full_load(st.pseudo_label_creator, dev)
+        if world == 1 and ssod and not args.no_eager_baseline:
+            try:
+                out["gpu_eager_baseline"] = gpu_eager_baseline(st, host, cb, dev)
+                out["gpu_eager_baseline"]["native_over_eager"] = value / out["gpu_eager_baseline"]["value"]
+            except Exception as exc:      # a baseline must never take the bench line down; say why it is missing
+                out["gpu_eager_baseline"] = {"unavailable": repr(exc)[:300]}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_quick()
         print(json.dumps(out), flush=True)

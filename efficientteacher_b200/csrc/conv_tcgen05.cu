@@ -821,7 +821,7 @@ extern "C" int etb_conv_fwd(const void* x_bf16, const void* w_bf16, const float*
   ETB_CHECK_ARG(Ho > 0 && Wo > 0);
   const bool det = (y_f32 != nullptr);
   if (!det) ETB_CHECK_ARG(cp->y_cstride % 8 == 0 && cp->y_coffset % 8 == 0 && cp->y_cstride >= cp->y_coffset + cp->Cout && (((uintptr_t)y_bf16) & 15) == 0);
-  if (residual_bf16) ETB_CHECK_ARG(!det && cp->res_cstride % 8 == 0 && cp->res_coffset % 8 == 0 && cp->Cout % 32 == 0);
+  if (residual_bf16) ETB_CHECK_ARG(!det && cp->res_cstride % 8 == 0 && cp->res_coffset % 8 == 0 && cp->Cout % 8 == 0);
   if (det) ETB_CHECK_ARG(cp->det_no > 0 && cp->Cout % cp->det_no == 0);
   ConvKArgs ka;
   memset(&ka, 0, sizeof(ka));

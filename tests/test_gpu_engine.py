@@ -209,10 +209,16 @@ def test_supervised_step_matches_cpu_reference(size, img):
     tg = synth.make_targets(5, 16, B)
     raw, _ = TrunkRef(sd, (1, 2, 3, 1), 1).forward(x, train=True, with_features=False)
     ref, _ = port.det_loss(raw, [port.build_targets(tg, synth.ANCHORS_GRID, synth.level_shapes(img))], [4.0, 1.0, 0.4], 0.05, 0.7, 0.3)
-    before = st.model.backbone.stage1.conv.weight.detach().clone()
+    # ni = 0 of the warm-up (trainer.py:385-395): conv-weight lr is 0, the BatchNorm weights step with warmup_bias_lr
+    before_w = st.model.backbone.stage1.conv.weight.detach().clone()
+    before_g = st.model.backbone.stage1.bn.weight.detach().clone()
     loss = st.train_step(x.to(DEV), torch.from_numpy(tg).to(DEV), 0)
     assert abs(loss.item() - ref.item()) <= 0.03 * abs(ref.item()), (loss.item(), ref.item())
-    assert not torch.equal(before, st.model.backbone.stage1.conv.weight.detach()) and st.ema.updates == 1
+    assert torch.equal(before_w, st.model.backbone.stage1.conv.weight.detach())
+    assert not torch.equal(before_g, st.model.backbone.stage1.bn.weight.detach()) and st.ema.updates == 1
+    loss2 = st.train_step_graphed(x.to(DEV), torch.from_numpy(tg).to(DEV), 1)       # accumulate = 1 this early in the warm-up
+    assert torch.isfinite(loss2).all() and st.ema.updates == 2 and loss2.item() < loss.item()
+    assert not torch.equal(before_w, st.model.backbone.stage1.conv.weight.detach())
 
 
 def test_device_prefetcher_roundtrip():
@@ -324,25 +330,35 @@ def test_multi_step_trajectory_tracks_cpu_oracle():
     assert ref[-1][0] < ref[0][0] and rows[-1][0] < rows[0][0], msg       # both arms are learning
     assert drift < 5e-3, drift
     # teacher state vs the oracle's teacher after the 12 EMA updates (fp32 state, bf16 student trajectory)
-    t_nat = torch.cat([v.flatten().float().cpu() for k, v in st.ema.ema.state_dict().items() if v.dtype.is_floating_point and "running" not in k])
-    t_cpu = torch.cat([v.flatten() for k, v in cpu.teacher.items() if v.dtype.is_floating_point and "running" not in k])
+    nat = st.ema.ema.state_dict()
+    keys = [k for k, v in cpu.teacher.items() if v.dtype.is_floating_point and "running" not in k and "anchor" not in k]
+    t_nat = torch.cat([nat[k].flatten().float().cpu() for k in keys])
+    t_cpu = torch.cat([cpu.teacher[k].flatten() for k in keys])
     assert float((t_nat - t_cpu).norm() / t_cpu.norm()) < 1e-3
 
 
 def test_multi_step_trajectory_full_yolov5l():
-    """30 consecutive steps of the full-depth YOLOv5l at 320 (2+2 images), all through the captured graphs after 2 eager
-    steps, against the torch-bf16 / cuDNN arm (Conv.NATIVE = False: same model, same trainer, library kernels) of the same
-    trajectory: the native path must stay as close to it as bf16 allows and keep a live teacher (pseudo labels at the last
-    step within 10 % of the first)."""
-    img, bl, bu = 320, 2, 2
-    rows, drift, _, _ = _run_native_trajectory('l', img, bl, bu, 2, 28)
-    lib_rows, lib_drift, _, _ = _run_native_trajectory('l', img, bl, bu, 30, 0, native=False)
-    msg = "\n".join("step %2d native loss %.4f rows %4d rv %.4g g %.4g | torch-bf16 loss %.4f rows %4d rv %.4g g %.4g" % (i, *a, *b)
-                    for i, (a, b) in enumerate(zip(rows, lib_rows)))
+    """20 consecutive steps of the full-depth YOLOv5l at 320 (2+2 images; 2 eager, 18 graph replays) in three arms: native,
+    torch-bf16 / cuDNN (Conv.NATIVE = False: same model and trainer, library kernels) and the fp32 CPU oracle.  The native
+    path must track the oracle at least as well as bf16 allows (<= 2x the deviation of the library-bf16 arm, with floors of
+    2 % loss / 6 % max|gamma| / 12 % max running_var) and keep a live teacher."""
+    from oracle.step_ref import CpuSSODStep
+    img, bl, bu, n = 320, 2, 2, 20
+    rows, drift, sd0, st = _run_native_trajectory('l', img, bl, bu, 2, n - 2)
+    lib_rows, lib_drift, _, _ = _run_native_trajectory('l', img, bl, bu, n, 0, native=False)
+    imgs_c, uw_c, us_c, tg_c, Ms_c = _traj_inputs(img, bl, bu)
+    cpu = CpuSSODStep(sd0, (3, 6, 9, 3), 3, batch_size=bl + bu, ema_updates=100000, bn_momentum=0.03,
+                      warmup=(st.nw, st.warmup_bias_lr, st.warmup_momentum))
+    ref = []
+    for i in range(n):
+        loss, k = cpu.step(imgs_c, tg_c, us_c, uw_c, Ms_c)
+        ref.append((loss, k) + _bn_ext(cpu.student.items()))
+    msg = "\n".join("step %2d native %.4f %4d %.4g %.4g | torch-bf16 %.4f %4d %.4g %.4g | cpu-fp32 %.4f %4d %.4g %.4g" % (i, *a, *b, *c)
+                    for i, (a, b, c) in enumerate(zip(rows, lib_rows, ref)))
     print(msg)
-    for i, (a, b) in enumerate(zip(rows, lib_rows)):
-        assert abs(a[0] - b[0]) <= 0.04 * abs(b[0]), (i, msg)
-        assert abs(a[2] - b[2]) <= 0.2 * b[2], (i, msg)
-        assert abs(a[3] - b[3]) <= 0.04 * b[3], (i, msg)
-    assert rows[0][1] > 0 and abs(rows[-1][1] - rows[0][1]) <= 0.1 * rows[0][1], msg
+    for col, floor in ((0, 0.02), (2, 0.12), (3, 0.06)):
+        e_nat = max(abs(a[col] - c[col]) / abs(c[col]) for a, c in zip(rows, ref))
+        e_lib = max(abs(b[col] - c[col]) / abs(c[col]) for b, c in zip(lib_rows, ref))
+        assert e_nat <= max(2.0 * e_lib, floor), (col, e_nat, e_lib, msg)
+    assert rows[0][1] > 0 and abs(rows[-1][1] - ref[-1][1]) <= 0.1 * ref[-1][1], msg
     assert drift < 1e-2 and lib_drift < 1e-2, (drift, lib_drift)

@@ -339,8 +339,6 @@ def test_fused_sgd_matches_torch_sgd():
             torch.testing.assert_close(oa.state[a]["momentum_buffer"], ob.state[b]["momentum_buffer"], rtol=2e-6, atol=1e-6)
 
 
-@pytest.mark.xfail(strict=False, reason="written after the round's GPU minutes were spent: first GPU run pending (the host logic it "
-                                        "adds is pinned to the live reference on the CPU, the device pipeline is FairPseudoLabel's)")
 def test_labelmatch_device_path_matches_reference(golden):
     """LabelMatch on the device pipeline: rows, the per-class score lists (async pinned copy + flush) and the epoch thresholds
     against the live-reference fixture (tests/golden/labelmatch.npz)."""
@@ -372,8 +370,6 @@ def test_labelmatch_device_path_matches_reference(golden):
     np.testing.assert_allclose(np.array(lm.cls_thr_high), g["thr_high_e0"], rtol=1e-9, atol=1e-12)
 
 
-@pytest.mark.xfail(strict=False, reason="etb_nms_val was written after the round's GPU minutes were spent: first GPU run pending "
-                                        "(the oracle it is compared with is pinned bit-exactly to the live reference)")
 @pytest.mark.parametrize("name", ["ml_cap", "ml_few", "ml_agn"])
 def test_val_nms_multi_label_vs_reference_golden(golden, name):
     """val.py path: non_max_suppression(multi_label=True) on the device (radix top-30000 + shared NMS kernels) against the

@@ -86,6 +86,11 @@ def run(variant, args):
         st.semi_ema.ema.load_state_dict(st.model.state_dict())
         (_, raw0), _ = st.ema.ema(uw)
         raw0 = [t.clone() for t in raw0]
+        # determinism self-check of the teacher engine: the same forward twice more, per level
+        for rep in range(2):
+            (_, rawr), _ = st.ema.ema(uw)
+            print("   teacher forward repeat %d: per-level rel diff vs first call %s, |raw0| %s" % (
+                rep, ["%.3g" % float((a - b).norm() / b.norm()) for a, b in zip(rawr, raw0)], ["%.4g" % float(b.norm()) for b in raw0]), flush=True)
     groups = [[p for p in g["params"]] for g in st.optimizer.param_groups]
     print("== variant %s (graph=%s) updates=%d" % (variant, graph, args.updates), flush=True)
     for i in range(args.steps):
@@ -99,7 +104,10 @@ def run(variant, args):
             st._optimizer_ema(i)
         with torch.no_grad():
             (_, raw1), _ = st.ema.ema(uw)
-        drift = max(float((a - b).norm() / b.norm()) for a, b in zip(raw1, raw0))
+        drifts = [float((a - b).norm() / b.norm()) for a, b in zip(raw1, raw0)]
+        drift = max(drifts)
+        if i < 2:
+            print("        per-level drift %s" % ["%.4g" % d for d in drifts], flush=True)
         print("step %2d loss %.4f rows %d teacher drift %.5f | student BN (var,|mean|,|g|,|b|) %s | teacher %s | max|grad| bias/w/bnw %s" % (
             i, float(loss), int(st.pseudo_label_creator.last_count_dev.item()), drift, "%.3g %.3g %.3g %.3g" % bn_ext(st.model), "%.3g %.3g %.3g %.3g" % bn_ext(st.ema.ema), gmax), flush=True)
         if i in (0, args.steps - 1) or drift > 0.05:
