@@ -89,11 +89,13 @@ class ClockSampler(threading.Thread):
 def synth_batch(rank, device=None, pinned=False, bl=B_L, bu=B_U, img=IMG):
     """Per-rank seeded synthetic batch (SURVEY.md 8d, config #3): uint8 images like the loaders produce, 8 targets/img."""
     import synth
-    r = np.random.RandomState(1 + rank)
-    mk = lambda n: torch.from_numpy(r.randint(0, 256, (n, 3, img, img), dtype=np.uint8))  # noqa: E731
-    imgs, u_weak = mk(bl), mk(max(bu, 1))
+    tg = synth.make_targets(100 + rank, 8 * bl, bl)
+    # structured images (smooth colour field + textured rectangles, on the labeled batch at the ground-truth boxes): i.i.d.
+    # noise images make a random-init trunk ~7x more sensitive to parameter perturbations (tools/debug_teacher_sens.py)
+    imgs = torch.from_numpy(synth.make_images(1 + rank, bl, img, tg))
+    u_weak = torch.from_numpy(synth.make_images(1001 + rank, max(bu, 1), img))
     u_strong = u_weak.flip(3).contiguous()
-    targets = torch.from_numpy(synth.make_targets(100 + rank, 8 * bl, bl))
+    targets = torch.from_numpy(tg)
     Ms = torch.from_numpy(synth.make_Ms(200 + rank, max(bu, 1), img))
     out = dict(imgs=imgs, u_weak=u_weak, u_strong=u_strong, targets=targets, Ms=Ms)
     if pinned:
@@ -341,6 +343,7 @@ def main():
     ap.add_argument("--no-eager-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end leg")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of replaying the captured CUDA graphs of the step")
+    ap.add_argument("--allow-invalid", action="store_true", help="dev: print the line (marked invalid) even when the self-check fails")
     ap.add_argument("--nvtx-step", action="store_true", help="dev: wrap ONE extra eager step in the NVTX range 'etb_step' (ncu --nvtx --nvtx-include etb_step)")
     ap.add_argument("--kernel-table", default="", help="dev: write a per-kernel time table (torch.profiler/CUPTI, 2 eager steps) to this file")
     args = ap.parse_args()
@@ -392,7 +395,6 @@ def main():
     # statistics of the synthetic data (one train-mode pass with momentum 1) and start teacher = student; (2) rescale / shift
     # the Detect head's objectness rows and biases so ~2% of the predictions/img have obj > 0.3 (robustly above the 0.1
     # NMS threshold) and class scores are ~0.96.  Everything else stays random-init.
-    cand_per_img = det_per_img0 = None
     with torch.no_grad():
         bns = [m for m in st.model.modules() if isinstance(m, torch.nn.BatchNorm2d)]
         for m in bns:
@@ -404,6 +406,13 @@ def main():
         st.ema.ema.load_state_dict(st.model.state_dict())
         if ssod:
             st.semi_ema.ema.load_state_dict(st.model.state_dict())
+
+    def calibrate_teacher_head(first):
+        """(2): objectness of the TEACHER's Detect head so that ~2 % of its predictions are NMS candidates on this batch.
+        A random-init trunk amplifies parameter perturbations by 10^2-10^3 (tools/debug_teacher_sens.py), so the few 1e-4
+        EMA steps of a run move the teacher's logits visibly; the calibration is therefore repeated (bias only) right before
+        every timed window -- outside the timed regions -- and the self-check below verifies the load over the window."""
+        with torch.no_grad():
             (pred, raw), _ = st.ema.ema(d_uw)
             for l, m in enumerate(st.ema.ema.head.m):
                 # A random-init head gives objectness logits with std ~0.15: (2a) widen them to std 3 by scaling the three
@@ -412,17 +421,20 @@ def main():
                 b = m.bias.view(3, -1)
                 w = m.weight.view(3, -1, m.weight.shape[1])
                 lin = (raw[l][..., 4].float() - b[:, 4].float().view(1, 3, 1, 1)).flatten()
-                sc = 3.0 / max(float(lin.std()), 1e-6)
+                sc = 3.0 / max(float(lin.std()), 1e-6) if first else 1.0
                 q98 = torch.quantile(sc * lin[:2_000_000], 0.98).item()
-                w[:, 4] *= sc
+                if first:
+                    w[:, 4] *= sc
+                    b[:, 5:] += 8.0
                 b[:, 4] = float(np.log(0.3 / 0.7)) - q98
-                b[:, 5:] += 8.0
-                for other in (st.model, st.semi_ema.ema):
-                    other.head.m[l].bias.data.copy_(m.bias.data)
-                    other.head.m[l].weight.data.copy_(m.weight.data)
+                if first:
+                    for other in (st.model, st.semi_ema.ema):
+                        other.head.m[l].bias.data.copy_(m.bias.data)
+                        other.head.m[l].weight.data.copy_(m.weight.data)
             (pred, raw), _ = st.ema.ema(d_uw)
-            cand_per_img = float((pred[..., 4] > cfg.SSOD.nms_conf_thres).sum(1).float().mean().item())
-            del pred, raw
+            return float((pred[..., 4] > cfg.SSOD.nms_conf_thres).sum(1).float().mean().item())
+
+    cand_per_img = calibrate_teacher_head(True) if ssod else None
 
     use_graph = not args.no_graph
 
@@ -485,14 +497,26 @@ def main():
     for _ in range(args.warmup):
         step_resident(ni); ni += 1
     torch.cuda.synchronize()
-    if ssod:
-        n_pl0, det_per_img0 = pl_state()
+    cand_start = calibrate_teacher_head(False) if ssod else None     # synthetic-state maintenance, outside the timed region
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    ms = timed(step_resident, args.steps, ni); ni += args.steps
+    pl_probe = []
+
+    def step_resident_probed(i):          # device-side copies of the pseudo-label counters of the first / last timed step (no sync)
+        out = step_resident(i)
+        if ssod and (i == probe_first or i == probe_last):
+            c = st.pseudo_label_creator
+            pl_probe.append((c.last_count_dev.clone(), c.last_det[1].float().mean()))
+        return out
+    probe_first, probe_last = ni, ni + args.steps - 1
+    ms = timed(step_resident_probed, args.steps, ni); ni += args.steps
     if ssod:
-        n_pl_timed, det_timed = pl_state()       # pseudo-label load at the LAST TIMED step
+        (n_pl0, det_per_img0), (n_pl_timed, det_timed) = [(int(a.item()), float(b.item())) for a, b in pl_probe]
+        with torch.no_grad():
+            (pred_t, _r), _f = st.ema.ema(d_uw)
+            cand_timed_end = float((pred_t[..., 4] > cfg.SSOD.nms_conf_thres).sum(1).float().mean())
+            del pred_t, _r, _f
     # kernel-launch count and per-phase CUDA-event times come from an eager (un-graphed) pass of the same step
     step_eager(ni); ni += 1     # one eager step first: lazy one-time work
     torch.cuda.synchronize()
@@ -506,12 +530,17 @@ def main():
     launches = (lib.etb_launch_count() - l0) / nprof
     phases = {k: v / nprof for k, v in st.phase_times_ms().items()} if ssod else {}
     st.profile = False
+    n_pl_e2e = None
     if args.no_e2e:
         ms_e2e = float("nan")
     else:
         for _ in range(3):
             step_e2e(ni); ni += 1
+        if ssod:
+            calibrate_teacher_head(False)
         ms_e2e = timed(step_e2e, args.steps, ni); ni += args.steps
+        if ssod:
+            n_pl_e2e = pl_state()[0]
     clocks = sampler.summary() if sampler else None
     if args.nvtx_step and rank == 0:
         torch.cuda.synchronize()
@@ -526,24 +555,21 @@ def main():
     # ---- self-check: the run is only a measurement if the whole step really ran at load --------------------------------
     health = {}
     if ssod:
-        n_pl_end, det_end = pl_state()
-        with torch.no_grad():
-            (pred_e, _raw_e), _f = st.ema.ema(d_uw)
-            cand_end = float((pred_e[..., 4] > cfg.SSOD.nms_conf_thres).sum(1).float().mean())
-            del pred_e, _raw_e, _f
-
         def _bnmax(mod):
             bb = [q for q in mod.modules() if isinstance(q, torch.nn.BatchNorm2d)]
-            return [max(float(q.running_var.max()) for q in bb), max(float(q.running_mean.abs().max()) for q in bb),
-                    max(float(q.weight.abs().max()) for q in bb), max(float(q.bias.abs().max()) for q in bb)]
-        health = {"nms_candidates_per_img_at_start": cand_per_img, "nms_candidates_per_img_at_end": cand_end,
+            return [max(float(q.running_var.detach().max()) for q in bb), max(float(q.running_mean.detach().abs().max()) for q in bb),
+                    max(float(q.weight.detach().abs().max()) for q in bb), max(float(q.bias.detach().abs().max()) for q in bb)]
+        health = {"nms_candidates_per_img_after_first_calibration": cand_per_img,
+                  "nms_candidates_per_img_at_start_of_timed_window": cand_start, "nms_candidates_per_img_at_end_of_timed_window": cand_timed_end,
                   "nms_detections_per_img_first_timed_step": det_per_img0, "nms_detections_per_img_last_timed_step": det_timed,
                   "pseudo_label_rows_first_timed_step": n_pl0, "pseudo_label_rows_last_timed_step": n_pl_timed,
-                  "pseudo_label_rows_end_of_run": n_pl_end,
+                  "pseudo_label_rows_last_e2e_step": n_pl_e2e,
                   "student_bn_max[running_var,|running_mean|,|gamma|,|beta|]": _bnmax(st.model),
-                  "teacher_bn_max[running_var,|running_mean|,|gamma|,|beta|]": _bnmax(st.ema.ema), "steps_total": ni}
-        ok = (n_pl_timed > 0 and n_pl_end > 0 and cand_per_img > 0 and 0.5 * cand_per_img <= cand_end <= 2.0 * cand_per_img
-              and 0.5 * n_pl0 <= n_pl_timed <= 2.0 * n_pl0 and all(np.isfinite(health["student_bn_max[running_var,|running_mean|,|gamma|,|beta|]"])))
+                  "teacher_bn_max[running_var,|running_mean|,|gamma|,|beta|]": _bnmax(st.ema.ema), "steps_total": ni,
+                  "rule": "valid iff over the timed window: pseudo-label rows > 0 at both ends, last/first within [0.5, 2], NMS candidates/img at the end within [0.5, 2] x start, BN state finite"}
+        ok = (n_pl0 > 0 and n_pl_timed > 0 and 0.5 * n_pl0 <= n_pl_timed <= 2.0 * n_pl0 and cand_start > 0
+              and 0.5 * cand_start <= cand_timed_end <= 2.0 * cand_start and (n_pl_e2e is None or n_pl_e2e > 0)
+              and all(np.isfinite(health["student_bn_max[running_var,|running_mean|,|gamma|,|beta|]"])))
         flags = torch.tensor([0 if ok else 1], device=dev)
         if world > 1:
             import torch.distributed as dist
@@ -551,7 +577,9 @@ def main():
         if int(flags.item()):
             print("[bench] INVALID RUN (rank %d): the pseudo-label branch did not stay loaded / the state diverged: %s" % (rank, json.dumps(health)),
                   file=sys.stderr, flush=True)
-            sys.exit(3)
+            if not args.allow_invalid:
+                sys.exit(3)
+            health["INVALID"] = True
 
     if rank == 0:
         pk, pk_kind = peaks()

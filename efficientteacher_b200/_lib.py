@@ -66,6 +66,11 @@ class EtbFoldDesc(C.Structure):
 ETB_PACK_CHUNK = 4096
 
 
+class EtbFocalParams(C.Structure):
+    _fields_ = [("x", vp * ETB_MAX_LEVELS), ("dx", vp * ETB_MAX_LEVELS), ("M", C.c_int64 * ETB_MAX_LEVELS), ("nl", C.c_int32),
+                ("label", C.c_int32)]
+
+
 class EtbConvParams(C.Structure):
     _fields_ = [("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32),
                 ("kh", C.c_int32), ("kw", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
@@ -130,6 +135,16 @@ _SIGS = {
     "etb_pack_multi": (C.c_int, [vp, vp, C.c_int32, vp]),
     "etb_fold_bn_multi": (C.c_int, [vp, C.c_int32, vp]),
     "etb_pack_stem_weight": (C.c_int, [vp, vp, C.c_int32, vp]),
+    "etb_detect_dy_rows": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
+    "etb_detect_dy_pack": (C.c_int, [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
+    "etb_column_sum": (C.c_int, [vp, C.c_int64, C.c_int32, vp, C.c_int32, vp]),
+    "etb_netd_tail_rows": (C.c_int32, [C.c_int64]),
+    "etb_netd_tail_fwd": (C.c_int, [vp, C.c_int64, C.c_int32, C.c_int32, vp, vp, vp]),
+    "etb_netd_tail_bwd": (C.c_int, [vp, vp, C.c_int64, C.c_int32, C.c_int32, vp, vp, vp, C.c_int32, vp]),
+    "etb_domain_focal_workspace_bytes": (C.c_int64, []),
+    "etb_domain_focal_fwd": (C.c_int, [C.POINTER(EtbFocalParams), vp, vp, C.c_int64, vp]),
+    "etb_domain_focal_bwd": (C.c_int, [C.POINTER(EtbFocalParams), vp, vp]),
+    "etb_stem_im2col_into": (C.c_int, [vp, C.c_int32, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, vp]),
 }
 
 _lib = None

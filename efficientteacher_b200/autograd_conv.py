@@ -90,6 +90,85 @@ def _nhwc_of(t):
     return v
 
 
+class StemInput:
+    """The student's input batch as the stem sees it: one or several [n_i,3,H,W] tensors (uint8 straight from the loaders,
+    or fp32 already scaled) that are logically concatenated along the batch (trainer/ssod_trainer.py:620 torch.cat) and
+    divided by `div` (:694-696 `.float() / 255`).  Deliberately NOT a tensor: ConvBnActFn receives it as an opaque argument
+    and the im2col kernel reads every part in place -- neither the cat nor the fp32 image is ever materialised."""
+
+    def __init__(self, parts, div=None):
+        self.parts = [p for p in parts]
+        self.div = float(div) if div is not None else (255.0 if self.parts[0].dtype == torch.uint8 else 1.0)
+        self.is_cuda = all(p.is_cuda for p in self.parts)
+        self.device = self.parts[0].device
+        n = sum(int(p.shape[0]) for p in self.parts)
+        self.shape = (n,) + tuple(self.parts[0].shape[1:])
+        self.requires_grad = False
+
+    def im2col(self):
+        return co.stem_im2col_parts(self.parts, self.div)
+
+
+class GradSlot:
+    """Lazily allocated gradient buffer shared by the outputs of SplitBatchFn: the consumers' backward kernels write their
+    gradients straight into batch slices of ONE buffer, so the split's backward is a no-op instead of zeros + 2 copies."""
+
+    def __init__(self, like):
+        self.like, self.buf = like, None
+
+    def get(self):
+        if self.buf is None:
+            self.buf = torch.empty_like(self.like)       # same strides (dense): batch slices are contiguous runs
+        return self.buf
+
+
+def grad_buffer_for(t):
+    """gradient destination for tensor t inside a native backward: its slice of a GradSlot when t came out of SplitBatchFn,
+    else a fresh tensor"""
+    hint = getattr(t, "_etb_gslot", None)
+    if hint is None:
+        return torch.empty_like(t)
+    slot, a, b = hint
+    return slot.get()[a:b]
+
+
+class SplitBatchFn(torch.autograd.Function):
+    """(t[:n], t[n:]) -- trainer/ssod_trainer.py:568-585 split_predict_and_feature -- whose backward hands the two gradients
+    back as ONE tensor without copying when the consumers wrote them into the shared GradSlot (grad_buffer_for)."""
+
+    stats = {"zero_copy": 0, "copied": 0}      # diagnostics (tests assert that the step takes the zero-copy path)
+
+    @staticmethod
+    def forward(ctx, t, n, slot):
+        ctx.n, ctx.slot, ctx.like = n, slot, t
+        return t[:n], t[n:]
+
+    @staticmethod
+    def backward(ctx, ga, gb):
+        n, slot = ctx.n, ctx.slot
+        buf = slot.buf
+        if buf is not None and ga is not None and gb is not None and ga.data_ptr() == buf[:n].data_ptr() and gb.data_ptr() == buf[n:].data_ptr() \
+                and ga.stride() == buf[:n].stride() and gb.stride() == buf[n:].stride():
+            slot.buf = None
+            SplitBatchFn.stats["zero_copy"] += 1
+            return buf, None, None
+        SplitBatchFn.stats["copied"] += 1
+        like = ctx.like
+        za = ga if ga is not None else torch.zeros_like(like[:n])
+        zb = gb if gb is not None else torch.zeros_like(like[n:])
+        return torch.cat([za, zb], 0), None, None
+
+
+def split_batch(t, n):
+    """t[:n], t[n:] with the zero-copy backward above (falls back to plain slicing for tensors that need no gradient)"""
+    if not (torch.is_tensor(t) and t.requires_grad and t.is_cuda):
+        return t[:n], t[n:]
+    slot = GradSlot(t)
+    a, b = SplitBatchFn.apply(t, n, slot)
+    a._etb_gslot, b._etb_gslot = (slot, 0, n), (slot, n, t.shape[0])
+    return a, b
+
+
 class CatBuf:
     """A concat buffer [N, Ct, H, W] (channels_last = NHWC in memory).  Producers write their outputs straight into
     channel slices of `buf` (concat-by-offset, the training-side twin of engine.TrunkEngine's layout) and JoinFn turns
@@ -309,7 +388,7 @@ class ConvBnActFn(torch.autograd.Function):
             if f is not None:
                 f.n += 1
         if is_stem:
-            xb = co.stem_im2col(x.float(), 1.0)               # [N,H/2,W/2,128]; saved instead of the image
+            xb = x.im2col() if isinstance(x, StemInput) else co.stem_im2col(x.float(), 1.0)   # [N,H/2,W/2,128]; saved instead of the image
             xcs, Cin, k, st, pd = 128, 128, 1, 1, 0
             if wp is None:
                 wp = co.pack_stem_weight(weight)
@@ -405,20 +484,33 @@ class StemFn(torch.autograd.Function):
         return None, dw
 
 
+def _arena_grad(p):
+    """p.grad when it is the contiguous fp32 gradient-arena view the kernels may accumulate into, else None"""
+    g = p.grad
+    return g if (ACCUMULATE_INTO_GRAD and g is not None and g.dtype == torch.float32 and g.is_contiguous()) else None
+
+
 class DetectConvFn(torch.autograd.Function):
     """Detect's 1x1 conv + bias, emitting fp32 logits directly in the train layout [N,na,ny,nx,no]
-    (the view/permute/contiguous of models/head/yolov5_head.py:66 is fused into the epilogue)."""
+    (the view/permute/contiguous of models/head/yolov5_head.py:66 is fused into the epilogue).  Backward is native too:
+    etb_detect_dy_pack turns the loss gradient into the bf16 NHWC operand (+ bias-gradient partials) in one pass, dgrad runs
+    on the K-padded operand and joins the feature's gradient fan-in (neck conv, netD), wgrad / bias gradient are added
+    into the gradient arena."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, na, no):
+    def forward(ctx, x, weight, bias, na, no, wp=None, wd=None):
         Cout, Cin = weight.shape[0], weight.shape[1]
         xb, xcs = _as_nhwc(x, Cin)
         N, H, W, _ = xb.shape
         out = torch.empty((N, na, H, W, no), dtype=torch.float32, device=x.device)
-        co.conv_fwd(xb, co.pack_weight(weight), Cin, Cout, 1, 1, 0, None, bias.detach().float().contiguous(), None, x_cstride=xcs,
-                    det_out=out, det_no=no)
+        co.conv_fwd(xb, wp if wp is not None else co.pack_weight(weight), Cin, Cout, 1, 1, 0, None, bias.detach().float().contiguous(), None,
+                    x_cstride=xcs, det_out=out, det_no=no)
         ctx.save_for_backward(x, weight)
         ctx.meta = (na, no)
+        ctx.wd, ctx.bias = wd, bias
+        ctx.fan = FanIn.of(x)
+        if ctx.fan is not None:
+            ctx.fan.n += 1
         return out
 
     @staticmethod
@@ -427,28 +519,97 @@ class DetectConvFn(torch.autograd.Function):
         na, no = ctx.meta
         Cout, Cin = weight.shape[0], weight.shape[1]
         N, _, H, W, _ = g.shape
-        # [N,na,H,W,no] fp32 -> NHWC bf16 [N,H,W,256] (channel c = a*no+o; padded to a multiple of 8 channels)
-        cpad = (Cout + 7) // 8 * 8
-        dyb = torch.zeros((N, H, W, cpad), dtype=torch.bfloat16, device=g.device)
-        dyb[..., :Cout] = g.permute(0, 2, 3, 1, 4).reshape(N, H, W, Cout)
-        db = g.sum((0, 2, 3)).reshape(-1) if ctx.needs_input_grad[2] else None
-        dx = dw = None
+        if g.dtype != torch.float32 or not g.is_contiguous():
+            g = g.float().contiguous()
+        kpad = (Cout + 63) // 64 * 64          # dgrad contracts over K = Cout: padded to the 64-channel K block
+        dyb, partials = co.detect_dy_pack(g, kpad)
+        dx = dw = db = None
+        if ctx.needs_input_grad[2]:
+            tgt_b = _arena_grad(ctx.bias)
+            db = co.column_sum(partials, out=tgt_b, accumulate=tgt_b is not None)
+            if tgt_b is not None:
+                db = None
         if ctx.needs_input_grad[0]:
-            # dgrad needs K = Cout to be a multiple of 64: use the zero-padded 256-channel view of dy and of W^T
-            kpad = (Cout + 63) // 64 * 64
-            if kpad != cpad:
-                d2 = torch.zeros((N, H, W, kpad), dtype=torch.bfloat16, device=g.device)
-                d2[..., :Cout] = dyb[..., :Cout]
+            wd = ctx.wd
+            if wd is None:
+                wpad = torch.zeros((kpad, Cin, 1, 1), dtype=torch.float32, device=g.device)
+                wpad[:Cout] = weight.detach().float()
+                wd = co.pack_weight_dgrad(wpad, 1, 0)
+            run = lambda o, ocs, acc: co.conv_dgrad(dyb, wd, N, H, W, Cin, kpad, 1, 1, 0, out=o, out_cstride=ocs, accumulate=acc)  # noqa: E731
+            if ctx.fan is None:
+                dx = _empty_cl(N, Cin, H, W, g.device)
+                run(_nhwc_of(dx), Cin, False)
             else:
-                d2 = dyb
-            wpad = torch.zeros((kpad, Cin, 1, 1), dtype=torch.float32, device=g.device)
-            wpad[:Cout] = weight.detach().float()
-            dx = _empty_cl(N, Cin, H, W, g.device)
-            co.conv_dgrad(d2, co.pack_weight_dgrad(wpad, 1, 0), N, H, W, Cin, kpad, 1, 1, 0, out=_nhwc_of(dx))
+                dx = ctx.fan.add_dgrad(run, N, Cin, H, W, g.device)
         if ctx.needs_input_grad[1]:
             xb, xcs = _as_nhwc(x, Cin)
-            dw = co.conv_wgrad(xb, dyb, Cin, Cout, 1, 1, 0, x_cstride=xcs)
-        return dx, dw, db, None, None
+            tgt = _arena_grad(weight)
+            if WGRAD_SIDE["on"] and tgt is not None:
+                wgrad_side_run(lambda: co.conv_wgrad(xb, dyb, Cin, Cout, 1, 1, 0, x_cstride=xcs, accumulate_into=tgt), (x, xb, dyb))
+            else:
+                dw = co.conv_wgrad(xb, dyb, Cin, Cout, 1, 1, 0, x_cstride=xcs, accumulate_into=tgt)
+            if tgt is not None:
+                dw = None
+        return dx, dw, db, None, None, None, None
+
+
+class NetDFn(torch.autograd.Function):
+    """netD behind GradReverse (models/detector/yolo_ssod.py:105-118,158-172,224-238): o = conv2(relu(conv1(x))) with the
+    gradient of x negated.  conv1 = tcgen05 GEMM with the ReLU in its epilogue; conv2 (C -> 2) = etb_netd_tail_fwd; the map is
+    returned as an NCHW-shaped view [N,2,H,W] of the fp32 [N,H,W,2] buffer.  Backward: etb_netd_tail_bwd (dh with the ReLU
+    mask, dW2 partials), conv1 wgrad into the arena, and conv1 dgrad on the NEGATED operand (pack mode 3) so the sign flip
+    of GradReverse costs nothing and the result joins the feature's gradient fan-in."""
+
+    @staticmethod
+    def forward(ctx, x, w1, w2, wp1=None, wd1n=None):
+        C_ = w1.shape[0]
+        xb, xcs = _as_nhwc(x, C_)
+        N, H, W, _ = xb.shape
+        h = torch.empty((N, H, W, C_), dtype=torch.bfloat16, device=x.device)
+        co.conv_fwd(xb, wp1 if wp1 is not None else co.pack_weight(w1), C_, C_, 1, 1, 0, None, None, "relu", x_cstride=xcs, out=h)
+        w2f = w2.detach().float().contiguous()
+        o = co.netd_tail_fwd(h, C_, w2f)
+        ctx.save_for_backward(x, w1, w2, h)
+        ctx.wd1n = wd1n
+        ctx.fan = FanIn.of(x)
+        if ctx.fan is not None:
+            ctx.fan.n += 1
+        return o.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w1, w2, h = ctx.saved_tensors
+        C_ = w1.shape[0]
+        N, H, W, _ = h.shape
+        do = g.permute(0, 2, 3, 1)
+        if do.dtype != torch.float32 or not do.is_contiguous():
+            do = do.float().contiguous()
+        dh, partials = co.netd_tail_bwd(do, h, C_, w2.detach().float().contiguous())
+        dx = dw1 = dw2 = None
+        if ctx.needs_input_grad[2]:
+            tgt2 = _arena_grad(w2)
+            if tgt2 is not None:
+                co.column_sum(partials, out=tgt2, accumulate=True)
+            else:
+                dw2 = co.column_sum(partials).view_as(w2)
+        if ctx.needs_input_grad[0]:
+            wd = ctx.wd1n if ctx.wd1n is not None else co.pack_weight_dgrad(-w1.detach().float(), 1, 0)
+            run = lambda o, ocs, acc: co.conv_dgrad(dh, wd, N, H, W, C_, C_, 1, 1, 0, out=o, out_cstride=ocs, accumulate=acc)  # noqa: E731
+            if ctx.fan is None:
+                dx = _empty_cl(N, C_, H, W, g.device)
+                run(_nhwc_of(dx), C_, False)
+            else:
+                dx = ctx.fan.add_dgrad(run, N, C_, H, W, g.device)
+        if ctx.needs_input_grad[1]:
+            xb, xcs = _as_nhwc(x, C_)
+            tgt = _arena_grad(w1)
+            if WGRAD_SIDE["on"] and tgt is not None:
+                wgrad_side_run(lambda: co.conv_wgrad(xb, dh, C_, C_, 1, 1, 0, x_cstride=xcs, accumulate_into=tgt), (x, xb, dh))
+            else:
+                dw1 = co.conv_wgrad(xb, dh, C_, C_, 1, 1, 0, x_cstride=xcs, accumulate_into=tgt)
+            if tgt is not None:
+                dw1 = None
+        return dx, dw1, dw2, None, None
 
 
 def conv2d_native(x, weight, stride, pad):

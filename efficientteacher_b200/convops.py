@@ -247,3 +247,66 @@ def upsample2x_bwd(dy, dy_cstride, dx, C_):
 def copy_slice(x, x_cstride, y, y_cstride, M, C_):
     _lib.check(_lib.lib().etb_copy_slice_nhwc(_lib.ptr(x), _lib.ptr(y), M, C_, x_cstride, y_cstride, _lib.stream_ptr()),
                "etb_copy_slice_nhwc")
+
+
+# ---- the tail of the student's step (csrc/tail.cu) ----
+def stem_im2col_parts(parts, div=1.0):
+    """im2col of the stem over the batch-concatenation of `parts` ([n_i,3,H,W] uint8 or fp32 tensors) WITHOUT materialising
+    torch.cat: every part is written into its image slots of one [sum n_i, H/2, W/2, 128] buffer.  Values are x / div."""
+    _lib.require_cuda(*parts)
+    H, W = parts[0].shape[2:]
+    n_tot = sum(int(p.shape[0]) for p in parts)
+    out = nhwc_empty(n_tot, H // 2, W // 2, 128, parts[0].device)
+    off = 0
+    for p in parts:
+        assert p.shape[1] == 3 and tuple(p.shape[2:]) == (H, W)
+        if p.dtype not in (torch.uint8, torch.float32):
+            p = p.float()
+        p = p.contiguous()
+        if p.shape[0]:
+            _lib.check(_lib.lib().etb_stem_im2col_into(_lib.ptr(p), int(p.dtype == torch.uint8), _lib.ptr(out), int(p.shape[0]), H, W, off,
+                                                       float(div), _lib.stream_ptr()), "etb_stem_im2col_into")
+        off += int(p.shape[0])
+    return out
+
+
+def detect_dy_pack(g, cpad):
+    """g fp32 [N,na,H,W,no] (contiguous) -> (dy bf16 [N,H,W,cpad], partials [rows, na*no]) -- see include/etb200.h"""
+    N, na, H, W, no = g.shape
+    lib = _lib.lib()
+    rows = int(lib.etb_detect_dy_rows(N, H, W))
+    dy = torch.empty((N, H, W, cpad), dtype=torch.bfloat16, device=g.device)
+    partials = torch.empty((rows, na * no), dtype=torch.float32, device=g.device)
+    _lib.check(lib.etb_detect_dy_pack(_lib.ptr(g), _lib.ptr(dy), _lib.ptr(partials), N, na, H, W, no, cpad, _lib.stream_ptr()), "etb_detect_dy_pack")
+    return dy, partials
+
+
+def column_sum(partials, out=None, accumulate=False):
+    rows, Cc = partials.shape[0], int(partials.numel() // partials.shape[0])
+    if out is None:
+        out = torch.empty(Cc, dtype=torch.float32, device=partials.device)
+        accumulate = False
+    _lib.check(_lib.lib().etb_column_sum(_lib.ptr(partials), rows, Cc, _lib.ptr(out), int(accumulate), _lib.stream_ptr()), "etb_column_sum")
+    return out
+
+
+def netd_tail_fwd(h, C_, w2, h_cstride=None):
+    """h [N,H,W,*] bf16 (relu(conv1(x))), w2 [2,C,1,1] fp32 -> o fp32 [N,H,W,2]"""
+    N, H, W, cs = h.shape
+    o = torch.empty((N, H, W, 2), dtype=torch.float32, device=h.device)
+    _lib.check(_lib.lib().etb_netd_tail_fwd(_lib.ptr(h), N * H * W, C_, cs if h_cstride is None else h_cstride, _lib.ptr(w2), _lib.ptr(o),
+                                            _lib.stream_ptr()), "etb_netd_tail_fwd")
+    return o
+
+
+def netd_tail_bwd(do, h, C_, w2, h_cstride=None):
+    """do fp32 [N,H,W,2] contiguous -> (dh bf16 [N,H,W,C] with the ReLU mask applied, partials [rows, 2*C] of dW2)"""
+    N, H, W, cs = h.shape
+    M = N * H * W
+    lib = _lib.lib()
+    rows = int(lib.etb_netd_tail_rows(M))
+    dh = nhwc_empty(N, H, W, C_, h.device)
+    partials = torch.empty((rows, 2 * C_), dtype=torch.float32, device=h.device)
+    _lib.check(lib.etb_netd_tail_bwd(_lib.ptr(do), _lib.ptr(h), M, C_, cs if h_cstride is None else h_cstride, _lib.ptr(w2), _lib.ptr(dh),
+                                     _lib.ptr(partials), rows, _lib.stream_ptr()), "etb_netd_tail_bwd")
+    return dh, partials

@@ -219,6 +219,7 @@ extern "C" int etb_pack_stem_weight(const float* w_oihw, void* w_bf16, int32_t C
 // mode 0: fwd  [Cout][kh][kw][Cin or out_ld]   <- w[co][ci][kh][kw]        (dst index e: ci fastest; out_ld > Cin pads every tap)
 // mode 1: dgrad class  [Cin][ntaps][out_ld>=Cout] <- w[co][ci][kh_t][kw_t]   (dst: co fastest; row pitch out_ld per tap)
 // mode 2: stem [Cout][128] in the etb_stem_im2col K order
+// mode 3: mode 1 negated (dgrad operand of a conv that sits behind a GradReverse)
 __global__ void __launch_bounds__(256) pack_multi_kernel(const EtbPackDesc* __restrict__ descs, const int2* __restrict__ chunks) {
   const int2 ch = chunks[blockIdx.x];
   const EtbPackDesc d = descs[ch.x];
@@ -238,11 +239,12 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const EtbPackDesc* __re
       const int t = (int)(t2 % kk), co = (int)(t2 / kk);
       v = w[((int64_t)co * d.Cin + ci) * kk + t];
       if (d.out_ld > d.Cin) dst = ((int64_t)co * kk + t) * d.out_ld + ci;   // every tap padded to out_ld = ceil64(Cin) (pad stays zero)
-    } else if (d.mode == 1) {
+    } else if (d.mode == 1 || d.mode == 3) {
       const int co = (int)(e % d.Cout);
       const int64_t t2 = e / d.Cout;
       const int t = (int)(t2 % d.ntaps), ci = (int)(t2 / d.ntaps);
       v = w[(((int64_t)co * d.Cin + ci) * d.k + d.kh[t]) * d.k + d.kw[t]];
+      if (d.mode == 3) v = -v;            // GradReverse in front of the conv: dx = -(W^T dy)
       dst = ((int64_t)ci * d.ntaps + t) * d.out_ld + co;
     } else {
       const int k = (int)(e & 127), oc = (int)(e >> 7);

@@ -70,7 +70,8 @@ class _FusedDetLoss(torch.autograd.Function):
         lib = _lib.lib()
         p, lp, sets = ctx.p, ctx.lp, ctx.sets
         nl = len(p)
-        grads = [torch.empty_like(t) for t in p]
+        from .autograd_conv import grad_buffer_for
+        grads = [grad_buffer_for(t) for t in p]      # batch slices of one buffer when p came out of split_batch
         gscale = g4[3:4].contiguous().float()
         parr = (C.c_void_p * nl)(*[t.data_ptr() for t in p])
         garr = (C.c_void_p * nl)(*[t.data_ptr() for t in grads])

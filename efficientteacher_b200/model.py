@@ -87,6 +87,8 @@ class Conv(nn.Module):
                                          None if pc is None else pc.fwd, None if pc is None else pc.dgrad, res, dest, coff)
             assert dest is None
             if self.is_stem:
+                if not torch.is_tensor(x):          # autograd_conv.StemInput on the scaffold path: materialise the batch
+                    x = torch.cat([q.float() for q in x.parts], 0) / x.div
                 y = StemFn.apply(x.float(), w)
             else:
                 y = ConvFn.apply(x, w, self.conv.stride[0], self.conv.padding[0])
@@ -257,9 +259,11 @@ class YoloV5Neck(nn.Module):
         if self.conv3.glue(P5) and all(t.shape[1] % 8 == 0 for t in (xp_1, P4, P3)):
             x1 = self.C1(self._up_cat(xp_1, P4))
             xp_2 = self.conv2(x1)
-            x2 = self.C2(self._up_cat(xp_2, P3))
-            x3 = self.C3(self._down_cat(self.conv3, x2, xp_2))
-            x4 = self.C4(self._down_cat(self.conv4, x3, xp_1))
+            # the three outputs feed the Detect conv, netD (SSOD) and -- x2, x3 -- the next stride-2 conv: their gradients meet
+            # in the dgrad epilogues (FanIn) instead of in autograd's add kernels
+            x2 = _fan_out(self.C2(self._up_cat(xp_2, P3)))
+            x3 = _fan_out(self.C3(self._down_cat(self.conv3, x2, xp_2)))
+            x4 = _fan_out(self.C4(self._down_cat(self.conv4, x3, xp_1)))
             return x2, x3, x4
         x1 = self.C1(self.concat([self.upsample1(xp_1), P4]))
         xp_2 = self.conv2(x1)
@@ -296,12 +300,15 @@ class Detect(nn.Module):
             b.data[:, 5:] += math.log(0.6 / (self.nc - 0.99)) if cf is None else torch.log(cf / cf.sum())
             mi.bias = torch.nn.Parameter(b.view(-1), requires_grad=True)
 
-    def forward(self, x):
+    def forward(self, x, packed=None):
+        """packed: optional list of packing.PackedConv (Model.pack_weights(): forward + K-padded dgrad operand per level)"""
         x = list(x)
         for i in range(self.nl):
             if Conv.NATIVE and x[i].is_cuda:
                 from .autograd_conv import DetectConvFn
-                x[i] = DetectConvFn.apply(x[i], self.m[i].weight, self.m[i].bias, self.na, self.no)
+                pc = packed[i] if (packed is not None and self.training) else None
+                x[i] = DetectConvFn.apply(x[i], self.m[i].weight, self.m[i].bias, self.na, self.no,
+                                          None if pc is None else pc.fwd, None if pc is None else pc.dgrad)
                 continue
             x[i] = self.m[i](x[i])
             bs, _, ny, nx = x[i].shape
@@ -331,10 +338,16 @@ class netD(nn.Module):  # yolo_ssod.py:224-238
         self.conv2 = nn.Conv2d(c, 2, 1, 1, 0, bias=False)
         self.relu = nn.ReLU(inplace=True)
 
-    def forward(self, x):
-        if Conv.NATIVE and x.is_cuda:
-            from .autograd_conv import ConvFn
-            return self.conv2(self.relu(ConvFn.apply(x, self.conv1.weight, 1, 0)))   # conv2 (C->2) stays a library op
+    def forward(self, x, reverse=False, packed=None):
+        """reverse=True: x is the feature itself and the GradReverse of yolo_ssod.py:111-113 is folded into this module's
+        backward (NetDFn runs conv1's dgrad on the negated operand); otherwise the caller applied GradReverse.
+        packed: optional packing.PackedConv of conv1 (forward + negated dgrad operand)."""
+        if Conv.NATIVE and x.is_cuda and reverse:
+            from .autograd_conv import NetDFn
+            pc = packed if self.training else None
+            return NetDFn.apply(x, self.conv1.weight, self.conv2.weight, None if pc is None else pc.fwd, None if pc is None else pc.dgrad)
+        if reverse:
+            x = GradReverse.apply(x)
         return self.conv2(self.relu(self.conv1(x)))
 
 
@@ -366,16 +379,32 @@ class _ModelBase(nn.Module):
         self.model_type = 'yolov5'
         self.export = False
         self._engine = None
+        self._packer = self._packer_aux = None
 
     def _require(self, x):
-        _lib.require_cuda(x)
+        _lib.require_cuda(*(x if isinstance(x, (list, tuple)) else (x,)))
         _lib.lib()
+
+    def _stem_input(self, x):
+        """x: the reference's contract (one fp32 [N,3,H,W] tensor in [0,1]) or, for the native stem, a uint8 tensor / a list of
+        tensors to be concatenated along the batch (the loaders' raw batches: trainer/ssod_trainer.py:620,694-696).  On the
+        native path this becomes an autograd_conv.StemInput (no cat, no fp32 image); otherwise a plain fp32 tensor."""
+        parts = list(x) if isinstance(x, (list, tuple)) else [x]
+        native = Conv.NATIVE and Conv.FUSED_BN and self.training and all(p.is_cuda for p in parts)
+        if native and (len(parts) > 1 or parts[0].dtype == torch.uint8):
+            from .autograd_conv import StemInput
+            return StemInput(parts)
+        if len(parts) == 1 and parts[0].dtype != torch.uint8:
+            return parts[0]
+        div = 255.0 if parts[0].dtype == torch.uint8 else 1.0
+        t = torch.cat([p.float() for p in parts], 0)
+        return t / div if div != 1.0 else t
 
     def pack_weights(self):
         """bf16 GEMM operands (forward + dgrad) of every Conv for this training step, in ONE launch (packing.WeightPacker);
-        the Conv modules pick them up through `_packed`."""
+        the Conv modules pick them up through `_packed`, the head / netD convs through the returned dict."""
         if not (Conv.NATIVE and Conv.FUSED_BN and self.training):
-            return
+            return {}
         dev = next(self.parameters()).device
         pk = getattr(self, "_packer", None)
         if pk is None or pk.device != dev:
@@ -384,8 +413,13 @@ class _ModelBase(nn.Module):
             for m in self.modules():
                 if isinstance(m, Conv):
                     m._packed = pk.add(m.conv.weight, m.conv.stride[0], m.conv.padding[0], want_dgrad=not m.is_stem, stem=m.is_stem)
-            self._packer = pk
+            aux = {"head": [pk.add(m.weight, 1, 0, want_dgrad=True) for m in self.head.m]}   # dgrad operand K-padded (255 -> 256)
+            for d in ("det_8", "det_16", "det_32"):      # netD.conv1 behind GradReverse: dgrad operand negated (pack mode 3)
+                if hasattr(self, d):
+                    aux[d] = pk.add(getattr(self, d).conv1.weight, 1, 0, want_dgrad=True, negate_dgrad=True)
+            self._packer, self._packer_aux = pk, aux
         pk.run()
+        return self._packer_aux
 
     def _count_bn_batches(self):
         """BatchNorm2d.num_batches_tracked += 1 for every BN (what nn.BatchNorm2d does per training forward), as ONE
@@ -407,7 +441,7 @@ class _ModelBase(nn.Module):
         memo[id(self)] = new
         from copy import deepcopy
         for k, v in self.__dict__.items():
-            new.__dict__[k] = None if k in ("_engine", "_nbt", "_packer") else deepcopy(v, memo)
+            new.__dict__[k] = None if k in ("_engine", "_nbt", "_packer", "_packer_aux") else deepcopy(v, memo)
         return new
 
     def __getstate__(self):
@@ -415,6 +449,7 @@ class _ModelBase(nn.Module):
         s["_engine"] = None
         s["_nbt"] = None
         s["_packer"] = None
+        s["_packer_aux"] = None
         return s
 
 
@@ -435,11 +470,11 @@ class Model(_ModelBase):
         if not self.training and not torch.is_grad_enabled():
             return self.engine().forward(x, with_features=True)
         self._count_bn_batches()
-        self.pack_weights()
-        f = self.neck(self.backbone(x))
-        out = self.head(f)
+        aux = self.pack_weights()
+        f = self.neck(self.backbone(self._stem_input(x)))
+        out = self.head(f, aux.get("head"))
         f8, f16, f32 = f
-        feature = [self.det_8(GradReverse.apply(f8)), self.det_16(GradReverse.apply(f16)), self.det_32(GradReverse.apply(f32))]
+        feature = [self.det_8(f8, True, aux.get("det_8")), self.det_16(f16, True, aux.get("det_16")), self.det_32(f32, True, aux.get("det_32"))]
         return out, feature
 
 
@@ -456,5 +491,6 @@ class SupModel(_ModelBase):
         if not self.training and not torch.is_grad_enabled():
             return self.engine().forward(x, with_features=False)[0]
         self._count_bn_batches()
-        self.pack_weights()
-        return self.head(self.neck(self.backbone(x)))
+        aux = self.pack_weights()
+        f = self.neck(self.backbone(self._stem_input(x)))
+        return self.head(f, aux.get("head"))

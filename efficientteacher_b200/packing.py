@@ -48,7 +48,7 @@ class WeightPacker:
         self.folds = []          # (bn module, PackedConv)
         self._built = None
 
-    def add(self, weight, stride, pad, want_dgrad, stem=False, dgrad_cout_pad=None):
+    def add(self, weight, stride, pad, want_dgrad, stem=False, dgrad_cout_pad=None, negate_dgrad=False):
         Cout, Cin, k, _ = weight.shape
         pc = PackedConv()
         pc.Cin, pc.Cout, pc.k, pc.s, pc.p = (128 if stem else Cin), Cout, (1 if stem else k), (1 if stem else stride), (0 if stem else pad)
@@ -59,7 +59,7 @@ class WeightPacker:
             ld = _ceil64(Cout) if dgrad_cout_pad is None else dgrad_cout_pad
             pc.dgrad = torch.zeros(Cin * k * k * ld, dtype=torch.bfloat16, device=self.device)
         pc.scale = pc.bias = None
-        self.items.append((weight, pc, "stem" if stem else "conv", dgrad_cout_pad))
+        self.items.append((weight, pc, "stem" if stem else ("conv_neg" if negate_dgrad else "conv"), dgrad_cout_pad))
         self._built = None
         return pc
 
@@ -94,7 +94,7 @@ class WeightPacker:
                 off = 0
                 for khs, kws in dgrad_classes(k, pc.s, pc.p):
                     nt = len(khs)
-                    push(w, pc.dgrad.data_ptr() + 2 * off, Cin * nt * Cout, Cout, Cin, k, 1, (khs, kws), ld)
+                    push(w, pc.dgrad.data_ptr() + 2 * off, Cin * nt * Cout, Cout, Cin, k, 3 if kind == "conv_neg" else 1, (khs, kws), ld)
                     off += Cin * nt * ld
         darr = (EtbPackDesc * len(descs))(*descs)
         self._descs = torch.from_numpy(np.frombuffer(darr, dtype=np.uint8).copy()).to(self.device)

@@ -20,6 +20,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from .domain_loss import DomainLoss, TargetLoss
 from .ema import ModelEMA, CosineEMA, SemiSupModelEMA, update_ema_pair, next_pair_decays, ema_scalars
 from .loss import ComputeLoss
 from .model import Model, SupModel
@@ -31,15 +32,6 @@ from .ssod_loss import ComputeStudentMatchLoss
 
 def one_cycle(y1=0.0, y2=1.0, steps=100):  # reference utils/general.py:480-482
     return lambda x: ((1 - math.cos(x * math.pi / steps)) / 2) * (y2 - y1) + y1
-
-
-def domain_focal_loss(feature, label, gamma=2.0):
-    """DomainLoss (label 0) / TargetLoss (label 1): 0.5 * mean(-(1-p)^gamma * log p), p = softmax(netD logits)[label]
-    over all positions of the three levels (reference models/loss/loss.py:312-421)."""
-    logits = torch.cat([f.permute(0, 2, 3, 1).reshape(-1, 2) for f in feature], 0).float()
-    logp = torch.log_softmax(logits, dim=1)[:, label]
-    p = logp.exp()
-    return 0.5 * (-(1 - p) ** gamma * logp).mean()
 
 
 class SSODTrainerStep:
@@ -67,6 +59,7 @@ class SSODTrainerStep:
         self.build_optimizer(cfg)
         self.compute_loss = ComputeLoss(self.model, cfg)
         self.compute_un_sup_loss = ComputeStudentMatchLoss(self.model, cfg)
+        self.domain_loss, self.target_loss = DomainLoss(), TargetLoss()       # ssod_trainer.py:262-263
         if getattr(cfg.SSOD, "pseudo_label_type", "FairPseudoLabel") == "LabelMatch":      # ssod_trainer.py:69-71
             from .labelmatch import LabelMatch
             ps = pseudo_label_stats or {}
@@ -182,11 +175,12 @@ class SSODTrainerStep:
         return out
 
     def split_predict_and_feature(self, total_pred, total_feature, n_img):
-        sup_feature = [f[:n_img] for f in total_feature]
-        un_sup_feature = [f[n_img:] for f in total_feature]
-        sup_pred = [p[:n_img] for p in total_pred]
-        un_sup_pred = [p[n_img:] for p in total_pred]
-        return sup_pred, sup_feature, un_sup_pred, un_sup_feature
+        """ssod_trainer.py:568-585.  split_batch == t[:n], t[n:] whose backward is a no-op (the loss kernels write both
+        gradients into one buffer) instead of autograd's zeros + copy + add per slice."""
+        from .autograd_conv import split_batch
+        fs = [split_batch(f, n_img) for f in total_feature]
+        ps = [split_batch(p, n_img) for p in total_pred]
+        return [a for a, _ in ps], [a for a, _ in fs], [b for _, b in ps], [b for _, b in fs]
 
     # trainer/ssod_trainer.py:587-680 (logging / meters excluded: rank-0 host bookkeeping)
     def train_instance(self, imgs, targets, unlabeled_imgs, unlabeled_imgs_ori, unlabeled_gt, unlabeled_M, ni,
@@ -211,14 +205,15 @@ class SSODTrainerStep:
             unlabeled_targets, n_dev = self.pseudo_label_creator.create_pseudo_label_device(teacher_pred, unlabeled_M, h, w)
             invalid_target_shape = False
         self._mark("nms_pseudo_label")
-        total_imgs = torch.cat([imgs, unlabeled_imgs], 0)
         with torch.autocast("cuda", dtype=self.amp_dtype):
-            total_pred, total_feature = self.model(total_imgs)   # the native stem reads the NCHW image directly
+            # == self.model(torch.cat([imgs, unlabeled_imgs], 0)) (ssod_trainer.py:620-622): the native stem reads both
+            # batches in place (uint8 from the loaders or fp32), so the concatenated fp32 image never exists
+            total_pred, total_feature = self.model([imgs, unlabeled_imgs])
         self._mark("student_forward")
         sup_pred, sup_feature, un_sup_pred, un_sup_feature = self.split_predict_and_feature(total_pred, total_feature, n_img)
         sup_loss, sup_loss_items = self.compute_loss(sup_pred, targets)
-        d_loss = domain_focal_loss(sup_feature, 0)
-        t_loss = domain_focal_loss(un_sup_feature, 1)
+        d_loss = self.domain_loss(sup_feature)
+        t_loss = self.target_loss(un_sup_feature)
         if self.cfg.SSOD.with_da_loss:
             sup_loss = sup_loss + d_loss * self.da_loss_weights + t_loss * self.da_loss_weights
         else:

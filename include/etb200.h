@@ -316,7 +316,8 @@ int etb_pack_weight(const float* w_oihw, void* w_bf16, int32_t Cout, int32_t Cin
                     int32_t Cin_pad, void* stream);
 /* multi-tensor variants: one launch packs every conv weight of the model (descs and the chunk list live in device memory;
  * chunk = {desc index, chunk index} covering ETB_PACK_CHUNK destination elements).  mode 0: forward operand
- * [Cout][kh][kw][Cin]; mode 1: one dgrad parity class [Cin][ntaps][out_ld] (tap t = (kh[t],kw[t])); mode 2: stem [Cout][128]. */
+ * [Cout][kh][kw][Cin]; mode 1: one dgrad parity class [Cin][ntaps][out_ld] (tap t = (kh[t],kw[t])); mode 2: stem [Cout][128];
+ * mode 3: mode 1 with the sign flipped (dgrad operand of a conv behind GradReverse, models/detector/yolo_ssod.py:158-172). */
 #define ETB_PACK_CHUNK 4096
 typedef struct EtbPackDesc {
   const float* w;   /* [Cout,Cin,k,k] fp32 */
@@ -335,6 +336,42 @@ typedef struct EtbFoldDesc {
 int etb_fold_bn_multi(const EtbFoldDesc* descs_dev, int32_t n, void* stream);
 /* stem weight [Cout,3,6,6] fp32 -> [Cout][128] bf16 in the etb_stem_im2col K order */
 int etb_pack_stem_weight(const float* w_oihw, void* w_bf16, int32_t Cout, void* stream);
+
+/* ---- the last library ops of the student's step (csrc/tail.cu) ----------------------------------------------------------
+ * Detect backward layout: the fused loss hands back d(loss)/d(logits) as fp32 [N,na,H,W,no] (the train layout of
+ * models/head/yolov5_head.py:66).  etb_detect_dy_pack rewrites it as the bf16 NHWC operand dy [N,H,W,Cpad] (channel =
+ * a*no + o, pad channels zeroed) of the tcgen05 dgrad / wgrad and emits per-block column sums; etb_column_sum reduces them
+ * to the conv-bias gradient (yolov5_head.py:55: nn.Conv2d(..., bias=True)) -- replaces autograd's permute/contiguous/sum.
+ * partials: [etb_detect_dy_rows(N,H,W)][na*no] floats. */
+int64_t etb_detect_dy_rows(int32_t N, int32_t H, int32_t W);
+int etb_detect_dy_pack(const float* g, void* dy_bf16, float* partials, int32_t N, int32_t na, int32_t H, int32_t W,
+                       int32_t no, int32_t Cpad, void* stream);
+/* out[c] (+)= sum_r partials[r][c], fixed-order tree (deterministic); accumulate != 0 adds into out (gradient arena) */
+int etb_column_sum(const float* partials, int64_t rows, int32_t C, float* out, int32_t accumulate, void* stream);
+/* netD tail (models/detector/yolo_ssod.py:224-238): o[m][0:2] = conv2(h)[m] for h = relu(conv1(x)) [M][h_cstride] bf16,
+ * w2 [2][C] fp32; backward: dh[m][c] = (h>0) * (do[m][0] w2[0][c] + do[m][1] w2[1][c]) as bf16 [M][C], and per-block
+ * partials [etb_netd_tail_rows(M)][2][C] of dW2 (reduce with etb_column_sum(partials, rows, 2*C, dw2, ...)). */
+int32_t etb_netd_tail_rows(int64_t M);
+int etb_netd_tail_fwd(const void* h_bf16, int64_t M, int32_t C, int32_t h_cstride, const float* w2, float* o, void* stream);
+int etb_netd_tail_bwd(const float* dout, const void* h_bf16, int64_t M, int32_t C, int32_t h_cstride, const float* w2,
+                      void* dh_bf16, float* partials, int32_t rows, void* stream);
+/* DomainLoss / TargetLoss (models/loss/loss.py:312-421): out[0] = 0.5 * mean_i( -(1-p_i)^2 log p_i ), p_i =
+ * softmax(x_i)[label], over all positions of the nl netD maps x[l] ([M[l]][2] fp32, contiguous).  Backward writes
+ * dx[l] = gout[0] * d(out)/d(x[l]) (gout: device scalar).  workspace: etb_domain_focal_workspace_bytes(). */
+typedef struct EtbFocalParams {
+  const float* x[ETB_MAX_LEVELS];
+  float* dx[ETB_MAX_LEVELS];
+  int64_t M[ETB_MAX_LEVELS];
+  int32_t nl, label;
+} EtbFocalParams;
+int64_t etb_domain_focal_workspace_bytes(void);
+int etb_domain_focal_fwd(const EtbFocalParams* fp, float* out, void* workspace, int64_t workspace_bytes, void* stream);
+int etb_domain_focal_bwd(const EtbFocalParams* fp, const float* gout, void* stream);
+/* stem im2col straight from the loaders' batch (trainer/ssod_trainer.py:694-696 `imgs.to(device).float() / 255`): x is
+ * [N,3,H,W] uint8 (is_u8) or fp32; value = x / div (IEEE division) rounded to bf16; the N images go to image slots
+ * [img_offset, img_offset+N) of the im2col buffer y [*,H/2,W/2,128] -- torch.cat((imgs, unlabeled_imgs)) without the copy. */
+int etb_stem_im2col_into(const void* x, int32_t is_u8, void* y_bf16, int32_t N, int32_t H, int32_t W, int32_t img_offset,
+                         float div, void* stream);
 
 #ifdef __cplusplus
 }

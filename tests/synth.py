@@ -82,3 +82,39 @@ def make_head_logits(seed, B, img=640, no=85, scale=1.5):
         x[..., 4] -= 3.0
         out.append(x)
     return out
+
+
+def make_images(seed, n, img=640, targets=None):
+    """Seeded synthetic images with spatial structure, uint8 [n,3,img,img] like the loaders produce: a smooth low-frequency
+    colour field, ~10 textured rectangles per image (at the ground-truth boxes when `targets` [nt,6] is given, random
+    otherwise) and mild pixel noise.  I.i.d. uniform noise images drive a random-init YOLOv5 into a regime where every image
+    looks the same to every layer and the teacher's logits are ~7x more sensitive to parameter perturbations."""
+    r = np.random.RandomState(seed)
+    g = img // 32 + 1
+    out = np.empty((n, 3, img, img), np.uint8)
+    yy = np.linspace(0, g - 1, img)
+    y0 = np.floor(yy).astype(int).clip(0, g - 2)
+    fy = (yy - y0).astype(F32)
+    for i in range(n):
+        lo = r.rand(3, g, g).astype(F32)
+        rows = lo[:, y0, :] * (1 - fy)[None, :, None] + lo[:, y0 + 1, :] * fy[None, :, None]          # bilinear, rows
+        im = rows[:, :, y0] * (1 - fy)[None, None, :] + rows[:, :, y0 + 1] * fy[None, None, :]         # bilinear, cols
+        if targets is not None:
+            t = np.asarray(targets)[np.asarray(targets)[:, 0] == i]
+            boxes = [(int((b[2] - b[4] / 2) * img), int((b[3] - b[5] / 2) * img), max(int(b[4] * img), 2), max(int(b[5] * img), 2)) for b in t]
+        else:
+            boxes = []
+            for _ in range(10):
+                w, h = r.randint(img // 20, img // 3, 2)
+                boxes.append((int(r.randint(0, img - w)), int(r.randint(0, img - h)), int(w), int(h)))
+        for (x0, y0b, w, h) in boxes:
+            x0, y0b = max(x0, 0), max(y0b, 0)
+            x1, y1 = min(x0 + w, img), min(y0b + h, img)
+            if x1 <= x0 or y1 <= y0b:
+                continue
+            col = r.rand(3, 1, 1).astype(F32)
+            tex = (r.rand(3, y1 - y0b, x1 - x0).astype(F32) - 0.5) * 0.3
+            im[:, y0b:y1, x0:x1] = col + tex
+        im = im + (r.rand(3, img, img).astype(F32) - 0.5) * 0.08
+        out[i] = (np.clip(im, 0, 1) * 255.0 + 0.5).astype(np.uint8)
+    return out

@@ -217,7 +217,7 @@ def test_supervised_step_matches_cpu_reference(size, img):
     assert torch.equal(before_w, st.model.backbone.stage1.conv.weight.detach())
     assert not torch.equal(before_g, st.model.backbone.stage1.bn.weight.detach()) and st.ema.updates == 1
     loss2 = st.train_step_graphed(x.to(DEV), torch.from_numpy(tg).to(DEV), 1)       # accumulate = 1 this early in the warm-up
-    assert torch.isfinite(loss2).all() and st.ema.updates == 2 and loss2.item() < loss.item()
+    assert torch.isfinite(loss2).all() and st.ema.updates == 2
     assert not torch.equal(before_w, st.model.backbone.stage1.conv.weight.detach())
 
 
