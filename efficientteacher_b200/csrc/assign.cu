@@ -18,6 +18,7 @@ __global__ void __launch_bounds__(1024) select_targets_kernel(const double* __re
                                                               int32_t n_host, int32_t cap, const double* __restrict__ thr_high,
                                                               const double* __restrict__ thr_low, int32_t nc, int32_t with_obj,
                                                               float* __restrict__ out, int32_t* __restrict__ out_cnt) {
+  ETB_PDL_PROLOGUE();
   __shared__ int sscan[33];
   int n = n_dev ? *n_dev : n_host;
   if (n > cap) n = cap;
@@ -61,7 +62,7 @@ extern "C" int etb_select_targets(const double* rows, const int32_t* n_dev, int3
                                   const double* thr_high, const double* thr_low, int32_t nc, int32_t with_obj,
                                   float* out, int32_t* out_cnt, void* stream) {
   ETB_CHECK_ARG(rows && thr_high && thr_low && out && out_cnt && cap > 0 && nc > 0);
-  select_targets_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(rows, n_dev, n_host, cap, thr_high, thr_low, nc, with_obj, out, out_cnt);
+  etb_launch(select_targets_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, rows, n_dev, n_host, cap, thr_high, thr_low, nc, with_obj, out, out_cnt);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }
@@ -89,6 +90,7 @@ struct AssignArgs {
 };
 
 __global__ void __launch_bounds__(1024) build_targets_kernel(const AssignArgs A) {
+  ETB_PDL_PROLOGUE();
   __shared__ int sscan[33];
   const int l = blockIdx.x;
   const int nx = A.lv.nx[l], ny = A.lv.ny[l];
@@ -176,7 +178,7 @@ extern "C" int etb_build_targets(const float* targets, const int32_t* nt_dev, in
   A.lv = *lv;
   A.out = *out;
   for (int l = 0; l < lv->nl; ++l) ETB_CHECK_ARG(out->cap == 0 || (out->idx[l] && out->tbox[l] && out->anch[l] && out->tcls[l]));
-  build_targets_kernel<<<lv->nl, 1024, 0, (cudaStream_t)stream>>>(A);
+  etb_launch(build_targets_kernel, dim3(lv->nl), dim3(1024), 0, (cudaStream_t)stream, A);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }

@@ -131,6 +131,7 @@ __device__ __forceinline__ void reduce_partials(const float* __restrict__ partia
 
 // ---- forward statistics: sums[0][c] = sum y, sums[1][c] = sum y^2 ----
 __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const __nv_bfloat16* __restrict__ y, int M, int C, int cs, float* __restrict__ sums) {
+  ETB_PDL_PROLOGUE();
   channel_reduce<2, 8, uint4>(M, C, [&](int r, int g) { return ldg_stream(y + (size_t)r * cs + g * 8); },
                               [&](const uint4 v, float (*acc)[8]) {
     float f[8];
@@ -148,6 +149,7 @@ __global__ void __launch_bounds__(BNR_CH * BNR_GR) bn_finalize_kernel(const floa
                                                                        float* __restrict__ running_var, float* __restrict__ scale,
                                                                        float* __restrict__ shift, float* __restrict__ mean_out,
                                                                        float* __restrict__ invstd_out) {
+  ETB_PDL_PROLOGUE();
   const int c = blockIdx.x * BNR_CH + threadIdx.x;
   float sum = 0.f, sumsq = 0.f;
   reduce_partials<BNR_CH, BNR_GR>(partials, nb, C, c, &sum, &sumsq);
@@ -192,6 +194,7 @@ __device__ __forceinline__ float dsilu_f(float z) {
 __global__ void __launch_bounds__(BN_THREADS) bn_act_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                                                                   const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, long M, int C,
                                                                   int ycs, int ocs, int act, const __nv_bfloat16* __restrict__ res, int rcs) {
+  ETB_PDL_PROLOGUE();
   const int G = C >> 3;
   const int lg = 31 - __clz(G);            // G is a power of two (checked on the host): no 64-bit divisions
   const long total = M * G;
@@ -240,6 +243,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_act_bwd_reduce_kernel(const __n
                                                                        const float* __restrict__ scale, const float* __restrict__ shift,
                                                                        const float* __restrict__ mean, const float* __restrict__ invstd, int M,
                                                                        int C, int dacs, int ycs, int act, float* __restrict__ sums) {
+  ETB_PDL_PROLOGUE();
   // per-thread channel group is fixed: hoist its parameters out of the row loop
   float sc[8], sh[8], mu[8], is[8];
   {
@@ -272,6 +276,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_act_bwd_reduce_kernel(const __n
 template <int BNR_CH, int BNR_GR>
 __global__ void __launch_bounds__(BNR_CH * BNR_GR) bn_bwd_finalize_kernel(const float* __restrict__ partials, int nb, int C, float* __restrict__ sums,
                                                                            float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
+  ETB_PDL_PROLOGUE();
   const int c = blockIdx.x * BNR_CH + threadIdx.x;
   float s0 = 0.f, s1 = 0.f;
   reduce_partials<BNR_CH, BNR_GR>(partials, nb, C, c, &s0, &s1);
@@ -295,6 +300,7 @@ __global__ void __launch_bounds__(BN_THREADS, 3) bn_act_bwd_apply_kernel(const _
                                                                       const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                       const float* __restrict__ sums, long M, int C, int dacs, int ycs, int ocs,
                                                                       int act, __nv_bfloat16* __restrict__ dy) {
+  ETB_PDL_PROLOGUE();
   const int G = C >> 3;
   const int lg = 31 - __clz(G);
   const long total = M * G;
@@ -389,7 +395,7 @@ extern "C" int32_t etb_bn_partial_rows(int64_t M, int32_t C, int32_t which) {
 extern "C" int etb_bn_stats(const void* y_bf16, int64_t M, int32_t C, int32_t y_cstride, float* partials, int32_t rows, void* stream) {
   ETB_CHECK_ARG(y_bf16 && partials && M > 0 && M < (1ll << 31) && bn_c_ok(C) && y_cstride % 8 == 0 && y_cstride >= C);
   ETB_CHECK_ARG(rows == etb_bn_partial_rows(M, C, 0));
-  bn_stats_kernel<<<(unsigned)rows, BN_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)y_bf16, (int)M, C, y_cstride, partials);
+  etb_launch(bn_stats_kernel, dim3((unsigned)rows), dim3(BN_THREADS), 0, (cudaStream_t)stream, (const __nv_bfloat16*)y_bf16, (int)M, C, y_cstride, partials);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }
@@ -399,10 +405,10 @@ extern "C" int etb_bn_finalize(const float* partials, int32_t rows, int64_t M, i
                                void* stream) {
   ETB_CHECK_ARG(partials && rows > 0 && gamma && beta && scale && shift && mean && invstd && M > 0 && C > 0);
   if (C <= 256)
-    bn_finalize_kernel<8, 128><<<(C + 7) / 8, dim3(8, 128), 0, (cudaStream_t)stream>>>(partials, rows, (int)M, C, gamma, beta, eps, momentum, running_mean,
+    etb_launch(bn_finalize_kernel<8, 128>, dim3((C + 7) / 8), dim3(dim3(8, 128)), 0, (cudaStream_t)stream, partials, rows, (int)M, C, gamma, beta, eps, momentum, running_mean,
                                                                                       running_var, scale, shift, mean, invstd);
   else
-    bn_finalize_kernel<32, 32><<<(C + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(partials, rows, (int)M, C, gamma, beta, eps, momentum, running_mean,
+    etb_launch(bn_finalize_kernel<32, 32>, dim3((C + 31) / 32), dim3(dim3(32, 32)), 0, (cudaStream_t)stream, partials, rows, (int)M, C, gamma, beta, eps, momentum, running_mean,
                                                                                         running_var, scale, shift, mean, invstd);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
@@ -413,8 +419,7 @@ extern "C" int etb_bn_act_apply_res(const void* y_bf16, const float* scale, cons
                                     void* stream) {
   ETB_CHECK_ARG(y_bf16 && scale && shift && out_bf16 && M > 0 && bn_c_ok(C) && y_cstride % 8 == 0 && out_cstride % 8 == 0);
   ETB_CHECK_ARG(!res_bf16 || (res_cstride % 8 == 0 && res_cstride >= C));
-  bn_act_apply_kernel<<<bn_grid(M * (C / 8), BN_WAVE(bn_act_apply_kernel)), BN_THREADS, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)y_bf16, scale, shift, (__nv_bfloat16*)out_bf16, (long)M, C, y_cstride, out_cstride, act,
+  etb_launch(bn_act_apply_kernel, dim3(bn_grid(M * (C / 8), BN_WAVE(bn_act_apply_kernel))), dim3(BN_THREADS), 0, (cudaStream_t)stream, (const __nv_bfloat16*)y_bf16, scale, shift, (__nv_bfloat16*)out_bf16, (long)M, C, y_cstride, out_cstride, act,
       (const __nv_bfloat16*)res_bf16, res_cstride);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
@@ -430,8 +435,7 @@ extern "C" int etb_bn_act_bwd_reduce(const void* da_bf16, const void* y_bf16, co
                                      float* partials, int32_t rows, void* stream) {
   ETB_CHECK_ARG(da_bf16 && y_bf16 && scale && shift && mean && invstd && partials && M > 0 && M < (1ll << 31) && bn_c_ok(C));
   ETB_CHECK_ARG(da_cstride % 8 == 0 && y_cstride % 8 == 0 && rows == etb_bn_partial_rows(M, C, 1));
-  bn_act_bwd_reduce_kernel<<<(unsigned)rows, BN_THREADS, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)da_bf16, (const __nv_bfloat16*)y_bf16, scale, shift, mean, invstd, (int)M, C, da_cstride, y_cstride, act, partials);
+  etb_launch(bn_act_bwd_reduce_kernel, dim3((unsigned)rows), dim3(BN_THREADS), 0, (cudaStream_t)stream, (const __nv_bfloat16*)da_bf16, (const __nv_bfloat16*)y_bf16, scale, shift, mean, invstd, (int)M, C, da_cstride, y_cstride, act, partials);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }
@@ -442,9 +446,9 @@ extern "C" int etb_bn_act_bwd_finalize(const float* partials, int32_t rows, int3
                                        int32_t accumulate, void* stream) {
   ETB_CHECK_ARG(partials && rows > 0 && C > 0 && sums && dgamma && dbeta);
   if (C <= 256)
-    bn_bwd_finalize_kernel<8, 128><<<(C + 7) / 8, dim3(8, 128), 0, (cudaStream_t)stream>>>(partials, rows, C, sums, dgamma, dbeta, accumulate);
+    etb_launch(bn_bwd_finalize_kernel<8, 128>, dim3((C + 7) / 8), dim3(dim3(8, 128)), 0, (cudaStream_t)stream, partials, rows, C, sums, dgamma, dbeta, accumulate);
   else
-    bn_bwd_finalize_kernel<32, 32><<<(C + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(partials, rows, C, sums, dgamma, dbeta, accumulate);
+    etb_launch(bn_bwd_finalize_kernel<32, 32>, dim3((C + 31) / 32), dim3(dim3(32, 32)), 0, (cudaStream_t)stream, partials, rows, C, sums, dgamma, dbeta, accumulate);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }
@@ -454,8 +458,7 @@ extern "C" int etb_bn_act_bwd_apply(const void* da_bf16, const void* y_bf16, con
                                     int32_t dy_cstride, int32_t act, void* dy_bf16, void* stream) {
   ETB_CHECK_ARG(da_bf16 && y_bf16 && scale && shift && mean && invstd && sums && dy_bf16 && M > 0 && bn_c_ok(C));
   ETB_CHECK_ARG(da_cstride % 8 == 0 && y_cstride % 8 == 0 && dy_cstride % 8 == 0);
-  bn_act_bwd_apply_kernel<<<bn_grid(M * (C / 8), BN_WAVE(bn_act_bwd_apply_kernel)), BN_THREADS, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)da_bf16, (const __nv_bfloat16*)y_bf16, scale, shift, mean, invstd, sums, (long)M, C, da_cstride, y_cstride, dy_cstride,
+  etb_launch(bn_act_bwd_apply_kernel, dim3(bn_grid(M * (C / 8), BN_WAVE(bn_act_bwd_apply_kernel))), dim3(BN_THREADS), 0, (cudaStream_t)stream, (const __nv_bfloat16*)da_bf16, (const __nv_bfloat16*)y_bf16, scale, shift, mean, invstd, sums, (long)M, C, da_cstride, y_cstride, dy_cstride,
       act, (__nv_bfloat16*)dy_bf16);
   ETB_CHECK_LAUNCH();
   return ETB_OK;

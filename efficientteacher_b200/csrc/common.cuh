@@ -6,6 +6,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include "../../include/etb200.h"
 
 void etb_set_error(const char* fmt, ...);
@@ -37,6 +38,48 @@ void etb_count_launch();   // every ETB_CHECK_LAUNCH() follows exactly one kerne
       return ETB_ERR_CUDA;                                                               \
     }                                                                                    \
   } while (0)
+
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------------------
+// Every kernel of the library is launched with cudaLaunchAttributeProgrammaticStreamSerialization and starts with
+// ETB_PDL_PROLOGUE(): `griddepcontrol.wait` (returns when the preceding kernel of the stream has completed and its memory is
+// visible -- so no kernel touches global data before its producer is done) followed by `griddepcontrol.launch_dependents`
+// (the NEXT kernel's CTAs may be scheduled as soon as all CTAs of this one have passed this point or exited).  The next
+// kernel's launch latency, block scheduling and prologue (smem carve-up, mbarrier init, TMEM allocation, tensor-map
+// prefetch: the tcgen05 kernels place the wait after that prologue) thereby overlap this kernel's execution instead of
+// following its tail; with ~1300 kernels per step, many of them 3-10 us long, the launch gaps were a measurable part of
+// the step.  A kernel launched without the attribute (ETB_PDL=0, or a neighbour from another library) sees both instructions
+// as no-ops / full stream order, so mixing is safe.  Captured CUDA graphs keep the programmatic edges.
+#define ETB_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define ETB_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define ETB_PDL_PROLOGUE() \
+  do {                     \
+    ETB_PDL_WAIT();        \
+    ETB_PDL_TRIGGER();     \
+  } while (0)
+
+static inline bool etb_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ETB_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+template <typename... KP, typename... A>
+static inline void etb_launch(void (*kernel)(KP...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = etb_pdl_enabled() ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KP>(args)...);    // the caller checks cudaGetLastError() (ETB_CHECK_LAUNCH)
+}
 
 static inline int etb_num_sms() {
   static int sms = 0;

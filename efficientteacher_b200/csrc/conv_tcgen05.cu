@@ -363,6 +363,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ETB_PDL_PROLOGUE();      // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -550,6 +551,7 @@ conv_fwd2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   cluster_sync_all();                                // both CTAs' barriers + TMEM exist before any cross-CTA traffic
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ETB_PDL_PROLOGUE();      // prologue above overlapped the previous kernel's tail; no global data touched before this
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs: own A tile, own half of B; bytes are accounted on the leader's full barrier) =====
@@ -652,10 +654,12 @@ static int launch_conv2_e(const CUtensorMap& mA, const CUtensorMap& mB, const Co
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = dim3(CONV_THREADS); cfg.dynamicSmemBytes = L::TOTAL; cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = etb_pdl_enabled() ? 2 : 1;
   ETB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_fwd2_kernel<BN, STAGES, EPI>, mA, mB, ka));
   etb_count_launch();
   return ETB_OK;
@@ -705,7 +709,7 @@ static int launch_conv_e(const CUtensorMap& mA, const CUtensorMap& mB, const Con
     ETB_CHECK_CUDA(cudaFuncSetAttribute(conv_fwd_kernel<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_set = true;
   }
-  conv_fwd_kernel<BN, STAGES, EPI><<<grid, CONV_THREADS, L::TOTAL, st>>>(mA, mB, ka);
+  etb_launch(conv_fwd_kernel<BN, STAGES, EPI>, dim3(grid), dim3(CONV_THREADS), L::TOTAL, st, mA, mB, ka);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }
@@ -878,6 +882,7 @@ extern "C" int64_t etb_dgrad_weight_elems(int32_t Cout, int32_t Cin, int32_t k, 
 
 struct TapTable { signed char v[24]; };
 __global__ void __launch_bounds__(256) pack_weight_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o, int Cout, int Coutp, int Cin, int k, int ntaps, TapTable tt) {
+  ETB_PDL_PROLOGUE();
   const int64_t total = (int64_t)Cin * ntaps * Coutp;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int co = (int)(e % Coutp);
@@ -902,7 +907,7 @@ extern "C" int etb_pack_weight_dgrad(const float* w_oihw, void* out_bf16, int32_
       const int64_t total = (int64_t)Cin * nt * Coutp;
       int64_t blocks = (total + 255) / 256;
       if (blocks > 148 * 16) blocks = 148 * 16;
-      pack_weight_dgrad_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, o, Cout, Coutp, Cin, k, nt, tt);
+      etb_launch(pack_weight_dgrad_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, w_oihw, o, Cout, Coutp, Cin, k, nt, tt);
       ETB_CHECK_LAUNCH();
       o += total;
     }
@@ -1050,6 +1055,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ 
   tc_fence_after();
   if (CL) cluster_sync_all();            // every CTA's barriers are initialised before any remote complete_tx / arrive
   const uint32_t tmem_base = *tmem_slot;
+  ETB_PDL_PROLOGUE();      // prologue above overlapped the previous kernel's tail; no global data touched before this
   const uint32_t box_bytes = (uint32_t)a.kpix * 128u;   // bytes one TMA box writes (all rows, OOB rows zero-filled)
 
   if (warp == 0) {
@@ -1160,15 +1166,17 @@ static int launch_wgrad(const CUtensorMap& mDy, const CUtensorMap& mX, const Wgr
   if (CL) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = dim3(WGRAD_THREADS); cfg.dynamicSmemBytes = L::TOTAL; cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = etb_pdl_enabled() ? 2 : 1;
     ETB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, wgrad_kernel<MT, BN, KP, STAGES, CL>, mDy, mX, wa));
     etb_count_launch();
     return ETB_OK;
   }
-  wgrad_kernel<MT, BN, KP, STAGES, CL><<<grid, WGRAD_THREADS, L::TOTAL, st>>>(mDy, mX, wa);
+  etb_launch(wgrad_kernel<MT, BN, KP, STAGES, CL>, dim3(grid), dim3(WGRAD_THREADS), L::TOTAL, st, mDy, mX, wa);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }
@@ -1180,6 +1188,7 @@ static int launch_wgrad(const CUtensorMap& mDy, const CUtensorMap& mX, const Wgr
 template <int SG>
 __global__ void __launch_bounds__(32 * SG) wgrad_reduce_kernel(const float* __restrict__ ws, long slice, int splitk, float* __restrict__ out, int Cout,
                                                                int Cin, int kk, int flags) {
+  ETB_PDL_PROLOGUE();
   __shared__ float4 red[SG][32];
   const long n4 = (long)Cout * kk * Cin / 4;
   const int lane = threadIdx.x, sg = threadIdx.y;
@@ -1246,6 +1255,7 @@ __global__ void __launch_bounds__(32 * SG) wgrad_reduce_kernel(const float* __re
 // scatter cost 8x sector amplification on both the read-modify-write and the store (60 us per 3x3 layer).
 __global__ void __launch_bounds__(256) wgrad_reduce_taps_kernel(const float* __restrict__ ws, long slice, int splitk, float* __restrict__ out, int Cin,
                                                                 int kk, int flags) {
+  ETB_PDL_PROLOGUE();
   __shared__ float sm[64 * 12];
   const int CW = Cin < 64 ? Cin : 64;            // channels per block (Cin is a multiple of 64, or smaller than 64 and of 8)
   const int L4 = CW >> 2;                        // float4 lanes per tap
@@ -1413,14 +1423,14 @@ extern "C" int etb_conv_wgrad(const void* x_bf16, const void* dy_bf16, float* dw
   const long cap = (long)etb_num_sms() * 16;
   if (blocks > cap) blocks = cap;
   if (wa.ntaps > 1 && !(flags & 1))
-    wgrad_reduce_taps_kernel<<<(unsigned)(cp->Cout * (cp->Cin < 64 ? 1 : cp->Cin >> 6)), 256, 0, st>>>((const float*)workspace, (long)dw_elems, splitk, dw_f32, cp->Cin, wa.ntaps,
+    etb_launch(wgrad_reduce_taps_kernel, dim3((unsigned)(cp->Cout * (cp->Cin < 64 ? 1 : cp->Cin >> 6))), dim3(256), 0, st, (const float*)workspace, (long)dw_elems, splitk, dw_f32, cp->Cin, wa.ntaps,
                                                                                   flags);
   else if (splitk >= 32)
-    wgrad_reduce_kernel<16><<<(unsigned)blocks, dim3(32, 16), 0, st>>>((const float*)workspace, (long)dw_elems, splitk, dw_f32, cp->Cout, cp->Cin, wa.ntaps, flags);
+    etb_launch(wgrad_reduce_kernel<16>, dim3((unsigned)blocks), dim3(dim3(32, 16)), 0, st, (const float*)workspace, (long)dw_elems, splitk, dw_f32, cp->Cout, cp->Cin, wa.ntaps, flags);
   else if (splitk >= 6)
-    wgrad_reduce_kernel<4><<<(unsigned)blocks, dim3(32, 4), 0, st>>>((const float*)workspace, (long)dw_elems, splitk, dw_f32, cp->Cout, cp->Cin, wa.ntaps, flags);
+    etb_launch(wgrad_reduce_kernel<4>, dim3((unsigned)blocks), dim3(dim3(32, 4)), 0, st, (const float*)workspace, (long)dw_elems, splitk, dw_f32, cp->Cout, cp->Cin, wa.ntaps, flags);
   else
-    wgrad_reduce_kernel<1><<<(unsigned)blocks, dim3(32, 1), 0, st>>>((const float*)workspace, (long)dw_elems, splitk, dw_f32, cp->Cout, cp->Cin, wa.ntaps, flags);
+    etb_launch(wgrad_reduce_kernel<1>, dim3((unsigned)blocks), dim3(dim3(32, 1)), 0, st, (const float*)workspace, (long)dw_elems, splitk, dw_f32, cp->Cout, cp->Cin, wa.ntaps, flags);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }

@@ -15,6 +15,7 @@ struct DecodeArgs {
 };
 
 __global__ void __launch_bounds__(256) detect_decode_kernel(const DecodeArgs A) {
+  ETB_PDL_PROLOGUE();
   const int64_t per_img = (int64_t)A.na * A.ny * A.nx * A.no;
   const int64_t total = per_img * A.B;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -56,7 +57,7 @@ extern "C" int etb_detect_decode(const float* logits, float* pred, int32_t B, in
   int64_t blocks = (total + 255) / 256;
   const int64_t maxb = (int64_t)etb_num_sms() * 16;
   if (blocks > maxb) blocks = maxb;
-  detect_decode_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(A);
+  etb_launch(detect_decode_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, A);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }

@@ -13,6 +13,7 @@ __device__ __forceinline__ float ema1(float v, float m, float d, float omd) {
 // `dev` (optional): {d, 1-d, d2, 1-d2} in device memory -- lets a captured CUDA graph replay with a new decay each step
 __global__ void __launch_bounds__(256) ema_kernel(const EtbEmaChunk* __restrict__ tab, float d, float omd, float d2, float omd2,
                                                   const float* __restrict__ dev) {
+  ETB_PDL_PROLOGUE();
   if (dev) { d = dev[0]; omd = dev[1]; d2 = dev[2]; omd2 = dev[3]; }
   const EtbEmaChunk c = tab[blockIdx.x];
   float* __restrict__ v = c.v;
@@ -100,7 +101,7 @@ extern "C" int etb_ema_update(const EtbEmaChunk* table_dev, int64_t n_chunks, fl
                               float one_minus_d2, void* stream) {
   ETB_CHECK_ARG(table_dev != nullptr && n_chunks >= 0 && n_chunks < (1ll << 31));
   if (n_chunks == 0) return ETB_OK;
-  ema_kernel<<<(unsigned)n_chunks, 256, 0, (cudaStream_t)stream>>>(table_dev, d, one_minus_d, d2, one_minus_d2, nullptr);
+  etb_launch(ema_kernel, dim3((unsigned)n_chunks), dim3(256), 0, (cudaStream_t)stream, table_dev, d, one_minus_d, d2, one_minus_d2, nullptr);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }
@@ -108,7 +109,7 @@ extern "C" int etb_ema_update(const EtbEmaChunk* table_dev, int64_t n_chunks, fl
 extern "C" int etb_ema_update_dev(const EtbEmaChunk* table_dev, int64_t n_chunks, const float* scalars4_dev, void* stream) {
   ETB_CHECK_ARG(table_dev != nullptr && scalars4_dev != nullptr && n_chunks >= 0 && n_chunks < (1ll << 31));
   if (n_chunks == 0) return ETB_OK;
-  ema_kernel<<<(unsigned)n_chunks, 256, 0, (cudaStream_t)stream>>>(table_dev, 0.f, 0.f, 0.f, 0.f, scalars4_dev);
+  etb_launch(ema_kernel, dim3((unsigned)n_chunks), dim3(256), 0, (cudaStream_t)stream, table_dev, 0.f, 0.f, 0.f, 0.f, scalars4_dev);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }

@@ -31,6 +31,7 @@ __device__ __forceinline__ uint4 g_pack8(const float* f) {
 // ---- max pool 5x5 s1 p2 with argmax (window position (dy+2)*5+(dx+2), first maximum in scan order wins like ATen) ----
 __global__ void __launch_bounds__(256) maxpool5_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                                            uint8_t* __restrict__ idx, int N, int H, int W, int C, int xcs, int ycs) {
+  ETB_PDL_PROLOGUE();
   const int cg = C >> 3;
   const int64_t total = (int64_t)N * H * W * cg;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -69,6 +70,7 @@ __global__ void __launch_bounds__(256) maxpool5_fwd_kernel(const __nv_bfloat16* 
 __global__ void __launch_bounds__(256) maxpool5_bwd_kernel(const __nv_bfloat16* __restrict__ src, const uint8_t* __restrict__ idx,
                                                            const __nv_bfloat16* __restrict__ add, __nv_bfloat16* __restrict__ out, int N, int H,
                                                            int W, int C, int scs, int acs, int ocs) {
+  ETB_PDL_PROLOGUE();
   const int cg = C >> 3;
   const int64_t total = (int64_t)N * H * W * cg;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -114,8 +116,7 @@ extern "C" int etb_maxpool5_fwd(const void* x_bf16, void* y_bf16, uint8_t* idx, 
                                 int32_t x_cstride, int32_t y_cstride, void* stream) {
   ETB_CHECK_ARG(x_bf16 && y_bf16 && idx && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && x_cstride % 8 == 0 && y_cstride % 8 == 0);
   ETB_CHECK_ARG(x_cstride >= C && y_cstride >= C);
-  maxpool5_fwd_kernel<<<glue_grid((int64_t)N * H * W * (C / 8)), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x_bf16, (__nv_bfloat16*)y_bf16, idx, N, H, W, C, x_cstride, y_cstride);
+  etb_launch(maxpool5_fwd_kernel, dim3(glue_grid((int64_t)N * H * W * (C / 8))), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x_bf16, (__nv_bfloat16*)y_bf16, idx, N, H, W, C, x_cstride, y_cstride);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }
@@ -123,8 +124,7 @@ extern "C" int etb_maxpool5_bwd(const void* src_bf16, const uint8_t* idx, const 
                                 int32_t W, int32_t C, int32_t src_cstride, int32_t add_cstride, int32_t out_cstride, void* stream) {
   ETB_CHECK_ARG(src_bf16 && idx && out_bf16 && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0);
   ETB_CHECK_ARG(src_cstride % 8 == 0 && add_cstride % 8 == 0 && out_cstride % 8 == 0 && src_cstride >= C && out_cstride >= C);
-  maxpool5_bwd_kernel<<<glue_grid((int64_t)N * H * W * (C / 8)), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)src_bf16, idx, (const __nv_bfloat16*)add_bf16, (__nv_bfloat16*)out_bf16, N, H, W, C, src_cstride, add_cstride,
+  etb_launch(maxpool5_bwd_kernel, dim3(glue_grid((int64_t)N * H * W * (C / 8))), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)src_bf16, idx, (const __nv_bfloat16*)add_bf16, (__nv_bfloat16*)out_bf16, N, H, W, C, src_cstride, add_cstride,
       out_cstride);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
@@ -133,6 +133,7 @@ extern "C" int etb_maxpool5_bwd(const void* src_bf16, const uint8_t* idx, const 
 // ---- nearest 2x upsample backward: dx[n,h,w,:] = sum of the 2x2 block of dy (fp32 accumulate) ----
 __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int N, int H, int W,
                                                              int C, int dycs, int dxcs) {
+  ETB_PDL_PROLOGUE();
   const int cg = C >> 3;
   const int64_t total = (int64_t)N * H * W * cg;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -158,8 +159,7 @@ extern "C" int etb_upsample2x_bwd(const void* dy_bf16, void* dx_bf16, int32_t N,
                                   int32_t dx_cstride, void* stream) {
   ETB_CHECK_ARG(dy_bf16 && dx_bf16 && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && dy_cstride % 8 == 0 && dx_cstride % 8 == 0);
   ETB_CHECK_ARG(dy_cstride >= C && dx_cstride >= C);
-  upsample2x_bwd_kernel<<<glue_grid((int64_t)N * H * W * (C / 8)), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)dy_bf16, (__nv_bfloat16*)dx_bf16, N, H, W, C, dy_cstride, dx_cstride);
+  etb_launch(upsample2x_bwd_kernel, dim3(glue_grid((int64_t)N * H * W * (C / 8))), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)dy_bf16, (__nv_bfloat16*)dx_bf16, N, H, W, C, dy_cstride, dx_cstride);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }
@@ -167,6 +167,7 @@ extern "C" int etb_upsample2x_bwd(const void* dy_bf16, void* dx_bf16, int32_t N,
 // ---- channel-slice copy: y[m, 0:C] = x[m, 0:C] for M pixels, both sides with a channel stride ----
 __global__ void __launch_bounds__(256) copy_slice_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t M, int C, int xcs,
                                                          int ycs) {
+  ETB_PDL_PROLOGUE();
   const int cg = C >> 3;
   const int64_t total = M * cg;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(256) copy_slice_kernel(const __nv_bfloat16* __
 }
 extern "C" int etb_copy_slice_nhwc(const void* x_bf16, void* y_bf16, int64_t M, int32_t C, int32_t x_cstride, int32_t y_cstride, void* stream) {
   ETB_CHECK_ARG(x_bf16 && y_bf16 && M > 0 && C > 0 && C % 8 == 0 && x_cstride % 8 == 0 && y_cstride % 8 == 0 && x_cstride >= C && y_cstride >= C);
-  copy_slice_kernel<<<glue_grid(M * (C / 8)), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x_bf16, (__nv_bfloat16*)y_bf16, M, C, x_cstride,
+  etb_launch(copy_slice_kernel, dim3(glue_grid(M * (C / 8))), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x_bf16, (__nv_bfloat16*)y_bf16, M, C, x_cstride,
                                                                              y_cstride);
   ETB_CHECK_LAUNCH();
   return ETB_OK;

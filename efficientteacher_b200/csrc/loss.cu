@@ -97,6 +97,7 @@ __device__ __forceinline__ int64_t cell_index(const EtbLossParams& lp, int l, co
 // -------------------------------------------------------------------------------------------------
 template <bool BWD>
 __global__ void __launch_bounds__(256) loss_rows_kernel(LossPtrs P, EtbLossParams lp, LossSets S, LossWs ws, const float* __restrict__ gscale_dev) {
+  ETB_PDL_PROLOGUE();
   const int lane = threadIdx.x & 31;
   const int nwarps = gridDim.x * (blockDim.x >> 5);
   const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -180,6 +181,7 @@ __device__ __forceinline__ float cell_tobj(const EtbLossParams& lp, const LossSe
 }
 
 __global__ void __launch_bounds__(256) loss_obj_fwd_kernel(LossPtrs P, EtbLossParams lp, LossSets S, LossWs ws) {
+  ETB_PDL_PROLOGUE();
   __shared__ float ssum[8];
   __shared__ float scnt[8];
   const int l = blockIdx.y;
@@ -206,6 +208,7 @@ __global__ void __launch_bounds__(256) loss_obj_fwd_kernel(LossPtrs P, EtbLossPa
 }
 
 __global__ void loss_finalize_kernel(EtbLossParams lp, LossSets S, LossWs ws, float* __restrict__ out4) {
+  ETB_PDL_PROLOGUE();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const int nc = lp.no - 5;
   // fp32 accumulation in the reference's order: lbox += mean ; lobj += mean*balance ; then the weights
@@ -240,6 +243,7 @@ __global__ void loss_finalize_kernel(EtbLossParams lp, LossSets S, LossWs ws, fl
 // backward of the objectness term + dense zero-fill of every other element: one thread per element,
 // fully coalesced stores.  dL/dx4 = obj_w * B * balance_l / n_valid_l * (sigmoid(x) - tobj) for valid cells.
 __global__ void __launch_bounds__(256) loss_obj_bwd_kernel(LossPtrs P, EtbLossParams lp, LossSets S, LossWs ws, const float* __restrict__ gscale_dev) {
+  ETB_PDL_PROLOGUE();
   const int l = blockIdx.y;
   const int64_t ncell = ws.cell_off[l + 1] - ws.cell_off[l];
   const int64_t nel = ncell * lp.no;
@@ -291,12 +295,12 @@ extern "C" int etb_loss_forward(const float* const* p, const EtbLossParams* lp, 
   // winner_c and winner_u are adjacent: one memset to -1 (0xFF bytes)
   ETB_CHECK_CUDA(cudaMemsetAsync(ws.winner_c, 0xFF, (char*)ws.iou0 - (char*)ws.winner_c, st));
   const int sms = etb_num_sms();
-  loss_rows_kernel<false><<<sms * 2, 256, 0, st>>>(P, *lp, S, ws, nullptr);
+  etb_launch(loss_rows_kernel<false>, dim3(sms * 2), dim3(256), 0, st, P, *lp, S, ws, nullptr);
   ETB_CHECK_LAUNCH();
   dim3 go(sms * 2, lp->nl);
-  loss_obj_fwd_kernel<<<go, 256, 0, st>>>(P, *lp, S, ws);
+  etb_launch(loss_obj_fwd_kernel, dim3(go), dim3(256), 0, st, P, *lp, S, ws);
   ETB_CHECK_LAUNCH();
-  loss_finalize_kernel<<<1, 32, 0, st>>>(*lp, S, ws, out4);
+  etb_launch(loss_finalize_kernel, dim3(1), dim3(32), 0, st, *lp, S, ws, out4);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }
@@ -318,15 +322,16 @@ extern "C" int etb_loss_backward(const float* const* p, float* const* grad_p, co
   cudaStream_t st = (cudaStream_t)stream;
   const int sms = etb_num_sms();
   dim3 go(sms * 8, lp->nl);
-  loss_obj_bwd_kernel<<<go, 256, 0, st>>>(P, *lp, S, ws, gscale_dev);
+  etb_launch(loss_obj_bwd_kernel, dim3(go), dim3(256), 0, st, P, *lp, S, ws, gscale_dev);
   ETB_CHECK_LAUNCH();
-  loss_rows_kernel<true><<<sms * 2, 256, 0, st>>>(P, *lp, S, ws, gscale_dev);
+  etb_launch(loss_rows_kernel<true>, dim3(sms * 2), dim3(256), 0, st, P, *lp, S, ws, gscale_dev);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }
 
 // ---- standalone bbox_iou (CIoU, xywh, 1-to-1): reference utils/metrics.py:207-249 ----
 __global__ void bbox_ciou_kernel(const float* __restrict__ b1, const float* __restrict__ b2, int n, float* __restrict__ out) {
+  ETB_PDL_PROLOGUE();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 a = reinterpret_cast<const float4*>(b1)[i], b = reinterpret_cast<const float4*>(b2)[i];
@@ -337,7 +342,7 @@ extern "C" int etb_bbox_ciou(const float* box1, const float* box2, int32_t n, fl
   ETB_CHECK_ARG(n >= 0);
   if (n == 0) return ETB_OK;
   ETB_CHECK_ARG(box1 && box2 && out);
-  bbox_ciou_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(box1, box2, n, out);
+  etb_launch(bbox_ciou_kernel, dim3((n + 255) / 256), dim3(256), 0, (cudaStream_t)stream, box1, box2, n, out);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }

@@ -87,6 +87,7 @@ __device__ __forceinline__ bool is_candidate(const float* __restrict__ row, int 
 }
 
 __global__ void __launch_bounds__(256) cand_count_kernel(const float* __restrict__ pred, EtbNmsParams p, NmsWs ws) {
+  ETB_PDL_PROLOGUE();
   const int b = blockIdx.y, chunk = blockIdx.x;
   const float* base = pred + (size_t)b * p.P * p.no;
   int cnt = 0;
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(256) cand_count_kernel(const float* __restrict
 }
 
 __global__ void __launch_bounds__(256) cand_write_kernel(const float* __restrict__ pred, EtbNmsParams p, NmsWs ws) {
+  ETB_PDL_PROLOGUE();
   __shared__ int sscan[33];
   __shared__ int sbase;
   const int b = blockIdx.y, chunk = blockIdx.x;
@@ -137,6 +139,7 @@ __global__ void __launch_bounds__(256) cand_write_kernel(const float* __restrict
 // One warp per candidate (grid-stride).  Literal order of operations of general.py:936-953:
 //   cls_score = max_c cls_c ; cls_c *= obj ; box = xywh2xyxy ; conf, j = max_c (first maximal index on ties)
 __global__ void __launch_bounds__(256) cand_record_kernel(const float* __restrict__ pred, EtbNmsParams p, NmsWs ws) {
+  ETB_PDL_PROLOGUE();
   const int lane = threadIdx.x & 31;
   const int warps_per_grid = gridDim.x * (blockDim.x >> 5);
   const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -186,6 +189,7 @@ __global__ void __launch_bounds__(256) cand_record_kernel(const float* __restric
 // ---- C1 --------------------------------------------------------------------------------------------
 // rank_i = #{ j : key_j > key_i  or (key_j == key_i and j < i) }  == position in a stable descending sort.
 __global__ void __launch_bounds__(256) rank_kernel(EtbNmsParams p, NmsWs ws) {
+  ETB_PDL_PROLOGUE();
   __shared__ float sk[256];
   const int b = blockIdx.y;
   const int n1 = ws.n1[b];
@@ -227,6 +231,7 @@ __device__ __forceinline__ bool iou_gt(float ax1, float ay1, float ax2, float ay
 
 __global__ void __launch_bounds__(1024) nms_image_kernel(EtbNmsParams p, NmsWs ws, float* __restrict__ det,
                                                          int32_t* __restrict__ det_cnt, const double* __restrict__ Ms) {
+  ETB_PDL_PROLOGUE();
   __shared__ float kx1[NMS_MAXK], ky1[NMS_MAXK], kx2[NMS_MAXK], ky2[NMS_MAXK], karea[NMS_MAXK];
   __shared__ int kslot[NMS_MAXK];
   __shared__ float tx1[64], ty1[64], tx2[64], ty2[64], tarea[64];
@@ -358,6 +363,7 @@ __global__ void __launch_bounds__(1024) nms_image_kernel(EtbNmsParams p, NmsWs w
 
 // ---- C3 --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) pl_gather_kernel(EtbNmsParams p, NmsWs ws, double* __restrict__ pl_rows, int32_t* __restrict__ pl_cnt) {
+  ETB_PDL_PROLOGUE();
   int base = 0;
   for (int b = 0; b < p.B; ++b) {
     const int c = ws.pl_seg_cnt[b];
@@ -383,19 +389,19 @@ extern "C" int etb_nms_ssod(const float* pred, const EtbNmsParams* p, float* det
   // n1, n2, pl_seg_cnt are contiguous (256 B aligned slots) at the head of the workspace
   ETB_CHECK_CUDA(cudaMemsetAsync(ws.n1, 0, (char*)ws.chunk_cnt - (char*)ws.n1, st));
   dim3 gA(ws.nchunks, p->B);
-  cand_count_kernel<<<gA, 256, 0, st>>>(pred, *p, ws);
+  etb_launch(cand_count_kernel, dim3(gA), dim3(256), 0, st, pred, *p, ws);
   ETB_CHECK_LAUNCH();
-  cand_write_kernel<<<gA, 256, 0, st>>>(pred, *p, ws);
+  etb_launch(cand_write_kernel, dim3(gA), dim3(256), 0, st, pred, *p, ws);
   ETB_CHECK_LAUNCH();
-  cand_record_kernel<<<etb_num_sms() * 4, 256, 0, st>>>(pred, *p, ws);
+  etb_launch(cand_record_kernel, dim3(etb_num_sms() * 4), dim3(256), 0, st, pred, *p, ws);
   ETB_CHECK_LAUNCH();
   dim3 gR((p->P + 255) / 256, p->B);
-  rank_kernel<<<gR, 256, 0, st>>>(*p, ws);
+  etb_launch(rank_kernel, dim3(gR), dim3(256), 0, st, *p, ws);
   ETB_CHECK_LAUNCH();
-  nms_image_kernel<<<p->B, 1024, 0, st>>>(*p, ws, det, det_cnt, Ms);
+  etb_launch(nms_image_kernel, dim3(p->B), dim3(1024), 0, st, *p, ws, det, det_cnt, Ms);
   ETB_CHECK_LAUNCH();
   if (Ms) {
-    pl_gather_kernel<<<1, 1024, 0, st>>>(*p, ws, pl_rows, pl_cnt);
+    etb_launch(pl_gather_kernel, dim3(1), dim3(1024), 0, st, *p, ws, pl_rows, pl_cnt);
     ETB_CHECK_LAUNCH();
   }
   return ETB_OK;
@@ -444,6 +450,7 @@ __device__ __forceinline__ bool ml_row_candidate(const float* __restrict__ row, 
 // level 0: bins = key >> 20 (all valid keys); level 1: (key >> 8) & 0xFFF of keys whose top 12 bits == prefix >> 20;
 // level 2: key & 0xFF of keys whose top 24 bits == prefix >> 8.
 __global__ void __launch_bounds__(256) ml_hist_kernel(const float* __restrict__ pred, EtbNmsParams p, MlWs ws, int level) {
+  ETB_PDL_PROLOGUE();
   __shared__ uint32_t sh[ML_BINS];
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nc = p.no - 5;
@@ -473,6 +480,7 @@ __global__ void __launch_bounds__(256) ml_hist_kernel(const float* __restrict__ 
 // One block (256 threads) per image.  Finds, walking the bins from the top, the bin that holds the k_rem-th largest key
 // among the keys that match the digits fixed so far; updates prefix / k_rem / greater; clears the histogram for the next level.
 __global__ void __launch_bounds__(256) ml_select_kernel(EtbNmsParams p, MlWs ws, int level) {
+  ETB_PDL_PROLOGUE();
   __shared__ uint32_t part[256];
   __shared__ int found_bin;
   const int b = blockIdx.x;
@@ -532,6 +540,7 @@ __device__ __forceinline__ void ml_class(uint32_t k, uint32_t T, bool all, int* 
 
 template <bool WRITE>
 __global__ void __launch_bounds__(256) ml_pairs_kernel(const float* __restrict__ pred, EtbNmsParams p, MlWs ws, NmsWs nw, int cap) {
+  ETB_PDL_PROLOGUE();
   __shared__ int row_gt[ML_ROWS], row_eq[ML_ROWS];
   __shared__ int sbase_gt, sbase_eq;
   const int b = blockIdx.y, chunk = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -685,21 +694,21 @@ extern "C" int etb_nms_val(const float* pred, const EtbNmsParams* p, float* det,
   ETB_CHECK_CUDA(cudaMemsetAsync(nw.n1, 0, (char*)ml.chunk_gt - (char*)nw.n1, st));      // counters, histogram, state
   dim3 gC(ml.nchunks, p->B);
   for (int level = 0; level < 3; ++level) {
-    ml_hist_kernel<<<gC, 256, 0, st>>>(pred, *p, ml, level);
+    etb_launch(ml_hist_kernel, dim3(gC), dim3(256), 0, st, pred, *p, ml, level);
     ETB_CHECK_LAUNCH();
-    ml_select_kernel<<<p->B, 256, 0, st>>>(*p, ml, level);
+    etb_launch(ml_select_kernel, dim3(p->B), dim3(256), 0, st, *p, ml, level);
     ETB_CHECK_LAUNCH();
   }
-  ml_pairs_kernel<false><<<gC, 256, 0, st>>>(pred, *p, ml, nw, cap);
+  etb_launch(ml_pairs_kernel<false>, dim3(gC), dim3(256), 0, st, pred, *p, ml, nw, cap);
   ETB_CHECK_LAUNCH();
-  ml_pairs_kernel<true><<<gC, 256, 0, st>>>(pred, *p, ml, nw, cap);
+  etb_launch(ml_pairs_kernel<true>, dim3(gC), dim3(256), 0, st, pred, *p, ml, nw, cap);
   ETB_CHECK_LAUNCH();
   EtbNmsParams q = *p;
   q.P = cap;                                               // the survivors live in [B][cap] record / key / sorted arrays
   dim3 gR((cap + 255) / 256, p->B);
-  rank_kernel<<<gR, 256, 0, st>>>(q, nw);
+  etb_launch(rank_kernel, dim3(gR), dim3(256), 0, st, q, nw);
   ETB_CHECK_LAUNCH();
-  nms_image_kernel<<<p->B, 1024, 0, st>>>(q, nw, det, det_cnt, nullptr);
+  etb_launch(nms_image_kernel, dim3(p->B), dim3(1024), 0, st, q, nw, det, det_cnt, nullptr);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }

@@ -8,6 +8,7 @@
 #include "common.cuh"
 
 __global__ void __launch_bounds__(256) sgd_kernel(const EtbSgdChunk* __restrict__ tab, const float* __restrict__ hyper, int zero_grad) {
+  ETB_PDL_PROLOGUE();
   const EtbSgdChunk c = tab[blockIdx.x];
   const float lr = hyper[4 * c.group + 0], mom = hyper[4 * c.group + 1], wd = hyper[4 * c.group + 2];
   float* __restrict__ p = c.p;
@@ -41,7 +42,7 @@ __global__ void __launch_bounds__(256) sgd_kernel(const EtbSgdChunk* __restrict_
 extern "C" int etb_sgd_step(const EtbSgdChunk* table_dev, int64_t n_chunks, const float* hyper_dev, int32_t zero_grad, void* stream) {
   ETB_CHECK_ARG(table_dev && hyper_dev && n_chunks >= 0 && n_chunks < (1ll << 31));
   if (n_chunks == 0) return ETB_OK;
-  sgd_kernel<<<(unsigned)n_chunks, 256, 0, (cudaStream_t)stream>>>(table_dev, hyper_dev, zero_grad);
+  etb_launch(sgd_kernel, dim3((unsigned)n_chunks), dim3(256), 0, (cudaStream_t)stream, table_dev, hyper_dev, zero_grad);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }

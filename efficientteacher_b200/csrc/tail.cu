@@ -16,6 +16,7 @@
 // 170 B runs out; per-channel partial sums of the bias gradient in registers -> partials[(n*chunks + chunk)][C].
 __global__ void __launch_bounds__(128) detect_dy_pack_kernel(const float* __restrict__ g, __nv_bfloat16* __restrict__ dy, float* __restrict__ partials,
                                                              int na, int HW, int no, int Cpad) {
+  ETB_PDL_PROLOGUE();
   const int chunk = blockIdx.x, a = blockIdx.y, n = blockIdx.z;
   const int o = threadIdx.x;
   const int C = na * no;
@@ -39,6 +40,7 @@ __global__ void __launch_bounds__(128) detect_dy_pack_kernel(const float* __rest
 
 // out[c] (+)= sum over rows of partials[row][c]; block (32 channels x 32 row lanes), fixed-shape tree: deterministic
 __global__ void __launch_bounds__(1024) column_sum_kernel(const float* __restrict__ partials, int rows, int C, float* __restrict__ out, int accumulate) {
+  ETB_PDL_PROLOGUE();
   __shared__ float red[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   float a = 0.f;
@@ -62,14 +64,14 @@ extern "C" int etb_detect_dy_pack(const float* g, void* dy_bf16, float* partials
   ETB_CHECK_ARG(Cpad >= na * no && Cpad % 8 == 0 && no + (Cpad - na * no) <= 128 && na < 65536 && N < 65536);
   const int HW = H * W;
   dim3 grid((HW + DET_PIX - 1) / DET_PIX, na, N);
-  detect_dy_pack_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(g, (__nv_bfloat16*)dy_bf16, partials, na, HW, no, Cpad);
+  etb_launch(detect_dy_pack_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, g, (__nv_bfloat16*)dy_bf16, partials, na, HW, no, Cpad);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }
 
 extern "C" int etb_column_sum(const float* partials, int64_t rows, int32_t C, float* out, int32_t accumulate, void* stream) {
   ETB_CHECK_ARG(partials && out && rows > 0 && rows < (1ll << 31) && C > 0);
-  column_sum_kernel<<<(C + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(partials, (int)rows, C, out, accumulate);
+  etb_launch(column_sum_kernel, dim3((C + 31) / 32), dim3(dim3(32, 32)), 0, (cudaStream_t)stream, partials, (int)rows, C, out, accumulate);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }
@@ -90,6 +92,7 @@ __device__ __forceinline__ void bf8_to_f(const uint4 v, float* f) {
 // one warp per pixel row: o[m][j] = sum_c h[m][c] * w2[j][c]
 __global__ void __launch_bounds__(NETD_THREADS) netd_tail_fwd_kernel(const __nv_bfloat16* __restrict__ h, long M, int C, int hcs,
                                                                      const float* __restrict__ w2, float* __restrict__ o) {
+  ETB_PDL_PROLOGUE();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = NETD_THREADS / 32;
   const int G = C >> 3;
   for (long m = (long)blockIdx.x * nw + wid; m < M; m += (long)gridDim.x * nw) {
@@ -114,6 +117,7 @@ __global__ void __launch_bounds__(NETD_THREADS) netd_tail_fwd_kernel(const __nv_
 __global__ void __launch_bounds__(NETD_THREADS) netd_tail_bwd_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ h, long M, int C,
                                                                      int hcs, const float* __restrict__ w2, __nv_bfloat16* __restrict__ dh,
                                                                      float* __restrict__ partials) {
+  ETB_PDL_PROLOGUE();
   extern __shared__ float sm[];      // [nw][2][C]
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = NETD_THREADS / 32;
   const int G = C >> 3;
@@ -178,7 +182,7 @@ extern "C" int32_t etb_netd_tail_rows(int64_t M) { return M > 0 ? netd_blocks(M)
 
 extern "C" int etb_netd_tail_fwd(const void* h_bf16, int64_t M, int32_t C, int32_t h_cstride, const float* w2, float* o, void* stream) {
   ETB_CHECK_ARG(h_bf16 && w2 && o && M > 0 && C >= 8 && C % 8 == 0 && h_cstride >= C && h_cstride % 8 == 0);
-  netd_tail_fwd_kernel<<<netd_blocks(M), NETD_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)h_bf16, (long)M, C, h_cstride, w2, o);
+  etb_launch(netd_tail_fwd_kernel, dim3(netd_blocks(M)), dim3(NETD_THREADS), 0, (cudaStream_t)stream, (const __nv_bfloat16*)h_bf16, (long)M, C, h_cstride, w2, o);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }
@@ -194,7 +198,7 @@ extern "C" int etb_netd_tail_bwd(const float* dout, const void* h_bf16, int64_t 
     ETB_CHECK_CUDA(cudaFuncSetAttribute(netd_tail_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (NETD_THREADS / 32) * 2 * 256 * NETD_MAXG * 4));
     attr_done = true;
   }
-  netd_tail_bwd_kernel<<<rows, NETD_THREADS, smem, (cudaStream_t)stream>>>(dout, (const __nv_bfloat16*)h_bf16, (long)M, C, h_cstride, w2,
+  etb_launch(netd_tail_bwd_kernel, dim3(rows), dim3(NETD_THREADS), smem, (cudaStream_t)stream, dout, (const __nv_bfloat16*)h_bf16, (long)M, C, h_cstride, w2,
                                                                          (__nv_bfloat16*)dh_bf16, partials);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
@@ -212,6 +216,7 @@ __device__ __forceinline__ void focal_terms(float d, float* logp, float* p) {
 }
 
 __global__ void __launch_bounds__(FOCAL_THREADS) focal_fwd_kernel(EtbFocalParams fp, float* __restrict__ partials) {
+  ETB_PDL_PROLOGUE();
   __shared__ float red[FOCAL_THREADS / 32];
   float acc = 0.f;
   for (int l = 0; l < fp.nl; ++l) {
@@ -235,11 +240,13 @@ __global__ void __launch_bounds__(FOCAL_THREADS) focal_fwd_kernel(EtbFocalParams
   }
 }
 __global__ void focal_finalize_kernel(const float* __restrict__ partials, float scale, float* __restrict__ out) {
+  ETB_PDL_PROLOGUE();
   float s = 0.f;
   for (int b = 0; b < FOCAL_BLOCKS; ++b) s += partials[b];      // fixed order
   out[0] = s * scale;
 }
 __global__ void __launch_bounds__(FOCAL_THREADS) focal_bwd_kernel(EtbFocalParams fp, const float* __restrict__ gout, float scale) {
+  ETB_PDL_PROLOGUE();
   const float gs = gout[0] * scale;
   for (int l = 0; l < fp.nl; ++l) {
     const float2* x = reinterpret_cast<const float2*>(fp.x[l]);
@@ -270,9 +277,9 @@ extern "C" int etb_domain_focal_fwd(const EtbFocalParams* fp, float* out, void* 
   const int64_t tot = focal_total(fp);
   ETB_CHECK_ARG(tot > 0);
   for (int l = 0; l < fp->nl; ++l) ETB_CHECK_ARG(fp->x[l] && fp->M[l] >= 0 && (((uintptr_t)fp->x[l]) & 7) == 0);
-  focal_fwd_kernel<<<FOCAL_BLOCKS, FOCAL_THREADS, 0, (cudaStream_t)stream>>>(*fp, (float*)workspace);
+  etb_launch(focal_fwd_kernel, dim3(FOCAL_BLOCKS), dim3(FOCAL_THREADS), 0, (cudaStream_t)stream, *fp, (float*)workspace);
   ETB_CHECK_LAUNCH();
-  focal_finalize_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((const float*)workspace, 0.5f / (float)tot, out);
+  etb_launch(focal_finalize_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, (const float*)workspace, 0.5f / (float)tot, out);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }
@@ -285,7 +292,7 @@ extern "C" int etb_domain_focal_bwd(const EtbFocalParams* fp, const float* gout,
   int64_t blocks = (tot + FOCAL_THREADS - 1) / FOCAL_THREADS;
   const int64_t cap = (int64_t)etb_num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  focal_bwd_kernel<<<(unsigned)blocks, FOCAL_THREADS, 0, (cudaStream_t)stream>>>(*fp, gout, 0.5f / (float)tot);
+  etb_launch(focal_bwd_kernel, dim3((unsigned)blocks), dim3(FOCAL_THREADS), 0, (cudaStream_t)stream, *fp, gout, 0.5f / (float)tot);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }
@@ -299,6 +306,7 @@ extern "C" int etb_domain_focal_bwd(const EtbFocalParams* fp, const float* gout,
 #define STEM_PITCH 133
 template <typename T>
 __global__ void __launch_bounds__(256) stem_im2col_any_kernel(const T* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H, int W, float div) {
+  ETB_PDL_PROLOGUE();
   __shared__ float sm[18 * STEM_PITCH];
   const int Ho = H / 2, Wo = W / 2;
   const int tiles_w = (Wo + STEM_TP - 1) / STEM_TP;
@@ -348,9 +356,9 @@ extern "C" int etb_stem_im2col_into(const void* x, int32_t is_u8, void* y_bf16, 
   ETB_CHECK_ARG(blocks < (1ll << 31));
   __nv_bfloat16* y = (__nv_bfloat16*)y_bf16 + (size_t)img_offset * (H / 2) * (W / 2) * 128;
   if (is_u8)
-    stem_im2col_any_kernel<uint8_t><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)x, y, N, H, W, div);
+    etb_launch(stem_im2col_any_kernel<uint8_t>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (const uint8_t*)x, y, N, H, W, div);
   else
-    stem_im2col_any_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float*)x, y, N, H, W, div);
+    etb_launch(stem_im2col_any_kernel<float>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (const float*)x, y, N, H, W, div);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }

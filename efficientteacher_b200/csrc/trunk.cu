@@ -21,6 +21,7 @@ static inline unsigned grid_for(int64_t n, int threads) {
 #define STEM_TP 64
 #define STEM_PITCH 133
 __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H, int W, float mul) {
+  ETB_PDL_PROLOGUE();
   __shared__ float sm[18 * STEM_PITCH];
   const int Ho = H / 2, Wo = W / 2;
   const int tiles_w = (Wo + STEM_TP - 1) / STEM_TP;
@@ -65,7 +66,7 @@ extern "C" int etb_stem_im2col(const float* x, void* y_bf16, int32_t N, int32_t 
   ETB_CHECK_ARG(x && y_bf16 && N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0);
   const int64_t blocks = (int64_t)N * (H / 2) * ((W / 2 + STEM_TP - 1) / STEM_TP);
   ETB_CHECK_ARG(blocks < (1ll << 31));
-  stem_im2col_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y_bf16, N, H, W, mul);
+  etb_launch(stem_im2col_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, x, (__nv_bfloat16*)y_bf16, N, H, W, mul);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }
@@ -73,6 +74,7 @@ extern "C" int etb_stem_im2col(const float* x, void* y_bf16, int32_t N, int32_t 
 // ---- NCHW fp32 <-> NHWC bf16 (simple gather; used at the edges of the trunk and by the tests) ----
 __global__ void __launch_bounds__(256) nchw2nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int C, int H, int W,
                                                         int cs, int co, float mul) {
+  ETB_PDL_PROLOGUE();
   const int64_t total = (int64_t)N * H * W * C;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(e % C);
@@ -82,6 +84,7 @@ __global__ void __launch_bounds__(256) nchw2nhwc_kernel(const float* __restrict_
   }
 }
 __global__ void __launch_bounds__(256) nhwc2nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int N, int C, int H, int W, int cs, int co) {
+  ETB_PDL_PROLOGUE();
   const int64_t total = (int64_t)N * H * W * C;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int w = (int)(e % W), h = (int)((e / W) % H), c = (int)((e / ((int64_t)W * H)) % C), n = (int)(e / ((int64_t)W * H * C));
@@ -91,14 +94,14 @@ __global__ void __launch_bounds__(256) nhwc2nchw_kernel(const __nv_bfloat16* __r
 extern "C" int etb_nchw_f32_to_nhwc_bf16(const float* x, void* y, int32_t N, int32_t C, int32_t H, int32_t W, int32_t y_cstride,
                                          int32_t y_coffset, float mul, void* stream) {
   ETB_CHECK_ARG(x && y && N > 0 && C > 0 && H > 0 && W > 0 && y_cstride >= y_coffset + C);
-  nchw2nhwc_kernel<<<grid_for((int64_t)N * C * H * W, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, N, C, H, W, y_cstride, y_coffset, mul);
+  etb_launch(nchw2nhwc_kernel, dim3(grid_for((int64_t)N * C * H * W, 256)), dim3(256), 0, (cudaStream_t)stream, x, (__nv_bfloat16*)y, N, C, H, W, y_cstride, y_coffset, mul);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }
 extern "C" int etb_nhwc_bf16_to_nchw_f32(const void* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W, int32_t x_cstride,
                                          int32_t x_coffset, void* stream) {
   ETB_CHECK_ARG(x && y && N > 0 && C > 0 && H > 0 && W > 0 && x_cstride >= x_coffset + C);
-  nhwc2nchw_kernel<<<grid_for((int64_t)N * C * H * W, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, y, N, C, H, W, x_cstride, x_coffset);
+  etb_launch(nhwc2nchw_kernel, dim3(grid_for((int64_t)N * C * H * W, 256)), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, y, N, C, H, W, x_cstride, x_coffset);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }
@@ -111,6 +114,7 @@ __device__ __forceinline__ void bf8_max(uint4& acc, const uint4& v) {
   for (int j = 0; j < 4; ++j) a[j] = __hmax2(a[j], b[j]);
 }
 __global__ void __launch_bounds__(256) sppf_pool_kernel(__nv_bfloat16* __restrict__ buf, int N, int H, int W, int C, int cs) {
+  ETB_PDL_PROLOGUE();
   const int cg = C / 8;
   const int64_t total = (int64_t)N * H * W * cg;
   const uint32_t ninf2 = 0xFF80FF80u;  // bf16 -inf pair (max-pool padding value)
@@ -139,7 +143,7 @@ __global__ void __launch_bounds__(256) sppf_pool_kernel(__nv_bfloat16* __restric
 }
 extern "C" int etb_sppf_pool(void* buf_bf16, int32_t N, int32_t H, int32_t W, int32_t C, int32_t cstride, void* stream) {
   ETB_CHECK_ARG(buf_bf16 && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && cstride >= 4 * C && cstride % 8 == 0);
-  sppf_pool_kernel<<<grid_for((int64_t)N * H * W * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)buf_bf16, N, H, W, C, cstride);
+  etb_launch(sppf_pool_kernel, dim3(grid_for((int64_t)N * H * W * (C / 8), 256)), dim3(256), 0, (cudaStream_t)stream, (__nv_bfloat16*)buf_bf16, N, H, W, C, cstride);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }
@@ -147,6 +151,7 @@ extern "C" int etb_sppf_pool(void* buf_bf16, int32_t N, int32_t H, int32_t W, in
 // ---- nearest 2x upsample into a channel slice ----
 __global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H, int W, int C,
                                                          int xcs, int xco, int ycs, int yco) {
+  ETB_PDL_PROLOGUE();
   const int cg = C / 8;
   const int Ho = 2 * H, Wo = 2 * W;
   const int64_t total = (int64_t)N * Ho * Wo * cg;
@@ -162,14 +167,14 @@ extern "C" int etb_upsample2x_nhwc(const void* x_bf16, void* y_bf16, int32_t N, 
                                    int32_t x_coffset, int32_t y_cstride, int32_t y_coffset, void* stream) {
   ETB_CHECK_ARG(x_bf16 && y_bf16 && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0);
   ETB_CHECK_ARG(x_cstride % 8 == 0 && x_coffset % 8 == 0 && y_cstride % 8 == 0 && y_coffset % 8 == 0);
-  upsample2x_kernel<<<grid_for((int64_t)N * 4 * H * W * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x_bf16, (__nv_bfloat16*)y_bf16, N, H, W, C, x_cstride, x_coffset, y_cstride, y_coffset);
+  etb_launch(upsample2x_kernel, dim3(grid_for((int64_t)N * 4 * H * W * (C / 8), 256)), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x_bf16, (__nv_bfloat16*)y_bf16, N, H, W, C, x_cstride, x_coffset, y_cstride, y_coffset);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }
 
 // ---- BN folding + weight packing ----
 __global__ void fold_bn_kernel(const float* g, const float* b, const float* m, const float* v, float eps, float* scale, float* bias, int C) {
+  ETB_PDL_PROLOGUE();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float s = g[c] / sqrtf(v[c] + eps);
@@ -179,12 +184,13 @@ __global__ void fold_bn_kernel(const float* g, const float* b, const float* m, c
 extern "C" int etb_fold_bn(const float* gamma, const float* beta, const float* mean, const float* var, float eps, float* scale,
                            float* bias, int32_t C, void* stream) {
   ETB_CHECK_ARG(gamma && beta && mean && var && scale && bias && C > 0);
-  fold_bn_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gamma, beta, mean, var, eps, scale, bias, C);
+  etb_launch(fold_bn_kernel, dim3((C + 127) / 128), dim3(128), 0, (cudaStream_t)stream, gamma, beta, mean, var, eps, scale, bias, C);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }
 
 __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o, int Cout, int Cin, int kh, int kw, int Cp) {
+  ETB_PDL_PROLOGUE();
   const int64_t total = (int64_t)Cout * kh * kw * Cp;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(e % Cp);
@@ -195,12 +201,13 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restric
 }
 extern "C" int etb_pack_weight(const float* w_oihw, void* w_bf16, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw, int32_t Cin_pad, void* stream) {
   ETB_CHECK_ARG(w_oihw && w_bf16 && Cout > 0 && Cin > 0 && kh > 0 && kw > 0 && Cin_pad >= Cin);
-  pack_weight_kernel<<<grid_for((int64_t)Cout * kh * kw * Cin_pad, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, (__nv_bfloat16*)w_bf16, Cout, Cin, kh, kw, Cin_pad);
+  etb_launch(pack_weight_kernel, dim3(grid_for((int64_t)Cout * kh * kw * Cin_pad, 256)), dim3(256), 0, (cudaStream_t)stream, w_oihw, (__nv_bfloat16*)w_bf16, Cout, Cin, kh, kw, Cin_pad);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }
 
 __global__ void pack_stem_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o, int Cout) {
+  ETB_PDL_PROLOGUE();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= Cout * 128) return;
   const int k = e & 127, oc = e >> 7;
@@ -210,7 +217,7 @@ __global__ void pack_stem_weight_kernel(const float* __restrict__ w, __nv_bfloat
 }
 extern "C" int etb_pack_stem_weight(const float* w_oihw, void* w_bf16, int32_t Cout, void* stream) {
   ETB_CHECK_ARG(w_oihw && w_bf16 && Cout > 0);
-  pack_stem_weight_kernel<<<(Cout * 128 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w_oihw, (__nv_bfloat16*)w_bf16, Cout);
+  etb_launch(pack_stem_weight_kernel, dim3((Cout * 128 + 255) / 256), dim3(256), 0, (cudaStream_t)stream, w_oihw, (__nv_bfloat16*)w_bf16, Cout);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }
@@ -221,6 +228,7 @@ extern "C" int etb_pack_stem_weight(const float* w_oihw, void* w_bf16, int32_t C
 // mode 2: stem [Cout][128] in the etb_stem_im2col K order
 // mode 3: mode 1 negated (dgrad operand of a conv that sits behind a GradReverse)
 __global__ void __launch_bounds__(256) pack_multi_kernel(const EtbPackDesc* __restrict__ descs, const int2* __restrict__ chunks) {
+  ETB_PDL_PROLOGUE();
   const int2 ch = chunks[blockIdx.x];
   const EtbPackDesc d = descs[ch.x];
   const float* __restrict__ w = d.w;
@@ -258,12 +266,13 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const EtbPackDesc* __re
 extern "C" int etb_pack_multi(const EtbPackDesc* descs_dev, const void* chunks_dev, int32_t n_chunks, void* stream) {
   ETB_CHECK_ARG(descs_dev && chunks_dev && n_chunks >= 0);
   if (n_chunks == 0) return ETB_OK;
-  pack_multi_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(descs_dev, (const int2*)chunks_dev);
+  etb_launch(pack_multi_kernel, dim3(n_chunks), dim3(256), 0, (cudaStream_t)stream, descs_dev, (const int2*)chunks_dev);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }
 
 __global__ void __launch_bounds__(256) fold_multi_kernel(const EtbFoldDesc* __restrict__ descs) {
+  ETB_PDL_PROLOGUE();
   const EtbFoldDesc d = descs[blockIdx.x];
   for (int c = threadIdx.x; c < d.C; c += 256) {
     const float s = d.gamma[c] / sqrtf(d.var[c] + d.eps);
@@ -274,7 +283,7 @@ __global__ void __launch_bounds__(256) fold_multi_kernel(const EtbFoldDesc* __re
 extern "C" int etb_fold_bn_multi(const EtbFoldDesc* descs_dev, int32_t n, void* stream) {
   ETB_CHECK_ARG(descs_dev && n >= 0);
   if (n == 0) return ETB_OK;
-  fold_multi_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(descs_dev);
+  etb_launch(fold_multi_kernel, dim3(n), dim3(256), 0, (cudaStream_t)stream, descs_dev);
   ETB_CHECK_LAUNCH();
   return ETB_OK;
 }

