@@ -144,6 +144,8 @@ _SIGS = {
     "etb_domain_focal_workspace_bytes": (C.c_int64, []),
     "etb_domain_focal_fwd": (C.c_int, [C.POINTER(EtbFocalParams), vp, vp, C.c_int64, vp]),
     "etb_domain_focal_bwd": (C.c_int, [C.POINTER(EtbFocalParams), vp, vp]),
+    "etb_val_process_batch": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int32, vp, C.c_int32, vp, vp, vp]),
+    "etb_nms_boxes": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, vp, vp, vp]),
     "etb_stem_im2col_into": (C.c_int, [vp, C.c_int32, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, vp]),
 }
 

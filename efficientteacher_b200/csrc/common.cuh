@@ -46,8 +46,8 @@ void etb_count_launch();   // every ETB_CHECK_LAUNCH() follows exactly one kerne
 // (the NEXT kernel's CTAs may be scheduled as soon as all CTAs of this one have passed this point or exited).  The next
 // kernel's launch latency, block scheduling and prologue (smem carve-up, mbarrier init, TMEM allocation, tensor-map
 // prefetch: the tcgen05 kernels place the wait after that prologue) thereby overlap this kernel's execution instead of
-// following its tail; with ~1300 kernels per step, many of them 3-10 us long, the launch gaps were a measurable part of
-// the step.  A kernel launched without the attribute (ETB_PDL=0, or a neighbour from another library) sees both instructions
+// following its tail.  Measured on the SSOD step: no gain once the step is replayed as a CUDA graph (the graph's kernel-to-kernel
+// latency is already ~1 us), so the attribute is only set with ETB_PDL=1 (eager-launch experiments).  A kernel launched without the attribute (ETB_PDL=0, or a neighbour from another library) sees both instructions
 // as no-ops / full stream order, so mixing is safe.  Captured CUDA graphs keep the programmatic edges.
 #define ETB_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
 #define ETB_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
@@ -61,7 +61,7 @@ static inline bool etb_pdl_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("ETB_PDL");
-    v = (e && e[0] == '0') ? 0 : 1;
+    v = (e && e[0] == '1') ? 1 : 0;       // opt-in: measured neutral under CUDA-graph replay (33.0 vs 32.8 ms/step, profiles/r2_ablation.md)
   }
   return v != 0;
 }

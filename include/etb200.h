@@ -373,6 +373,20 @@ int etb_domain_focal_bwd(const EtbFocalParams* fp, const float* gout, void* stre
 int etb_stem_im2col_into(const void* x, int32_t is_u8, void* y_bf16, int32_t N, int32_t H, int32_t W, int32_t img_offset,
                          float div, void* stream);
 
+/* validation matching (val.py:123-145 process_batch), all images of a batch in one launch: correct[b][d][i] = detection d of
+ * image b is a true positive at IoU threshold iouv[i].  det [B][max_det][det_ld>=6] fp32 rows (x1,y1,x2,y2,conf,cls) in the
+ * labels' coordinate space, det_cnt [B] valid rows per image (NULL: max_det); labels [nt][6] fp32 (img,cls,x1,y1,x2,y2);
+ * correct [B][max_det][T] uint8, fully written; *overflow_dev = 1 if an image carries more than 1024 labels. */
+int etb_val_process_batch(const float* det, const int32_t* det_cnt, int32_t B, int32_t max_det, int32_t det_ld,
+                          const float* labels, int32_t nt, const float* iouv, int32_t T, uint8_t* correct,
+                          int32_t* overflow_dev, void* stream);
+
+/* class-agnostic greedy NMS over ready-made detection rows (extra-teachers merge, utils/self_supervised_utils.py:256-274,
+ * torchvision.ops.nms semantics): rows [B][nmax<=1024][ld>=5] fp32 (x1,y1,x2,y2,score,...), cnt [B]; kept rows are written
+ * to out [B][nmax][ld] in descending-score (stable) order, out_cnt [B]. */
+int etb_nms_boxes(const float* rows, const int32_t* cnt, int32_t B, int32_t nmax, int32_t ld, float iou_thres, float* out,
+                  int32_t* out_cnt, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -330,3 +330,55 @@ def ema_update(v, m, d):
     """v <- v*d ; v += (1-d)*m  with the python scalars rounded to fp32.  numpy fp32 arrays."""
     v = np.asarray(v, dtype=F32); m = np.asarray(m, dtype=F32)
     return (v * F32(d)) + (F32(1.0 - d) * m)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# validation matching -- val.py:123-145 (process_batch) ; utils/metrics.py:252-273 (box_iou)
+# ---------------------------------------------------------------------------------------------------------
+def process_batch(detections, labels, iouv):
+    """detections [N,6] (x1,y1,x2,y2,conf,cls), labels [M,5] (cls,x1,y1,x2,y2), iouv [T] -> correct [N,T] bool.
+    Restated closed form of the reference's sort / np.unique sequence (see csrc/val.cu): per detection the best class-matching
+    label (later label on IoU ties); a detection is correct at threshold t iff its IoU >= t and no EARLIER detection with the
+    same best label also reaches t."""
+    det = np.asarray(detections, dtype=F32); lab = np.asarray(labels, dtype=F32); thr = np.asarray(iouv, dtype=F32)
+    N, M = len(det), len(lab)
+    correct = np.zeros((N, len(thr)), bool)
+    if N == 0 or M == 0:
+        return correct
+    a1 = (lab[:, 3] - lab[:, 1]) * (lab[:, 4] - lab[:, 2])
+    a2 = (det[:, 2] - det[:, 0]) * (det[:, 3] - det[:, 1])
+    w = np.maximum(np.minimum(lab[:, None, 3], det[None, :, 2]) - np.maximum(lab[:, None, 1], det[None, :, 0]), F32(0))
+    h = np.maximum(np.minimum(lab[:, None, 4], det[None, :, 3]) - np.maximum(lab[:, None, 2], det[None, :, 1]), F32(0))
+    inter = (w * h).astype(F32)
+    iou = inter / (a1[:, None] + a2[None, :] - inter)
+    same = lab[:, 0:1] == det[None, :, 5]
+    iou_m = np.where(same, iou, F32(-1))
+    best_l = (M - 1) - np.argmax(iou_m[::-1], axis=0)            # last maximal label
+    best = iou_m[best_l, np.arange(N)]
+    for i, t in enumerate(thr):
+        taken = set()
+        for d in range(N):
+            if best[d] >= t and best[d] >= 0:
+                if best_l[d] not in taken:
+                    correct[d, i] = True
+                    taken.add(best_l[d])
+    return correct
+
+
+# ---------------------------------------------------------------------------------------------------------
+# extra-teachers merge -- utils/self_supervised_utils.py:256-274 (the part of the method that can execute)
+# ---------------------------------------------------------------------------------------------------------
+def merge_extra_teachers(pred, extra_preds, class_maps, conf_thres, iou_thres):
+    """pred / extra_preds[t]: [B,P,5+nc] fp32; class_maps[t]: {origin_cls: new_cls}.  -> list of [k,6] fp32 arrays."""
+    cur = nms_val(pred, conf_thres, iou_thres, multi_label=False)
+    for t, tp in enumerate(extra_preds):
+        td = nms_val(tp, conf_thres, iou_thres, multi_label=False)
+        for i in range(len(cur)):
+            d = td[i].copy()
+            for r in d:                                            # :264-268
+                if int(r[5]) in class_maps[t]:
+                    r[5] = F32(class_maps[t][int(r[5])])
+            x = np.concatenate([cur[i], d], 0)                     # :270
+            keep = greedy_nms(x[:, :4], x[:, 4], iou_thres)        # :272-274 (c = 0: class-agnostic)
+            cur[i] = x[keep]
+    return cur

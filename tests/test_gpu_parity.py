@@ -386,3 +386,34 @@ def test_val_nms_multi_label_vs_reference_golden(golden, name):
         got = dets[b].cpu().numpy()
         assert got.shape == want.shape, (name, b, got.shape, want.shape)
         np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("name", ["a", "b", "c", "d"])
+def test_val_process_batch_vs_reference_golden(name):
+    """val.py:123-145 on the device (etb_val_process_batch) against the live-reference fixture, single image and batched"""
+    import os
+    from efficientteacher_b200 import val as etb_val
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "val_process_batch.npz"))
+    det, lab, want = g[name + "_det"], g[name + "_lab"], g[name + "_correct"]
+    iouv = torch.linspace(0.5, 0.95, 10).to(DEV)
+    got = etb_val.process_batch(torch.from_numpy(det).to(DEV), torch.from_numpy(lab).to(DEV), iouv)
+    assert np.array_equal(got.cpu().numpy(), want)
+    # batched: the same image twice plus an empty one, padded rows, per-image counts
+    n = det.shape[0]
+    pad = torch.zeros((3, n + 5, 6), device=DEV)
+    pad[0, :n] = torch.from_numpy(det).to(DEV); pad[2, :n] = torch.from_numpy(det).to(DEV)
+    cnt = torch.tensor([n, 0, n], dtype=torch.int32, device=DEV)
+    labs = torch.cat([torch.cat([torch.full((len(lab), 1), float(i)), torch.from_numpy(lab)], 1) for i in (0, 2)], 0).to(DEV)
+    out = etb_val.process_batch_batched(pad, cnt, labs, iouv).cpu().numpy()
+    assert np.array_equal(out[0, :n], want) and np.array_equal(out[2, :n], want) and not out[1].any() and not out[0, n:].any()
+
+
+def test_extra_teachers_merge_vs_reference_golden():
+    """device merge (NMS of every teacher + class remap + class-agnostic etb_nms_boxes per teacher) vs the live-reference fixture"""
+    import os
+    from efficientteacher_b200.pseudo_label import merge_extra_teacher_detections
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "extra_teachers.npz"))
+    B, P = 2, 4000
+    mk = lambda s, f: torch.from_numpy(synth.make_teacher_pred(s, B, P, cand_frac=f)).to(DEV)  # noqa: E731
+    got = merge_extra_teacher_detections(mk(21, 0.05), [mk(22, 0.04), mk(23, 0.03)], [{3: 70, 5: 1, 7: 7}, {}], float(g["conf"]), float(g["iou"]))
+    assert np.array_equal(got[0].cpu().numpy(), g["out0"]) and np.array_equal(got[1].cpu().numpy(), g["out1"])
