@@ -1287,6 +1287,238 @@ __global__ void __launch_bounds__(256) wgrad_reduce_taps_kernel(const float* __r
   for (int i = threadIdx.x; i < CW * kk; i += 256) o[i] = (flags & 2) ? o[i] + sm[i] : sm[i];
 }
 
+// =====================================================================================================================
+// wgrad2: 2-SM (cta_group::2) weight gradient with several accumulators per tile -- the L2-traffic-optimal variant for the
+// wide layers (Cout >= 256, Cin >= 128), which carry most of the weight-gradient FLOPs.
+//   The 1-SM kernel above is bound by the L2 -> SM operand stream: a 128(co) x 128(ci) x 1-tap CTA ingests 64 KB per 128-pixel
+//   K block for 512 MMA cycles = 128 B/clk/SM, ~3x what L2 sustains with all SMs pulling.  Here a cluster of two CTAs owns
+//   256 co x 128 ci x NT "virtual columns" (a virtual column = one (ci tile, filter tap) pair; 3 taps of one filter row for
+//   the 3x3 layers, up to 4 ci tiles for the pointwise ones): per 64-pixel K block each SM loads ITS 128 co of dy (16 KB, used
+//   by all NT accumulators) and its 64-ci HALF of each of the NT x tiles (8 KB each), and the pair issues NT x 4
+//   tcgen05.mma.cta_group::2 (M=256, N=128, K=16).  Bytes per MMA cycle and SM: (16 + 8 NT) KB / (256 NT) clk = 53 B/clk at
+//   NT = 3, 47 B/clk at NT = 4 -- 2.4-2.7x less than the 1-SM kernel.  TMEM: NT x 128 fp32 columns per CTA (<= 512).
+//   Both operands are MN-major straight from the NHWC tensors (LBO = 64-channel group stride), split-K over the pixel blocks
+//   with per-slice partial tiles in the workspace exactly like the 1-SM kernel (same reduce kernels).
+//   Barrier protocol = conv_fwd2_kernel's: both producers complete_tx on the LEADER's full barrier, tcgen05.commit multicasts
+//   to both CTAs' empty / tmem_full barriers.
+// =====================================================================================================================
+struct Wgrad2Args {
+  int ntaps;
+  signed char tap_dh[12], tap_dw[12];
+  int stride;
+  int TW, TH, tiles_w, tiles_h, nimg;
+  int kpix;                 // TW*TH, multiple of 16, <= KP
+  int NT;                   // virtual columns per cluster tile
+  int nvirt;                // ci_tiles * ntaps
+  int groups;               // ceil(nvirt / NT)
+  int Cout, Cin;
+  float* dw;
+  long dw_split_stride;
+};
+
+template <int KP, int STAGES>
+struct Wgrad2Smem {
+  static constexpr int GROUP_BYTES = KP * 128;            // one 64-channel group, KP pixel rows
+  static constexpr int A_BYTES = 2 * GROUP_BYTES;         // this CTA's 128 co of dy
+  static constexpr int B_MAX = 4 * GROUP_BYTES;           // up to 4 virtual columns x this CTA's 64 ci
+  static constexpr int STAGE_BYTES = A_BYTES + B_MAX;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+};
+
+template <int KP, int STAGES>
+__global__ void __launch_bounds__(WGRAD_THREADS, 1)
+wgrad2_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ CUtensorMap mapX, const Wgrad2Args a) {
+  using L = Wgrad2Smem<KP, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + L::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();           // 0 = leader
+  const int ct = blockIdx.x >> 1;                    // cluster tile: virtual-column group fastest, then the co pair
+  const int grp = ct % a.groups;
+  const int cop = ct / a.groups;
+  const int v0 = grp * a.NT;
+  const int nt = min(a.NT, a.nvirt - v0);            // virtual columns of this tile (the last group may be short)
+  const int co0 = cop * 256 + (int)rank * 128;       // this CTA's 128 co rows
+  const uint32_t tmem_cols = a.NT <= 1 ? 128u : (a.NT == 2 ? 256u : 512u);
+
+  const int total_kb = a.nimg * a.tiles_h * a.tiles_w;
+  const int chunk = (total_kb + gridDim.y - 1) / gridDim.y;
+  const int kb0 = blockIdx.y * chunk;
+  const int kb1 = min(total_kb, kb0 + chunk);
+  const int kiters = max(kb1 - kb0, 0);              // uniform for the cluster (host guarantees no empty slice)
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&mapDy);
+    tma_prefetch_desc(&mapX);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  ETB_PDL_PROLOGUE();
+  const uint32_t box_bytes = (uint32_t)a.kpix * 128u;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < kiters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+        int kb = kb0 + it;
+        const int tw_i = kb % a.tiles_w; kb /= a.tiles_w;
+        const int th_i = kb % a.tiles_h; kb /= a.tiles_h;
+        const int img = kb;
+        const int w0 = tw_i * a.TW, h0 = th_i * a.TH;
+        mbar_wait(&empty[s], ph ^ 1u);
+        uint8_t* sa = smem + s * L::STAGE_BYTES;
+        uint8_t* sb = sa + L::A_BYTES;
+        if (rank == 0) mbar_expect_tx(&full[s], 2u * box_bytes * (uint32_t)(2 + nt));
+        else mbar_arrive_leader(&full[s]);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) tma_load_4d_2sm(&mapDy, &full[s], sa + g * L::GROUP_BYTES, co0 + 64 * g, w0, h0, img);
+        for (int t = 0; t < nt; ++t) {
+          const int v = v0 + t;
+          const int ci_t = v / a.ntaps, tap = v - ci_t * a.ntaps;
+          tma_load_4d_2sm(&mapX, &full[s], sb + t * L::GROUP_BYTES, ci_t * 128 + 64 * (int)rank, w0 * a.stride + a.tap_dw[tap],
+                          h0 * a.stride + a.tap_dh[tap], img);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16_mn(256, 128);
+      const int ksteps = a.kpix / 16;
+      for (int it = 0; it < kiters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+        const uint64_t adesc = make_mnmajor_sw128_desc(sa, L::GROUP_BYTES);
+        for (int t = 0; t < nt; ++t) {
+          const uint64_t bdesc = make_mnmajor_sw128_desc(sa + L::A_BYTES + t * L::GROUP_BYTES, L::GROUP_BYTES);
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16_2sm(tmem_base + (uint32_t)(t * 128), adesc + (uint64_t)(k * (2048 >> 4)), bdesc + (uint64_t)(k * (2048 >> 4)), idesc,
+                          (it | k) != 0 ? 1u : 0u);
+        }
+        umma_commit_2sm(&empty[s]);
+      }
+      umma_commit_2sm(tmem_full);
+    }
+  } else if (kiters > 0) {
+    const int row = 32 * (warp & 3) + lane;
+    const int co = co0 + row;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    for (int t = 0; t < nt; ++t) {
+      const int v = v0 + t;
+      const int ci_t = v / a.ntaps, tap = v - ci_t * a.ntaps;
+      const int ci0 = ci_t * 128;
+      const uint32_t lane_addr = tmem_base + (uint32_t)(t * 128) + ((uint32_t)(32 * (warp & 3)) << 16);
+      float* dst = a.dw + (size_t)blockIdx.y * a.dw_split_stride + ((size_t)co * a.ntaps + tap) * a.Cin + ci0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        if (ci0 + c0 >= a.Cin) break;
+        uint32_t v32[32];
+        tmem_ld32(lane_addr + (uint32_t)c0, v32);
+        if (co < a.Cout) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            reinterpret_cast<float4*>(dst + c0)[q] = make_float4(__uint_as_float(v32[4 * q]), __uint_as_float(v32[4 * q + 1]),
+                                                                 __uint_as_float(v32[4 * q + 2]), __uint_as_float(v32[4 * q + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, tmem_cols);
+  }
+}
+
+static bool wgrad2_eligible(const EtbConvParams* cp, int32_t flags) {
+  // opt-in (ETB_WGRAD2=1, read per call so tests can toggle it): correct, but measured SLOWER than the 1-SM kernel -- 153 vs
+  // 116 us on 3x3 256->256 @40 b32, tensor pipe 24 % vs 36 % active (profiles/r2_wgrad_ncu.md).  The operand stream it was
+  // built to shrink (xbar->L1 393 MB vs 944 MB) is not what bounds either kernel: lts throughput is 13-19 % of peak; the
+  // MN-major tcgen05.mma itself issues at ~2.3-4x its ideal cycle count.
+  const char* e = getenv("ETB_WGRAD2");
+  const int on = (e && e[0] == '1') ? 1 : 0;
+  const int ntaps = cp->kh * cp->kw;
+  return on && !(flags & 1) && cp->Cout >= 256 && cp->Cin >= 128 && cp->Cin % 64 == 0 && (ntaps == 1 || ntaps % 3 == 0) && ntaps <= 12;
+}
+
+// tiling + split-K of the 2-SM kernel (shared by the workspace query and the launch)
+static void wgrad2_plan(const EtbConvParams* cp, int* NT_, int* TW, int* TH, int* tiles_w, int* tiles_h, int* nimg, int* groups_, int* co_pairs_,
+                        int* splitk) {
+  constexpr int KP = 64;
+  const int Ho = (cp->H + 2 * cp->pad - cp->kh) / cp->stride + 1;
+  const int Wo = (cp->W + 2 * cp->pad - cp->kw) / cp->stride + 1;
+  const bool flat = (cp->kh == 1 && cp->kw == 1 && cp->stride == 1 && cp->pad == 0);
+  if (flat) {
+    const long npix = (long)cp->N * cp->H * cp->W;
+    *TW = KP; *TH = 1; *tiles_w = (int)((npix + KP - 1) / KP); *tiles_h = 1; *nimg = 1;
+  } else {
+    pick_tile16(Wo, Ho, KP, TW, TH);
+    *tiles_w = (Wo + *TW - 1) / *TW; *tiles_h = (Ho + *TH - 1) / *TH; *nimg = cp->N;
+  }
+  const int ntaps = cp->kh * cp->kw;
+  const int ci_tiles = (cp->Cin + 127) / 128;
+  const int nvirt = ci_tiles * ntaps;
+  int NT = (ntaps % 3 == 0) ? 3 : (ci_tiles >= 4 ? 4 : ci_tiles);
+  const int groups = (nvirt + NT - 1) / NT;
+  const int co_pairs = (cp->Cout + 255) / 256;
+  const int clusters = groups * co_pairs;
+  const int total_kb = *nimg * *tiles_h * *tiles_w;
+  // split-K: whole waves of (SMs / 2) clusters; cost per cluster = K blocks * NT * 4 MMAs (64 cycles each at M=256) + fixed
+  const int slots = etb_num_sms() / 2;
+  const double t_kb = 0.135 * NT * (double)(*TW * *TH) / 64.0, t_fixed = 7.0 + 1.2 * NT;
+  int sk = 1;
+  double best = 1e30;
+  const int sk_max = total_kb < 512 ? total_kb : 512;
+  for (int c = 1; c <= sk_max; ++c) {
+    const long cl = (long)clusters * c;
+    if (cl > 8L * slots) break;
+    const long rounds = (cl + slots - 1) / slots;
+    const int per = (total_kb + c - 1) / c;
+    if ((long)(c - 1) * per >= total_kb) continue;          // would leave an empty slice
+    const double cost = (double)rounds * (per * t_kb + t_fixed) + 0.004 * c;
+    if (cost < best) { best = cost; sk = c; }
+  }
+  *NT_ = NT; *groups_ = groups; *co_pairs_ = co_pairs; *splitk = sk;
+}
+
+static int launch_wgrad2(const CUtensorMap& mDy, const CUtensorMap& mX, const Wgrad2Args& wa, int clusters, int splitk, cudaStream_t st) {
+  using L = Wgrad2Smem<64, 4>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ETB_CHECK_CUDA(cudaFuncSetAttribute(wgrad2_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * clusters), (unsigned)splitk); cfg.blockDim = dim3(WGRAD_THREADS); cfg.dynamicSmemBytes = L::TOTAL; cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = etb_pdl_enabled() ? 2 : 1;
+  ETB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, wgrad2_kernel<64, 4>, mDy, mX, wa));
+  etb_count_launch();
+  return ETB_OK;
+}
+
 static void wgrad_plan(const EtbConvParams* cp, int* BN_, int* KP_, int* TW, int* TH, int* tiles_w, int* tiles_h, int* nimg, int* out_tiles,
                        int* splitk, int* MT_ = nullptr) {
   const int Ho = (cp->H + 2 * cp->pad - cp->kh) / cp->stride + 1;
@@ -1297,6 +1529,9 @@ static void wgrad_plan(const EtbConvParams* cp, int* BN_, int* KP_, int* TW, int
   if (cfg_mode == 1 && cp->Cin >= 256) { BN = 256; KP = 64; }
   if (cfg_mode == 2 && cp->Cout >= 256 && cp->Cin >= 128) { MT = 2; BN = 128; KP = 64; }
   if (cfg_mode == 3 && cp->Cout >= 256 && cp->Cin >= 256) { MT = 2; BN = 256; KP = 64; }
+  // default: 256x256 tiles for the wide 3x3 layers (measured per shape, tools/conv_bench.py batch 32: 3x3 256->256 @40 116 -> 110 us,
+  // 3x3 512->512 @20 116 -> 100 us; the pointwise layers and everything narrower stay on 128x128: profiles/r2_conv_bench_wgcfg*.json)
+  if (cfg_mode == 0 && cp->kh * cp->kw >= 9 && cp->stride == 1 && cp->Cout >= 256 && cp->Cin >= 256) { MT = 2; BN = 256; KP = 64; }
   if (MT_) *MT_ = MT;
   const bool flat = (cp->kh == 1 && cp->kw == 1 && cp->stride == 1 && cp->pad == 0);
   if (flat) {
@@ -1333,6 +1568,11 @@ extern "C" size_t etb_conv_wgrad_workspace_bytes(const EtbConvParams* cp) {
   if (!cp || cp->Cin <= 0 || cp->Cout <= 0) return 0;
   int BN, KP, TW, TH, tw, th, ni, ot, sk;
   wgrad_plan(cp, &BN, &KP, &TW, &TH, &tw, &th, &ni, &ot, &sk);
+  if (wgrad2_eligible(cp, 0)) {          // the caller may run either kernel on this shape: size for the larger split
+    int NT, g, cpz, sk2;
+    wgrad2_plan(cp, &NT, &TW, &TH, &tw, &th, &ni, &g, &cpz, &sk2);
+    if (sk2 > sk) sk = sk2;
+  }
   return (size_t)sk * cp->Cout * cp->kh * cp->kw * cp->Cin * sizeof(float);
 }
 
@@ -1353,10 +1593,18 @@ extern "C" int etb_conv_wgrad(const void* x_bf16, const void* dy_bf16, float* dw
   }
   const int Ho = (cp->H + 2 * cp->pad - cp->kh) / cp->stride + 1;
   const int Wo = (cp->W + 2 * cp->pad - cp->kw) / cp->stride + 1;
+  const bool use2 = wgrad2_eligible(cp, flags);
   WgradArgs wa;
   memset(&wa, 0, sizeof(wa));
   int BN, KP, out_tiles, splitk, MT;
   wgrad_plan(cp, &BN, &KP, &wa.TW, &wa.TH, &wa.tiles_w, &wa.tiles_h, &wa.nimg, &out_tiles, &splitk, &MT);
+  Wgrad2Args w2;
+  memset(&w2, 0, sizeof(w2));
+  int groups2 = 0, co_pairs2 = 0;
+  if (use2) {
+    wgrad2_plan(cp, &w2.NT, &wa.TW, &wa.TH, &wa.tiles_w, &wa.tiles_h, &wa.nimg, &groups2, &co_pairs2, &splitk);
+    KP = 64;
+  }
   wa.kpix = wa.TW * wa.TH;
   wa.ntaps = cp->kh * cp->kw;
   for (int kh = 0; kh < cp->kh; ++kh)
@@ -1409,8 +1657,22 @@ extern "C" int etb_conv_wgrad(const void* x_bf16, const void* dy_bf16, float* dw
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((unsigned)out_tiles, (unsigned)splitk);
   int rc;
+  if (use2) {
+    w2.ntaps = wa.ntaps;
+    memcpy(w2.tap_dh, wa.tap_dh, sizeof(w2.tap_dh));
+    memcpy(w2.tap_dw, wa.tap_dw, sizeof(w2.tap_dw));
+    w2.stride = wa.stride; w2.TW = wa.TW; w2.TH = wa.TH; w2.tiles_w = wa.tiles_w; w2.tiles_h = wa.tiles_h; w2.nimg = wa.nimg;
+    w2.kpix = wa.kpix;
+    w2.nvirt = ((cp->Cin + 127) / 128) * wa.ntaps;
+    w2.groups = groups2;
+    w2.Cout = cp->Cout; w2.Cin = cp->Cin;
+    w2.dw = wa.dw; w2.dw_split_stride = wa.dw_split_stride;
+    rc = launch_wgrad2(mDy, mX, w2, groups2 * co_pairs2, splitk, st);
+    if (rc != ETB_OK) return rc;
+  }
   const bool cluster = (MT == 1 && BN == 128) && (wa.co_tiles % 2 == 0) && (wa.ci_tiles % 2 == 0) && getenv("ETB_WGRAD_CLUSTER");
-  if (cluster) rc = launch_wgrad<1, 128, 128, 3, 1>(mDy, mX, wa, grid, st);
+  if (use2) rc = ETB_OK;
+  else if (cluster) rc = launch_wgrad<1, 128, 128, 3, 1>(mDy, mX, wa, grid, st);
   else if (MT == 2 && BN == 256) rc = launch_wgrad<2, 256, 64, 3, 0>(mDy, mX, wa, grid, st);
   else if (MT == 2) rc = launch_wgrad<2, 128, 64, 4, 0>(mDy, mX, wa, grid, st);
   else if (BN == 256) rc = launch_wgrad<1, 256, 64, 4, 0>(mDy, mX, wa, grid, st);

@@ -187,7 +187,21 @@ WGRAD_CASES = [
     (32, 2048, 20, 20, 1024, 1, 1, 0),
     (32, 256, 40, 40, 256, 3, 1, 1),
     (32, 128, 160, 160, 256, 3, 2, 1),
+    # 2-SM multi-accumulator kernel (wgrad2: Cout >= 256, Cin >= 128): tails in co / ci, short last virtual-column group
+    (4, 512, 20, 20, 512, 3, 1, 1),
+    (2, 1024, 20, 20, 512, 1, 1, 0),   # 8 ci tiles -> two groups of 4 virtual columns
+    (2, 128, 16, 16, 320, 1, 1, 0),    # co tail: 256 + 64
+    (2, 192, 16, 16, 256, 3, 1, 1),    # ci tail: 128 + 64
+    (2, 640, 12, 12, 256, 1, 1, 0),    # 5 ci tiles: groups of 4 + 1
+    (3, 256, 24, 24, 512, 3, 2, 1),    # stride 2
 ]
+
+
+@pytest.mark.parametrize("case", [c for c in WGRAD_CASES if c[4] >= 256 and c[1] >= 128])
+def test_conv_wgrad_2sm_kernel(case, monkeypatch):
+    """the opt-in cta_group::2 multi-accumulator kernel (ETB_WGRAD2=1) on every shape it accepts"""
+    monkeypatch.setenv("ETB_WGRAD2", "1")
+    test_conv_wgrad(case)
 
 
 @pytest.mark.parametrize("case", WGRAD_CASES)
@@ -216,10 +230,13 @@ def test_stem_wgrad():
     assert err <= 2e-3 * max(ref.abs().max().item(), 1.0), (err, ref.abs().max().item())
 
 
-@pytest.mark.parametrize("C_,H,act", [(64, 16, "silu"), (256, 20, "silu"), (1024, 8, "silu"), (128, 12, "relu")])
-def test_fused_bn_act_forward_backward(C_, H, act):
-    """Training-mode BatchNorm+activation kernels vs torch (fp32 math on the same bf16 inputs), incl. running stats."""
+@pytest.mark.parametrize("one_launch", [True, False])
+@pytest.mark.parametrize("C_,H,act", [(64, 16, "silu"), (256, 20, "silu"), (1024, 8, "silu"), (128, 12, "relu"), (64, 160, "silu"), (2048, 4, "silu")])
+def test_fused_bn_act_forward_backward(C_, H, act, one_launch, monkeypatch):
+    """Training-mode BatchNorm+activation kernels vs torch (fp32 math on the same bf16 inputs), incl. running stats; both the
+    one-launch cooperative kernels (default) and the three-kernel sequences."""
     from efficientteacher_b200 import convops as co
+    monkeypatch.setattr(co, "BN_FUSED", one_launch)
     N = 4
     y = _rand((N, C_, H, H), 51) * 2.0 + 0.3
     da = _rand((N, C_, H, H), 52)
