@@ -474,15 +474,16 @@ def main():
 
     def step_e2e(i):
         # every step: H2D of this step's uint8 batch from pinned memory (staged on a side stream, so the copy of step i+1
-        # overlaps the kernels of step i), uint8 -> float/255 on the compute stream, the step, D2H read of the loss
+        # overlaps the kernels of step i), the step, D2H read of the loss
         if pf.pending == 0:
             pf.put(host_batch)
         b = pf.get()
+        # the uint8 batches go straight into the step: the native stem (student) and the teacher engine read uint8 and divide by
+        # 255 inside their im2col kernels (== `.float() / 255`, trainer/ssod_trainer.py:694-696), no fp32 image is materialised
         if ssod:
-            imgs, us, uw = b["imgs"].float() / 255.0, b["u_strong"].float() / 255.0, b["u_weak"].float() / 255.0
-            loss = (st.train_instance_graphed if use_graph else st.train_instance)(imgs, b["targets"], us, uw, None, b["Ms"], i)
+            loss = (st.train_instance_graphed if use_graph else st.train_instance)(b["imgs"], b["targets"], b["u_strong"], b["u_weak"], None, b["Ms"], i)
         else:
-            loss = (st.train_step_graphed if use_graph else st.train_step)(b["imgs"].float() / 255.0, b["targets"], i)
+            loss = (st.train_step_graphed if use_graph else st.train_step)(b["imgs"], b["targets"], i)
         pf.release()
         pf.put(host_batch)                   # next step's inputs start moving now
         return float(loss.item())            # D2H read of the step's result

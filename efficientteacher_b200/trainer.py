@@ -295,7 +295,8 @@ class SSODTrainerStep:
         written to device memory before B is replayed, so the schedule needs no re-capture."""
         if self.semi_ema is None:
             raise NotImplementedError("graphed step needs the fused ema/semi_ema pair (burn_epochs == 0)")
-        shapes = (tuple(imgs.shape), tuple(targets.shape), tuple(unlabeled_imgs.shape), tuple(unlabeled_M.shape))
+        shapes = (tuple(imgs.shape), tuple(targets.shape), tuple(unlabeled_imgs.shape), tuple(unlabeled_M.shape),
+                  imgs.dtype, unlabeled_imgs.dtype, unlabeled_imgs_ori.dtype)      # uint8 loader batches vs fp32: different static buffers
         if self._graph is not None and self._graph["shapes"] != shapes:
             self.reset_graph()
         if self._graph is None:
@@ -454,7 +455,7 @@ class SupTrainerStep:
     def train_step_graphed(self, imgs, targets, ni):
         """train_step with forward + loss + backward replayed from one captured CUDA graph (static shapes); the optimizer /
         EMA launches (2 kernels, host-side decay) stay eager on the iterations the cadence asks for."""
-        shapes = (tuple(imgs.shape), tuple(targets.shape))
+        shapes = (tuple(imgs.shape), tuple(targets.shape), imgs.dtype)
         if self._graph is None or self._graph["shapes"] != shapes:
             self._ensure_arena()
             st = dict(shapes=shapes, imgs=imgs.clone(), targets=targets.clone())
