@@ -126,14 +126,38 @@ class SSODTrainerStep:
                                       for k in (0, 1))
         return self._arena
 
+    # Communication modes (WORLD_SIZE > 1).  Default = the round-1 scheme that the 1->8 GPU scaling runs were measured with: ONE
+    # eager all-reduce of the arena between graph A and graph B, plus one eager broadcast of rank 0's BN statistics before the
+    # step.  ETB_COMM_OVERLAP=1: the all-reduce is issued in 3 chunks from autograd marks during backward on a communication
+    # stream (eager steps); ETB_COMM_IN_GRAPH=1 additionally captures the NCCL calls inside graph A (no host round-trip).
+    COMM_OVERLAP = os.environ.get("ETB_COMM_OVERLAP", "0") == "1"
+    COMM_IN_GRAPH = os.environ.get("ETB_COMM_IN_GRAPH", "0") == "1"
+
     def _overlap_comm(self):
         """the chunked all-reduce may run INSIDE backward only when every backward is followed by an optimizer step
         (accumulate == 1): gradients accumulate in the arena across iterations, so they must be reduced once per step"""
-        return self.WORLD_SIZE > 1 and (self.fixed_accumulate or max(round(64 / self.batch_size), 1) == 1)
+        if self.WORLD_SIZE <= 1 or not (self.fixed_accumulate or max(round(64 / self.batch_size), 1) == 1):
+            return False
+        if torch.cuda.is_current_stream_capturing():
+            return self.COMM_IN_GRAPH
+        return self.COMM_OVERLAP or self.COMM_IN_GRAPH
 
     def _allreduce_grads(self):
-        """WORLD_SIZE > 1: SUM all-reduce of the gradient arena -- the chunks that were not already issued during backward"""
-        self._arena.finish(self.WORLD_SIZE)
+        """WORLD_SIZE > 1: SUM all-reduce of the gradient arena (the chunks that were not already issued during backward)"""
+        if self.WORLD_SIZE <= 1:
+            return
+        if self._arena._next == 0 and not (self.COMM_OVERLAP or self.COMM_IN_GRAPH):
+            self._arena.all_reduce_sum(self.WORLD_SIZE)          # one collective over the whole arena
+        else:
+            self._arena.finish(self.WORLD_SIZE)
+
+    def _bn_broadcast(self):
+        """DDP broadcast_buffers=True: rank 0's BN running statistics overwrite every rank's before each forward"""
+        if self.WORLD_SIZE > 1:
+            if self._bn_sync is None:
+                from .parallel import BnBufferSync
+                self._bn_sync = BnBufferSync(self.model)
+            self._bn_sync.broadcast(self.WORLD_SIZE)
 
     # trainer/ssod_trainer.py:458-488 (bf16 autocast needs no GradScaler; loss scale == 1), in three parts so that the
     # gradient all-reduce can sit between two captured CUDA graphs when WORLD_SIZE > 1
@@ -207,11 +231,8 @@ class SSODTrainerStep:
                        host_pseudo_labels=False, _stop_after_backward=False):
         n_img = imgs.shape[0]
         self._mark("start")
-        if self.WORLD_SIZE > 1:          # DDP broadcast_buffers=True: rank 0's BN running statistics before every forward
-            if self._bn_sync is None:
-                from .parallel import BnBufferSync
-                self._bn_sync = BnBufferSync(self.model)
-            self._bn_sync.broadcast(self.WORLD_SIZE)
+        if self.WORLD_SIZE > 1 and (self.COMM_IN_GRAPH or not torch.cuda.is_current_stream_capturing()):
+            self._bn_broadcast()         # (captured steps: train_instance_graphed issues it before the replay)
         # The teacher forward + NMS + pseudo-label transform feed nothing but the unsupervised loss, and the student forward
         # does not depend on them: with the device-resident pseudo labels they run on a side stream, concurrently with the
         # student forward (the teacher's batch-16 kernels leave SMs idle on the deep, small maps; the student's fill them),
@@ -307,11 +328,14 @@ class SSODTrainerStep:
         g["us"].copy_(unlabeled_imgs, non_blocking=True)
         g["uw"].copy_(unlabeled_imgs_ori, non_blocking=True)
         g["Ms"].copy_(unlabeled_M, non_blocking=True)
+        comm_in_a = self.WORLD_SIZE > 1 and self.COMM_IN_GRAPH and (self.fixed_accumulate or max(round(64 / self.batch_size), 1) == 1)
+        if self.WORLD_SIZE > 1 and not self.COMM_IN_GRAPH:
+            self._bn_broadcast()
         g["graph"].replay()
         if self._warmup(ni):                 # host: accumulate / lr / momentum of iteration ni
-            if self.WORLD_SIZE > 1 and not self._overlap_comm():
+            if self.WORLD_SIZE > 1 and not comm_in_a:
                 self._arena.begin_step()
-                self._allreduce_grads()      # accumulate > 1: one SUM all-reduce per optimizer step, between the two graphs
+                self._allreduce_grads()      # one SUM all-reduce per optimizer step, between the two graphs
             d1, d2 = next_pair_decays(self.ema, self.semi_ema)
             # pageable source: the runtime stages the 16 bytes before returning, so the next step cannot overwrite them early
             self._ema_scalars_dev.copy_(torch.tensor(ema_scalars(d1, d2), dtype=torch.float32))
@@ -363,7 +387,7 @@ class SSODTrainerStep:
         with torch.cuda.stream(side):
             for _ in range(2):
                 self.train_instance(st["imgs"], st["targets"], st["us"], st["uw"], None, st["Ms"], ni, _stop_after_backward=True)
-                if not self._overlap_comm():
+                if self._arena._next == 0:      # not already reduced inside train_instance (overlapped mode)
                     self._allreduce_grads()
                 self._warmup(ni)
                 self._step_and_ema()          # the optimizer + EMA branch is exercised (and later captured) unconditionally

@@ -25,9 +25,14 @@ def _net():
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from efficientteacher_b200.parallel import GradArena
+    from efficientteacher_b200.parallel import BnBufferSync, GradArena
     net = _net()
-    arena = GradArena(net.parameters())
+    # backward-completion order + one chunk boundary, like the trainer builds it
+    arena = GradArena(net.parameters(), reverse=True, chunk_ends=[net[3].weight])
+    assert arena.n_chunks() == 2 and arena.bounds[0] == 0 and arena.bounds[-1] == arena.flat.numel()
+    assert arena.params[0] is net[3].bias and arena.params[-1] is net[0].weight
+    sync = BnBufferSync(net)
+    assert net[1].running_mean.data_ptr() == sync.flat.data_ptr() and "running_var" in dict(net[1].named_buffers())
     opt = torch.optim.SGD(net.parameters(), lr=0.1, momentum=0.9, nesterov=True)
     g = torch.Generator().manual_seed(10 + rank)          # per-rank shard, like init_seeds(1+RANK)
     for step in range(3):
@@ -38,6 +43,13 @@ def _worker(rank, world, port, out):
         arena.all_reduce_sum(world)
         opt.step()
         arena.zero()
+        # DDP broadcast_buffers=True: before the next forward every rank holds rank 0's running statistics
+        mine = sync.flat.clone()
+        sync.broadcast(world)
+        both = [torch.zeros_like(sync.flat) for _ in range(world)]
+        dist.all_gather(both, sync.flat)
+        assert torch.equal(both[0], both[1]) and (rank == 0 or not torch.equal(mine, sync.flat))
+        assert torch.equal(net[1].running_var, sync.flat[8:16])
     flat = torch.cat([p.detach().flatten() for p in net.parameters()])
     gathered = [torch.zeros_like(flat) for _ in range(world)]
     dist.all_gather(gathered, flat)

@@ -1,6 +1,9 @@
 """2-GPU check of the data-parallel step (torchrun --nproc-per-node 2 tools/check_ddp2.py):
-  * the overlapped, chunked all-reduce captured inside the step graph gives the same weights as ONE eager all-reduce after
-    backward (bitwise: NCCL SUM of the same numbers, chunking does not change the per-element reduction),
+  modes (argv[1], comma separated): single = eager step, one all-reduce after backward (default scheme); graph = captured graphs A / B
+  with the all-reduce between them (default scheme); overlap = eager step, chunked all-reduce issued during backward
+  (ETB_COMM_OVERLAP); overlap_graph = the same through the graphed entry point; ingraph = NCCL captured inside graph A
+  (ETB_COMM_IN_GRAPH).
+  * every mode gives the same weights as the first one listed (to bf16-training run-to-run noise),
   * replicas stay bit-identical (student weights) across ranks,
   * BatchNorm running statistics at the start of a forward equal rank 0's (DDP broadcast_buffers semantics).
 Prints PASS / FAIL lines; exit code != 0 on failure."""
@@ -25,8 +28,8 @@ def run(mode, rank, world, dev, steps=3):
     cfg = yolov5_ssod_cfg('l_shallow', batch_size=(bl + bu) * world, img_size=img)
     cfg.SSOD.fixed_accumulate = True
     st = SSODTrainerStep(cfg, dev, rank=rank, world_size=world, epochs=300)
-    if mode == "single":
-        st._overlap_comm = lambda: False
+    SSODTrainerStep.COMM_OVERLAP = mode in ("overlap", "overlap_graph", "ingraph")
+    SSODTrainerStep.COMM_IN_GRAPH = mode == "ingraph"
     st.ema.updates = 100000
     with torch.no_grad():
         for mm in (st.model, st.ema.ema, st.semi_ema.ema):
@@ -41,8 +44,11 @@ def run(mode, rank, world, dev, steps=3):
     Ms = torch.from_numpy(synth.make_Ms(9 + rank, bu, img)).to(dev)
     bn_equal = True
     for i in range(steps):
-        f = st.train_instance if mode in ("single", "eager") else st.train_instance_graphed
+        f = st.train_instance if mode in ("single", "overlap") else st.train_instance_graphed
         f(imgs, tg, us, uw, None, Ms, i)
+        torch.cuda.synchronize()
+        if rank == 0:
+            print("   %s step %d done" % (mode, i), flush=True)
         # after the step every rank has updated its own copy of the running statistics from rank 0's: they differ now,
         # and the NEXT forward must start from rank 0's again -- checked through the flat buffer after an explicit broadcast
     torch.cuda.synchronize()
@@ -69,17 +75,18 @@ def main():
     dist.barrier()
     ok = True
     res = {}
-    for mode in ("single", "eager", "graph"):
+    modes = sys.argv[1].split(",") if len(sys.argv) > 1 else ["single", "graph"]
+    for mode in modes:
         w, same, bn_same = run(mode, rank, world, dev)
         res[mode] = w
         if rank == 0:
             print("%s: replicas identical %s, BN buffers follow rank 0 %s" % (mode, same, bn_same), flush=True)
         ok = ok and same and bn_same
-    for mode in ("eager", "graph"):
-        d = float((res[mode] - res["single"]).abs().max())
-        rel = float((res[mode] - res["single"]).norm() / res["single"].norm())
+    for mode in modes[1:]:
+        d = float((res[mode] - res[modes[0]]).abs().max())
+        rel = float((res[mode] - res[modes[0]]).norm() / res[modes[0]].norm())
         if rank == 0:
-            print("%s vs single all-reduce: max |dw| %.3g rel %.3g" % (mode, d, rel), flush=True)
+            print("%s vs %s: max |dw| %.3g rel %.3g" % (mode, modes[0], d, rel), flush=True)
         ok = ok and rel < 1e-3          # bf16 training, run-to-run noise of the step itself (fp32 atomics-free but stream-order dependent sums)
     if rank == 0:
         print("PASS" if ok else "FAIL", flush=True)
