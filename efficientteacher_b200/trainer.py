@@ -454,8 +454,15 @@ class SupTrainerStep:
 
     _warmup = SSODTrainerStep._warmup
     _ensure_arena = SSODTrainerStep._ensure_arena
+    _bn_broadcast = SSODTrainerStep._bn_broadcast
+    _bn_sync = None
+
+    def _overlap_comm(self):          # the supervised step keeps the single all-reduce after backward
+        return False
 
     def _forward_backward(self, imgs, targets):
+        if self.WORLD_SIZE > 1 and not torch.cuda.is_current_stream_capturing():
+            self._bn_broadcast()      # DDP broadcast_buffers=True (captured steps: issued before the replay)
         with torch.autocast("cuda", dtype=self.amp_dtype):
             pred = self.model(imgs)
         loss, loss_items = self.compute_loss(pred, targets)
@@ -503,6 +510,7 @@ class SupTrainerStep:
         g = self._graph
         g["imgs"].copy_(imgs, non_blocking=True)
         g["targets"].copy_(targets, non_blocking=True)
+        self._bn_broadcast()
         g["graph"].replay()
         if self._warmup(ni):
             self._arena.all_reduce_sum(self.WORLD_SIZE)

@@ -339,6 +339,36 @@ def test_fused_sgd_matches_torch_sgd():
             torch.testing.assert_close(oa.state[a]["momentum_buffer"], ob.state[b]["momentum_buffer"], rtol=2e-6, atol=1e-6)
 
 
+def test_fused_sgd_load_state_dict_restores_momentum():
+    """resume (trainer/trainer.py:251 optimizer.load_state_dict): the restored momentum buffers must be the ones the fused
+    kernel reads -- a step after load_state_dict equals the step of the optimizer the state was saved from"""
+    from efficientteacher_b200.optim import FusedSGD
+    mk = lambda: [torch.nn.Parameter(torch.randn(s, generator=torch.Generator().manual_seed(i)).to(DEV)) for i, s in enumerate([(33,), (16, 8, 3, 3)])]  # noqa: E731
+    pa, pb = mk(), mk()
+    grads = [[torch.randn(p.shape, generator=torch.Generator().manual_seed(50 + 10 * k + i)).to(DEV) for i, p in enumerate(pa)] for k in range(3)]
+
+    def step(opt, ps, k):
+        for p, g in zip(ps, grads[k]):
+            p.grad = g.clone() if p.grad is None else p.grad.copy_(g)
+        opt.step()
+    oa = FusedSGD(pa, lr=0.01, momentum=0.9, nesterov=True)
+    step(oa, pa, 0); step(oa, pa, 1)
+    sd = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in oa.state_dict().items()}
+    sd["state"] = {k: {"momentum_buffer": v["momentum_buffer"].clone()} for k, v in oa.state_dict()["state"].items()}
+    ob = FusedSGD(pb, lr=0.01, momentum=0.9, nesterov=True)
+    with torch.no_grad():
+        for a, b in zip(pa, pb):
+            b.copy_(a)
+    step(ob, pb, 2)                      # builds ob's flat buffer (with a wrong history) ...
+    with torch.no_grad():
+        for a, b in zip(pa, pb):
+            b.copy_(a)
+    ob.load_state_dict(sd)               # ... which load_state_dict must overwrite
+    step(oa, pa, 2); step(ob, pb, 2)
+    for a, b in zip(pa, pb):
+        assert torch.equal(a.detach(), b.detach())
+
+
 def test_labelmatch_device_path_matches_reference(golden):
     """LabelMatch on the device pipeline: rows, the per-class score lists (async pinned copy + flush) and the epoch thresholds
     against the live-reference fixture (tests/golden/labelmatch.npz)."""
