@@ -329,17 +329,23 @@ class SSODTrainerStep:
         g["uw"].copy_(unlabeled_imgs_ori, non_blocking=True)
         g["Ms"].copy_(unlabeled_M, non_blocking=True)
         comm_in_a = self.WORLD_SIZE > 1 and self.COMM_IN_GRAPH and (self.fixed_accumulate or max(round(64 / self.batch_size), 1) == 1)
-        if self.WORLD_SIZE > 1 and not self.COMM_IN_GRAPH:
-            self._bn_broadcast()
-        g["graph"].replay()
-        if self._warmup(ni):                 # host: accumulate / lr / momentum of iteration ni
-            if self.WORLD_SIZE > 1 and not comm_in_a:
-                self._arena.begin_step()
-                self._allreduce_grads()      # one SUM all-reduce per optimizer step, between the two graphs
+        # everything the host contributes to this iteration is enqueued BEFORE graph A, so that A, the all-reduce and B follow
+        # each other on the stream without a host gap: accumulate / lr / momentum of iteration ni (host scalars), and -- when
+        # the optimizer is due -- the EMA decays and the SGD hyper-parameters (stream-ordered copies: the previous replay of B
+        # has consumed the old values by the time they land)
+        due = self._warmup(ni)
+        if due:
             d1, d2 = next_pair_decays(self.ema, self.semi_ema)
             # pageable source: the runtime stages the 16 bytes before returning, so the next step cannot overwrite them early
             self._ema_scalars_dev.copy_(torch.tensor(ema_scalars(d1, d2), dtype=torch.float32))
             self.optimizer.refresh_hyper()   # lr / momentum of this step -> device memory read by the captured SGD kernel
+        if self.WORLD_SIZE > 1 and not self.COMM_IN_GRAPH:
+            self._bn_broadcast()
+        g["graph"].replay()
+        if due:
+            if self.WORLD_SIZE > 1 and not comm_in_a:
+                self._arena.begin_step()
+                self._allreduce_grads()      # one SUM all-reduce per optimizer step, between the two graphs (enqueued, no host sync)
             g["graph_b"].replay()
             self.last_opt_step = ni
         if hasattr(self.pseudo_label_creator, "stage_detections"):   # LabelMatch: the captured step cannot stage its detections itself
