@@ -93,11 +93,69 @@ def gen_labelmatch(ns):
     print("labelmatch thr_high[:8]", out["thr_high_e0"][:8], "thr_low[:8]", out["thr_low_e0"][:8])
 
 
+def gen_val_process_batch(ns):
+    """val.py:123-145 process_batch of the live reference on seeded detections / labels (no exact IoU ties)"""
+    os.environ.setdefault("WANDB_MODE", "disabled")
+    import val as V
+    r = np.random.RandomState(11)
+    cases = {}
+    for name, (N, M) in {"a": (300, 40), "b": (50, 120), "c": (7, 1), "d": (200, 200)}.items():
+        lab = np.zeros((M, 5), np.float32)
+        lab[:, 0] = r.randint(0, 5, M)
+        xy = r.uniform(50, 550, (M, 2)); wh = r.uniform(20, 200, (M, 2))
+        lab[:, 1:3] = xy - wh / 2; lab[:, 3:5] = xy + wh / 2
+        det = np.zeros((N, 6), np.float32)
+        src = r.randint(0, M, N)
+        det[:, :4] = lab[src, 1:5] + r.normal(0, 12, (N, 4)).astype(np.float32)
+        det[:, 4] = np.sort(r.uniform(0.001, 1, N))[::-1]
+        det[:, 5] = np.where(r.uniform(size=N) < 0.8, lab[src, 0], r.randint(0, 5, N))
+        want = V.process_batch(torch.from_numpy(det), torch.from_numpy(lab), torch.linspace(0.5, 0.95, 10)).numpy()
+        cases[name + "_det"] = det; cases[name + "_lab"] = lab; cases[name + "_correct"] = want
+    np.savez_compressed(os.path.join(HERE, "val_process_batch.npz"), **cases)
+
+
+def gen_extra_teachers(ns):
+    """FairPseudoLabel.create_pseudo_label_online_with_extra_teachers (self_supervised_utils.py:249-313) up to the point where
+    the reference raises: output_to_target_ssod unpacks 8 columns from the 6-column rows (plots.py:488).  The harness
+    intercepts that call and keeps its argument = the merged per-image detections."""
+    import utils.self_supervised_utils as U
+    fp = ns.FairPseudoLabel(ref_harness.make_cfg(SSOD_YAML))
+    captured = {}
+
+    class _Stop(Exception):
+        pass
+
+    def capture(out):
+        captured["out"] = [o.clone() for o in out]
+        raise _Stop()
+    orig, U.output_to_target_ssod = U.output_to_target_ssod, capture
+    try:
+        B, P = 2, 4000
+        pred = synth.make_teacher_pred(21, B, P, cand_frac=0.05)
+        e1 = synth.make_teacher_pred(22, B, P, cand_frac=0.04)
+        e2 = synth.make_teacher_pred(23, B, P, cand_frac=0.03)
+        try:
+            fp.create_pseudo_label_online_with_extra_teachers(torch.from_numpy(pred), [torch.from_numpy(e1), torch.from_numpy(e2)],
+                                                              torch.zeros(B, 3, 640, 640), torch.from_numpy(synth.make_Ms(9, B, 640)),
+                                                              [{3: 70, 5: 1, 7: 7}, {}], -1)
+        except _Stop:
+            pass
+    finally:
+        U.output_to_target_ssod = orig
+    ref = [o.numpy() for o in captured["out"]]
+    np.savez_compressed(os.path.join(HERE, "extra_teachers.npz"), conf=np.float32(fp.nms_conf_thres), iou=np.float32(fp.nms_iou_thres),
+                        n0=len(ref[0]), out0=ref[0], out1=ref[1])
+
+
 def main():
     ns = ref_harness.load_reference()
     if len(sys.argv) > 1 and sys.argv[1] == "--only-val-nms":      # adds one fixture without touching the others
         torch.set_num_threads(8)
         gen_val_nms(ns)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "--only-val-extra":      # val.process_batch + extra-teachers merge fixtures
+        gen_val_process_batch(ns)
+        gen_extra_teachers(ns)
         return
     if len(sys.argv) > 1 and sys.argv[1] == "--only-labelmatch":
         torch.set_num_threads(8)
@@ -244,6 +302,8 @@ def main():
         out.update({f"ssup{step}_{k}": v.numpy().copy() for k, v in ssup.ema.state_dict().items()})
     out["semi_decay"] = semi.decay
     np.savez_compressed(os.path.join(HERE, "ema.npz"), **out)
+    gen_val_process_batch(ns)
+    gen_extra_teachers(ns)
     print("done")
 
 
