@@ -219,17 +219,24 @@ __global__ void __launch_bounds__(BN_THREADS) bn_act_apply_kernel(const __nv_bfl
       for (int j = 0; j < 8; ++j) f[j] += q[j];
     }
   };
-  for (; e + stride < total; e += 2 * stride) {
-    const long r0 = e >> lg, r1 = (e + stride) >> lg;
-    float f0[8], f1[8];
-    load8(y + r0 * ycs, f0);
-    load8(y + r1 * ycs, f1);
-    body(f0, r0);
-    body(f1, r1);
-    store8(out + r0 * ocs, f0);
-    store8(out + r1 * ocs, f1);
+  // 4 rows (4 x 16 B loads) in flight per thread: the loop is latency-bound, not bandwidth-bound, on the mid-size layers
+  for (; e + 3 * stride < total; e += 4 * stride) {
+    long r[4];
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      r[u] = (e + u * stride) >> lg;
+      v[u] = *reinterpret_cast<const uint4*>(y + r[u] * ycs);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+      unpack8(v[u], f);
+      body(f, r[u]);
+      store8(out + r[u] * ocs, f);
+    }
   }
-  if (e < total) {
+  for (; e < total; e += stride) {
     const long r0 = e >> lg;
     float f0[8];
     load8(y + r0 * ycs, f0);
@@ -295,7 +302,7 @@ __global__ void __launch_bounds__(BNR_CH * BNR_GR) bn_bwd_finalize_kernel(const 
 // ---- backward apply: dy = gamma*invstd * (dz - sum_dz/M - xhat*sum_dz_xhat/M) ----
 // Same fixed-channel-group structure as the forward apply: the six per-channel vectors are folded into five register
 // arrays once per thread.
-__global__ void __launch_bounds__(BN_THREADS, 3) bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ y,
+__global__ void __launch_bounds__(BN_THREADS, 2) bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ y,
                                                                       const float* __restrict__ scale, const float* __restrict__ shift,
                                                                       const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                       const float* __restrict__ sums, long M, int C, int dacs, int ycs, int ocs,
@@ -333,19 +340,26 @@ __global__ void __launch_bounds__(BN_THREADS, 3) bn_act_bwd_apply_kernel(const _
       fd[j] = fmaf(sc[j], dz, fmaf(fy[j], P[j], Q[j]));   // sc = gamma*invstd
     }
   };
-  for (; e + stride < total; e += 2 * stride) {
-    const long r0 = e >> lg, r1 = (e + stride) >> lg;
-    float y0[8], d0[8], y1[8], d1[8];
-    load8(y + r0 * ycs, y0);
-    load8(da + r0 * dacs, d0);
-    load8(y + r1 * ycs, y1);
-    load8(da + r1 * dacs, d1);
-    body(y0, d0);
-    body(y1, d1);
-    store8(dy + r0 * ocs, d0);
-    store8(dy + r1 * ocs, d1);
+  // 4 rows (8 x 16 B loads) in flight per thread
+  for (; e + 3 * stride < total; e += 4 * stride) {
+    long r[4];
+    uint4 vy[4], vd[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      r[u] = (e + u * stride) >> lg;
+      vy[u] = *reinterpret_cast<const uint4*>(y + r[u] * ycs);
+      vd[u] = *reinterpret_cast<const uint4*>(da + r[u] * dacs);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float fy[8], fd[8];
+      unpack8(vy[u], fy);
+      unpack8(vd[u], fd);
+      body(fy, fd);
+      store8(dy + r[u] * ocs, fd);
+    }
   }
-  if (e < total) {
+  for (; e < total; e += stride) {
     const long r0 = e >> lg;
     float y0[8], d0[8];
     load8(y + r0 * ycs, y0);
