@@ -162,10 +162,11 @@ def dominant_kernel_roofline(dev, peak_tflops, peak_kind):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full capture
-DOMINANT_TRAFFIC = 27.42e6 + 13.82e6
-DOMINANT_TRAFFIC_NOTE = ("dram__bytes_read+write per launch from ncu --set full (profiles/prof_conv_fwd2_raw_3x3_256.ncu-rep, mean of 2 "
-                         "launches: 27.42 MB read, 12.5-15.1 MB written); algorithmic bytes 26.2 MB in + 1.2 MB weights + 26.2 MB out "
-                         "(the rest of the output is still L2-resident at kernel end): no re-reads")
+DOMINANT_TRAFFIC = 27.45e6 + 0.01e6
+DOMINANT_TRAFFIC_NOTE = ("dram__bytes_read+write per launch from ncu --set full (profiles/r2_prof_conv_fwd2_raw_3x3_256.ncu-rep, 2 launches: 27.45 MB "
+                         "read, 6-13 KB written: under ncu's serialised replay the 26.2 MB output stays L2-resident at kernel end; round 1's capture "
+                         "with a cold L2 between launches showed 12.5-15.1 MB written); algorithmic bytes 26.2 MB in + 1.2 MB weights + 26.2 MB out: "
+                         "no re-reads; tensor pipe 75.8 % active")
 
 
 def kernel_table(step, ni, path, graph_ms):
@@ -531,7 +532,8 @@ def main():
     probe_first, probe_last = ni, ni + args.steps - 1
     ms = timed(step_resident_probed, args.steps, ni); ni += args.steps
     if ssod:
-        (n_pl0, det_per_img0), (n_pl_timed, det_timed) = [(int(a.item()), float(b.item())) for a, b in pl_probe]
+        probes = [(int(a.item()), float(b.item())) for a, b in pl_probe]
+        (n_pl0, det_per_img0), (n_pl_timed, det_timed) = probes[0], probes[-1]        # --steps 1: first == last
         with torch.no_grad():
             (pred_t, _r), _f = st.ema.ema(d_uw)
             cand_timed_end = float((pred_t[..., 4] > cfg.SSOD.nms_conf_thres).sum(1).float().mean())
