@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_act_apply_kernel(const __nv_bfl
 }
 
 // ---- backward reduce: sums[0][c] = sum dz, sums[1][c] = sum dz*xhat,  dz = da * act'(z) ----
-__global__ void __launch_bounds__(BN_THREADS, 3) bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ y,
+__global__ void __launch_bounds__(BN_THREADS) bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ y,
                                                                        const float* __restrict__ scale, const float* __restrict__ shift,
                                                                        const float* __restrict__ mean, const float* __restrict__ invstd, int M,
                                                                        int C, int dacs, int ycs, int act, float* __restrict__ sums) {
