@@ -23,6 +23,9 @@
 #define CONV_BLOCK_K 64
 #define CONV_THREADS 320     // warp0 TMA, warp1 MMA, warps2-9 epilogue
 #define WGRAD_THREADS 192
+#ifndef ETB_WGRAD2_DEFAULT
+#define ETB_WGRAD2_DEFAULT 0     // 2-SM weight-gradient kernels: 0 off, 1 NW = 128, 2 NW = 256 (env ETB_WGRAD2 overrides)
+#endif
 
 // ------------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -54,6 +57,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       __trap();
     }
   }
+}
+// One lane of a CONVERGED warp (elect.sync).  The producer / MMA warps run their loops with all 32 lanes (warp-uniform
+// control flow, operands in uniform registers) and wrap only the TMA / tcgen05 instructions in `if (elect_one())`: issued from
+// inside an `if (lane == 0)` region every UTCHMMA / UTMALDG / UTCBAR is emitted as an ELECT + R2UR.BROADCAST + BRA.U.ANY
+// waterfall loop (~50 cycles per instruction on the single issuing thread, measured with tools/mma_probe.cu), which bounds
+// every tile with N < 256 by instruction issue instead of by the tensor pipe.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -366,54 +383,57 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   ETB_PDL_PROLOGUE();      // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      const uint32_t a_bytes = (uint32_t)(a.TW * a.TH * 128);
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n0 = (tile % n_tiles) * BN;
-        int t = tile / n_tiles;
-        const int tw_i = t % a.tiles_w; t /= a.tiles_w;
-        const int th_i = t % a.tiles_h; t /= a.tiles_h;
-        const int img = t;
-        const int w0 = tw_i * a.TW, h0 = th_i * a.TH;
-        for (int tp = 0; tp < a.ntaps; ++tp)
-          for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
-            const int s = it % STAGES;
-            const uint32_t ph = (uint32_t)((it / STAGES) & 1);
-            mbar_wait(&empty[s], ph ^ 1u);
-            uint8_t* sa = smem + s * L::STAGE_BYTES;
-            uint8_t* sb = sa + L::A_BYTES;
+    // ===== TMA producer: the whole warp runs the loop (uniform), one elected lane issues =====
+    const uint32_t a_bytes = (uint32_t)(a.TW * a.TH * 128);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n0 = (tile % n_tiles) * BN;
+      int t = tile / n_tiles;
+      const int tw_i = t % a.tiles_w; t /= a.tiles_w;
+      const int th_i = t % a.tiles_h; t /= a.tiles_h;
+      const int img = t;
+      const int w0 = tw_i * a.TW, h0 = th_i * a.TH;
+      for (int tp = 0; tp < a.ntaps; ++tp)
+        for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+          mbar_wait(&empty[s], ph ^ 1u);
+          uint8_t* sa = smem + s * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          if (elect_one()) {
             mbar_expect_tx(&full[s], a_bytes + (uint32_t)L::B_BYTES);
             tma_load_4d(&mapA, &full[s], sa, kb * CONV_BLOCK_K, w0 * a.stride + a.tap_dw[tp], h0 * a.stride + a.tap_dh[tp], img);
             tma_load_2d(&mapB, &full[s], sb, (tp * a.kblocks + kb) * CONV_BLOCK_K, n0);
           }
-      }
+          __syncwarp();
+        }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(CONV_BLOCK_M, BN);
-      int it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
-        const int acc = lt & 1;
-        mbar_wait(&tmem_empty[acc], (uint32_t)(((lt >> 1) & 1) ^ 1));   // epilogue drained this accumulator
+    // ===== MMA issuer: warp-uniform loop, one elected lane issues the MMAs and their commit =====
+    constexpr uint32_t idesc = make_idesc_bf16(CONV_BLOCK_M, BN);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    int it = 0, lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      const int acc = lt & 1;
+      mbar_wait(&tmem_empty[acc], (uint32_t)(((lt >> 1) & 1) ^ 1));   // epilogue drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_u + (uint32_t)(acc * BN);
+      for (int ki = 0; ki < kiters; ++ki, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+        mbar_wait(&full[s], ph);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        for (int ki = 0; ki < kiters; ++ki, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (uint32_t)((it / STAGES) & 1);
-          mbar_wait(&full[s], ph);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
-          const uint64_t adesc = make_kmajor_sw128_desc(sa);
-          const uint64_t bdesc = make_kmajor_sw128_desc(sa + L::A_BYTES);
+        const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+        const uint64_t adesc = make_kmajor_sw128_desc(sa);
+        const uint64_t bdesc = make_kmajor_sw128_desc(sa + L::A_BYTES);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < CONV_BLOCK_K / 16; ++k)  // +32 B per UMMA_K step inside the 128 B swizzle atom
             umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ki | k) != 0 ? 1u : 0u);
           umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
+          if (ki == kiters - 1) umma_commit(&tmem_full[acc]);  // accumulator complete
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete
+        __syncwarp();
       }
     }
   } else {
@@ -555,40 +575,43 @@ conv_fwd2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs: own A tile, own half of B; bytes are accounted on the leader's full barrier) =====
-    if (lane == 0) {
-      const uint32_t a_bytes = (uint32_t)(a.TW * a.TH * 128);
-      int it = 0;
-      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
-        const int n0 = (tile % n_tiles) * BN;
-        int t = (tile / n_tiles) * 2 + (int)rank;    // this CTA's m tile (may be == m_tiles for the odd tail: OOB -> zeros)
-        const int tw_i = t % a.tiles_w; t /= a.tiles_w;
-        const int th_i = t % a.tiles_h; t /= a.tiles_h;
-        const int img = t;
-        const int w0 = tw_i * a.TW, h0 = th_i * a.TH;
-        for (int tp = 0; tp < a.ntaps; ++tp)
-          for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
-            const int s = it % STAGES;
-            const uint32_t ph = (uint32_t)((it / STAGES) & 1);
-            mbar_wait(&empty[s], ph ^ 1u);           // my own smem stage is free (commit is multicast to both CTAs)
-            uint8_t* sa = smem + s * L::STAGE_BYTES;
-            uint8_t* sb = sa + L::A_BYTES;
+    // (warp-uniform loop, one elected lane issues: see elect_one)
+    const uint32_t a_bytes = (uint32_t)(a.TW * a.TH * 128);
+    int it = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+      const int n0 = (tile % n_tiles) * BN;
+      int t = (tile / n_tiles) * 2 + (int)rank;    // this CTA's m tile (may be == m_tiles for the odd tail: OOB -> zeros)
+      const int tw_i = t % a.tiles_w; t /= a.tiles_w;
+      const int th_i = t % a.tiles_h; t /= a.tiles_h;
+      const int img = t;
+      const int w0 = tw_i * a.TW, h0 = th_i * a.TH;
+      for (int tp = 0; tp < a.ntaps; ++tp)
+        for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+          mbar_wait(&empty[s], ph ^ 1u);           // my own smem stage is free (commit is multicast to both CTAs)
+          uint8_t* sa = smem + s * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          if (elect_one()) {
             if (rank == 0) mbar_expect_tx(&full[s], 2u * (a_bytes + (uint32_t)L::B_BYTES));
             else mbar_arrive_leader(&full[s]);
             tma_load_4d_2sm(&mapA, &full[s], sa, kb * CONV_BLOCK_K, w0 * a.stride + a.tap_dw[tp], h0 * a.stride + a.tap_dh[tp], img);
             tma_load_2d_2sm(&mapB, &full[s], sb, (tp * a.kblocks + kb) * CONV_BLOCK_K, n0 + (BN / 2) * (int)rank);
           }
-      }
+          __syncwarp();
+        }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: leader CTA only, one thread, for the pair =====
-    if (rank == 0 && lane == 0) {
+    // ===== MMA issuer: leader CTA only, for the pair (warp-uniform loop, one elected lane issues) =====
+    if (rank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(256, BN);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       int it = 0, lt = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++lt) {
         const int acc = lt & 1;
         mbar_wait(&tmem_empty[acc], (uint32_t)(((lt >> 1) & 1) ^ 1));   // both CTAs' epilogues drained this accumulator
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t tmem_d = tmem_u + (uint32_t)(acc * BN);
         for (int ki = 0; ki < kiters; ++ki, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (uint32_t)((it / STAGES) & 1);
@@ -597,12 +620,15 @@ conv_fwd2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
           const uint64_t adesc = make_kmajor_sw128_desc(sa);
           const uint64_t bdesc = make_kmajor_sw128_desc(sa + L::A_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < CONV_BLOCK_K / 16; ++k)
-            umma_bf16_2sm(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ki | k) != 0 ? 1u : 0u);
-          umma_commit_2sm(&empty[s]);
+            for (int k = 0; k < CONV_BLOCK_K / 16; ++k)
+              umma_bf16_2sm(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ki | k) != 0 ? 1u : 0u);
+            umma_commit_2sm(&empty[s]);
+            if (ki == kiters - 1) umma_commit_2sm(&tmem_full[acc]);
+          }
+          __syncwarp();
         }
-        umma_commit_2sm(&tmem_full[acc]);
       }
     }
   } else {
@@ -1059,18 +1085,19 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ 
   const uint32_t box_bytes = (uint32_t)a.kpix * 128u;   // bytes one TMA box writes (all rows, OOB rows zero-filled)
 
   if (warp == 0) {
-    if (lane == 0) {
-      for (int it = 0; it < kiters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)((it / STAGES) & 1);
-        int kb = kb0 + it;
-        const int tw_i = kb % a.tiles_w; kb /= a.tiles_w;
-        const int th_i = kb % a.tiles_h; kb /= a.tiles_h;
-        const int img = kb;
-        const int w0 = tw_i * a.TW, h0 = th_i * a.TH;
-        mbar_wait(&empty[s], ph ^ 1u);
-        uint8_t* sa = smem + s * L::STAGE_BYTES;
-        uint8_t* sb = sa + L::A_BYTES;
+    // warp-uniform loop, one elected lane issues (see elect_one)
+    for (int it = 0; it < kiters; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+      int kb = kb0 + it;
+      const int tw_i = kb % a.tiles_w; kb /= a.tiles_w;
+      const int th_i = kb % a.tiles_h; kb /= a.tiles_h;
+      const int img = kb;
+      const int w0 = tw_i * a.TW, h0 = th_i * a.TH;
+      mbar_wait(&empty[s], ph ^ 1u);
+      uint8_t* sa = smem + s * L::STAGE_BYTES;
+      uint8_t* sb = sa + L::A_BYTES;
+      if (elect_one()) {
         mbar_expect_tx(&full[s], box_bytes * (2u * MT + BN / 64));
         if (CL) {
           const int ga = (int)(crank & 1), gb = (int)(crank >> 1);   // my share: one dy group, one x group
@@ -1084,29 +1111,34 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ 
             tma_load_4d(&mapX, &full[s], sb + g * L::GROUP_BYTES, ci0 + 64 * g, w0 * a.stride + a.tap_dw[tap], h0 * a.stride + a.tap_dh[tap], img);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16_mn(128, BN);
-      const int ksteps = a.kpix / 16;
-      for (int it = 0; it < kiters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)((it / STAGES) & 1);
-        mbar_wait(&full[s], ph);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
-        const uint64_t bdesc = make_mnmajor_sw128_desc(sa + L::A_BYTES, L::GROUP_BYTES);
+    constexpr uint32_t idesc = make_idesc_bf16_mn(128, BN);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const int ksteps = a.kpix / 16;
+    for (int it = 0; it < kiters; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+      const uint64_t bdesc = make_mnmajor_sw128_desc(sa + L::A_BYTES, L::GROUP_BYTES);
+      if (elect_one()) {
+        // k outer, m tile inner: consecutive MMAs go to different accumulators
+        for (int k = 0; k < ksteps; ++k) {   // 16 K rows = two 1024 B atoms per UMMA_K step
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          const uint64_t adesc = make_mnmajor_sw128_desc(sa + mt * 2 * L::GROUP_BYTES, L::GROUP_BYTES);
-          for (int k = 0; k < ksteps; ++k)   // 16 K rows = two 1024 B atoms per UMMA_K step
-            umma_bf16(tmem_base + (uint32_t)(mt * BN), adesc + (uint64_t)(k * (2048 >> 4)), bdesc + (uint64_t)(k * (2048 >> 4)), idesc,
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint64_t adesc = make_mnmajor_sw128_desc(sa + mt * 2 * L::GROUP_BYTES, L::GROUP_BYTES);
+            umma_bf16(tmem_u + (uint32_t)(mt * BN), adesc + (uint64_t)(k * (2048 >> 4)), bdesc + (uint64_t)(k * (2048 >> 4)), idesc,
                       (it | k) != 0 ? 1u : 0u);
+          }
         }
         if (CL) umma_commit_mc(&empty[s], (uint16_t)(mask_a | mask_b));   // me + the two CTAs that write into my stage
         else umma_commit(&empty[s]);
+        if (it == kiters - 1) umma_commit(tmem_full);
       }
-      umma_commit(tmem_full);
+      __syncwarp();
     }
   } else {
     const int row = 32 * (warp & 3) + lane;
@@ -1309,8 +1341,9 @@ struct Wgrad2Args {
   int TW, TH, tiles_w, tiles_h, nimg;
   int kpix;                 // TW*TH, multiple of 16, <= KP
   int NT;                   // virtual columns per cluster tile
-  int nvirt;                // ci_tiles * ntaps
+  int nvirt;                // virtual columns of the layer
   int groups;               // ceil(nvirt / NT)
+  int cit;                  // NW = 256: Cin / 256 (ci tiles per tap)
   int Cout, Cin;
   float* dw;
   long dw_split_stride;
@@ -1320,16 +1353,36 @@ template <int KP, int STAGES>
 struct Wgrad2Smem {
   static constexpr int GROUP_BYTES = KP * 128;            // one 64-channel group, KP pixel rows
   static constexpr int A_BYTES = 2 * GROUP_BYTES;         // this CTA's 128 co of dy
-  static constexpr int B_MAX = 4 * GROUP_BYTES;           // up to 4 virtual columns x this CTA's 64 ci
+  static constexpr int B_MAX = 4 * GROUP_BYTES;           // NT virtual columns x this CTA's NW/2 ci = up to four 64-channel groups
   static constexpr int STAGE_BYTES = A_BYTES + B_MAX;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;
 };
 
-template <int KP, int STAGES>
+// virtual column -> (filter tap, first input channel).  NW = 128: a (128-ci tile, tap) pair, taps fastest (a tile of NT = 3
+// columns is one filter row of one ci tile); NW = 256: a (tap, 256-ci tile) pair, ci tiles fastest (Cin % 256 == 0).
+template <int NW>
+__device__ __forceinline__ void wgrad2_vcol(const Wgrad2Args& a, int v, int* tap, int* cbase) {
+  if (NW == 128) {
+    const int ci_t = v / a.ntaps;
+    *tap = v - ci_t * a.ntaps;
+    *cbase = ci_t * 128;
+  } else {
+    const int tp = v / a.cit;
+    *tap = tp;
+    *cbase = (v - tp * a.cit) * 256;
+  }
+}
+
+// NW = MMA N = accumulator width.  tools/mma_probe.cu: tcgen05.mma (SS) reaches the tensor-pipe floor for N >= 128 when the
+// issuing warp is converged, but the operand feed does not: per 64-pixel K block and SM the NW = 128 tile ingests
+// (16 + 8 NT) KB for 256 NT MMA cycles (53 B/clk at NT = 3), the NW = 256 tile (16 + 16 NT) KB for 512 NT cycles (47 B/clk at
+// NT = 1, 31 B/clk at NT = 2) -- and the wide MMA halves the instructions per FLOP.
+template <int KP, int STAGES, int NW>
 __global__ void __launch_bounds__(WGRAD_THREADS, 1)
 wgrad2_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ CUtensorMap mapX, const Wgrad2Args a) {
   using L = Wgrad2Smem<KP, STAGES>;
+  constexpr int GPC = NW / 128;                      // 64-channel x groups per virtual column and CTA
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = (uint64_t*)(smem + L::BAR_OFF);
@@ -1344,7 +1397,8 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__
   const int v0 = grp * a.NT;
   const int nt = min(a.NT, a.nvirt - v0);            // virtual columns of this tile (the last group may be short)
   const int co0 = cop * 256 + (int)rank * 128;       // this CTA's 128 co rows
-  const uint32_t tmem_cols = a.NT <= 1 ? 128u : (a.NT == 2 ? 256u : 512u);
+  const int acc_cols = a.NT * NW;
+  const uint32_t tmem_cols = acc_cols <= 128 ? 128u : (acc_cols <= 256 ? 256u : 512u);
 
   const int total_kb = a.nimg * a.tiles_h * a.tiles_w;
   const int chunk = (total_kb + gridDim.y - 1) / gridDim.y;
@@ -1369,33 +1423,38 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__
   const uint32_t box_bytes = (uint32_t)a.kpix * 128u;
 
   if (warp == 0) {
-    if (lane == 0) {
-      for (int it = 0; it < kiters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)((it / STAGES) & 1);
-        int kb = kb0 + it;
-        const int tw_i = kb % a.tiles_w; kb /= a.tiles_w;
-        const int th_i = kb % a.tiles_h; kb /= a.tiles_h;
-        const int img = kb;
-        const int w0 = tw_i * a.TW, h0 = th_i * a.TH;
-        mbar_wait(&empty[s], ph ^ 1u);
-        uint8_t* sa = smem + s * L::STAGE_BYTES;
-        uint8_t* sb = sa + L::A_BYTES;
-        if (rank == 0) mbar_expect_tx(&full[s], 2u * box_bytes * (uint32_t)(2 + nt));
+    // warp-uniform loop, one elected lane issues (see elect_one)
+    for (int it = 0; it < kiters; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+      int kb = kb0 + it;
+      const int tw_i = kb % a.tiles_w; kb /= a.tiles_w;
+      const int th_i = kb % a.tiles_h; kb /= a.tiles_h;
+      const int img = kb;
+      const int w0 = tw_i * a.TW, h0 = th_i * a.TH;
+      mbar_wait(&empty[s], ph ^ 1u);
+      uint8_t* sa = smem + s * L::STAGE_BYTES;
+      uint8_t* sb = sa + L::A_BYTES;
+      if (elect_one()) {
+        if (rank == 0) mbar_expect_tx(&full[s], 2u * box_bytes * (uint32_t)(2 + nt * GPC));
         else mbar_arrive_leader(&full[s]);
 #pragma unroll
         for (int g = 0; g < 2; ++g) tma_load_4d_2sm(&mapDy, &full[s], sa + g * L::GROUP_BYTES, co0 + 64 * g, w0, h0, img);
         for (int t = 0; t < nt; ++t) {
-          const int v = v0 + t;
-          const int ci_t = v / a.ntaps, tap = v - ci_t * a.ntaps;
-          tma_load_4d_2sm(&mapX, &full[s], sb + t * L::GROUP_BYTES, ci_t * 128 + 64 * (int)rank, w0 * a.stride + a.tap_dw[tap],
-                          h0 * a.stride + a.tap_dh[tap], img);
+          int tap, cbase;
+          wgrad2_vcol<NW>(a, v0 + t, &tap, &cbase);
+#pragma unroll
+          for (int g = 0; g < GPC; ++g)
+            tma_load_4d_2sm(&mapX, &full[s], sb + (t * GPC + g) * L::GROUP_BYTES, cbase + (NW / 2) * (int)rank + 64 * g,
+                            w0 * a.stride + a.tap_dw[tap], h0 * a.stride + a.tap_dh[tap], img);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (rank == 0 && lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16_mn(256, 128);
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16_mn(256, NW);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const int ksteps = a.kpix / 16;
       for (int it = 0; it < kiters; ++it) {
         const int s = it % STAGES;
@@ -1404,15 +1463,18 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
         const uint64_t adesc = make_mnmajor_sw128_desc(sa, L::GROUP_BYTES);
-        for (int t = 0; t < nt; ++t) {
-          const uint64_t bdesc = make_mnmajor_sw128_desc(sa + L::A_BYTES + t * L::GROUP_BYTES, L::GROUP_BYTES);
+        if (elect_one()) {
           for (int k = 0; k < ksteps; ++k)
-            umma_bf16_2sm(tmem_base + (uint32_t)(t * 128), adesc + (uint64_t)(k * (2048 >> 4)), bdesc + (uint64_t)(k * (2048 >> 4)), idesc,
-                          (it | k) != 0 ? 1u : 0u);
+            for (int t = 0; t < nt; ++t) {
+              const uint64_t bdesc = make_mnmajor_sw128_desc(sa + L::A_BYTES + t * GPC * L::GROUP_BYTES, L::GROUP_BYTES);
+              umma_bf16_2sm(tmem_u + (uint32_t)(t * NW), adesc + (uint64_t)(k * (2048 >> 4)), bdesc + (uint64_t)(k * (2048 >> 4)), idesc,
+                            (it | k) != 0 ? 1u : 0u);
+            }
+          umma_commit_2sm(&empty[s]);
+          if (it == kiters - 1) umma_commit_2sm(tmem_full);
         }
-        umma_commit_2sm(&empty[s]);
+        __syncwarp();
       }
-      umma_commit_2sm(tmem_full);
     }
   } else if (kiters > 0) {
     const int row = 32 * (warp & 3) + lane;
@@ -1420,13 +1482,12 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     for (int t = 0; t < nt; ++t) {
-      const int v = v0 + t;
-      const int ci_t = v / a.ntaps, tap = v - ci_t * a.ntaps;
-      const int ci0 = ci_t * 128;
-      const uint32_t lane_addr = tmem_base + (uint32_t)(t * 128) + ((uint32_t)(32 * (warp & 3)) << 16);
+      int tap, ci0;
+      wgrad2_vcol<NW>(a, v0 + t, &tap, &ci0);
+      const uint32_t lane_addr = tmem_base + (uint32_t)(t * NW) + ((uint32_t)(32 * (warp & 3)) << 16);
       float* dst = a.dw + (size_t)blockIdx.y * a.dw_split_stride + ((size_t)co * a.ntaps + tap) * a.Cin + ci0;
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+      for (int c0 = 0; c0 < NW; c0 += 32) {
         if (ci0 + c0 >= a.Cin) break;
         uint32_t v32[32];
         tmem_ld32(lane_addr + (uint32_t)c0, v32);
@@ -1448,20 +1509,21 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__
   }
 }
 
-static bool wgrad2_eligible(const EtbConvParams* cp, int32_t flags) {
-  // opt-in (ETB_WGRAD2=1, read per call so tests can toggle it): correct, but measured SLOWER than the 1-SM kernel -- 153 vs
-  // 116 us on 3x3 256->256 @40 b32, tensor pipe 24 % vs 36 % active (profiles/r2_wgrad_ncu.md).  The operand stream it was
-  // built to shrink (xbar->L1 393 MB vs 944 MB) is not what bounds either kernel: lts throughput is 13-19 % of peak; the
-  // MN-major tcgen05.mma itself issues at ~2.3-4x its ideal cycle count.
+// which 2-SM weight-gradient kernel runs on this shape: 0 none (1-SM kernels), 1 the NW = 128 multi-accumulator tile, 2 the
+// NW = 256 tile.  ETB_WGRAD2 is read per call so tests and benchmarks can toggle it.
+static int wgrad2_mode(const EtbConvParams* cp, int32_t flags) {
   const char* e = getenv("ETB_WGRAD2");
-  const int on = (e && e[0] == '1') ? 1 : 0;
+  const int want = e ? atoi(e) : ETB_WGRAD2_DEFAULT;
   const int ntaps = cp->kh * cp->kw;
-  return on && !(flags & 1) && cp->Cout >= 256 && cp->Cin >= 128 && cp->Cin % 64 == 0 && (ntaps == 1 || ntaps % 3 == 0) && ntaps <= 12;
+  if ((flags & 1) || cp->Cout < 256 || ntaps > 12) return 0;
+  if (want == 2 && cp->Cin % 256 == 0) return 2;
+  if (want == 1 && cp->Cin >= 128 && cp->Cin % 64 == 0 && (ntaps == 1 || ntaps % 3 == 0)) return 1;
+  return 0;
 }
 
-// tiling + split-K of the 2-SM kernel (shared by the workspace query and the launch)
-static void wgrad2_plan(const EtbConvParams* cp, int* NT_, int* TW, int* TH, int* tiles_w, int* tiles_h, int* nimg, int* groups_, int* co_pairs_,
-                        int* splitk) {
+// tiling + split-K of the 2-SM kernels (shared by the workspace query and the launch)
+static void wgrad2_plan(const EtbConvParams* cp, int mode, int* NT_, int* TW, int* TH, int* tiles_w, int* tiles_h, int* nimg, int* groups_,
+                        int* co_pairs_, int* nvirt_, int* splitk) {
   constexpr int KP = 64;
   const int Ho = (cp->H + 2 * cp->pad - cp->kh) / cp->stride + 1;
   const int Wo = (cp->W + 2 * cp->pad - cp->kw) / cp->stride + 1;
@@ -1474,16 +1536,28 @@ static void wgrad2_plan(const EtbConvParams* cp, int* NT_, int* TW, int* TH, int
     *tiles_w = (Wo + *TW - 1) / *TW; *tiles_h = (Ho + *TH - 1) / *TH; *nimg = cp->N;
   }
   const int ntaps = cp->kh * cp->kw;
-  const int ci_tiles = (cp->Cin + 127) / 128;
-  const int nvirt = ci_tiles * ntaps;
-  int NT = (ntaps % 3 == 0) ? 3 : (ci_tiles >= 4 ? 4 : ci_tiles);
+  int nvirt, NT;
+  double mma_us;                           // one virtual column of one 64-pixel K block: 4 MMAs
+  if (mode == 2) {
+    nvirt = ntaps * (cp->Cin / 256);
+    NT = nvirt >= 2 ? 2 : 1;
+    const char* e = getenv("ETB_WGRAD2_NT");          // tuning override (1 | 2)
+    if (e && atoi(e) >= 1 && atoi(e) <= 2) NT = atoi(e);
+    mma_us = 0.27;
+  } else {
+    const int ci_tiles = (cp->Cin + 127) / 128;
+    nvirt = ci_tiles * ntaps;
+    NT = (ntaps % 3 == 0) ? 3 : (ci_tiles >= 4 ? 4 : ci_tiles);
+    mma_us = 0.135;
+  }
   const int groups = (nvirt + NT - 1) / NT;
   const int co_pairs = (cp->Cout + 255) / 256;
   const int clusters = groups * co_pairs;
   const int total_kb = *nimg * *tiles_h * *tiles_w;
-  // split-K: whole waves of (SMs / 2) clusters; cost per cluster = K blocks * NT * 4 MMAs (64 cycles each at M=256) + fixed
+  // split-K: whole waves of (SMs / 2) clusters; cost per cluster = K blocks * NT columns * 4 MMAs + fixed (launch, TMEM
+  // allocation, pipeline fill, the epilogue's partial-tile stores)
   const int slots = etb_num_sms() / 2;
-  const double t_kb = 0.135 * NT * (double)(*TW * *TH) / 64.0, t_fixed = 7.0 + 1.2 * NT;
+  const double t_kb = mma_us * NT * (double)(*TW * *TH) / 64.0, t_fixed = 7.0 + (mode == 2 ? 1.6 : 1.2) * NT;
   int sk = 1;
   double best = 1e30;
   const int sk_max = total_kb < 512 ? total_kb : 512;
@@ -1496,14 +1570,15 @@ static void wgrad2_plan(const EtbConvParams* cp, int* NT_, int* TW, int* TH, int
     const double cost = (double)rounds * (per * t_kb + t_fixed) + 0.004 * c;
     if (cost < best) { best = cost; sk = c; }
   }
-  *NT_ = NT; *groups_ = groups; *co_pairs_ = co_pairs; *splitk = sk;
+  *NT_ = NT; *groups_ = groups; *co_pairs_ = co_pairs; *nvirt_ = nvirt; *splitk = sk;
 }
 
+template <int NW>
 static int launch_wgrad2(const CUtensorMap& mDy, const CUtensorMap& mX, const Wgrad2Args& wa, int clusters, int splitk, cudaStream_t st) {
   using L = Wgrad2Smem<64, 4>;
   static bool attr_set = false;
   if (!attr_set) {
-    ETB_CHECK_CUDA(cudaFuncSetAttribute(wgrad2_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    ETB_CHECK_CUDA(cudaFuncSetAttribute(wgrad2_kernel<64, 4, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
@@ -1514,7 +1589,7 @@ static int launch_wgrad2(const CUtensorMap& mDy, const CUtensorMap& mX, const Wg
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = etb_pdl_enabled() ? 2 : 1;
-  ETB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, wgrad2_kernel<64, 4>, mDy, mX, wa));
+  ETB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, wgrad2_kernel<64, 4, NW>, mDy, mX, wa));
   etb_count_launch();
   return ETB_OK;
 }
@@ -1568,9 +1643,10 @@ extern "C" size_t etb_conv_wgrad_workspace_bytes(const EtbConvParams* cp) {
   if (!cp || cp->Cin <= 0 || cp->Cout <= 0) return 0;
   int BN, KP, TW, TH, tw, th, ni, ot, sk;
   wgrad_plan(cp, &BN, &KP, &TW, &TH, &tw, &th, &ni, &ot, &sk);
-  if (wgrad2_eligible(cp, 0)) {          // the caller may run either kernel on this shape: size for the larger split
-    int NT, g, cpz, sk2;
-    wgrad2_plan(cp, &NT, &TW, &TH, &tw, &th, &ni, &g, &cpz, &sk2);
+  const int mode2 = wgrad2_mode(cp, 0);
+  if (mode2) {                           // the caller may run either kernel on this shape: size for the larger split
+    int NT, g, cpz, nv, sk2;
+    wgrad2_plan(cp, mode2, &NT, &TW, &TH, &tw, &th, &ni, &g, &cpz, &nv, &sk2);
     if (sk2 > sk) sk = sk2;
   }
   return (size_t)sk * cp->Cout * cp->kh * cp->kw * cp->Cin * sizeof(float);
@@ -1593,7 +1669,8 @@ extern "C" int etb_conv_wgrad(const void* x_bf16, const void* dy_bf16, float* dw
   }
   const int Ho = (cp->H + 2 * cp->pad - cp->kh) / cp->stride + 1;
   const int Wo = (cp->W + 2 * cp->pad - cp->kw) / cp->stride + 1;
-  const bool use2 = wgrad2_eligible(cp, flags);
+  const int mode2 = wgrad2_mode(cp, flags);
+  const bool use2 = mode2 != 0;
   WgradArgs wa;
   memset(&wa, 0, sizeof(wa));
   int BN, KP, out_tiles, splitk, MT;
@@ -1602,7 +1679,7 @@ extern "C" int etb_conv_wgrad(const void* x_bf16, const void* dy_bf16, float* dw
   memset(&w2, 0, sizeof(w2));
   int groups2 = 0, co_pairs2 = 0;
   if (use2) {
-    wgrad2_plan(cp, &w2.NT, &wa.TW, &wa.TH, &wa.tiles_w, &wa.tiles_h, &wa.nimg, &groups2, &co_pairs2, &splitk);
+    wgrad2_plan(cp, mode2, &w2.NT, &wa.TW, &wa.TH, &wa.tiles_w, &wa.tiles_h, &wa.nimg, &groups2, &co_pairs2, &w2.nvirt, &splitk);
     KP = 64;
   }
   wa.kpix = wa.TW * wa.TH;
@@ -1663,11 +1740,12 @@ extern "C" int etb_conv_wgrad(const void* x_bf16, const void* dy_bf16, float* dw
     memcpy(w2.tap_dw, wa.tap_dw, sizeof(w2.tap_dw));
     w2.stride = wa.stride; w2.TW = wa.TW; w2.TH = wa.TH; w2.tiles_w = wa.tiles_w; w2.tiles_h = wa.tiles_h; w2.nimg = wa.nimg;
     w2.kpix = wa.kpix;
-    w2.nvirt = ((cp->Cin + 127) / 128) * wa.ntaps;
     w2.groups = groups2;
+    w2.cit = cp->Cin / 256;
     w2.Cout = cp->Cout; w2.Cin = cp->Cin;
     w2.dw = wa.dw; w2.dw_split_stride = wa.dw_split_stride;
-    rc = launch_wgrad2(mDy, mX, w2, groups2 * co_pairs2, splitk, st);
+    rc = mode2 == 2 ? launch_wgrad2<256>(mDy, mX, w2, groups2 * co_pairs2, splitk, st)
+                    : launch_wgrad2<128>(mDy, mX, w2, groups2 * co_pairs2, splitk, st);
     if (rc != ETB_OK) return rc;
   }
   const bool cluster = (MT == 1 && BN == 128) && (wa.co_tiles % 2 == 0) && (wa.ci_tiles % 2 == 0) && getenv("ETB_WGRAD_CLUSTER");

@@ -199,8 +199,26 @@ WGRAD_CASES = [
 
 @pytest.mark.parametrize("case", [c for c in WGRAD_CASES if c[4] >= 256 and c[1] >= 128])
 def test_conv_wgrad_2sm_kernel(case, monkeypatch):
-    """the opt-in cta_group::2 multi-accumulator kernel (ETB_WGRAD2=1) on every shape it accepts"""
+    """the cta_group::2 multi-accumulator kernel with 128-wide accumulators (ETB_WGRAD2=1) on every shape it accepts"""
     monkeypatch.setenv("ETB_WGRAD2", "1")
+    test_conv_wgrad(case)
+
+
+WGRAD2_WIDE_CASES = [c for c in WGRAD_CASES if c[4] >= 256 and c[1] % 256 == 0] + [
+    (2, 256, 16, 16, 256, 1, 1, 0),    # one virtual column (NT = 1)
+    (2, 512, 12, 12, 320, 1, 1, 0),    # two columns in one tile, co tail 256 + 64
+    (2, 768, 12, 12, 256, 1, 1, 0),    # three columns: tile of 2 + short tile of 1
+    (2, 256, 20, 20, 256, 3, 1, 1),    # nine columns (taps): 4 tiles of 2 + 1, K tiles with out-of-image rows
+    (2, 256, 16, 16, 512, 3, 2, 1),    # stride 2, two co pairs
+    (32, 512, 20, 20, 512, 3, 1, 1),   # real shape, deep split-K
+    (32, 512, 40, 40, 256, 1, 1, 0),
+]
+
+
+@pytest.mark.parametrize("case", WGRAD2_WIDE_CASES)
+def test_conv_wgrad_2sm_wide_kernel(case, monkeypatch):
+    """the cta_group::2 kernel with 256-wide accumulators (ETB_WGRAD2=2: Cout >= 256, Cin % 256 == 0)"""
+    monkeypatch.setenv("ETB_WGRAD2", "2")
     test_conv_wgrad(case)
 
 

@@ -143,6 +143,119 @@ __global__ void __launch_bounds__(64, 1) probe_kernel(int kblocks, int stages, u
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
+
+// ---- second probe: resident operands only; independent accumulators (ACC, round-robin), A from TMEM (TS) and cta_group::2 ----
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// A operand in TMEM (128 lanes x 8 columns per K16 step of bf16)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// N: MMA N (<= 256; in cta_group::2 each CTA supplies N/2 rows of B); ACC accumulators used round-robin; TS: A from TMEM;
+// CG: cta_group.  K-major operands, 64-element K block = 4 MMAs.
+template <int N, int ACC, bool TS, int CG>
+__global__ void __launch_bounds__(64, 1) probe2_kernel(int kblocks, long long* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr int A_BYTES = 128 * 128, B_BYTES = 256 * 128, STAGE = A_BYTES + B_BYTES, STAGES = 2;
+  uint64_t* done = (uint64_t*)(smem + STAGES * STAGE);
+  uint32_t* slot = (uint32_t*)(done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  for (int i = threadIdx.x; i < STAGES * STAGE / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) { mbar_init(done, 1); fence_barrier_init(); }
+  fence_proxy_async();
+  if (warp == 1) { if (CG == 2) tmem_alloc_2sm(slot, 512); else tmem_alloc(slot, 512); }
+  tc_fence_before();
+  __syncthreads();
+  if (CG == 2) cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = *slot;
+  if (warp == 1 && lane == 0 && rank == 0) {
+    constexpr uint32_t idesc = idesc_bf16(128 * CG, N, false);
+    const long long t0 = clock64();
+    uint32_t j = 0;
+    for (int it = 0; it < kblocks; ++it) {
+      const uint32_t sa = smem_u32(smem + (it & 1) * STAGE);
+#pragma unroll
+      for (int k = 0; k < 4; ++k, ++j) {
+        const uint32_t acc = tmem + (j % ACC) * (uint32_t)N;
+        const uint64_t bd = kmajor_desc(sa + A_BYTES) + (uint64_t)(k * (32 >> 4));
+        if (TS) umma_bf16_ts(acc, tmem + 480u + (uint32_t)(k * 8), bd, idesc, j >= ACC ? 1u : 0u);
+        else if (CG == 2) umma_bf16_2sm(acc, kmajor_desc(sa) + (uint64_t)(k * (32 >> 4)), bd, idesc, j >= ACC ? 1u : 0u);
+        else umma_bf16(acc, kmajor_desc(sa) + (uint64_t)(k * (32 >> 4)), bd, idesc, j >= ACC ? 1u : 0u);
+      }
+    }
+    if (CG == 2) umma_commit_2sm(done); else umma_commit(done);
+    mbar_wait(done, 0);
+    const long long t1 = clock64();
+    out[blockIdx.x / CG] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CG == 2) cluster_sync_all();
+  if (warp == 1) { tc_fence_after(); if (CG == 2) tmem_dealloc_2sm(tmem, 512); else tmem_dealloc(tmem, 512); }
+}
+
+template <int N, int ACC, bool TS, int CG>
+static void run2(const char* name, long long* dout, int sms) {
+  static_assert(ACC * N + (TS ? 32 : 0) <= 512, "TMEM columns");
+  const int kblocks = 4096;
+  const size_t smem = (size_t)2 * (128 * 128 + 256 * 128) + 256 + 1024;
+  cudaFuncSetAttribute(probe2_kernel<N, ACC, TS, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int ctas = sms / CG * CG, n = ctas / CG;
+  for (int rep = 0; rep < 2; ++rep) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas); cfg.blockDim = dim3(64); cfg.dynamicSmemBytes = smem; cfg.stream = 0;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, probe2_kernel<N, ACC, TS, CG>, kblocks, dout);
+  }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("%-44s ERROR %s\n", name, cudaGetErrorString(e)); return; }
+  std::vector<long long> h(n);
+  cudaMemcpy(h.data(), dout, n * sizeof(long long), cudaMemcpyDeviceToHost);
+  std::sort(h.begin(), h.end());
+  const double per = (double)h[n / 2] / (kblocks * 4.0), ideal = N / 2.0;   // per SM: 128 rows x N x K16 at 8192 FLOP/clk
+  printf("%-30s cta_group::%d M=%3d N=%3d acc=%d  cycles/MMA median %.1f (min %.1f max %.1f)  ideal %.0f  -> %.2f of peak\n", name, CG, 128 * CG, N, ACC, per,
+         (double)h[0] / (kblocks * 4.0), (double)h[n - 1] / (kblocks * 4.0), ideal, ideal / per);
+}
+
 template <int N, bool MN>
 static void run(const char* name, int stages, uint32_t load_bytes, const uint8_t* src, long long* dout, int sms) {
   const int kblocks = 4096;
@@ -184,6 +297,27 @@ int main() {
   run<128, true>("MN-major half streamed", 4, 128 * 128, src, dout, sms);
   run<256, true>("MN-major half streamed", 4, 128 * 128 + 128 * 128, src, dout, sms);
   run<256, false>("K-major  half streamed", 4, 128 * 128 + 128 * 128, src, dout, sms);
+  // is the ~132-cycle floor a dependent-accumulator latency or a per-instruction cost?
+  run2<64, 1, false, 1>("SS", dout, sms);
+  run2<64, 2, false, 1>("SS", dout, sms);
+  run2<64, 4, false, 1>("SS", dout, sms);
+  run2<128, 1, false, 1>("SS", dout, sms);
+  run2<128, 2, false, 1>("SS", dout, sms);
+  run2<128, 4, false, 1>("SS", dout, sms);
+  run2<256, 1, false, 1>("SS", dout, sms);
+  run2<256, 2, false, 1>("SS", dout, sms);
+  // A operand from TMEM
+  run2<64, 1, true, 1>("TS (A in TMEM)", dout, sms);
+  run2<64, 4, true, 1>("TS (A in TMEM)", dout, sms);
+  run2<128, 1, true, 1>("TS (A in TMEM)", dout, sms);
+  run2<128, 2, true, 1>("TS (A in TMEM)", dout, sms);
+  run2<256, 1, true, 1>("TS (A in TMEM)", dout, sms);
+  // cta_group::2
+  run2<64, 1, false, 2>("SS 2-SM", dout, sms);
+  run2<128, 1, false, 2>("SS 2-SM", dout, sms);
+  run2<128, 2, false, 2>("SS 2-SM", dout, sms);
+  run2<256, 1, false, 2>("SS 2-SM", dout, sms);
+  run2<256, 2, false, 2>("SS 2-SM", dout, sms);
   cudaFree(src);
   cudaFree(dout);
   return 0;
