@@ -23,6 +23,7 @@
 #define CONV_BLOCK_K 64
 #define CONV_THREADS 320     // warp0 TMA, warp1 MMA, warps2-9 epilogue
 #define WGRAD_THREADS 192
+#define EPI_TILE_BYTES 4096  // one warp's epilogue staging tile: 32 rows x 128 B
 #ifndef ETB_WGRAD2_DEFAULT
 #define ETB_WGRAD2_DEFAULT 0     // 2-SM weight-gradient kernels: 0 off, 1 NW = 128, 2 NW = 256 (env ETB_WGRAD2 overrides)
 #endif
@@ -176,6 +177,7 @@ struct ConvKArgs {
   int y_cstride, y_coffset;
   int res_cstride, res_coffset;
   int act;                // 0 none, 1 SiLU, 2 ReLU
+  int epi_staged;         // bf16 epilogues store through the shared-memory staging tile (128 contiguous bytes per pixel row)
   int out_mode;           // 0: bf16 NHWC ; 1: fp32 Detect layout [N, na, Ho, Wo, no] with c = a*no + o
   int det_no, det_hw;     // outputs per anchor, pixels per image (Detect layout)
   const float* scale;     // [Cout] or null (=1)
@@ -191,12 +193,25 @@ struct ConvSmem {
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 256 + 1024;        // barriers + slack for the 1024 B alignment
+  static constexpr int EPI_OFF = BAR_OFF + 256;             // 8 epilogue warps x one staging tile
+  static constexpr int TOTAL = EPI_OFF + 8 * EPI_TILE_BYTES + 1024;   // + slack for the 1024 B alignment
   static constexpr int TMEM_COLS = 2 * BN;                  // double-buffered accumulator
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Epilogue store staging.  tcgen05.ld hands every lane ONE accumulator row, so a direct store instruction touches 32
+// different output rows with 16 B each (32 partial-sector transactions).  A warp instead parks a 32-row x 128-byte tile
+// (row = lane, 8 pieces of 16 B, XOR-swizzled: conflict-free both ways) in shared memory and reads it back so that store
+// instruction i covers rows 4i..4i+3 with 128 contiguous bytes each (4 full lines).
+__device__ __forceinline__ void stage_write(uint8_t* tile, int lane, int piece, const uint4& v) {
+  *reinterpret_cast<uint4*>(tile + lane * 128 + ((piece ^ (lane & 7)) << 4)) = v;
+}
+__device__ __forceinline__ uint4 stage_read(const uint8_t* tile, int lane, int i) {
+  const int p = 4 * i + (lane >> 3), c = lane & 7;
+  return *reinterpret_cast<const uint4*>(tile + p * 128 + ((c ^ (p & 7)) << 4));
 }
 
 // Epilogue of one accumulator tile for one warp: columns [chalf*BN/2, (chalf+1)*BN/2) of the BN-wide tile starting at
@@ -332,10 +347,102 @@ __device__ __forceinline__ void epilogue_preload(const ConvKArgs& a, int n0, int
   }
 }
 
+// 64 output channels [cc, cc+64) of this warp's 32 pixel rows, stored through the staging tile: every lane converts its own
+// row (two tcgen05.ld of 32 columns -> 8 pieces of 8 bf16), parks it, and store instruction i then writes pixels 4i..4i+3 with
+// 128 contiguous bytes each.  Same arithmetic as conv_epilogue_chunk's whole-chunk branch; a tail (Cout % 64) takes that path.
+template <int BN, int EPI>
+__device__ __forceinline__ bool conv_epilogue_chunk64(const ConvKArgs& a, uint32_t lane_addr, int n0, int chalf, bool row_ok, size_t pix, int cc,
+                                                      const uint4* pre, uint8_t* tile, int lane) {
+  constexpr int HALF = BN / 2;
+  const int c0 = chalf * HALF + cc;
+  const int gc0 = n0 + c0;
+  if (gc0 >= a.Cout) return false;                 // warp-uniform
+  if (gc0 + 64 > a.Cout) {
+    if (!conv_epilogue_chunk<BN, EPI>(a, lane_addr, n0, chalf, row_ok, pix, cc, pre)) return false;
+    return conv_epilogue_chunk<BN, EPI>(a, lane_addr, n0, chalf, row_ok, pix, cc + 32, EPI == 0 ? pre + 4 : pre);
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint32_t v[32];
+    tmem_ld32(lane_addr + (uint32_t)(c0 + 32 * h), v);
+    const int gch = gc0 + 32 * h;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[q * 8 + j]);
+      if (EPI == 1) {
+        const float4 s0 = a.scale ? __ldg(reinterpret_cast<const float4*>(a.scale + gch) + 2 * q) : make_float4(1.f, 1.f, 1.f, 1.f);
+        const float4 s1 = a.scale ? __ldg(reinterpret_cast<const float4*>(a.scale + gch) + 2 * q + 1) : make_float4(1.f, 1.f, 1.f, 1.f);
+        const float4 b0 = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + gch) + 2 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 b1 = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + gch) + 2 * q + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        const float bi[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float x = fmaf(f[j], sc[j], bi[j]);
+          if (a.act == 1) { const float hh = 0.5f * x; float th; asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(hh)); x = fmaf(hh, th, hh); }
+          else if (a.act == 2) x = fmaxf(x, 0.0f);
+          f[j] = x;
+        }
+        if (a.residual && row_ok) {
+          const uint4 rv = __ldg(reinterpret_cast<const uint4*>(a.residual + pix * a.res_cstride + a.res_coffset + gch) + q);
+          const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 rf = __bfloat1622float2(r2[j]);
+            f[2 * j] += rf.x;
+            f[2 * j + 1] += rf.y;
+          }
+        }
+      }
+      if (EPI == 0 && a.accumulate && row_ok) {
+        const uint4 pv = pre[4 * h + q];
+        const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&pv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 pf = __bfloat1622float2(p2[j]);
+          f[2 * j] += pf.x;
+          f[2 * j + 1] += pf.y;
+        }
+      }
+      uint4 ov;
+      __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+      stage_write(tile, lane, 4 * h + q, ov);
+    }
+  }
+  __syncwarp();
+  const unsigned long long row_off = (unsigned long long)pix * (unsigned long long)a.y_cstride;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = 4 * i + (lane >> 3);
+    const unsigned long long off_r = __shfl_sync(0xffffffffu, row_off, r);
+    const int ok_r = __shfl_sync(0xffffffffu, (int)row_ok, r);
+    const uint4 o = stage_read(tile, lane, i);
+    if (ok_r) *reinterpret_cast<uint4*>(a.y + off_r + a.y_coffset + gc0 + (lane & 7) * 8) = o;
+  }
+  __syncwarp();
+  return true;
+}
+
 template <int BN, int EPI>
 __device__ __forceinline__ void conv_epilogue_cols(const ConvKArgs& a, uint32_t lane_addr, int n0, int chalf, bool row_ok, size_t pix,
-                                                   const EpiPre<BN, EPI>& pre) {
+                                                   const EpiPre<BN, EPI>& pre, uint8_t* tile, int lane) {
   constexpr int HALF = BN / 2;
+  if (EPI != 2 && HALF % 64 == 0 && a.epi_staged) {   // warp-uniform
+    if (EPI == 0) {
+#pragma unroll
+      for (int cc = 0; cc < HALF; cc += 64)
+        if (!conv_epilogue_chunk64<BN, EPI>(a, lane_addr, n0, chalf, row_ok, pix, cc, pre.v + cc / 8, tile, lane)) break;
+    } else {
+#pragma unroll 1
+      for (int cc = 0; cc < HALF; cc += 64)
+        if (!conv_epilogue_chunk64<BN, EPI>(a, lane_addr, n0, chalf, row_ok, pix, cc, pre.v, tile, lane)) break;
+    }
+    return;
+  }
   if (EPI == 0) {
 #pragma unroll
     for (int cc = 0; cc < HALF; cc += 32)
@@ -385,47 +492,51 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   if (warp == 0) {
     // ===== TMA producer: the whole warp runs the loop (uniform), one elected lane issues =====
     const uint32_t a_bytes = (uint32_t)(a.TW * a.TH * 128);
-    int it = 0;
+    int s = 0;                     // stage / phase advance incrementally: no divisions inside the K loop
+    uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n0 = (tile % n_tiles) * BN;
       int t = tile / n_tiles;
       const int tw_i = t % a.tiles_w; t /= a.tiles_w;
       const int th_i = t % a.tiles_h; t /= a.tiles_h;
       const int img = t;
-      const int w0 = tw_i * a.TW, h0 = th_i * a.TH;
-      for (int tp = 0; tp < a.ntaps; ++tp)
-        for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+      const int w0 = tw_i * a.TW * a.stride, h0 = th_i * a.TH * a.stride;
+      int bk = 0;                  // K coordinate of the weight tile
+      for (int tp = 0; tp < a.ntaps; ++tp) {
+        const int wc = w0 + a.tap_dw[tp], hc = h0 + a.tap_dh[tp];
+        for (int kb = 0; kb < a.kblocks; ++kb, bk += CONV_BLOCK_K) {
           mbar_wait(&empty[s], ph ^ 1u);
           uint8_t* sa = smem + s * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
           if (elect_one()) {
             mbar_expect_tx(&full[s], a_bytes + (uint32_t)L::B_BYTES);
-            tma_load_4d(&mapA, &full[s], sa, kb * CONV_BLOCK_K, w0 * a.stride + a.tap_dw[tp], h0 * a.stride + a.tap_dh[tp], img);
-            tma_load_2d(&mapB, &full[s], sb, (tp * a.kblocks + kb) * CONV_BLOCK_K, n0);
+            tma_load_4d(&mapA, &full[s], sa, kb * CONV_BLOCK_K, wc, hc, img);
+            tma_load_2d(&mapB, &full[s], sb, bk, n0);
           }
           __syncwarp();
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
+      }
     }
   } else if (warp == 1) {
     // ===== MMA issuer: warp-uniform loop, one elected lane issues the MMAs and their commit =====
     constexpr uint32_t idesc = make_idesc_bf16(CONV_BLOCK_M, BN);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-    int it = 0, lt = 0;
+    // stage index, phase and the two operand descriptors advance incrementally (descriptor address field = bytes >> 4;
+    // the stage ring stays far below the field's 2^14 range, so a plain 64-bit add never carries out of it)
+    const uint64_t adesc0 = make_kmajor_sw128_desc(smem_u32(smem));
+    const uint64_t bdesc0 = make_kmajor_sw128_desc(smem_u32(smem) + L::A_BYTES);
+    uint64_t adesc = adesc0, bdesc = bdesc0;
+    int s = 0, lt = 0;
+    uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
       const int acc = lt & 1;
       mbar_wait(&tmem_empty[acc], (uint32_t)(((lt >> 1) & 1) ^ 1));   // epilogue drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_u + (uint32_t)(acc * BN);
-      for (int ki = 0; ki < kiters; ++ki, ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+      for (int ki = 0; ki < kiters; ++ki) {
         mbar_wait(&full[s], ph);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
-        const uint64_t adesc = make_kmajor_sw128_desc(sa);
-        const uint64_t bdesc = make_kmajor_sw128_desc(sa + L::A_BYTES);
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < CONV_BLOCK_K / 16; ++k)  // +32 B per UMMA_K step inside the 128 B swizzle atom
@@ -434,6 +545,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           if (ki == kiters - 1) umma_commit(&tmem_full[acc]);  // accumulator complete
         }
         __syncwarp();
+        adesc += (uint64_t)(L::STAGE_BYTES >> 4); bdesc += (uint64_t)(L::STAGE_BYTES >> 4);
+        if (++s == STAGES) { s = 0; ph ^= 1u; adesc = adesc0; bdesc = bdesc0; }
       }
     }
   } else {
@@ -464,7 +577,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       mbar_wait(&tmem_full[acc], (uint32_t)((lt >> 1) & 1));
       tc_fence_after();
       const uint32_t lane_addr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(32 * quad) << 16);
-      conv_epilogue_cols<BN, EPI>(a, lane_addr, n0, chalf, row_ok, pix, pre);
+      conv_epilogue_cols<BN, EPI>(a, lane_addr, n0, chalf, row_ok, pix, pre, smem + L::EPI_OFF + ew * EPI_TILE_BYTES, lane);
       // all tcgen05.ld of this warp have completed (wait::ld inside tmem_ld32): hand the accumulator back
       tc_fence_before();
       __syncwarp();
@@ -533,7 +646,8 @@ struct Conv2Smem {
   static constexpr int B_BYTES = (BN / 2) * 128;          // this CTA's half (BN/2 couts) of the BN-wide weight tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+  static constexpr int EPI_OFF = BAR_OFF + 256;
+  static constexpr int TOTAL = EPI_OFF + 8 * EPI_TILE_BYTES + 1024;
   static constexpr int TMEM_COLS = 2 * BN;                // two BN-column accumulators per CTA
 };
 
@@ -577,49 +691,51 @@ conv_fwd2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     // ===== TMA producer (both CTAs: own A tile, own half of B; bytes are accounted on the leader's full barrier) =====
     // (warp-uniform loop, one elected lane issues: see elect_one)
     const uint32_t a_bytes = (uint32_t)(a.TW * a.TH * 128);
-    int it = 0;
+    int s = 0;
+    uint32_t ph = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
-      const int n0 = (tile % n_tiles) * BN;
+      const int n0 = (tile % n_tiles) * BN + (BN / 2) * (int)rank;
       int t = (tile / n_tiles) * 2 + (int)rank;    // this CTA's m tile (may be == m_tiles for the odd tail: OOB -> zeros)
       const int tw_i = t % a.tiles_w; t /= a.tiles_w;
       const int th_i = t % a.tiles_h; t /= a.tiles_h;
       const int img = t;
-      const int w0 = tw_i * a.TW, h0 = th_i * a.TH;
-      for (int tp = 0; tp < a.ntaps; ++tp)
-        for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+      const int w0 = tw_i * a.TW * a.stride, h0 = th_i * a.TH * a.stride;
+      int bk = 0;
+      for (int tp = 0; tp < a.ntaps; ++tp) {
+        const int wc = w0 + a.tap_dw[tp], hc = h0 + a.tap_dh[tp];
+        for (int kb = 0; kb < a.kblocks; ++kb, bk += CONV_BLOCK_K) {
           mbar_wait(&empty[s], ph ^ 1u);           // my own smem stage is free (commit is multicast to both CTAs)
           uint8_t* sa = smem + s * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
           if (elect_one()) {
             if (rank == 0) mbar_expect_tx(&full[s], 2u * (a_bytes + (uint32_t)L::B_BYTES));
             else mbar_arrive_leader(&full[s]);
-            tma_load_4d_2sm(&mapA, &full[s], sa, kb * CONV_BLOCK_K, w0 * a.stride + a.tap_dw[tp], h0 * a.stride + a.tap_dh[tp], img);
-            tma_load_2d_2sm(&mapB, &full[s], sb, (tp * a.kblocks + kb) * CONV_BLOCK_K, n0 + (BN / 2) * (int)rank);
+            tma_load_4d_2sm(&mapA, &full[s], sa, kb * CONV_BLOCK_K, wc, hc, img);
+            tma_load_2d_2sm(&mapB, &full[s], sb, bk, n0);
           }
           __syncwarp();
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
+      }
     }
   } else if (warp == 1) {
     // ===== MMA issuer: leader CTA only, for the pair (warp-uniform loop, one elected lane issues) =====
     if (rank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(256, BN);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-      int it = 0, lt = 0;
+      const uint64_t adesc0 = make_kmajor_sw128_desc(smem_u32(smem));
+      const uint64_t bdesc0 = make_kmajor_sw128_desc(smem_u32(smem) + L::A_BYTES);
+      uint64_t adesc = adesc0, bdesc = bdesc0;
+      int s = 0, lt = 0;
+      uint32_t ph = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++lt) {
         const int acc = lt & 1;
         mbar_wait(&tmem_empty[acc], (uint32_t)(((lt >> 1) & 1) ^ 1));   // both CTAs' epilogues drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_u + (uint32_t)(acc * BN);
-        for (int ki = 0; ki < kiters; ++ki, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+        for (int ki = 0; ki < kiters; ++ki) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
-          const uint64_t adesc = make_kmajor_sw128_desc(sa);
-          const uint64_t bdesc = make_kmajor_sw128_desc(sa + L::A_BYTES);
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < CONV_BLOCK_K / 16; ++k)
@@ -628,6 +744,8 @@ conv_fwd2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             if (ki == kiters - 1) umma_commit_2sm(&tmem_full[acc]);
           }
           __syncwarp();
+          adesc += (uint64_t)(L::STAGE_BYTES >> 4); bdesc += (uint64_t)(L::STAGE_BYTES >> 4);
+          if (++s == STAGES) { s = 0; ph ^= 1u; adesc = adesc0; bdesc = bdesc0; }
         }
       }
     }
@@ -655,7 +773,7 @@ conv_fwd2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       mbar_wait(&tmem_full[acc], (uint32_t)((lt >> 1) & 1));
       tc_fence_after();
       const uint32_t lane_addr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(32 * quad) << 16);
-      conv_epilogue_cols<BN, EPI>(a, lane_addr, n0, chalf, row_ok, pix, pre);
+      conv_epilogue_cols<BN, EPI>(a, lane_addr, n0, chalf, row_ok, pix, pre, smem + L::EPI_OFF + ew * EPI_TILE_BYTES, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
@@ -768,6 +886,12 @@ static int launch_gemm(const GemmGeom& g, ConvKArgs ka, cudaStream_t st) {
   const int aCp = (g.aC + CONV_BLOCK_K - 1) / CONV_BLOCK_K * CONV_BLOCK_K;
   ETB_CHECK_ARG((((uintptr_t)g.a_ptr) & 15) == 0 && (((uintptr_t)g.b_ptr) & 15) == 0);
   ETB_CHECK_ARG(ka.ntaps >= 1 && ka.ntaps <= 12);
+  {
+    // epilogue store staging (conv_epilogue_chunk64): on unless ETB_EPI_STAGE=0; needs 16-byte aligned 64-channel runs
+    static int staged = -1;
+    if (staged < 0) { const char* e = getenv("ETB_EPI_STAGE"); staged = (e && e[0] == '0') ? 0 : 1; }
+    ka.epi_staged = staged && ka.y_cstride % 8 == 0 && ka.y_coffset % 8 == 0 && (((uintptr_t)ka.y) & 15) == 0;
+  }
   cuuint64_t gdim[4], gstr[3];
   cuuint32_t box[4], estr[4];
   int nimg;
@@ -1004,6 +1128,32 @@ struct WgradArgs {
   long dw_split_stride;     // elements per slice
 };
 
+// Partial-tile store of one accumulator (this warp's 32 rows x NCOLS fp32 columns) through the staging tile: per 32-column
+// chunk each lane parks its row (128 B), then store instruction i writes rows 4i..4i+3 x 128 contiguous bytes.
+// dst = this lane's row; rows are row_stride floats apart; row r is valid while co - lane + r < Cout; columns while < ncols_ok.
+template <int NCOLS>
+__device__ __forceinline__ void wgrad_store_tile(uint32_t lane_addr, float* dst, size_t row_stride, int co, int Cout, int ncols_ok, uint8_t* tile,
+                                                 int lane) {
+  const int co_base = co - lane;
+  float* base = dst - (size_t)lane * row_stride;              // row 0 of this warp's 32
+#pragma unroll 1
+  for (int c0 = 0; c0 < NCOLS; c0 += 32) {
+    if (c0 >= ncols_ok) break;                                // warp-uniform (Cin is a multiple of 8; tails are whole chunks)
+    uint32_t v[32];
+    tmem_ld32(lane_addr + (uint32_t)c0, v);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) stage_write(tile, lane, q, make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = 4 * i + (lane >> 3), c = (lane & 7) * 4;
+      const uint4 o = stage_read(tile, lane, i);
+      if (co_base + r < Cout && c0 + c < ncols_ok) *reinterpret_cast<uint4*>(base + (size_t)r * row_stride + c0 + c) = o;
+    }
+    __syncwarp();
+  }
+}
+
 // Tile = (128*MT co) x (BN ci) per CTA, K block = up to KP pixels.  Bigger tiles raise the FLOP per L2 byte
 // (128x128: 65, 256x256: 131 flop/B) -- the kernel is L2-bandwidth bound, not MMA bound.
 template <int MT, int BN, int KP, int STAGES>
@@ -1086,13 +1236,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ 
 
   if (warp == 0) {
     // warp-uniform loop, one elected lane issues (see elect_one)
+    // K-block coordinates, stage and phase advance incrementally: the producer is ONE warp of dependent integer code, and two
+    // runtime divisions per K block made it (not the tensor pipe, not L2) the bound of every weight-gradient tile shape
+    // (ncu source page: the producer never waited on an empty stage, the MMA warp always waited on a full one)
+    int tw_i = kb0 % a.tiles_w, th_i = (kb0 / a.tiles_w) % a.tiles_h, img = kb0 / (a.tiles_w * a.tiles_h);
+    const int xdw = a.tap_dw[tap], xdh = a.tap_dh[tap];
+    int s = 0;
+    uint32_t ph = 0;
     for (int it = 0; it < kiters; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (uint32_t)((it / STAGES) & 1);
-      int kb = kb0 + it;
-      const int tw_i = kb % a.tiles_w; kb /= a.tiles_w;
-      const int th_i = kb % a.tiles_h; kb /= a.tiles_h;
-      const int img = kb;
       const int w0 = tw_i * a.TW, h0 = th_i * a.TH;
       mbar_wait(&empty[s], ph ^ 1u);
       uint8_t* sa = smem + s * L::STAGE_BYTES;
@@ -1102,24 +1253,26 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ 
         if (CL) {
           const int ga = (int)(crank & 1), gb = (int)(crank >> 1);   // my share: one dy group, one x group
           tma_load_4d_mc(&mapDy, &full[s], sa + ga * L::GROUP_BYTES, co0 + 64 * ga, w0, h0, img, mask_a);
-          tma_load_4d_mc(&mapX, &full[s], sb + gb * L::GROUP_BYTES, ci0 + 64 * gb, w0 * a.stride + a.tap_dw[tap], h0 * a.stride + a.tap_dh[tap], img, mask_b);
+          tma_load_4d_mc(&mapX, &full[s], sb + gb * L::GROUP_BYTES, ci0 + 64 * gb, w0 * a.stride + xdw, h0 * a.stride + xdh, img, mask_b);
         } else {
 #pragma unroll
           for (int g = 0; g < 2 * MT; ++g) tma_load_4d(&mapDy, &full[s], sa + g * L::GROUP_BYTES, co0 + 64 * g, w0, h0, img);
 #pragma unroll
           for (int g = 0; g < BN / 64; ++g)
-            tma_load_4d(&mapX, &full[s], sb + g * L::GROUP_BYTES, ci0 + 64 * g, w0 * a.stride + a.tap_dw[tap], h0 * a.stride + a.tap_dh[tap], img);
+            tma_load_4d(&mapX, &full[s], sb + g * L::GROUP_BYTES, ci0 + 64 * g, w0 * a.stride + xdw, h0 * a.stride + xdh, img);
         }
       }
       __syncwarp();
+      if (++tw_i == a.tiles_w) { tw_i = 0; if (++th_i == a.tiles_h) { th_i = 0; ++img; } }
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc = make_idesc_bf16_mn(128, BN);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const int ksteps = a.kpix / 16;
+    int s = 0;
+    uint32_t ph = 0;
     for (int it = 0; it < kiters; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (uint32_t)((it / STAGES) & 1);
       mbar_wait(&full[s], ph);
       tc_fence_after();
       const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
@@ -1139,11 +1292,15 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ 
         if (it == kiters - 1) umma_commit(tmem_full);
       }
       __syncwarp();
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
     }
   } else {
     const int row = 32 * (warp & 3) + lane;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
+    // every MMA has completed (tmem_full) and every TMA box was consumed by one: the stage ring is free -> store staging
+    uint8_t* tile = smem + (warp - 2) * EPI_TILE_BYTES;
+    const size_t row_stride = (size_t)a.ntaps * a.Cin;        // floats between two co rows of the partial tile
 #pragma unroll 1
     for (int mt = 0; mt < MT; ++mt) {
       const int co = co0 + mt * 128 + row;
@@ -1151,18 +1308,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ 
       // two-stage split-K: every CTA writes its partial tile with plain coalesced stores into its own slice; the
       // slices are summed (and laid out as [Cout,Cin,kh,kw]) by wgrad_reduce_kernel.  No atomics, no memset.
       float* dst = a.dw + (size_t)blockIdx.y * a.dw_split_stride + ((size_t)co * a.ntaps + tap) * a.Cin + ci0;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        if (ci0 + c0 >= a.Cin) break;
-        uint32_t v[32];
-        tmem_ld32(lane_addr + (uint32_t)c0, v);
-        if (co < a.Cout) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            reinterpret_cast<float4*>(dst + c0)[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                                                                 __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
-        }
-      }
+      wgrad_store_tile<BN>(lane_addr, dst, row_stride, co, a.Cout, a.Cin - ci0, tile, lane);
     }
   }
   tc_fence_before();
@@ -1424,14 +1570,24 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__
 
   if (warp == 0) {
     // warp-uniform loop, one elected lane issues (see elect_one)
+    // per-column x coordinates are fixed for the whole K loop: hoisted into registers (statically indexed, MAXT columns);
+    // K-block coordinates, stage and phase advance incrementally (no divisions, no local-memory table reads in the loop)
+    constexpr int MAXT = 512 / NW;
+    int xc[MAXT], xdw[MAXT], xdh[MAXT];
+#pragma unroll
+    for (int t = 0; t < MAXT; ++t) {
+      int tap = 0, cbase = 0;
+      if (t < nt) wgrad2_vcol<NW>(a, v0 + t, &tap, &cbase);
+      xc[t] = cbase + (NW / 2) * (int)rank;
+      xdw[t] = a.tap_dw[tap];
+      xdh[t] = a.tap_dh[tap];
+    }
+    int tw_i = kb0 % a.tiles_w, th_i = (kb0 / a.tiles_w) % a.tiles_h, img = kb0 / (a.tiles_w * a.tiles_h);
+    int s = 0;
+    uint32_t ph = 0;
     for (int it = 0; it < kiters; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (uint32_t)((it / STAGES) & 1);
-      int kb = kb0 + it;
-      const int tw_i = kb % a.tiles_w; kb /= a.tiles_w;
-      const int th_i = kb % a.tiles_h; kb /= a.tiles_h;
-      const int img = kb;
       const int w0 = tw_i * a.TW, h0 = th_i * a.TH;
+      const int xw0 = w0 * a.stride, xh0 = h0 * a.stride;
       mbar_wait(&empty[s], ph ^ 1u);
       uint8_t* sa = smem + s * L::STAGE_BYTES;
       uint8_t* sb = sa + L::A_BYTES;
@@ -1440,25 +1596,27 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__
         else mbar_arrive_leader(&full[s]);
 #pragma unroll
         for (int g = 0; g < 2; ++g) tma_load_4d_2sm(&mapDy, &full[s], sa + g * L::GROUP_BYTES, co0 + 64 * g, w0, h0, img);
-        for (int t = 0; t < nt; ++t) {
-          int tap, cbase;
-          wgrad2_vcol<NW>(a, v0 + t, &tap, &cbase);
 #pragma unroll
-          for (int g = 0; g < GPC; ++g)
-            tma_load_4d_2sm(&mapX, &full[s], sb + (t * GPC + g) * L::GROUP_BYTES, cbase + (NW / 2) * (int)rank + 64 * g,
-                            w0 * a.stride + a.tap_dw[tap], h0 * a.stride + a.tap_dh[tap], img);
+        for (int t = 0; t < MAXT; ++t) {
+          if (t < nt) {
+#pragma unroll
+            for (int g = 0; g < GPC; ++g)
+              tma_load_4d_2sm(&mapX, &full[s], sb + (t * GPC + g) * L::GROUP_BYTES, xc[t] + 64 * g, xw0 + xdw[t], xh0 + xdh[t], img);
+          }
         }
       }
       __syncwarp();
+      if (++tw_i == a.tiles_w) { tw_i = 0; if (++th_i == a.tiles_h) { th_i = 0; ++img; } }
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
     }
   } else if (warp == 1) {
     if (rank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16_mn(256, NW);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const int ksteps = a.kpix / 16;
+      int s = 0;
+      uint32_t ph = 0;
       for (int it = 0; it < kiters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)((it / STAGES) & 1);
         mbar_wait(&full[s], ph);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
@@ -1474,6 +1632,7 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__
           if (it == kiters - 1) umma_commit_2sm(tmem_full);
         }
         __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
     }
   } else if (kiters > 0) {
@@ -1481,23 +1640,14 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__
     const int co = co0 + row;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
+    uint8_t* tile = smem + (warp - 2) * EPI_TILE_BYTES;      // the stage ring is free once tmem_full has fired
+    const size_t row_stride = (size_t)a.ntaps * a.Cin;
     for (int t = 0; t < nt; ++t) {
       int tap, ci0;
       wgrad2_vcol<NW>(a, v0 + t, &tap, &ci0);
       const uint32_t lane_addr = tmem_base + (uint32_t)(t * NW) + ((uint32_t)(32 * (warp & 3)) << 16);
       float* dst = a.dw + (size_t)blockIdx.y * a.dw_split_stride + ((size_t)co * a.ntaps + tap) * a.Cin + ci0;
-#pragma unroll 1
-      for (int c0 = 0; c0 < NW; c0 += 32) {
-        if (ci0 + c0 >= a.Cin) break;
-        uint32_t v32[32];
-        tmem_ld32(lane_addr + (uint32_t)c0, v32);
-        if (co < a.Cout) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            reinterpret_cast<float4*>(dst + c0)[q] = make_float4(__uint_as_float(v32[4 * q]), __uint_as_float(v32[4 * q + 1]),
-                                                                 __uint_as_float(v32[4 * q + 2]), __uint_as_float(v32[4 * q + 3]));
-        }
-      }
+      wgrad_store_tile<NW>(lane_addr, dst, row_stride, co, a.Cout, a.Cin - ci0, tile, lane);
     }
   }
   tc_fence_before();

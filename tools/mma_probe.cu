@@ -35,6 +35,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity))
     if (clock64() - t0 > 2000000000ll) { printf("probe: mbarrier timeout\n"); __trap(); }
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -77,7 +86,9 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, bool mn) {
 // 64 K rows x 128 B (8 KB each), A = 2 groups, B = N/64 groups.  Same bytes either way.  STAGES blocks are cycled.
 // load_bytes > 0: warp 0 keeps a bulk-copy stream of `load_bytes` per K block running into the stage the MMA warp released
 // (the real producer/consumer pipeline, global source = L2-resident buffer).
-template <int N, bool MN>
+// UNI = false: producer / MMA loops run inside `if (lane == 0)` (every UTCHMMA / bulk copy becomes an ELECT + BRA.U.ANY
+// waterfall loop); UNI = true: the whole warp runs the loop and one elected lane issues.
+template <int N, bool MN, bool UNI>
 __global__ void __launch_bounds__(64, 1) probe_kernel(int kblocks, int stages, uint32_t load_bytes, const uint8_t* __restrict__ src, long long* __restrict__ out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -99,44 +110,52 @@ __global__ void __launch_bounds__(64, 1) probe_kernel(int kblocks, int stages, u
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *slot;
-  if (warp == 0 && lane == 0 && load_bytes) {
+  const bool run = UNI ? true : (lane == 0);
+  if (warp == 0 && run && load_bytes) {
     const uint8_t* my = src + (size_t)blockIdx.x * (size_t)STAGE * 4;   // 4-stage window per CTA: stays in L2
     for (int it = 0; it < kblocks; ++it) {
       const int s = it % stages;
       mbar_wait(&empty[s], ((it / stages) & 1) ^ 1u);
-      mbar_expect_tx(&full[s], load_bytes);
-      uint32_t left = load_bytes, off = 0;
-      while (left) {
-        const uint32_t n = left > 16384u ? 16384u : left;
-        bulk_load(smem + s * STAGE + off, my + (size_t)(it & 3) * STAGE + off, n, &full[s]);
-        left -= n; off += n;
+      if (!UNI || elect_one()) {
+        mbar_expect_tx(&full[s], load_bytes);
+        uint32_t left = load_bytes, off = 0;
+        while (left) {
+          const uint32_t n = left > 16384u ? 16384u : left;
+          bulk_load(smem + s * STAGE + off, my + (size_t)(it & 3) * STAGE + off, n, &full[s]);
+          left -= n; off += n;
+        }
       }
+      if (UNI) __syncwarp();
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1 && run) {
     constexpr uint32_t idesc = idesc_bf16(128, N, MN);
+    const uint32_t tm = UNI ? __shfl_sync(0xffffffffu, tmem, 0) : tmem;
     const long long t0 = clock64();
     for (int it = 0; it < kblocks; ++it) {
       const int s = it % stages;
       if (load_bytes) { mbar_wait(&full[s], (it / stages) & 1); tc_fence_after(); }
       const uint32_t sa = smem_u32(smem + s * STAGE);
+      if (!UNI || elect_one()) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        uint64_t ad, bd;
-        if (MN) {
-          ad = mnmajor_desc(sa, 64 * 128) + (uint64_t)(k * (2048 >> 4));
-          bd = mnmajor_desc(sa + A_BYTES, 64 * 128) + (uint64_t)(k * (2048 >> 4));
-        } else {
-          ad = kmajor_desc(sa) + (uint64_t)(k * (32 >> 4));
-          bd = kmajor_desc(sa + A_BYTES) + (uint64_t)(k * (32 >> 4));
+        for (int k = 0; k < 4; ++k) {
+          uint64_t ad, bd;
+          if (MN) {
+            ad = mnmajor_desc(sa, 64 * 128) + (uint64_t)(k * (2048 >> 4));
+            bd = mnmajor_desc(sa + A_BYTES, 64 * 128) + (uint64_t)(k * (2048 >> 4));
+          } else {
+            ad = kmajor_desc(sa) + (uint64_t)(k * (32 >> 4));
+            bd = kmajor_desc(sa + A_BYTES) + (uint64_t)(k * (32 >> 4));
+          }
+          umma_bf16(tm, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
         }
-        umma_bf16(tmem, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+        if (load_bytes) umma_commit(&empty[s]);
+        if (it == kblocks - 1) umma_commit(done);
       }
-      if (load_bytes) umma_commit(&empty[s]);
+      if (UNI) __syncwarp();
     }
-    umma_commit(done);
     mbar_wait(done, 0);
     const long long t1 = clock64();
-    out[blockIdx.x] = t1 - t0;
+    if (lane == 0) out[blockIdx.x] = t1 - t0;
   }
   tc_fence_before();
   __syncthreads();
@@ -256,19 +275,19 @@ static void run2(const char* name, long long* dout, int sms) {
          (double)h[0] / (kblocks * 4.0), (double)h[n - 1] / (kblocks * 4.0), ideal, ideal / per);
 }
 
-template <int N, bool MN>
+template <int N, bool MN, bool UNI = false>
 static void run(const char* name, int stages, uint32_t load_bytes, const uint8_t* src, long long* dout, int sms) {
   const int kblocks = 4096;
   const size_t smem = (size_t)stages * (128 * 128 + N * 128) + 256 + 1024;
-  cudaFuncSetAttribute(probe_kernel<N, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  for (int rep = 0; rep < 2; ++rep) probe_kernel<N, MN><<<sms, 64, smem>>>(kblocks, stages, load_bytes, src, dout);
+  cudaFuncSetAttribute(probe_kernel<N, MN, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  for (int rep = 0; rep < 2; ++rep) probe_kernel<N, MN, UNI><<<sms, 64, smem>>>(kblocks, stages, load_bytes, src, dout);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("%-44s ERROR %s\n", name, cudaGetErrorString(e)); return; }
   std::vector<long long> h(sms);
   cudaMemcpy(h.data(), dout, sms * sizeof(long long), cudaMemcpyDeviceToHost);
   std::sort(h.begin(), h.end());
   const double per = (double)h[sms / 2] / (kblocks * 4.0), ideal = N / 2.0;   // M128 x N x K16 bf16: N/2 cycles at 8192 FLOP/clk/SM
-  printf("%-44s N=%3d stages=%d load=%6u B/blk  cycles/MMA median %.1f (min %.1f max %.1f)  ideal %.0f  -> %.2f of peak\n", name, N, stages, load_bytes,
+  printf("%-32s %s N=%3d stages=%d load=%6u B/blk  cycles/MMA median %.1f (min %.1f max %.1f)  ideal %.0f  -> %.2f of peak\n", name, UNI ? "converged-warp issue" : "lane-0 issue         ", N, stages, load_bytes,
          per, (double)h[0] / (kblocks * 4.0), (double)h[sms - 1] / (kblocks * 4.0), ideal, ideal / per);
 }
 
@@ -297,6 +316,20 @@ int main() {
   run<128, true>("MN-major half streamed", 4, 128 * 128, src, dout, sms);
   run<256, true>("MN-major half streamed", 4, 128 * 128 + 128 * 128, src, dout, sms);
   run<256, false>("K-major  half streamed", 4, 128 * 128 + 128 * 128, src, dout, sms);
+  // the same with converged-warp issue: what the operand feed itself sustains (all SMs pulling from L2)
+  run<128, false, true>("K-major  resident", 3, 0, src, dout, sms);
+  run<128, true, true>("MN-major resident", 3, 0, src, dout, sms);
+  run<256, false, true>("K-major  resident", 3, 0, src, dout, sms);
+  run<256, true, true>("MN-major resident", 3, 0, src, dout, sms);
+  run<64, true, true>("MN-major resident", 3, 0, src, dout, sms);
+  run<128, false, true>("K-major  A+B streamed", 4, 128 * 128 + 128 * 128, src, dout, sms);
+  run<128, true, true>("MN-major A+B streamed", 4, 128 * 128 + 128 * 128, src, dout, sms);
+  run<256, false, true>("K-major  A+B streamed", 4, 128 * 128 + 256 * 128, src, dout, sms);
+  run<256, true, true>("MN-major A+B streamed", 4, 128 * 128 + 256 * 128, src, dout, sms);
+  run<256, false, true>("K-major  A+B/2 streamed", 4, 128 * 128 + 128 * 128, src, dout, sms);
+  run<256, true, true>("MN-major A+B/2 streamed", 4, 128 * 128 + 128 * 128, src, dout, sms);
+  run<256, true, true>("MN-major A streamed", 4, 128 * 128, src, dout, sms);
+  run<128, true, true>("MN-major A streamed", 4, 128 * 128, src, dout, sms);
   // is the ~132-cycle floor a dependent-accumulator latency or a per-instruction cost?
   run2<64, 1, false, 1>("SS", dout, sms);
   run2<64, 2, false, 1>("SS", dout, sms);
