@@ -25,7 +25,7 @@
 #define WGRAD_THREADS 192
 #define EPI_TILE_BYTES 4096  // one warp's epilogue staging tile: 32 rows x 128 B
 #ifndef ETB_WGRAD2_DEFAULT
-#define ETB_WGRAD2_DEFAULT 0     // 2-SM weight-gradient kernels: 0 off, 1 NW = 128, 2 NW = 256 (env ETB_WGRAD2 overrides)
+#define ETB_WGRAD2_DEFAULT -1    // 2-SM weight-gradient kernels: -1 per-shape rule, 0 off, 1 NW = 128, 2 NW = 256 (env ETB_WGRAD2 overrides)
 #endif
 
 // ------------------------------------------------------------------------------------------------- PTX wrappers
@@ -1666,6 +1666,10 @@ static int wgrad2_mode(const EtbConvParams* cp, int32_t flags) {
   const int want = e ? atoi(e) : ETB_WGRAD2_DEFAULT;
   const int ntaps = cp->kh * cp->kw;
   if ((flags & 1) || cp->Cout < 256 || ntaps > 12) return 0;
+  // default: the 256-wide 2-SM tile where it measured faster than the 1-SM 256x256 / 128x128 tiles (tools/conv_bench.py, batch
+  // 32, profiles/r2_conv_bench_final*.json): the stride-2 3x3 layers (170 -> 135, 184 -> 133, 113 -> 94, 112 -> 86 us) and the
+  // deepest pointwise layer (2048 -> 1024: 86 -> 75 us); everywhere else the 1-SM tiles are equal or better
+  if (want < 0) return (cp->Cin % 256 == 0 && ((cp->stride == 2 && ntaps == 9) || (ntaps == 1 && cp->Cin >= 2048))) ? 2 : 0;
   if (want == 2 && cp->Cin % 256 == 0) return 2;
   if (want == 1 && cp->Cin >= 128 && cp->Cin % 64 == 0 && (ntaps == 1 || ntaps % 3 == 0)) return 1;
   return 0;

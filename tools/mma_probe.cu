@@ -1,8 +1,19 @@
-// mma_probe.cu -- microbenchmark: issue rate of tcgen05.mma (cta_group::1, bf16, M=128) with K-major vs MN-major SWIZZLE_128B
-// shared-memory operands, with and without a concurrent bulk-copy stream into the same shared memory.
+// mma_probe.cu -- microbenchmarks of the tcgen05.mma issue path on one CTA per SM (bf16, M = 128 per CTA, K = 16).
 //
-// Question it answers (profiles/r2_wgrad_ncu.md): the weight-gradient kernels need 2.3-4x the ideal tensor-pipe cycles per MMA.
-// Is that the MN-major operand mode itself, or the operand feed (shared-memory write bandwidth of the TMA stream)?
+// Written to find out why the weight-gradient kernels needed 2.3-4x the ideal tensor-pipe cycles per MMA
+// (profiles/r2_wgrad_ncu.md).  What it established (profiles/r2_mma_probe.log, B200):
+//   * probe2_kernel (operands resident in shared memory, nothing else in the loop): SS-mode MMAs run at the tensor-pipe floor
+//     for N >= 128 (64.0 / 128.0 cycles at N = 128 / 256, cta_group::1 and ::2, one or several accumulators, A from shared
+//     memory or from TMEM); N = 64 needs 54 cycles instead of 32 (49.5 with A in TMEM).  A dependent accumulator chain
+//     costs nothing.
+//   * probe_kernel (a producer / consumer pipeline like the real kernels): K-major and MN-major SWIZZLE_128B operands are
+//     indistinguishable in every configuration -- the operand mode is not the problem.
+//   * the same pipeline is bound by the ONE warp that issues: with a runtime `it % stages` and `it / stages` in the loop
+//     (two integer divisions, ~100 dependent instructions) it cannot start more than one 4-MMA K block per ~520-580 cycles,
+//     whatever N is and whether or not data is streamed.  Issuing from inside `if (lane == 0)` adds an ELECT / BRA.U.ANY
+//     waterfall per UTCHMMA on top (147 vs 130 cycles per MMA here).
+// The consequence for csrc/conv_tcgen05.cu: producer and MMA warps run converged with one elected lane, keep stage / phase /
+// tile coordinates / descriptors as loop-carried values, and contain no division inside the K loop.
 //
 // build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o tools/mma_probe tools/mma_probe.cu
 // run:   tools/mma_probe        (prints one line per configuration: cycles per MMA, median over the SMs)
