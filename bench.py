@@ -162,11 +162,11 @@ def dominant_kernel_roofline(dev, peak_tflops, peak_kind):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full capture
-DOMINANT_TRAFFIC = 27.45e6 + 0.01e6
-DOMINANT_TRAFFIC_NOTE = ("dram__bytes_read+write per launch from ncu --set full (profiles/r2_prof_conv_fwd2_raw_3x3_256.ncu-rep, 2 launches: 27.45 MB "
-                         "read, 6-13 KB written: under ncu's serialised replay the 26.2 MB output stays L2-resident at kernel end; round 1's capture "
-                         "with a cold L2 between launches showed 12.5-15.1 MB written); algorithmic bytes 26.2 MB in + 1.2 MB weights + 26.2 MB out: "
-                         "no re-reads; tensor pipe 75.8 % active")
+DOMINANT_TRAFFIC = 27.47e6 + 0.11e6
+DOMINANT_TRAFFIC_NOTE = ("dram__bytes_read+write per launch from ncu --set full (profiles/r2_prof_conv_fwd2_raw_3x3_256_final.ncu-rep, 2 launches: "
+                         "27.47 MB read, 0.11 MB written: under ncu's serialised replay the 26.2 MB output stays L2-resident at kernel end; round "
+                         "1's capture with a cold L2 between launches showed 12.5-15.1 MB written); algorithmic bytes 26.2 MB in + 1.2 MB weights "
+                         "+ 26.2 MB out: no re-reads; tensor pipe 81.2 % active")
 
 
 def kernel_table(step, ni, path, graph_ms):

@@ -929,11 +929,15 @@ static int launch_gemm(const GemmGeom& g, ConvKArgs ka, cudaStream_t st) {
   }
   const long Ktot = (long)ka.ntaps * aCp;
   const int BN = g.b_rows > 128 ? 256 : (g.b_rows > 64 ? 128 : 64);
-  static int two_sm = -1;                 // ETB_CONV_2SM=0 disables the cta_group::2 path
-  if (two_sm < 0) { const char* e = getenv("ETB_CONV_2SM"); two_sm = e ? atoi(e) : 1; }
+  // cta_group::2 (the pair halves each SM's weight ingest): always for the 256-wide tile; for the 128-wide tile on the
+  // multi-tap layers only (3x3 128->128 @80: 71 -> 64 us forward, 70 -> 62 us dgrad; the pointwise 128-wide layers are
+  // equal or slower: tools/conv_bench.py, profiles/r2_conv_bench_2sm*.json).  ETB_CONV_2SM = bit mask (1: 256-wide,
+  // 2: 128-wide) overrides the rule; 0 disables the 2-SM path.
+  static int two_sm = -2;
+  if (two_sm == -2) { const char* e = getenv("ETB_CONV_2SM"); two_sm = e ? atoi(e) : -1; }
   const long m_tiles_all = (long)ka.tiles_w * ka.tiles_h * nimg;
-  // cta_group::2 for the 256- and 128-wide tiles (two_sm & 1 / & 2): the pair halves each SM's weight ingest
-  const bool use2 = ((BN == 256 && (two_sm & 1)) || (BN == 128 && (two_sm & 2))) && m_tiles_all >= 2;
+  const bool want2 = two_sm < 0 ? (BN == 256 || (BN == 128 && ka.ntaps > 1)) : ((BN == 256 && (two_sm & 1)) || (BN == 128 && (two_sm & 2)));
+  const bool use2 = want2 && m_tiles_all >= 2;
   cuuint64_t wdim[2] = {(cuuint64_t)Ktot, (cuuint64_t)g.b_rows};
   cuuint64_t wstr[1] = {(cuuint64_t)Ktot * 2};
   cuuint32_t wbox[2] = {64, (cuuint32_t)(use2 ? BN / 2 : BN)};
