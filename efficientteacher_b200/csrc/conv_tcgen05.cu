@@ -347,6 +347,55 @@ __device__ __forceinline__ void epilogue_preload(const ConvKArgs& a, int n0, int
   }
 }
 
+// One 16-byte output piece (8 consecutive channels starting at gc, all < Cout) of this lane's pixel row: EPI 1 applies the
+// folded BN scale/bias, the activation and the shortcut; EPI 0 optionally adds the existing output (gradient fan-in).
+template <int EPI>
+__device__ __forceinline__ uint4 epi_piece(const ConvKArgs& a, const uint32_t* v8, int gc, bool row_ok, size_t pix, const uint4* preq) {
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v8[j]);
+  if (EPI == 1) {
+    const float4 s0 = a.scale ? __ldg(reinterpret_cast<const float4*>(a.scale + gc)) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 s1 = a.scale ? __ldg(reinterpret_cast<const float4*>(a.scale + gc) + 1) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 b0 = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + gc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 b1 = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + gc) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float bi[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float x = fmaf(f[j], sc[j], bi[j]);
+      if (a.act == 1) { const float hh = 0.5f * x; float th; asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(hh)); x = fmaf(hh, th, hh); }
+      else if (a.act == 2) x = fmaxf(x, 0.0f);
+      f[j] = x;
+    }
+    if (a.residual && row_ok) {
+      const uint4 rv = __ldg(reinterpret_cast<const uint4*>(a.residual + pix * a.res_cstride + a.res_coffset + gc));
+      const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 rf = __bfloat1622float2(r2[j]);
+        f[2 * j] += rf.x;
+        f[2 * j + 1] += rf.y;
+      }
+    }
+  }
+  if (EPI == 0 && a.accumulate && row_ok) {
+    const uint4 pv = *preq;
+    const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&pv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 pf = __bfloat1622float2(p2[j]);
+      f[2 * j] += pf.x;
+      f[2 * j + 1] += pf.y;
+    }
+  }
+  uint4 ov;
+  __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+  return ov;
+}
+
 // 64 output channels [cc, cc+64) of this warp's 32 pixel rows, stored through the staging tile: every lane converts its own
 // row (two tcgen05.ld of 32 columns -> 8 pieces of 8 bf16), parks it, and store instruction i then writes pixels 4i..4i+3 with
 // 128 contiguous bytes each.  Same arithmetic as conv_epilogue_chunk's whole-chunk branch; a tail (Cout % 64) takes that path.
@@ -365,53 +414,9 @@ __device__ __forceinline__ bool conv_epilogue_chunk64(const ConvKArgs& a, uint32
   for (int h = 0; h < 2; ++h) {
     uint32_t v[32];
     tmem_ld32(lane_addr + (uint32_t)(c0 + 32 * h), v);
-    const int gch = gc0 + 32 * h;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float f[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[q * 8 + j]);
-      if (EPI == 1) {
-        const float4 s0 = a.scale ? __ldg(reinterpret_cast<const float4*>(a.scale + gch) + 2 * q) : make_float4(1.f, 1.f, 1.f, 1.f);
-        const float4 s1 = a.scale ? __ldg(reinterpret_cast<const float4*>(a.scale + gch) + 2 * q + 1) : make_float4(1.f, 1.f, 1.f, 1.f);
-        const float4 b0 = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + gch) + 2 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 b1 = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + gch) + 2 * q + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-        const float bi[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float x = fmaf(f[j], sc[j], bi[j]);
-          if (a.act == 1) { const float hh = 0.5f * x; float th; asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(hh)); x = fmaf(hh, th, hh); }
-          else if (a.act == 2) x = fmaxf(x, 0.0f);
-          f[j] = x;
-        }
-        if (a.residual && row_ok) {
-          const uint4 rv = __ldg(reinterpret_cast<const uint4*>(a.residual + pix * a.res_cstride + a.res_coffset + gch) + q);
-          const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 rf = __bfloat1622float2(r2[j]);
-            f[2 * j] += rf.x;
-            f[2 * j + 1] += rf.y;
-          }
-        }
-      }
-      if (EPI == 0 && a.accumulate && row_ok) {
-        const uint4 pv = pre[4 * h + q];
-        const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&pv);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 pf = __bfloat1622float2(p2[j]);
-          f[2 * j] += pf.x;
-          f[2 * j + 1] += pf.y;
-        }
-      }
-      uint4 ov;
-      __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-      stage_write(tile, lane, 4 * h + q, ov);
-    }
+    for (int q = 0; q < 4; ++q)
+      stage_write(tile, lane, 4 * h + q, epi_piece<EPI>(a, v + 8 * q, gc0 + 32 * h + 8 * q, row_ok, pix, EPI == 0 ? pre + 4 * h + q : pre));
   }
   __syncwarp();
   const unsigned long long row_off = (unsigned long long)pix * (unsigned long long)a.y_cstride;
@@ -427,11 +432,93 @@ __device__ __forceinline__ bool conv_epilogue_chunk64(const ConvKArgs& a, uint32
   return true;
 }
 
+// The 64-wide tile (HALF = 32 channels = 64 B per row and warp): 32 rows x 64 B staged, store instruction i writes rows
+// 8i..8i+7 with 64 contiguous bytes each.  Swizzle: 16-byte piece q of row r sits at piece q ^ ((r >> 1) & 3).
+template <int BN, int EPI>
+__device__ __forceinline__ bool conv_epilogue_chunk32s(const ConvKArgs& a, uint32_t lane_addr, int n0, int chalf, bool row_ok, size_t pix,
+                                                       const uint4* pre, uint8_t* tile, int lane) {
+  constexpr int HALF = BN / 2;
+  const int c0 = chalf * HALF;
+  const int gc0 = n0 + c0;
+  if (gc0 >= a.Cout) return false;                 // warp-uniform
+  if (gc0 + 32 > a.Cout) return conv_epilogue_chunk<BN, EPI>(a, lane_addr, n0, chalf, row_ok, pix, 0, pre);
+  uint32_t v[32];
+  tmem_ld32(lane_addr + (uint32_t)c0, v);
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    *reinterpret_cast<uint4*>(tile + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = epi_piece<EPI>(a, v + 8 * q, gc0 + 8 * q, row_ok, pix, EPI == 0 ? pre + q : pre);
+  __syncwarp();
+  const unsigned long long row_off = (unsigned long long)pix * (unsigned long long)a.y_cstride;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = 8 * i + (lane >> 2), c = lane & 3;
+    const unsigned long long off_r = __shfl_sync(0xffffffffu, row_off, r);
+    const int ok_r = __shfl_sync(0xffffffffu, (int)row_ok, r);
+    const uint4 o = *reinterpret_cast<const uint4*>(tile + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+    if (ok_r) *reinterpret_cast<uint4*>(a.y + off_r + a.y_coffset + gc0 + c * 8) = o;
+  }
+  __syncwarp();
+  return true;
+}
+
+// Detect layout (EPI 2): y[img][anchor][pixel][o] fp32 with channel c = anchor * no + o (yolov5_head.py:66).  For one anchor the
+// outputs of consecutive pixels are contiguous, so the warp parks its 32 rows x 32 channels (+ bias) and then stores ONE pixel
+// row per instruction: 32 lanes = 32 consecutive channels = 128 contiguous bytes (two runs at an anchor boundary); the
+// channel -> (anchor, o) split is computed once per lane and chunk instead of once per element.
+template <int BN>
+__device__ __forceinline__ bool conv_epilogue_chunk_det(const ConvKArgs& a, uint32_t lane_addr, int n0, int chalf, bool row_ok, size_t pix, int cc,
+                                                        uint8_t* tile, int lane) {
+  constexpr int HALF = BN / 2;
+  const int c0 = chalf * HALF + cc;
+  const int gc0 = n0 + c0;
+  if (gc0 >= a.Cout) return false;                 // warp-uniform
+  uint32_t v[32];
+  tmem_ld32(lane_addr + (uint32_t)c0, v);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    float f[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gc = gc0 + 4 * q + j;
+      f[j] = __uint_as_float(v[4 * q + j]) + ((a.bias && gc < a.Cout) ? __ldg(a.bias + gc) : 0.0f);
+    }
+    stage_write(tile, lane, q, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])));
+  }
+  __syncwarp();
+  const size_t hw = (size_t)a.det_hw;
+  const int na = a.Cout / a.det_no;
+  const size_t img_r = pix / hw, pin = pix - img_r * hw;          // pix is the global pixel index in both tilings
+  const unsigned long long base = (unsigned long long)((img_r * na * hw + pin) * a.det_no);
+  const int gc = gc0 + lane;
+  const bool c_ok = gc < a.Cout;
+  const int an = gc / a.det_no, o = gc - an * a.det_no;
+  const unsigned long long coff = (unsigned long long)an * hw * a.det_no + o;
+#pragma unroll 4
+  for (int r = 0; r < 32; ++r) {
+    const unsigned long long base_r = __shfl_sync(0xffffffffu, base, r);
+    const int ok_r = __shfl_sync(0xffffffffu, (int)row_ok, r);
+    const float val = *reinterpret_cast<const float*>(tile + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
+    if (ok_r && c_ok) a.y_f32[base_r + coff] = val;
+  }
+  __syncwarp();
+  return true;
+}
+
 template <int BN, int EPI>
 __device__ __forceinline__ void conv_epilogue_cols(const ConvKArgs& a, uint32_t lane_addr, int n0, int chalf, bool row_ok, size_t pix,
                                                    const EpiPre<BN, EPI>& pre, uint8_t* tile, int lane) {
   constexpr int HALF = BN / 2;
-  if (EPI != 2 && HALF % 64 == 0 && a.epi_staged) {   // warp-uniform
+  if (EPI == 2 && a.epi_staged) {                     // warp-uniform
+#pragma unroll 1
+    for (int cc = 0; cc < HALF; cc += 32)
+      if (!conv_epilogue_chunk_det<BN>(a, lane_addr, n0, chalf, row_ok, pix, cc, tile, lane)) break;
+    return;
+  }
+  if (EPI != 2 && HALF == 32 && a.epi_staged) {
+    conv_epilogue_chunk32s<BN, EPI>(a, lane_addr, n0, chalf, row_ok, pix, pre.v, tile, lane);
+    return;
+  }
+  if (EPI != 2 && HALF % 64 == 0 && a.epi_staged) {
     if (EPI == 0) {
 #pragma unroll
       for (int cc = 0; cc < HALF; cc += 64)
