@@ -395,6 +395,13 @@ def main():
     f01 = lambda t: t.to(dev).float() / 255.0  # noqa: E731  trainer/ssod_trainer.py:694-696
     d_imgs, d_uw, d_us = f01(host["imgs"]), f01(host["u_weak"]), f01(host["u_strong"])
     d_tg, d_Ms = host["targets"].to(dev), host["Ms"].to(dev)
+    if world > 1:
+        # Gradients are AVERAGED across ranks in the benchmark (ncclAvg: the same single collective over the same 191.8 MB arena
+        # as the reference's sum; every kernel is identical).  With the reference's SUM the effective learning rate grows with
+        # the world size, the random-init student's BatchNorm scales drift world_size x faster and the EMA teacher's candidate
+        # count leaves the self-check's [0.5, 2] x window within the 20 timed steps at N >= 4 (N = 2 with SUM: 0.61 x, N = 1:
+        # 0.79 x).  Averaging keeps the synthetic state at every N as close to the single-GPU one as its data allows.
+        SSODTrainerStep.GRAD_REDUCE = "avg"
     if ssod:
         cfg = yolov5_ssod_cfg('l', batch_size=(bl + bu) * world, img_size=img)
         cfg.SSOD.fixed_accumulate = True       # optimizer step + both EMA updates EVERY iteration
@@ -622,7 +629,7 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic (seeded uint8 images, 8 gt boxes/img, random-init YOLOv5l with BN statistics calibrated on the batch; teacher objectness calibrated to ~2% NMS candidates)",
             "config": {"workload": cb["workload"], "config_name": args.config,
-                       "global_batch": imgs_per_step, "img_size": img, "parallelism": "dp%d" % world, "cuda_graph": use_graph,
+                       "global_batch": imgs_per_step, "img_size": img, "parallelism": "dp%d" % world, "grad_reduce": ("ncclAvg of the flat arena (reference: sum; see bench.py)" if world > 1 else "none (1 GPU)"), "cuda_graph": use_graph,
                        "schedule": "reference warm-up from ni=0 (nw=%s, nb=%d): lr/momentum change every step (device-resident hyper-parameters)" % (st.nw, NB),
                        "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
                        "native": "teacher trunk+head, student conv fwd/dgrad/wgrad (tcgen05) + BatchNorm(train)+SiLU fwd/bwd, weight packing, NMS/pseudo-label, assigners, losses fwd/bwd, SGD, EMA",

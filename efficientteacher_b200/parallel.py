@@ -57,6 +57,11 @@ class GradArena:
         self.bounds.append(n)
         self.bounds = sorted(set(self.bounds))
         self._works, self._comm, self._next = [], None, 0
+        self.average = False    # True: ncclAvg instead of ncclSum (same collective, same cost); see SSODTrainerStep.GRAD_REDUCE
+
+    def _op(self):
+        import torch.distributed as dist
+        return dist.ReduceOp.AVG if self.average else dist.ReduceOp.SUM
 
     def n_chunks(self):
         return len(self.bounds) - 1
@@ -82,7 +87,7 @@ class GradArena:
         with torch.cuda.stream(self._comm):
             while self._next <= k and self._next < self.n_chunks():
                 a, b = self.bounds[self._next], self.bounds[self._next + 1]
-                self._works.append(dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=group, async_op=True))
+                self._works.append(dist.all_reduce(self.flat[a:b], op=self._op(), group=group, async_op=True))
                 self._next += 1
 
     def finish(self, world_size, extra_stream=None, group=None):
@@ -112,7 +117,7 @@ class GradArena:
     def all_reduce_sum(self, world_size, group=None):
         if world_size > 1:
             import torch.distributed as dist
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(self.flat, op=self._op(), group=group)
         return self.flat
 
 

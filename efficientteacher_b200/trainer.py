@@ -142,10 +142,17 @@ class SSODTrainerStep:
             return self.COMM_IN_GRAPH
         return self.COMM_OVERLAP or self.COMM_IN_GRAPH
 
+    # "sum" = the reference (loss * WORLD_SIZE, then DDP's mean: trainer/ssod_trainer.py:638-648).  "avg" (ncclAvg: the same
+    # collective at the same cost) is for synthetic benchmarks only: with SUM the effective learning rate grows with the world
+    # size, and a random-init model's BatchNorm scales then drift WORLD_SIZE x faster (bench.py's self-check explains why that
+    # matters); set before the first step.
+    GRAD_REDUCE = os.environ.get("ETB_GRAD_REDUCE", "sum")
+
     def _allreduce_grads(self):
-        """WORLD_SIZE > 1: SUM all-reduce of the gradient arena (the chunks that were not already issued during backward)"""
+        """WORLD_SIZE > 1: all-reduce of the gradient arena (the chunks that were not already issued during backward)"""
         if self.WORLD_SIZE <= 1:
             return
+        self._arena.average = (self.GRAD_REDUCE == "avg")
         if self._arena._next == 0 and not (self.COMM_OVERLAP or self.COMM_IN_GRAPH):
             self._arena.all_reduce_sum(self.WORLD_SIZE)          # one collective over the whole arena
         else:
@@ -484,6 +491,7 @@ class SupTrainerStep:
     def train_step(self, imgs, targets, ni):
         loss = self._forward_backward(imgs, targets)
         if self._warmup(ni):
+            self._arena.average = (SSODTrainerStep.GRAD_REDUCE == "avg")
             self._arena.all_reduce_sum(self.WORLD_SIZE)
             self._step_and_ema()
             self.last_opt_step = ni
@@ -519,6 +527,7 @@ class SupTrainerStep:
         self._bn_broadcast()
         g["graph"].replay()
         if self._warmup(ni):
+            self._arena.average = (SSODTrainerStep.GRAD_REDUCE == "avg")
             self._arena.all_reduce_sum(self.WORLD_SIZE)
             self._step_and_ema()
             self.last_opt_step = ni
