@@ -118,3 +118,44 @@ def make_images(seed, n, img=640, targets=None):
         im = im + (r.rand(3, img, img).astype(F32) - 0.5) * 0.08
         out[i] = (np.clip(im, 0, 1) * 255.0 + 0.5).astype(np.uint8)
     return out
+
+
+def make_tal_inputs(seed, B, n_gt, img=640, nc=80, reg_max=16, score_pow=4, tiny=0):
+    """Inputs of TaskAlignedAssigner.forward as models/loss/tal_loss.py:76-101 would build them:
+    pd_scores ~ U(0,1)^score_pow [B,A,nc]; pd_bboxes = DFL-style boxes around each anchor point (ltrb distances ~ U(0, reg_max)
+    grid cells, times the stride) in pixels; n_gt[b] ground-truth boxes per image (xyxy pixels, centre U(.1,.9), size U(.02,.5)),
+    padded with label -1 / zero boxes to max(n_gt); `tiny` of the first image's boxes are smaller than one P3 cell (fewer than
+    13 anchor points inside -> the top-k runs over zeros).  Returns fp32 arrays (labels as float, like the reference's targets)."""
+    r = np.random.RandomState(seed)
+    shapes = level_shapes(img)
+    pts, st = [], []
+    for (h, w), s in zip(shapes, STRIDES):
+        yy, xx = np.meshgrid((np.arange(h, dtype=F32) + F32(0.5)) * F32(s), (np.arange(w, dtype=F32) + F32(0.5)) * F32(s), indexing="ij")
+        pts.append(np.stack([xx, yy], -1).reshape(-1, 2))
+        st.append(np.full((h * w, 1), s, F32))
+    anc, stride = np.concatenate(pts).astype(F32), np.concatenate(st)
+    A = anc.shape[0]
+    pd_scores = (r.uniform(0, 1, (B, A, nc)) ** score_pow).astype(F32)
+    dist = (r.uniform(0, reg_max, (B, A, 4)).astype(F32)) * stride[None]
+    pd_bboxes = np.concatenate([anc[None] - dist[..., :2], anc[None] + dist[..., 2:]], -1).astype(F32)
+    M = max(n_gt) if len(n_gt) else 0
+    gt_labels = np.full((B, M, 1), -1, F32)
+    gt_bboxes = np.zeros((B, M, 4), F32)
+    for b in range(B):
+        n = n_gt[b]
+        c = r.uniform(0.1, 0.9, (n, 2)) * img
+        wh = r.uniform(0.02, 0.5, (n, 2)) * img
+        if b == 0 and tiny:
+            wh[:tiny] = r.uniform(2.0, 7.0, (tiny, 2))
+        gt_bboxes[b, :n] = np.concatenate([c - wh / 2, c + wh / 2], -1).astype(F32)
+        gt_labels[b, :n, 0] = r.randint(0, nc, n)
+    mask_gt = (gt_bboxes.sum(-1, keepdims=True) > 0).astype(F32)
+    return dict(pd_scores=pd_scores, pd_bboxes=pd_bboxes, anc_points=anc, gt_labels=gt_labels, gt_bboxes=gt_bboxes, mask_gt=mask_gt,
+                stride=stride)
+
+
+def make_v8_head_logits(seed, B, img=640, nc=80, reg_max=16, scale=2.0):
+    """Train-layout outputs of YoloV8Detect (yolov8_head.py:117-135): cls [B,A,nc], reg [B,A,4*(reg_max+1)] fp32 logits."""
+    r = np.random.RandomState(seed)
+    A = sum(h * w for h, w in level_shapes(img))
+    return (r.randn(B, A, nc).astype(F32) * F32(scale) - F32(2.0)), (r.randn(B, A, 4 * (reg_max + 1)).astype(F32) * F32(scale))
