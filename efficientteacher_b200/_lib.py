@@ -71,6 +71,11 @@ class EtbFocalParams(C.Structure):
                 ("label", C.c_int32)]
 
 
+class EtbV8Levels(C.Structure):
+    _fields_ = [("nl", C.c_int32), ("h", C.c_int32 * ETB_MAX_LEVELS), ("w", C.c_int32 * ETB_MAX_LEVELS),
+                ("stride", C.c_float * ETB_MAX_LEVELS)]
+
+
 class EtbConvParams(C.Structure):
     _fields_ = [("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32),
                 ("kh", C.c_int32), ("kw", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
@@ -152,6 +157,10 @@ _SIGS = {
     "etb_bn_bwd_fused": (C.c_int, [vp, vp, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp, C.c_int32, vp,
                                   C.c_int32, vp, vp]),
     "etb_stem_im2col_into": (C.c_int, [vp, C.c_int32, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, vp]),
+    "etb_tal_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "etb_tal_assign": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float,
+                                C.c_float, vp, vp, vp, vp, vp, C.c_size_t, vp]),
+    "etb_v8_decode": (C.c_int, [vp, vp, C.POINTER(EtbV8Levels), C.c_int32, C.c_int32, C.c_int32, C.c_float, vp, vp, vp, vp, vp]),
 }
 
 _lib = None

@@ -402,6 +402,39 @@ int etb_bn_bwd_fused(const void* da_bf16, const void* y_bf16, const float* stats
                      int32_t y_cstride, int32_t dy_cstride, int32_t act, void* dy_bf16, float* sums, float* dgamma,
                      float* dbeta, int32_t accumulate, float* partials, int32_t rows, uint32_t* barrier, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Anchor-free (YOLOv8) pieces -- SURVEY.md section 8f row 5.  The reference defines no end-to-end step for this head
+ * (models/loss/tal_loss.py cannot be imported, trainer/ssod_trainer.py:598-606 rejects it): these are the importable
+ * operators, with the reference's call contracts.
+ *
+ * etb_tal_assign = TaskAlignedAssigner.forward (models/assigner/tal_assigner.py:29-80; helpers
+ * models/module/nanodet_utils.py:184-248) for n_max_boxes = M > 0, all tensors fp32 contiguous on the device:
+ *   pd_scores [B,A,nc] (already sigmoid), pd_bboxes [B,A,4] xyxy, anc_points [A,2], gt_labels [B,M] (the reference's
+ *   [B,M,1]), gt_bboxes [B,M,4] xyxy, mask_gt [B,M]
+ *   -> target_labels [B,A] int64, target_bboxes [B,A,4], target_scores [B,A,nc], fg_mask [B,A] uint8 (torch.bool).
+ * Ties inside the top-k go to the lowest anchor index (torch.topk promises no order).  A <= 51200, topk <= A.
+ * workspace: etb_tal_workspace_bytes(B, A, M), 16-byte aligned, contents irrelevant on entry.
+ * ------------------------------------------------------------------------------------------- */
+size_t etb_tal_workspace_bytes(int32_t B, int32_t A, int32_t M);
+int etb_tal_assign(const float* pd_scores, const float* pd_bboxes, const float* anc_points, const float* gt_labels,
+                   const float* gt_bboxes, const float* mask_gt, int32_t B, int32_t A, int32_t M, int32_t nc, int32_t topk,
+                   float alpha, float beta, float eps, int64_t* target_labels, float* target_bboxes, float* target_scores,
+                   uint8_t* fg_mask, void* workspace, size_t workspace_bytes, void* stream);
+
+/* etb_v8_decode = the DFL decode of YoloV8Detect's eval branch (models/head/yolov8_head.py:169-220) and of
+ * ComputeTalLoss.bbox_decode (models/loss/tal_loss.py:88-95,150-156) from the head's train-layout outputs
+ * cls [B,A,nc] / reg [B,A,4*(reg_max+1)] fp32 (levels concatenated along A, row-major inside a level; anchor points
+ * (x + grid_cell_offset, y + grid_cell_offset) as models/module/nanodet_utils.py:135-182 generates them).  Each output is
+ * optional (NULL):  pred [B,A,5+nc] = (cx,cy,w,h)*stride, 1, sigmoid(cls);  boxes_grid [B,A,4] xyxy in grid units;
+ * boxes_pix [B,A,4] = boxes_grid * stride (the assigner's pd_bboxes);  scores [B,A,nc] = sigmoid(cls) (its pd_scores). */
+typedef struct EtbV8Levels {
+  int32_t nl;
+  int32_t h[ETB_MAX_LEVELS], w[ETB_MAX_LEVELS];
+  float stride[ETB_MAX_LEVELS];
+} EtbV8Levels;
+int etb_v8_decode(const float* cls, const float* reg, const EtbV8Levels* levels, int32_t B, int32_t nc, int32_t reg_max,
+                  float grid_cell_offset, float* pred, float* boxes_grid, float* boxes_pix, float* scores, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,7 +39,7 @@ def test_library_exports_all_declared_symbols(built):
 
 
 def test_struct_layouts_match_c(built, tmp_path):
-    names = ["EtbEmaChunk", "EtbNmsParams", "EtbAssignLevels", "EtbAssignOut", "EtbLossParams", "EtbFocalParams", "EtbPackDesc", "EtbFoldDesc", "EtbSgdChunk"]
+    names = ["EtbEmaChunk", "EtbNmsParams", "EtbAssignLevels", "EtbAssignOut", "EtbLossParams", "EtbFocalParams", "EtbPackDesc", "EtbFoldDesc", "EtbSgdChunk", "EtbV8Levels"]
     if hasattr(built, "EtbConvParams") and "EtbConvParams" in open(os.path.join(ROOT, "include", "etb200.h")).read():
         names.append("EtbConvParams")
     src = '#include <stdio.h>\n#include "etb200.h"\nint main(){' + "".join(

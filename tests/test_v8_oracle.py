@@ -100,3 +100,32 @@ def test_tal_assign_vs_live_reference_fresh_seeds():
         labels, bboxes, scores, fg = port_v8.tal_assign(d["pd_scores"], d["pd_bboxes"], d["anc_points"], d["gt_labels"], d["gt_bboxes"], d["mask_gt"])
         assert np.array_equal(fg, rf.numpy()) and np.array_equal(labels, rl.numpy()) and np.array_equal(bboxes, rb.numpy())
         np.testing.assert_allclose(scores, rs.numpy(), rtol=1e-6, atol=1e-12)
+
+
+def test_mirror_generate_anchors_and_no_cpu_fallback():
+    """Host side of efficientteacher_b200/tal.py: the anchor tables equal the live reference's (they are constants, built with
+    torch on any device); the operators themselves raise without CUDA -- there is no CPU path."""
+    from efficientteacher_b200 import tal
+    g = np.load(os.path.join(GOLD, "v8_anchors.npz"))
+    for img in (320, 640):
+        feats = [torch.zeros(1, 1, h, w) for h, w in synth.level_shapes(img)]
+        pts, st = tal.generate_anchors(feats, [8, 16, 32], 5.0, 0.5, device='cpu', is_eval=True)
+        assert np.array_equal(pts.numpy(), g["eval_pts_%d" % img]) and np.array_equal(st.numpy(), g["eval_stride_%d" % img])
+        anchors, pts_t, counts, st_t = tal.generate_anchors(feats, [8, 16, 32], 5.0, 0.5, device='cpu', is_eval=False)
+        assert np.array_equal(pts_t.numpy(), g["train_pts_%d" % img]) and np.array_equal(st_t.numpy(), g["train_stride_%d" % img])
+        assert counts == [h * w for h, w in synth.level_shapes(img)] and anchors.shape == (sum(counts), 4)
+    if ref_harness.reference_available():
+        ref_harness.load_reference()
+        from models.module.nanodet_utils import generate_anchors as ref_ga
+        feats = [torch.zeros(1, 1, h, w) for h, w in synth.level_shapes(320)]
+        for a, b in zip(ref_ga(feats, [8, 16, 32], 5.0, 0.5, device='cpu', is_eval=False),
+                        tal.generate_anchors(feats, [8, 16, 32], 5.0, 0.5, device='cpu', is_eval=False)):
+            assert (a == b) if isinstance(a, list) else torch.equal(a, b)
+    if not torch.cuda.is_available():
+        d = synth.make_tal_inputs(1, 1, [2], img=320)
+        t = {k: torch.from_numpy(v) for k, v in d.items()}
+        with pytest.raises(RuntimeError):
+            tal.TaskAlignedAssigner()(t["pd_scores"], t["pd_bboxes"], t["anc_points"], t["gt_labels"], t["gt_bboxes"], t["mask_gt"])
+        cls, reg = synth.make_v8_head_logits(1, 1, img=320)
+        with pytest.raises(RuntimeError):
+            tal.decode_eval(torch.from_numpy(cls), torch.from_numpy(reg), synth.level_shapes(320), synth.STRIDES)
