@@ -17,7 +17,7 @@ Modules of the host application imported later with `from X import Y` see the pa
 import importlib
 import sys
 
-from . import _lib, ema, labelmatch, loss, model, nms, pseudo_label, ssod_loss, assigner
+from . import _lib, ema, labelmatch, loss, model, nms, pseudo_label, ssod_loss, assigner, tal
 
 _lib.lib()  # fail loudly now if the kernels are not built
 
@@ -60,6 +60,7 @@ _PATCHES = [
     ("models.loss.loss", "ComputeLoss", loss.ComputeLoss),
     ("models.loss.ssod.ssod_loss", "ComputeStudentMatchLoss", ssod_loss.ComputeStudentMatchLoss),
     ("models.assigner.yolo_anchor_assigner", "YOLOAnchorAssigner", assigner.YOLOAnchorAssigner),
+    ("models.assigner.tal_assigner", "TaskAlignedAssigner", tal.TaskAlignedAssigner),     # the only consumer, tal_loss.py, is unimportable
     ("models.detector.yolo_ssod", "Model", model.Model),
     ("models.detector.yolo", "Model", model.SupModel),
 ]

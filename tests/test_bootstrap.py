@@ -46,6 +46,8 @@ SCRIPT = textwrap.dedent('''
     b1, b2 = torch.rand(4, 7), torch.rand(7, 4)
     assert torch.equal(MT.bbox_iou(b1, b2, x1y1x2y2=False, CIoU=True), MT.bbox_iou.__wrapped__(b1, b2, x1y1x2y2=False, CIoU=True))  # CPU -> reference
     assert sys.modules["models.assigner"].YOLOAnchorAssigner is assigner.YOLOAnchorAssigner
+    from efficientteacher_b200 import tal
+    assert sys.modules["models.assigner.tal_assigner"].TaskAlignedAssigner is tal.TaskAlignedAssigner
     assert bs.apply() == []          # idempotent
     # nothing of the reference's own hot-path classes is left reachable from the trainers' namespaces
     for mod in (T, S):
