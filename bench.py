@@ -358,6 +358,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--config", default="ssod640", choices=sorted(CONFIGS), help="ssod640 = the headline (BASELINE.json metric); ssod1280 / sup32 = configs[4] / configs[1]")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, what the driver measures): the config's per-GPU batch at every N; strong: the config's batch is the "
+                         "GLOBAL batch, split evenly over the ranks (SURVEY.md 8d: 16+16 -> 8+8 -> 4+4 -> 2+2 per GPU at 1/2/4/8 GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end leg")
@@ -376,6 +379,9 @@ def main():
     assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
     cb = CONFIGS[args.config]
     bl, bu, img, ssod = cb["bl"], cb["bu"], cb["img"], cb["kind"] == "ssod"
+    if args.scaling == "strong":
+        assert bl % world == 0 and bu % world == 0, "strong scaling: the global batch must divide by the world size"
+        bl, bu = bl // world, bu // world
     import __graft_entry__ as g
     if rank == 0:
         g.build()
@@ -626,10 +632,10 @@ def main():
         h2d = sum(host[k].numel() * host[k].element_size() for k in keys)
         out = {
             "metric": cb["metric"], "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic (seeded uint8 images, 8 gt boxes/img, random-init YOLOv5l with BN statistics calibrated on the batch; teacher objectness calibrated to ~2% NMS candidates)",
             "config": {"workload": cb["workload"], "config_name": args.config,
-                       "global_batch": imgs_per_step, "img_size": img, "parallelism": "dp%d" % world, "grad_reduce": ("ncclAvg of the flat arena (reference: sum; see bench.py)" if world > 1 else "none (1 GPU)"), "cuda_graph": use_graph,
+                       "global_batch": imgs_per_step, "per_gpu_batch": [bl, bu], "img_size": img, "parallelism": "dp%d" % world, "grad_reduce": ("ncclAvg of the flat arena (reference: sum; see bench.py)" if world > 1 else "none (1 GPU)"), "cuda_graph": use_graph,
                        "schedule": "reference warm-up from ni=0 (nw=%s, nb=%d): lr/momentum change every step (device-resident hyper-parameters)" % (st.nw, NB),
                        "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
                        "native": "teacher trunk+head, student conv fwd/dgrad/wgrad (tcgen05) + BatchNorm(train)+SiLU fwd/bwd, weight packing, NMS/pseudo-label, assigners, losses fwd/bwd, SGD, EMA",
