@@ -3,8 +3,8 @@
 Labels / boxes / foreground masks bit-exact; target_scores within 1e-5 relative (the alignment metric goes through pow);
 decoded boxes within 1e-5 relative.
 
-This file sorts last on purpose: it was written after the round's GPU budget had been spent, so its first run on a B200 is the
-driver's; a failure here must not hide the results of the validated suite before it (pytest -x)."""
+This file sorts last on purpose: it was written when 5 GPU-minutes of the round were left (first B200 run: 11 passed,
+profiles/r2_v8_gpu_tests.log), and a failure here must never hide the results of the older suite before it (pytest -x)."""
 import os
 
 import numpy as np
